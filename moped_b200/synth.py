@@ -1,0 +1,126 @@
+"""Synthetic model databases and frames of the shape BASELINE.json names.
+
+There is no network for the reference's model set (moped2/download_models.sh wgets it), so every
+configuration runs on seeded synthetic data:
+
+* model DB: ``n_obj`` objects x ``pts_per_obj`` points; coord3D ~ U(-0.1, 0.1)^3 m; descriptor =
+  SIFT-like non-negative 128-d (16 cells x 8 bins ~ Gamma(0.5), L2-normalise, clip 0.2, renormalise —
+  the post-processing of libs.tgz!libsiftfast-1.1-src/libsiftfast.cpp:1504-1515).
+* frame: 640x480, K=(800,800,320,240), identity camera (moped2/moped_test.cpp:187-188);
+  ``n_visible`` objects posed in front of the camera, ``pts_visible`` of their points projected with
+  N(0, 0.5 px) noise and N(0, 0.02) descriptor noise; the rest of the Q features are distractors.
+
+Pure numpy; used by tests/ and bench.py (inputs only — no algorithm of the hot path lives here).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BASE_SEED = 20261017
+K_DEFAULT = np.array([800.0, 800.0, 320.0, 240.0], dtype=np.float32)
+CAM_IDENTITY = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float32)  # quat (x,y,z,w) + t
+
+
+def sift_like(rng: np.random.Generator, n: int, d: int = 128) -> np.ndarray:
+    x = rng.gamma(0.5, 1.0, size=(n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    np.minimum(x, 0.2, out=x)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x.astype(np.float32)
+
+
+def make_db(n_obj: int, pts_per_obj: int = 1000, d: int = 128, seed: int = BASE_SEED, ragged: bool = False):
+    """Returns dict(n_pts[int32 n_obj], xyz[N,3], desc[N,d], model_of_row[int32 N])."""
+    rng = np.random.default_rng(seed)
+    if ragged:
+        n_pts = rng.integers(max(8, pts_per_obj * 6 // 10), pts_per_obj * 3 + 1, size=n_obj).astype(np.int32)
+    else:
+        n_pts = np.full(n_obj, pts_per_obj, dtype=np.int32)
+    n = int(n_pts.sum())
+    xyz = rng.uniform(-0.1, 0.1, size=(n, 3)).astype(np.float32)
+    desc = np.empty((n, d), dtype=np.float32)
+    step = 1 << 16
+    for s in range(0, n, step):
+        desc[s:s + step] = sift_like(rng, min(step, n - s), d)
+    model_of_row = np.repeat(np.arange(n_obj, dtype=np.int32), n_pts)
+    return dict(n_pts=n_pts, xyz=xyz, desc=desc, model_of_row=model_of_row)
+
+
+def quat_to_R(q: np.ndarray) -> np.ndarray:
+    x, y, z, w = [float(v) for v in q]
+    return np.array([
+        [1 - 2 * y * y - 2 * z * z, 2 * x * y - 2 * w * z, 2 * x * z + 2 * w * y],
+        [2 * x * y + 2 * w * z, 1 - 2 * x * x - 2 * z * z, 2 * y * z - 2 * w * x],
+        [2 * x * z - 2 * w * y, 2 * y * z + 2 * w * x, 1 - 2 * x * x - 2 * y * y]], dtype=np.float64)
+
+
+def make_frame(db, q_feats: int = 2000, n_visible: int = 8, pts_visible: int = 60, frame_id: int = 0,
+               seed: int = BASE_SEED, image_idx: int = 0, K: np.ndarray = K_DEFAULT,
+               pix_noise: float = 0.5, desc_noise: float = 0.02, objects=None):
+    """Returns dict(desc[Q,d], xy[Q,2], image_idx[int32 Q], gt_model[int32 V], gt_pose[V,7], src_row[int32 Q])."""
+    rng = np.random.default_rng(seed + 7919 * (frame_id + 1))
+    n_obj = len(db["n_pts"])
+    d = db["desc"].shape[1]
+    starts = np.concatenate([[0], np.cumsum(db["n_pts"])])
+    if objects is None:
+        objects = rng.choice(n_obj, size=min(n_visible, n_obj), replace=False)
+    descs, xys, src = [], [], []
+    poses = []
+    for o in objects:
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        t = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), rng.uniform(0.6, 1.4)])
+        poses.append(np.concatenate([q, t]).astype(np.float32))
+        R = quat_to_R(q)
+        npts = int(db["n_pts"][o])
+        rows = starts[o] + rng.choice(npts, size=min(pts_visible, npts), replace=False)
+        X = db["xyz"][rows].astype(np.float64) @ R.T + t
+        u = X[:, 0] / X[:, 2] * K[0] + K[2] + rng.normal(0, pix_noise, size=len(rows))
+        v = X[:, 1] / X[:, 2] * K[1] + K[3] + rng.normal(0, pix_noise, size=len(rows))
+        dd = db["desc"][rows] + rng.normal(0, desc_noise, size=(len(rows), d)).astype(np.float32)
+        np.maximum(dd, 0, out=dd)
+        dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+        descs.append(dd.astype(np.float32))
+        xys.append(np.stack([u, v], axis=1).astype(np.float32))
+        src.append(rows.astype(np.int32))
+    n_planted = sum(len(x) for x in descs)
+    n_dis = max(0, q_feats - n_planted)
+    descs.append(sift_like(rng, n_dis, d))
+    xys.append(np.stack([rng.uniform(0, 640, n_dis), rng.uniform(0, 480, n_dis)], axis=1).astype(np.float32))
+    src.append(np.full(n_dis, -1, dtype=np.int32))
+    desc = np.concatenate(descs)[:q_feats]
+    xy = np.concatenate(xys)[:q_feats]
+    src_row = np.concatenate(src)[:q_feats]
+    perm = rng.permutation(len(desc))
+    return dict(desc=np.ascontiguousarray(desc[perm]), xy=np.ascontiguousarray(xy[perm]),
+                image_idx=np.full(len(desc), image_idx, dtype=np.int32),
+                gt_model=np.asarray(objects, dtype=np.int32), gt_pose=np.stack(poses) if poses else np.zeros((0, 7), np.float32),
+                src_row=np.ascontiguousarray(src_row[perm]))
+
+
+def make_ransac_clusters(n_clusters: int = 64, pts: int = 80, outlier_frac: float = 0.5, seed: int = BASE_SEED,
+                         K: np.ndarray = K_DEFAULT, pix_noise: float = 0.5):
+    """RANSAC-heavy config (BASELINE.json configs[3]): n_clusters clusters of `pts` 2D-3D
+    correspondences, `outlier_frac` of them uniform-pixel outliers. One model per cluster.
+    Returns dict(offsets[int32 n+1], xy[M,2], xyz[M,3], image[int32 M], gt_pose[n,7])."""
+    rng = np.random.default_rng(seed + 104729)
+    xy, xyz, poses = [], [], []
+    for _ in range(n_clusters):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        t = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), rng.uniform(0.6, 1.4)])
+        R = quat_to_R(q)
+        X = rng.uniform(-0.1, 0.1, size=(pts, 3))
+        Xc = X @ R.T + t
+        u = Xc[:, 0] / Xc[:, 2] * K[0] + K[2] + rng.normal(0, pix_noise, pts)
+        v = Xc[:, 1] / Xc[:, 2] * K[1] + K[3] + rng.normal(0, pix_noise, pts)
+        n_out = int(round(pts * outlier_frac))
+        out = rng.choice(pts, size=n_out, replace=False)
+        u[out] = rng.uniform(0, 640, n_out)
+        v[out] = rng.uniform(0, 480, n_out)
+        xy.append(np.stack([u, v], axis=1))
+        xyz.append(X)
+        poses.append(np.concatenate([q, t]))
+    offsets = (np.arange(n_clusters + 1) * pts).astype(np.int32)
+    return dict(offsets=offsets, xy=np.concatenate(xy).astype(np.float32), xyz=np.concatenate(xyz).astype(np.float32),
+                image=np.zeros(n_clusters * pts, dtype=np.int32), gt_pose=np.stack(poses).astype(np.float32))
