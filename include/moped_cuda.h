@@ -1,0 +1,164 @@
+/*
+ * moped_cuda.h — C ABI of libmoped_cuda.so, the B200 (sm_100a) implementation of MOPED's
+ * data-parallel recognition core. Plain pointers and sizes only; no C++/torch types.
+ *
+ * One entry point per reference stage `process()` (the drop-in boundary is
+ * `virtual void MopedAlg::process(FrameData&)`, moped2/libmoped/src/util.hpp:147); the header-only
+ * stage classes in moped_b200/stages/ (MATCH_CUDA, CLUSTER_MEAN_SHIFT_CUDA, POSE_RANSAC_LM_CUDA,
+ * FILTER_PROJECTION_CUDA) flatten FrameData into these calls. All citations are relative to
+ * /root/reference/.
+ *
+ * Conventions
+ *  - every function returns MC_OK (0) or a negative mc_status; mc_last_error() gives the text.
+ *    There is NO CPU fallback: without a usable CUDA device every call fails with MC_ERR_CUDA.
+ *  - "host" pointers are ordinary host memory (pinned memory makes the copies asynchronous);
+ *    "dev" pointers are device memory of the context's GPU. Ownership always stays with the caller.
+ *  - all work is enqueued on the context's stream (mc_set_stream; default = a private stream).
+ *    Host-buffer calls synchronise that stream before returning; *_dev calls do not.
+ *  - squared distances everywhere; quaternions are (x, y, z, w); poses are quat + translation
+ *    (7 floats, Pose::operator[] order, moped2/libmoped/include/moped.hpp:136-164).
+ *  - CSR layout: `offsets[n+1]` ascending, group g owns [offsets[g], offsets[g+1]).
+ */
+#ifndef MOPED_CUDA_H
+#define MOPED_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mc_ctx mc_ctx;
+typedef int mc_status;
+
+enum {
+	MC_OK = 0,
+	MC_ERR_CUDA = -1,        /* CUDA runtime/driver error, or no sm_100 device */
+	MC_ERR_ARG = -2,         /* bad argument (null pointer, size, unsupported descriptor length) */
+	MC_ERR_STATE = -3,       /* call order (e.g. match before db upload) */
+	MC_ERR_CAPACITY = -4     /* an output buffer given by the caller is too small */
+};
+
+/* match modes */
+enum {
+	MC_MATCH_TENSOR = 0,     /* fp16 tcgen05 coarse top-k + exact fp32 re-rank + certificate, exact fallback scan */
+	MC_MATCH_EXACT = 1       /* exhaustive exact fp32 scan (the reference's Quality=0 arithmetic for every row) */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+mc_status mc_create(mc_ctx **ctx, int device);
+void mc_destroy(mc_ctx *ctx);
+const char *mc_last_error(const mc_ctx *ctx);
+const char *mc_version(void);
+/* Use an existing cudaStream_t (e.g. the caller framework's current stream). NULL = private stream. */
+mc_status mc_set_stream(mc_ctx *ctx, void *cuda_stream);
+mc_status mc_synchronize(mc_ctx *ctx);
+
+/* ---- model database: replaces MATCH_ANN_CPU::Update (kd-tree build),
+ *      moped2/libmoped/src/match/MATCH_ANN_CPU.hpp:72-109 ------------------------------------ */
+/* desc: N x D row-major fp32, ALREADY L2-normalised by the host stage (MATCH_ANN_CPU.hpp:94);
+ * xyz: N x 3 (Model::IP::coord3D); model_of_row: N (correspModel); rows are in model order.
+ * row_base = global id of row 0 (non-zero when this context holds one shard of an object-sharded DB). */
+mc_status mc_db_upload(mc_ctx *ctx, const float *desc, const float *xyz, const int32_t *model_of_row,
+                       int64_t n_rows, int desc_dim, int n_models, int64_t row_base);
+int64_t mc_db_rows(const mc_ctx *ctx);
+
+/* ---- cameras: FrameData::images[i]->{intrinsicLinearCalibration, cameraPose},
+ *      moped2/libmoped/include/moped.hpp:226-241 --------------------------------------------- */
+mc_status mc_set_cameras(mc_ctx *ctx, const float *K /* n x (fx,fy,cx,cy) */, const float *cam_pose /* n x 7 */, int n_images);
+
+/* ---- MATCH: replaces MATCH_ANN_CPU::process, MATCH_ANN_CPU.hpp:136-178 ---------------------- */
+/* q_desc: Q x D normalised queries (host). Outputs (host, query order): nn_row Q x 2 global row ids of the
+ * two nearest DB rows, nn_dist Q x 2 their squared distances (reference summation order), accepted Q =
+ * (nn_dist[0]/nn_dist[1] < ratio). stats (optional, 4 ints): {#queries certified by the coarse pass,
+ * #queries sent to the exact fallback scan, #candidates per query, #DB splits}. */
+mc_status mc_match(mc_ctx *ctx, const float *q_desc, int n_queries, float ratio, int mode,
+                   int32_t *nn_row, float *nn_dist, uint8_t *accepted, int32_t *stats);
+/* Same with device pointers, asynchronous on the context stream. */
+mc_status mc_match_dev(mc_ctx *ctx, const float *q_desc_dev, int n_queries, float ratio, int mode,
+                       int32_t *nn_row_dev, float *nn_dist_dev, uint8_t *accepted_dev);
+/* Object-sharded databases: after all-gathering every shard's (nn_row, nn_dist) — n_shards x Q x 2 each —
+ * pick the global two nearest per query (smaller distance, then smaller global row id) and redo the ratio test. */
+mc_status mc_match_merge_dev(mc_ctx *ctx, const int32_t *nn_row_all_dev, const float *nn_dist_all_dev, int n_shards,
+                             int n_queries, float ratio, int32_t *nn_row_dev, float *nn_dist_dev, uint8_t *accepted_dev);
+
+/* ---- CLUSTER: replaces CLUSTER_MEAN_SHIFT_CPU::process,
+ *      moped2/libmoped/src/cluster/CLUSTER_MEAN_SHIFT_CPU.hpp:182-199 ------------------------- */
+/* matches as CSR over models (match_offsets[n_models+1]); match_image / match_xy per match (host).
+ * Output clusters in reference order (model-major, image, surviving-canopy order): cluster_model[c],
+ * cluster_offsets[c+1], members (indices into the model's match list, splice order).
+ * Capacities: cluster_model/cluster_offsets >= n_matches+1, members >= n_matches. */
+mc_status mc_cluster_meanshift(mc_ctx *ctx, const int32_t *match_offsets, const int32_t *match_image, const float *match_xy,
+                               int n_models, int n_images, float radius, float merge, int min_pts, int max_iterations,
+                               int32_t *n_clusters, int32_t *cluster_model, int32_t *cluster_offsets, int32_t *members);
+
+/* ---- POSE: replaces POSE_RANSAC_LM_DIFF_REPROJECTION_CPU::process,
+ *      moped2/libmoped/src/pose/POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:264-307 -------------- */
+typedef struct {
+	int32_t max_ransac_tests;        /* MaxRANSACTests */
+	int32_t max_lm_tests;            /* MaxLMTests (LM itmax) */
+	int32_t max_objects_per_cluster; /* MaxObjectsPerCluster */
+	int32_t n_pts_align;             /* NPtsAlign (<= 8) */
+	int32_t min_npts_object;         /* MinNPtsObject (strict >) */
+	float error_threshold;           /* ErrorThreshold, px^2 */
+	uint64_t seed;                   /* RNG stream of this call */
+} mc_pose_params;
+
+/* Per-hypothesis evaluation on EXPLICIT (sample positions, initial quaternion) sets — the parity entry
+ * point: hypothesis h belongs to cluster hyp_cluster[h]; sample_pos[h*n_pts_align + j] = position inside
+ * that cluster. clusters given as CSR over points: pt_xy, pt_xyz, pt_image (host).
+ * Outputs per hypothesis (host): n_inliers (-1 = LM failed on the samples), pose_lm (after the sample
+ * fit), pose_refit (after the inlier refit, = pose_lm when not refitted), lm_err (2: ||e||^2 of both fits,
+ * -2 = no refit), inlier_mask (CSR-aligned: hyp h writes at mask_offsets = h-th prefix of its cluster size;
+ * pass NULL to skip). */
+mc_status mc_pose_hypotheses(mc_ctx *ctx, const int32_t *cluster_offsets, int n_clusters,
+                             const float *pt_xy, const float *pt_xyz, const int32_t *pt_image,
+                             const int32_t *hyp_cluster, const int32_t *sample_pos, const float *init_quat, int n_hyp,
+                             const mc_pose_params *params,
+                             int32_t *n_inliers, float *pose_lm, float *pose_refit, float *lm_err, uint8_t *inlier_mask);
+
+/* Full RANSAC per (cluster, try): tasks = clusters x max_objects_per_cluster; each task tests up to
+ * max_ransac_tests hypotheses (own counter-based RNG) and returns the FIRST successful one in hypothesis
+ * order, refitted on its inliers. Outputs (host): found[t], pose[t*7], n_tests[t] (hypotheses consumed). */
+mc_status mc_pose_ransac(mc_ctx *ctx, const int32_t *cluster_offsets, int n_clusters,
+                         const float *pt_xy, const float *pt_xyz, const int32_t *pt_image,
+                         const mc_pose_params *params, uint8_t *found, float *pose, int32_t *n_tests);
+
+/* ---- FILTER: replaces FILTER_PROJECTION_CPU::process,
+ *      moped2/libmoped/src/filter/FILTER_PROJECTION_CPU.hpp:80-162 ---------------------------- */
+/* matches as CSR over models (+ image, xy, xyz per match); objects in list order (obj_model, obj_pose).
+ * Outputs (host): keep[o], score[o]; clusters of the survivors ordered model-major then list order:
+ * cluster_offsets[n_survivors+1], members (indices into the model's match list, ascending).
+ * Capacities: cluster_offsets >= n_objects+1, members >= n_matches. */
+mc_status mc_filter_projection(mc_ctx *ctx, const int32_t *match_offsets, const int32_t *match_image, const float *match_xy,
+                               const float *match_xyz, int n_models, const int32_t *obj_model, const float *obj_pose, int n_objects,
+                               int min_points, float feature_distance, float min_score,
+                               uint8_t *keep, float *score, int32_t *n_survivors, int32_t *cluster_offsets, int32_t *members);
+
+/* ---- whole frame on the device: MATCH..FILTER2 chained without leaving HBM ---- */
+typedef struct {
+	float match_ratio; int32_t match_mode;
+	float cluster_radius, cluster_merge; int32_t cluster_min_pts, cluster_max_iterations;
+	mc_pose_params pose; int32_t filter_min_points; float filter_feature_distance, filter_min_score;
+	mc_pose_params pose2; int32_t filter2_min_points; float filter2_feature_distance, filter2_min_score;
+} mc_pipeline_params;
+void mc_pipeline_default_params(mc_pipeline_params *p);   /* moped2/libmoped/src/config.hpp:83-120 */
+
+/* Queries on the host: q_desc Q x D (normalised), q_xy Q x 2, q_image Q. Results: up to max_objects
+ * objects (model id, pose, score) in reference order. stage_ms (optional, 6 floats): device time per stage. */
+mc_status mc_process_frame(mc_ctx *ctx, const float *q_desc, const float *q_xy, const int32_t *q_image, int n_queries,
+                           const mc_pipeline_params *params, int max_objects,
+                           int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms);
+/* Same with the queries already resident in HBM (bench `value` leg). Results still land on the host. */
+mc_status mc_process_frame_dev(mc_ctx *ctx, const float *q_desc_dev, const float *q_xy_dev, const int32_t *q_image_dev, int n_queries,
+                               const mc_pipeline_params *params, int max_objects,
+                               int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms);
+
+/* ---- introspection for tests and bench ------------------------------------------------------ */
+/* number of kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t mc_kernel_launches(const mc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOPED_CUDA_H */

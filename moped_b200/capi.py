@@ -1,0 +1,272 @@
+"""ctypes binding of libmoped_cuda.so (include/moped_cuda.h) — the product's only compute path.
+
+There is no CPU fallback: if the library is missing it is built with nvcc (moped_b200.build), and if
+no B200 is visible `Context()` raises. Python here is plumbing for tests and bench.py; C/C++ hosts bind
+the same symbols directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+MATCH_TENSOR = 0
+MATCH_EXACT = 1
+
+
+class PoseParams(C.Structure):
+    _fields_ = [("max_ransac_tests", C.c_int32), ("max_lm_tests", C.c_int32), ("max_objects_per_cluster", C.c_int32),
+                ("n_pts_align", C.c_int32), ("min_npts_object", C.c_int32), ("error_threshold", C.c_float), ("seed", C.c_uint64)]
+
+    @classmethod
+    def of(cls, params, seed=1):
+        """params = (MaxRANSACTests, MaxLMTests, MaxObjectsPerCluster, NPtsAlign, MinNPtsObject, ErrorThreshold)"""
+        return cls(int(params[0]), int(params[1]), int(params[2]), int(params[3]), int(params[4]), float(params[5]), int(seed))
+
+
+class PipelineParams(C.Structure):
+    _fields_ = [("match_ratio", C.c_float), ("match_mode", C.c_int32),
+                ("cluster_radius", C.c_float), ("cluster_merge", C.c_float), ("cluster_min_pts", C.c_int32), ("cluster_max_iterations", C.c_int32),
+                ("pose", PoseParams), ("filter_min_points", C.c_int32), ("filter_feature_distance", C.c_float), ("filter_min_score", C.c_float),
+                ("pose2", PoseParams), ("filter2_min_points", C.c_int32), ("filter2_feature_distance", C.c_float), ("filter2_min_score", C.c_float)]
+
+
+# every symbol include/moped_cuda.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "mc_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "mc_destroy": (None, [C.c_void_p]),
+    "mc_last_error": (C.c_char_p, [C.c_void_p]),
+    "mc_version": (C.c_char_p, []),
+    "mc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mc_synchronize": (C.c_int, [C.c_void_p]),
+    "mc_db_upload": (C.c_int, [C.c_void_p, _f32p, _f32p, _i32p, C.c_int64, C.c_int, C.c_int, C.c_int64]),
+    "mc_db_rows": (C.c_int64, [C.c_void_p]),
+    "mc_set_cameras": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int]),
+    "mc_match": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_int, _i32p, _f32p, _u8p, C.c_void_p]),
+    "mc_match_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_match_merge_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_cluster_meanshift": (C.c_int, [C.c_void_p, _i32p, _i32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                       C.POINTER(C.c_int32), _i32p, _i32p, _i32p]),
+    "mc_pose_hypotheses": (C.c_int, [C.c_void_p, _i32p, C.c_int, _f32p, _f32p, _i32p, _i32p, _i32p, _f32p, C.c_int, C.POINTER(PoseParams),
+                                     _i32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "mc_pose_ransac": (C.c_int, [C.c_void_p, _i32p, C.c_int, _f32p, _f32p, _i32p, C.POINTER(PoseParams), _u8p, _f32p, _i32p]),
+    "mc_filter_projection": (C.c_int, [C.c_void_p, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                       _u8p, _f32p, C.POINTER(C.c_int32), _i32p, _i32p]),
+    "mc_pipeline_default_params": (None, [C.POINTER(PipelineParams)]),
+    "mc_process_frame": (C.c_int, [C.c_void_p, _f32p, _f32p, _i32p, C.c_int, C.POINTER(PipelineParams), C.c_int, C.POINTER(C.c_int32),
+                                   _i32p, _f32p, _f32p, C.c_void_p]),
+    "mc_process_frame_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PipelineParams), C.c_int,
+                                       C.POINTER(C.c_int32), _i32p, _f32p, _f32p, C.c_void_p]),
+    "mc_kernel_launches": (C.c_int64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) libmoped_cuda.so and type every exported symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class MopedCudaError(RuntimeError):
+    pass
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One GPU context: device-resident model database + cameras + scratch."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        st = self.L.mc_create(C.byref(h), device)
+        if st != 0:
+            raise MopedCudaError(f"mc_create failed ({st}): {self.L.mc_last_error(None).decode()}")
+        self.h = h
+        self.D = 128
+        self.n_models = 0
+
+    def _check(self, st, what):
+        if st != 0:
+            raise MopedCudaError(f"{what} failed ({st}): {self.L.mc_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_handle):
+        self._check(self.L.mc_set_stream(self.h, C.c_void_p(stream_handle) if stream_handle else None), "mc_set_stream")
+
+    def synchronize(self):
+        self._check(self.L.mc_synchronize(self.h), "mc_synchronize")
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.mc_kernel_launches(self.h))
+
+    # ---- database / cameras
+    def db_upload(self, desc, xyz, model_of_row, n_models, row_base=0):
+        desc, xyz, model_of_row = _f32(desc), _f32(xyz), _i32(model_of_row)
+        self.D = desc.shape[1]
+        self.n_models = int(n_models)
+        self._check(self.L.mc_db_upload(self.h, desc, xyz, model_of_row, desc.shape[0], desc.shape[1], int(n_models), int(row_base)), "mc_db_upload")
+
+    def set_cameras(self, K, cam_pose):
+        K, cam_pose = _f32(K).reshape(-1, 4), _f32(cam_pose).reshape(-1, 7)
+        self.n_images = len(K)
+        self._check(self.L.mc_set_cameras(self.h, K, cam_pose, len(K)), "mc_set_cameras")
+
+    # ---- MATCH
+    def match(self, q_desc, ratio=0.8, mode=MATCH_TENSOR):
+        q = _f32(q_desc)
+        Q = len(q)
+        nn_row = np.full((Q, 2), -1, np.int32)
+        nn_dist = np.zeros((Q, 2), np.float32)
+        acc = np.zeros(Q, np.uint8)
+        stats = np.zeros(4, np.int32)
+        self._check(self.L.mc_match(self.h, q, Q, ratio, mode, nn_row, nn_dist, acc, stats.ctypes.data), "mc_match")
+        return nn_row, nn_dist, acc.astype(bool), stats
+
+    def match_dev(self, q_ptr, Q, ratio, mode, nn_row_ptr, nn_dist_ptr, acc_ptr):
+        self._check(self.L.mc_match_dev(self.h, q_ptr, Q, ratio, mode, nn_row_ptr, nn_dist_ptr, acc_ptr), "mc_match_dev")
+
+    def match_merge_dev(self, rows_all_ptr, dist_all_ptr, n_shards, Q, ratio, nn_row_ptr, nn_dist_ptr, acc_ptr):
+        self._check(self.L.mc_match_merge_dev(self.h, rows_all_ptr, dist_all_ptr, n_shards, Q, ratio, nn_row_ptr, nn_dist_ptr, acc_ptr),
+                    "mc_match_merge_dev")
+
+    # ---- CLUSTER
+    def cluster(self, matches, n_images=1, radius=200.0, merge=20.0, minpts=7, maxiter=100):
+        off = _i32(matches["offsets"])
+        M = int(off[-1])
+        n = C.c_int32(0)
+        cm = np.zeros(M + 2, np.int32)
+        co = np.zeros(M + 2, np.int32)
+        mem = np.zeros(M + 2, np.int32)
+        img = _i32(matches["image"]) if M else np.zeros(1, np.int32)
+        xy = _f32(matches["xy"]) if M else np.zeros((1, 2), np.float32)
+        self._check(self.L.mc_cluster_meanshift(self.h, off, img, xy, len(off) - 1, n_images, radius, merge, minpts, maxiter,
+                                                C.byref(n), cm, co, mem), "mc_cluster_meanshift")
+        c = n.value
+        return dict(model=cm[:c].copy(), offsets=co[:c + 1].copy(), members=mem[:co[c]].copy())
+
+    # ---- POSE
+    def pose_hypotheses(self, cluster_offsets, pt_xy, pt_xyz, pt_image, hyp_cluster, sample_pos, init_quat, params, want_mask=True):
+        co = _i32(cluster_offsets)
+        hc, sp, iq = _i32(hyp_cluster), _i32(sample_pos), _f32(init_quat)
+        n_hyp = len(hc)
+        pp = params if isinstance(params, PoseParams) else PoseParams.of(params)
+        n_in = np.zeros(n_hyp, np.int32)
+        pose_lm = np.zeros((n_hyp, 7), np.float32)
+        pose_refit = np.zeros((n_hyp, 7), np.float32)
+        err = np.zeros((n_hyp, 2), np.float32)
+        sizes = (co[1:] - co[:-1])[hc]
+        mask = np.zeros(int(sizes.sum()) + 1, np.uint8) if want_mask else None
+        self._check(self.L.mc_pose_hypotheses(self.h, co, len(co) - 1, _f32(pt_xy), _f32(pt_xyz), _i32(pt_image), hc, sp, iq, n_hyp, C.byref(pp),
+                                              n_in, pose_lm, pose_refit, err, mask.ctypes.data if want_mask else None), "mc_pose_hypotheses")
+        masks = None
+        if want_mask:
+            o = np.concatenate([[0], np.cumsum(sizes)])
+            masks = [mask[o[h]:o[h + 1]].astype(bool) for h in range(n_hyp)]
+        return n_in, pose_lm, pose_refit, err, masks
+
+    def pose_ransac(self, cluster_offsets, pt_xy, pt_xyz, pt_image, params, seed=1):
+        co = _i32(cluster_offsets)
+        pp = params if isinstance(params, PoseParams) else PoseParams.of(params, seed)
+        n_tasks = (len(co) - 1) * pp.max_objects_per_cluster
+        found = np.zeros(n_tasks, np.uint8)
+        pose = np.zeros((n_tasks, 7), np.float32)
+        n_tests = np.zeros(n_tasks, np.int32)
+        self._check(self.L.mc_pose_ransac(self.h, co, len(co) - 1, _f32(pt_xy), _f32(pt_xyz), _i32(pt_image), C.byref(pp), found, pose, n_tests),
+                    "mc_pose_ransac")
+        return found.astype(bool), pose, n_tests
+
+    # ---- FILTER
+    def filter(self, matches, obj_model, obj_pose, params=(5, 4096.0, 2.0)):
+        off = _i32(matches["offsets"])
+        M = int(off[-1])
+        om, op = _i32(obj_model), _f32(obj_pose).reshape(-1, 7)
+        n = len(om)
+        keep = np.zeros(n + 1, np.uint8)
+        score = np.zeros(n + 1, np.float32)
+        ns = C.c_int32(0)
+        co = np.zeros(n + 2, np.int32)
+        mem = np.zeros(M + 2, np.int32)
+        img = _i32(matches["image"]) if M else np.zeros(1, np.int32)
+        xy = _f32(matches["xy"]) if M else np.zeros((1, 2), np.float32)
+        xyz = _f32(matches["xyz"]) if M else np.zeros((1, 3), np.float32)
+        if n == 0:
+            om, op = np.zeros(1, np.int32), np.zeros((1, 7), np.float32)
+        self._check(self.L.mc_filter_projection(self.h, off, img, xy, xyz, len(off) - 1, om, op, n, int(params[0]), float(params[1]), float(params[2]),
+                                                keep, score, C.byref(ns), co, mem), "mc_filter_projection")
+        s = ns.value
+        return dict(keep=keep[:n].astype(bool), score=score[:n].copy(), offsets=co[:s + 1].copy(), members=mem[:co[s]].copy())
+
+    # ---- whole frame
+    def default_params(self) -> PipelineParams:
+        p = PipelineParams()
+        self.L.mc_pipeline_default_params(C.byref(p))
+        return p
+
+    def process_frame(self, q_desc, q_xy, q_image, params=None, max_objects=256, want_times=False):
+        p = params or self.default_params()
+        q = _f32(q_desc)
+        n = C.c_int32(0)
+        om = np.zeros(max_objects, np.int32)
+        op = np.zeros((max_objects, 7), np.float32)
+        os_ = np.zeros(max_objects, np.float32)
+        ms = np.zeros(6, np.float32)
+        self._check(self.L.mc_process_frame(self.h, q, _f32(q_xy), _i32(q_image), len(q), C.byref(p), max_objects, C.byref(n), om, op, os_,
+                                            ms.ctypes.data if want_times else None), "mc_process_frame")
+        k = n.value
+        out = dict(model=om[:k].copy(), pose=op[:k].copy(), score=os_[:k].copy())
+        if want_times:
+            out["stage_ms"] = ms
+        return out
+
+    def process_frame_dev(self, q_ptr, xy_ptr, img_ptr, Q, params=None, max_objects=256, times=None):
+        p = params or self.default_params()
+        n = C.c_int32(0)
+        om = np.zeros(max_objects, np.int32)
+        op = np.zeros((max_objects, 7), np.float32)
+        os_ = np.zeros(max_objects, np.float32)
+        self._check(self.L.mc_process_frame_dev(self.h, q_ptr, xy_ptr, img_ptr, Q, C.byref(p), max_objects, C.byref(n), om, op, os_,
+                                                times.ctypes.data if times is not None else None), "mc_process_frame_dev")
+        k = n.value
+        return dict(model=om[:k].copy(), pose=op[:k].copy(), score=os_[:k].copy())

@@ -1,0 +1,115 @@
+// common.cuh — shared declarations of libmoped_cuda (B200 / sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/moped_cuda.h"
+
+namespace mc {
+
+// ---- sizes fixed by the tensor-core matcher -------------------------------------------------
+constexpr int kD = 128;                 // descriptor length of the tcgen05 path (SIFT)
+constexpr int kTileRows = 128;          // DB rows / query rows per operand tile image
+constexpr int kTileBytes = kTileRows * kD * 2;   // 32 KiB: fp16, two 128B-swizzle K atoms of 64 elements
+constexpr int kMTile = 256;             // queries per CTA (two 128-row halves)
+constexpr int kTopK = 8;                // coarse candidates kept per (query, DB split)
+constexpr int kMaxSplits = 64;
+
+struct Camera {            // FrameData::images[i]: K=(fx,fy,cx,cy), TM = 3x4 of cameraPose (moped.hpp:226-241)
+	float K[4];
+	float TM[12];
+};
+
+struct DevBuf {            // grow-only device scratch
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+} // namespace mc
+
+struct mc_ctx {
+	int device = 0;
+	int num_sms = 148;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	std::string err;
+	int64_t launches = 0;
+
+	// model database (device resident)
+	int64_t n_rows = 0, row_base = 0, n_tiles = 0;
+	int D = 0, n_models = 0;
+	float *d_db = nullptr;            // n_rows x D fp32, row-major (exact re-rank / exact scan)
+	__half *d_db_img = nullptr;       // n_tiles x 32 KiB pre-swizzled fp16 operand tiles (tcgen05 B operand)
+	float *d_xyz = nullptr;           // n_rows x 3
+	int32_t *d_model_of_row = nullptr;
+	float db_norm2_min = 1.f, db_norm2_max = 1.f;
+
+	// cameras
+	mc::Camera *d_cams = nullptr;
+	int n_images = 0;
+
+	// scratch
+	mc::DevBuf q_desc, q_img, q_norm2, tau, cand_score, cand_row, flag_list, flag_count, nn_key;
+	mc::DevBuf nn_row, nn_dist, accepted, q_xy, q_image;
+	mc::DevBuf scratch[24];
+	void *h_pinned = nullptr; size_t h_pinned_cap = 0;
+	int last_stats[4] = {0, 0, 0, 0};
+};
+
+namespace mc {
+
+#define MC_CUDA(call)                                                                         \
+	do {                                                                                      \
+		cudaError_t e__ = (call);                                                             \
+		if (e__ != cudaSuccess) {                                                             \
+			ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+			return MC_ERR_CUDA;                                                               \
+		}                                                                                     \
+	} while (0)
+
+#define MC_LAUNCH_CHECK()                                                                     \
+	do {                                                                                      \
+		ctx->launches++;                                                                      \
+		cudaError_t e__ = cudaGetLastError();                                                 \
+		if (e__ != cudaSuccess) {                                                             \
+			ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e__);              \
+			return MC_ERR_CUDA;                                                               \
+		}                                                                                     \
+	} while (0)
+
+#define MC_TRY(expr)                                                                          \
+	do {                                                                                      \
+		mc_status s__ = (expr);                                                               \
+		if (s__ != MC_OK) return s__;                                                         \
+	} while (0)
+
+inline mc_status reserve(mc_ctx *ctx, DevBuf &b, size_t bytes) {
+	if (bytes <= b.cap && b.p) return MC_OK;
+	if (b.p) { MC_CUDA(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+	size_t cap = bytes < 256 ? 256 : bytes + bytes / 4;
+	MC_CUDA(cudaMalloc(&b.p, cap));
+	b.cap = cap;
+	return MC_OK;
+}
+
+inline mc_status pinned(mc_ctx *ctx, size_t bytes) {
+	if (bytes <= ctx->h_pinned_cap) return MC_OK;
+	if (ctx->h_pinned) { MC_CUDA(cudaFreeHost(ctx->h_pinned)); ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0; }
+	size_t cap = bytes + bytes / 4 + 4096;
+	MC_CUDA(cudaMallocHost(&ctx->h_pinned, cap));
+	ctx->h_pinned_cap = cap;
+	return MC_OK;
+}
+
+// ---- stage entry points implemented in the .cu files (device pointers, async on ctx->stream) ----
+mc_status db_build_images(mc_ctx *ctx);
+mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mode,
+                       int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted);
+mc_status match_merge_device(mc_ctx *ctx, const int32_t *rows_all, const float *dist_all, int n_shards, int Q, float ratio,
+                             int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted);
+
+} // namespace mc

@@ -1,0 +1,200 @@
+// filter.cu — FILTER / FILTER2 steps: projection scoring, feature ownership, pruning, cluster rebuild.
+//
+// Replaces FILTER_PROJECTION_CPU::process (moped2/libmoped/src/filter/FILTER_PROJECTION_CPU.hpp:80-162).
+//   k_filter_score   one thread per object: reproject every match of its model (project(), moped.hpp:330-354),
+//                    in-cluster flag per (object, match), score = sum 1/(err+1) in match order (:95-115)
+//   k_filter_own     one thread per match: best (score, visit order) over the objects whose cluster holds a
+//                    match with the same (coord2D, image) key — `bestPoints` (:117-129)
+//   k_filter_rebuild one thread per object: owned matches of its own model -> new cluster; keep/prune (:135-160)
+//   k_filter_compact survivors' clusters in reference order (model-major, list order)
+#include "common.cuh"
+
+#include <math_constants.h>
+#include <float.h>
+
+namespace mc {
+
+__device__ __forceinline__ void pose_matrix(const float *q, const float *t, float *T) {
+	T[0] = 1 - 2 * q[1] * q[1] - 2 * q[2] * q[2]; T[1] = 2 * q[0] * q[1] - 2 * q[3] * q[2]; T[2] = 2 * q[0] * q[2] + 2 * q[3] * q[1]; T[3] = t[0];
+	T[4] = 2 * q[0] * q[1] + 2 * q[3] * q[2]; T[5] = 1 - 2 * q[0] * q[0] - 2 * q[2] * q[2]; T[6] = 2 * q[1] * q[2] - 2 * q[3] * q[0]; T[7] = t[1];
+	T[8] = 2 * q[0] * q[2] - 2 * q[3] * q[1]; T[9] = 2 * q[1] * q[2] + 2 * q[3] * q[0]; T[10] = 1 - 2 * q[0] * q[0] - 2 * q[1] * q[1]; T[11] = t[2];
+}
+
+// squared reprojection error of model point X under pose matrix T into camera cam vs observed (u0, v0)
+__device__ __forceinline__ float reproj_err(const float *T, const Camera &cam, const float *X, float u0, float v0) {
+	const float x = X[0] * T[0] + X[1] * T[1] + X[2] * T[2] + T[3];
+	const float y = X[0] * T[4] + X[1] * T[5] + X[2] * T[6] + T[7];
+	const float z = X[0] * T[8] + X[1] * T[9] + X[2] * T[10] + T[11];
+	const float a = x - cam.TM[3], b = y - cam.TM[7], c = z - cam.TM[11];
+	const float cx = a * cam.TM[0] + b * cam.TM[4] + c * cam.TM[8];
+	const float cy = a * cam.TM[1] + b * cam.TM[5] + c * cam.TM[9];
+	const float cz = a * cam.TM[2] + b * cam.TM[6] + c * cam.TM[10];
+	float u = FLT_MAX, v = FLT_MAX;
+	if (!((double)cz < 0.001)) {
+		u = cx / cz * cam.K[0] + cam.K[2];
+		v = cy / cz * cam.K[1] + cam.K[3];
+	}
+	const float du = u - u0, dv = v - v0;
+	return du * du + dv * dv;
+}
+
+// in_cluster: n_objects x max_per_model bytes, row o covers the matches of model(o) (index j - lo)
+__global__ void k_filter_score(const int32_t *__restrict__ match_offsets, const int32_t *__restrict__ match_image,
+                               const float *__restrict__ match_xy, const float *__restrict__ match_xyz, const Camera *__restrict__ cams,
+                               const int32_t *__restrict__ obj_model, const float *__restrict__ obj_pose, const int32_t *__restrict__ n_obj_p,
+                               int n_obj_cap, float feat_dist, int stride, uint8_t *__restrict__ in_cluster, float *__restrict__ score) {
+	const int o = blockIdx.x * blockDim.x + threadIdx.x;
+	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
+	if (o >= n_obj) return;
+	const int m = obj_model[o];
+	const int lo = match_offsets[m], hi = match_offsets[m + 1];
+	float T[12];
+	pose_matrix(obj_pose + 7 * o, obj_pose + 7 * o + 4, T);
+	float s = 0.f;
+	for (int j = lo; j < hi; j++) {
+		const float err = reproj_err(T, cams[match_image[j]], match_xyz + 3 * j, match_xy[2 * j], match_xy[2 * j + 1]);
+		const bool in = err < feat_dist;
+		in_cluster[(size_t)o * stride + (j - lo)] = in ? 1 : 0;
+		if (in) s = (float)((double)s + 1. / ((double)err + 1.));
+	}
+	score[o] = s;
+}
+
+__device__ __forceinline__ bool better(float s, int m, int o, float bs, int bm, int bo) {
+	// strictly higher score wins; on equal score the object visited first (model-major, then list order)
+	if (s != bs) return s > bs;
+	if (m != bm) return m < bm;
+	return o < bo;
+}
+
+// owner[j] = object owning match j's (coord2D, image) key, or -1
+__global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_models, const int32_t *__restrict__ match_image,
+                             const float *__restrict__ match_xy, const int32_t *__restrict__ match_model,
+                             const int32_t *__restrict__ obj_model, const int32_t *__restrict__ n_obj_p, int n_obj_cap, int stride,
+                             const uint8_t *__restrict__ in_cluster, const float *__restrict__ score, int32_t *__restrict__ owner) {
+	const int M = match_offsets[n_models];
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= M) return;
+	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
+	const float x = match_xy[2 * j], y = match_xy[2 * j + 1];
+	const int im = match_image[j];
+	float bs = 0.f; int bm = 0x7fffffff, bo = -1;
+	for (int j2 = 0; j2 < M; j2++) {
+		if (match_image[j2] != im || match_xy[2 * j2] != x || match_xy[2 * j2 + 1] != y) continue;
+		const int m2 = match_model[j2];
+		const int lo2 = match_offsets[m2];
+		for (int o = 0; o < n_obj; o++) {
+			if (obj_model[o] != m2 || !in_cluster[(size_t)o * stride + (j2 - lo2)]) continue;
+			const float s = score[o];
+			if (!(0.f < s)) continue;                  // `point.first < score` with point.first initially 0
+			if (bo < 0 || better(s, m2, o, bs, bm, bo)) { bs = s; bm = m2; bo = o; }
+		}
+	}
+	owner[j] = bo;
+}
+
+// per object: number of owned matches of its own model, keep flag
+__global__ void k_filter_rebuild(const int32_t *__restrict__ match_offsets, const int32_t *__restrict__ obj_model,
+                                 const int32_t *__restrict__ n_obj_p, int n_obj_cap, const int32_t *__restrict__ owner,
+                                 const float *__restrict__ score, int min_points, float min_score,
+                                 int32_t *__restrict__ owned, uint8_t *__restrict__ keep) {
+	const int o = blockIdx.x * blockDim.x + threadIdx.x;
+	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
+	if (o >= n_obj) return;
+	const int m = obj_model[o];
+	int c = 0;
+	for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) c += owner[j] == o;
+	owned[o] = c;
+	keep[o] = (c < min_points || score[o] < min_score) ? 0 : 1;
+}
+
+// one CTA: survivors in (model, list order) -> cluster CSR; also the surviving object list in list order.
+// out_n = {#survivors, #members}
+__global__ void k_filter_compact(const int32_t *__restrict__ match_offsets, int n_models, const int32_t *__restrict__ obj_model,
+                                 const float *__restrict__ obj_pose, const int32_t *__restrict__ n_obj_p, int n_obj_cap,
+                                 const int32_t *__restrict__ owner, const int32_t *__restrict__ owned, const uint8_t *__restrict__ keep,
+                                 const float *__restrict__ score,
+                                 int32_t *__restrict__ out_n, int32_t *__restrict__ cluster_model, int32_t *__restrict__ cluster_offsets,
+                                 int32_t *__restrict__ members, int32_t *__restrict__ surv_model, float *__restrict__ surv_pose,
+                                 float *__restrict__ surv_score) {
+	__shared__ int s_rank[1024];
+	__shared__ int s_tot[2];
+	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
+	const int tid = threadIdx.x;
+	if (tid == 0) { s_tot[0] = 0; s_tot[1] = 0; }
+	__syncthreads();
+	// rank of every survivor in (model, list index) order and start of its members: O(n_obj^2), n_obj is small
+	for (int o = tid; o < n_obj; o += blockDim.x) {
+		if (!keep[o]) continue;
+		int rank = 0, start = 0, list_rank = 0;
+		for (int p = 0; p < n_obj; p++) {
+			if (!keep[p]) continue;
+			const bool before = obj_model[p] < obj_model[o] || (obj_model[p] == obj_model[o] && p < o);
+			if (before) { rank++; start += owned[p]; }
+			if (p < o) list_rank++;
+		}
+		cluster_model[rank] = obj_model[o];
+		cluster_offsets[rank] = start;
+		const int m = obj_model[o], lo = match_offsets[m];
+		int t = start;
+		for (int j = lo; j < match_offsets[m + 1]; j++)
+			if (owner[j] == o) members[t++] = j - lo;
+		surv_model[list_rank] = m;
+		for (int k = 0; k < 7; k++) surv_pose[7 * list_rank + k] = obj_pose[7 * o + k];
+		surv_score[list_rank] = score[o];
+		atomicAdd(&s_tot[0], 1);
+		atomicAdd(&s_tot[1], owned[o]);
+	}
+	__syncthreads();
+	if (tid == 0) { cluster_offsets[s_tot[0]] = s_tot[1]; out_n[0] = s_tot[0]; out_n[1] = s_tot[1]; }
+	(void)s_rank;
+}
+
+__global__ void k_match_model_of(const int32_t *__restrict__ match_offsets, int n_models, int32_t *__restrict__ match_model) {
+	const int m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= n_models) return;
+	for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) match_model[j] = m;
+}
+
+// device entry. n_obj_dev (nullable) = device-side object count (<= n_obj_cap).
+// Outputs: keep/score per input object; out_n = {#survivors, #members}; survivors' clusters (model-major) and
+// the surviving objects in list order (surv_*), which is what the next POSE step appends to.
+mc_status filter_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
+                        const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
+                        const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score,
+                        uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets,
+                        int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score) {
+	if (!ctx->d_cams) { ctx->err = "filter: cameras not set (mc_set_cameras)"; return MC_ERR_STATE; }
+	DevBuf &b_in = ctx->scratch[5], &b_owner = ctx->scratch[6], &b_owned = ctx->scratch[7], &b_mm = ctx->scratch[8];
+	const int stride = max_matches > 0 ? max_matches : 1;
+	const int cap = n_obj_cap > 0 ? n_obj_cap : 1;
+	MC_TRY(reserve(ctx, b_in, (size_t)cap * stride));
+	MC_TRY(reserve(ctx, b_owner, sizeof(int32_t) * (size_t)(max_matches + 1)));
+	MC_TRY(reserve(ctx, b_owned, sizeof(int32_t) * (size_t)(cap + 1)));
+	MC_TRY(reserve(ctx, b_mm, sizeof(int32_t) * (size_t)(max_matches + 1)));
+	if (n_obj_cap > 0) {
+		k_filter_score<<<(n_obj_cap + 63) / 64, 64, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, d_match_xyz, ctx->d_cams, d_obj_model,
+		                                                          d_obj_pose, d_n_obj, n_obj_cap, feat_dist, stride, (uint8_t *)b_in.p, d_score);
+		MC_LAUNCH_CHECK();
+	}
+	k_match_model_of<<<(n_models + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, n_models, (int32_t *)b_mm.p);
+	MC_LAUNCH_CHECK();
+	if (max_matches > 0) {
+		k_filter_own<<<(max_matches + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy, (const int32_t *)b_mm.p,
+		                                                            d_obj_model, d_n_obj, n_obj_cap, stride, (const uint8_t *)b_in.p, d_score,
+		                                                            (int32_t *)b_owner.p);
+		MC_LAUNCH_CHECK();
+	}
+	if (n_obj_cap > 0) {
+		k_filter_rebuild<<<(n_obj_cap + 63) / 64, 64, 0, ctx->stream>>>(d_match_offsets, d_obj_model, d_n_obj, n_obj_cap, (const int32_t *)b_owner.p, d_score,
+		                                                            min_points, min_score, (int32_t *)b_owned.p, d_keep);
+		MC_LAUNCH_CHECK();
+	}
+	k_filter_compact<<<1, 256, 0, ctx->stream>>>(d_match_offsets, n_models, d_obj_model, d_obj_pose, d_n_obj, n_obj_cap, (const int32_t *)b_owner.p,
+	                                            (const int32_t *)b_owned.p, d_keep, d_score, d_out_n, d_cluster_model, d_cluster_offsets, d_members,
+	                                            d_surv_model, d_surv_pose, d_surv_score);
+	MC_LAUNCH_CHECK();
+	return MC_OK;
+}
+
+} // namespace mc

@@ -1,0 +1,674 @@
+// pose.cu — POSE / POSE2 steps: RANSAC hypotheses with Levenberg–Marquardt pose refinement on
+// reprojection error, inlier scoring, refit on inliers.
+//
+// Replaces POSE_RANSAC_LM_DIFF_REPROJECTION_CPU (moped2/libmoped/src/pose/POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:66-307)
+// and the slevmar_dif it calls (libs.tgz!levmar-2.4/lm_core.c:427-836, misc_core.c:135-168, Axb_core.c:888-1035).
+//
+// Mapping: a hypothesis is owned by a GROUP of G lanes of one warp — G=8 for the 5/6-point sample fit
+// (4 hypotheses per warp, one correspondence per lane), G=32 for the refit on the inliers (one warp,
+// correspondences strided over the lanes). Residuals, the finite-difference Jacobian and the Broyden
+// update are computed per lane for the lane's own correspondences; ||e||^2, J^T J and J^T e are
+// warp-shuffle (butterfly) reductions inside the group; the 7x7 damped normal equations are solved
+// redundantly by every lane (no communication). Inlier scoring is a ballot over the cluster's points.
+// Compiled with -ftz=true: the reference process runs with FTZ/DAZ and its dominant LM exit is an
+// underflow of ||Dp||^2.
+#include "common.cuh"
+
+#include <math_constants.h>
+#include <float.h>
+
+namespace mc {
+
+constexpr int kMaxAlign = 8;        // NPtsAlign <= 8 (5 and 6 in every reference config)
+constexpr int kRefitCap = 512;      // inliers used by the refit (16 per lane)
+
+struct LmPoint {                    // one 2D-3D correspondence of a lane
+	float u, v, X, Y, Z;
+	int cam;
+};
+
+template <int G> __device__ __forceinline__ float grp_sum(float v, unsigned mask) {
+#pragma unroll
+	for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+	return v;
+}
+template <int G> __device__ __forceinline__ int grp_sum_i(int v, unsigned mask) {
+#pragma unroll
+	for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+	return v;
+}
+
+// residual pair of one correspondence under the 3x4 pose matrix T (already built from the normalised
+// quaternion): (du^2, dv^2), or (-z+10, -z+10) behind the camera. lmFuncQuat, POSE_..._CPU.hpp:116-136.
+__device__ __forceinline__ void residual(const float *T, const Camera &cam, const LmPoint &pt, float &r0, float &r1) {
+	const float x = pt.X * T[0] + pt.Y * T[1] + pt.Z * T[2] + T[3];
+	const float y = pt.X * T[4] + pt.Y * T[5] + pt.Z * T[6] + T[7];
+	const float z = pt.X * T[8] + pt.Y * T[9] + pt.Z * T[10] + T[11];
+	const float a = x - cam.TM[3], b = y - cam.TM[7], c = z - cam.TM[11];
+	const float cx = a * cam.TM[0] + b * cam.TM[4] + c * cam.TM[8];
+	const float cy = a * cam.TM[1] + b * cam.TM[5] + c * cam.TM[9];
+	const float cz = a * cam.TM[2] + b * cam.TM[6] + c * cam.TM[10];
+	if (cz < 0.f) {
+		r0 = -cz + 10.f; r1 = -cz + 10.f;
+	} else {
+		const float du = cx / cz * cam.K[0] + cam.K[2] - pt.u;
+		const float dv = cy / cz * cam.K[1] + cam.K[3] - pt.v;
+		r0 = du * du; r1 = dv * dv;
+	}
+}
+
+// pose.rotation.norm() + TransformMatrix::init (moped.hpp:122,175-182)
+__device__ __forceinline__ void pose_to_T(const float *p, float *T) {
+	float d = p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3];
+	d = 1.0f / sqrtf(d);
+	const float q0 = p[0] * d, q1 = p[1] * d, q2 = p[2] * d, q3 = p[3] * d;
+	T[0] = 1 - 2 * q1 * q1 - 2 * q2 * q2; T[1] = 2 * q0 * q1 - 2 * q3 * q2; T[2] = 2 * q0 * q2 + 2 * q3 * q1; T[3] = p[4];
+	T[4] = 2 * q0 * q1 + 2 * q3 * q2; T[5] = 1 - 2 * q0 * q0 - 2 * q2 * q2; T[6] = 2 * q1 * q2 - 2 * q3 * q0; T[7] = p[5];
+	T[8] = 2 * q0 * q2 - 2 * q3 * q1; T[9] = 2 * q1 * q2 + 2 * q3 * q0; T[10] = 1 - 2 * q0 * q0 - 2 * q1 * q1; T[11] = p[6];
+}
+
+template <int S>
+__device__ __forceinline__ void eval_residuals(const float *p, const LmPoint (&pts)[S], int n_own, const Camera *cams, float (&out)[S][2]) {
+	float T[12];
+	pose_to_T(p, T);
+#pragma unroll
+	for (int s = 0; s < S; s++) {
+		if (s < n_own) residual(T, cams[pts[s].cam], pts[s], out[s][0], out[s][1]);
+		else { out[s][0] = 0.f; out[s][1] = 0.f; }
+	}
+}
+
+// Solve (A + mu I) x = b for symmetric 7x7 A (lower triangle packed, tri(i,j) = i(i+1)/2 + j), by Crout LU
+// with implicit row scaling and partial pivoting — sAx_eq_b_LU_noLapack, Axb_core.c:888-1035.
+// Every lane of the group runs it on identical data. Returns false if singular.
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+__device__ bool lu_solve7(const float (&A)[28], float mu, const float (&b)[7], float (&x)[7]) {
+	float a[7][7], work[7];
+#pragma unroll
+	for (int i = 0; i < 7; i++)
+#pragma unroll
+		for (int j = 0; j < 7; j++) a[i][j] = (i >= j) ? A[tri(i, j)] : A[tri(j, i)];
+#pragma unroll
+	for (int i = 0; i < 7; i++) { a[i][i] += mu; x[i] = b[i]; }
+	bool singular = false;
+#pragma unroll
+	for (int i = 0; i < 7; i++) {
+		float mx = 0.f;
+#pragma unroll
+		for (int j = 0; j < 7; j++) mx = fmaxf(mx, fabsf(a[i][j]));
+		if (mx == 0.f) singular = true;
+		work[i] = 1.0f / mx;
+	}
+	if (singular) return false;
+#pragma unroll
+	for (int j = 0; j < 7; j++) {
+#pragma unroll
+		for (int i = 0; i < j; i++) {
+			float sum = a[i][j];
+#pragma unroll
+			for (int k = 0; k < i; k++) sum -= a[i][k] * a[k][j];
+			a[i][j] = sum;
+		}
+		float mx = 0.f;
+		int maxi = j;
+#pragma unroll
+		for (int i = j; i < 7; i++) {
+			float sum = a[i][j];
+#pragma unroll
+			for (int k = 0; k < j; k++) sum -= a[i][k] * a[k][j];
+			a[i][j] = sum;
+			const float t = work[i] * fabsf(sum);
+			if (t >= mx) { mx = t; maxi = i; }
+		}
+		if (maxi != j) {
+#pragma unroll
+			for (int i = j + 1; i < 7; i++) {
+				const bool sw = (maxi == i);
+#pragma unroll
+				for (int k = 0; k < 7; k++) {
+					const float u = a[i][k], w = a[j][k];
+					a[i][k] = sw ? w : u; a[j][k] = sw ? u : w;
+				}
+				const float xu = x[i], xw = x[j];
+				x[i] = sw ? xw : xu; x[j] = sw ? xu : xw;
+				work[i] = sw ? work[j] : work[i];
+			}
+		}
+		if (a[j][j] == 0.f) a[j][j] = FLT_EPSILON;
+		if (j != 6) {
+			const float t = 1.0f / a[j][j];
+#pragma unroll
+			for (int i = j + 1; i < 7; i++) a[i][j] *= t;
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < 7; i++) {
+		float sum = x[i];
+#pragma unroll
+		for (int j = 0; j < i; j++) sum -= a[i][j] * x[j];
+		x[i] = sum;
+	}
+#pragma unroll
+	for (int i = 6; i >= 0; i--) {
+		float sum = x[i];
+#pragma unroll
+		for (int j = i + 1; j < 7; j++) sum -= a[i][j] * x[j];
+		x[i] = sum / a[i][i];
+	}
+	return true;
+}
+
+// slevmar_dif restated for a lane group: m = 7, target 0, default options (lm.h:83-85), forward-difference
+// Jacobian (misc_core.c:135-168), Broyden rank-1 updates, K = 10 (lm_core.c:484-836). `pts` holds this
+// lane's correspondences (n_own of them). On return p is the solution (if >= 0 is returned) and err = ||e||^2.
+// Returns the iteration count or -1 (LM_ERROR, stop = 4).
+template <int G, int S>
+__device__ int lm_dif(float (&p)[7], int itmax, const LmPoint (&pts)[S], int n_own, const Camera *cams, unsigned mask, float &err) {
+	const float tau = 1E-03f, eps1 = 1E-17f, eps2 = 1E-17f, eps2_sq = 1E-17f * 1E-17f, eps3 = 1E-17f, delta = 1E-06f;
+	float J[S][2][7], hx[S][2], wrk[S][2];
+	float jtj[28], jte[7], diag[7], Dp[7], pDp[7];
+	float mu = 0.f, jte_inf = 0.f, p_L2 = 0.f, p_eL2, pDp_eL2;
+	int nu = 20, stop = 0, updjac = 0, updp = 1, newjac = 0, k;
+	const int K = 10;
+
+	eval_residuals<S>(p, pts, n_own, cams, hx);
+	{
+		float s = 0.f;
+#pragma unroll
+		for (int i = 0; i < S; i++) s += hx[i][0] * hx[i][0] + hx[i][1] * hx[i][1];
+		p_eL2 = grp_sum<G>(s, mask);
+	}
+#pragma unroll
+	for (int i = 0; i < S; i++)
+#pragma unroll
+		for (int r = 0; r < 2; r++)
+#pragma unroll
+			for (int j = 0; j < 7; j++) J[i][r][j] = 0.f;
+
+	for (k = 0; k < itmax && !stop; ++k) {
+		if (p_eL2 <= eps3) { stop = 6; break; }
+
+		if ((updp && nu > 16) || updjac == K) {
+#pragma unroll
+			for (int j = 0; j < 7; j++) {
+				float d = fabsf(1E-04f * p[j]);
+				if (d < delta) d = delta;
+				const float save = p[j];
+				p[j] += d;
+				eval_residuals<S>(p, pts, n_own, cams, wrk);
+				p[j] = save;
+				d = 1.0f / d;
+#pragma unroll
+				for (int i = 0; i < S; i++) { J[i][0][j] = (wrk[i][0] - hx[i][0]) * d; J[i][1][j] = (wrk[i][1] - hx[i][1]) * d; }
+			}
+			nu = 2; updjac = 0; updp = 0; newjac = 1;
+		}
+
+		if (newjac) {
+			newjac = 0;
+#pragma unroll
+			for (int i = 0; i < 28; i++) jtj[i] = 0.f;
+#pragma unroll
+			for (int i = 0; i < 7; i++) jte[i] = 0.f;
+#pragma unroll
+			for (int s = 0; s < S; s++)
+#pragma unroll
+				for (int r = 0; r < 2; r++) {
+					const float e = -hx[s][r];                     // e = x - hx with x = 0
+#pragma unroll
+					for (int i = 0; i < 7; i++) {
+						const float alpha = J[s][r][i];
+#pragma unroll
+						for (int j = 0; j <= i; j++) jtj[tri(i, j)] += J[s][r][j] * alpha;
+						jte[i] += alpha * e;
+					}
+				}
+#pragma unroll
+			for (int i = 0; i < 28; i++) jtj[i] = grp_sum<G>(jtj[i], mask);
+#pragma unroll
+			for (int i = 0; i < 7; i++) jte[i] = grp_sum<G>(jte[i], mask);
+			p_L2 = 0.f; jte_inf = 0.f;
+#pragma unroll
+			for (int i = 0; i < 7; i++) {
+				jte_inf = fmaxf(jte_inf, fabsf(jte[i]));
+				diag[i] = jtj[tri(i, i)];
+				p_L2 += p[i] * p[i];
+			}
+		}
+
+		if (jte_inf <= eps1) { stop = 1; break; }
+
+		if (k == 0) {
+			float t = -FLT_MAX;
+#pragma unroll
+			for (int i = 0; i < 7; i++) t = fmaxf(t, diag[i]);
+			mu = tau * t;
+		}
+
+		const bool solved = lu_solve7(jtj, mu, jte, Dp);
+		if (solved) {
+			float Dp_L2 = 0.f;
+#pragma unroll
+			for (int i = 0; i < 7; i++) { pDp[i] = p[i] + Dp[i]; Dp_L2 += Dp[i] * Dp[i]; }
+			if (Dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
+			if (Dp_L2 >= (p_L2 + eps2) / (1E-12f * 1E-12f)) { stop = 4; break; }
+
+			eval_residuals<S>(pDp, pts, n_own, cams, wrk);
+			{
+				float s = 0.f;
+#pragma unroll
+				for (int i = 0; i < S; i++) s += wrk[i][0] * wrk[i][0] + wrk[i][1] * wrk[i][1];
+				pDp_eL2 = grp_sum<G>(s, mask);
+			}
+			const float dF = p_eL2 - pDp_eL2;
+			if (updp || dF > 0.f) {
+				const float inv = 1.0f / Dp_L2;
+#pragma unroll
+				for (int s = 0; s < S; s++)
+#pragma unroll
+					for (int r = 0; r < 2; r++) {
+						float t = 0.f;
+#pragma unroll
+						for (int l = 0; l < 7; l++) t += J[s][r][l] * Dp[l];
+						t = (wrk[s][r] - hx[s][r] - t) * inv;
+#pragma unroll
+						for (int j = 0; j < 7; j++) J[s][r][j] += t * Dp[j];
+					}
+				++updjac; newjac = 1;
+			}
+			float dL = 0.f;
+#pragma unroll
+			for (int i = 0; i < 7; i++) dL += Dp[i] * (mu * Dp[i] + jte[i]);
+			if (dL > 0.f && dF > 0.f) {
+				float t = 2.0f * dF / dL - 1.0f;
+				t = 1.0f - t * t * t;
+				mu = mu * ((t >= 0.3333333334f) ? t : 0.3333333334f);
+				nu = 2;
+#pragma unroll
+				for (int i = 0; i < 7; i++) p[i] = pDp[i];
+#pragma unroll
+				for (int s = 0; s < S; s++) { hx[s][0] = wrk[s][0]; hx[s][1] = wrk[s][1]; }
+				p_eL2 = pDp_eL2;
+				updp = 1;
+				continue;
+			}
+		}
+		mu *= nu;
+		const int nu2 = nu << 1;
+		if (nu2 <= nu) { stop = 5; break; }
+		nu = nu2;
+	}
+	err = p_eL2;
+	return (stop != 4) ? k : -1;
+}
+
+// optimizeCamera (POSE_..._CPU.hpp:140-164): LM, then re-normalise the quaternion. Returns false on LM_ERROR
+// (pose untouched).
+template <int G, int S>
+__device__ bool optimize_camera(float (&pose)[7], int itmax, const LmPoint (&pts)[S], int n_own, const Camera *cams, unsigned mask, float &err) {
+	float p[7];
+#pragma unroll
+	for (int i = 0; i < 7; i++) p[i] = pose[i];
+	const int r = lm_dif<G, S>(p, itmax, pts, n_own, cams, mask, err);
+	if (r < 0) { err = -1.f; return false; }
+	float d = p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3];
+	d = 1.0f / sqrtf(d);
+	pose[0] = p[0] * d; pose[1] = p[1] * d; pose[2] = p[2] * d; pose[3] = p[3] * d;
+	pose[4] = p[4]; pose[5] = p[5]; pose[6] = p[6];
+	return true;
+}
+
+// squared reprojection error used by testAllPoints / project() (POSE_..._CPU.hpp:166-180, moped.hpp:330-354)
+__device__ __forceinline__ float proj_err(const float *T, const Camera &cam, float X, float Y, float Z, float u0, float v0) {
+	const float x = X * T[0] + Y * T[1] + Z * T[2] + T[3];
+	const float y = X * T[4] + Y * T[5] + Z * T[6] + T[7];
+	const float z = X * T[8] + Y * T[9] + Z * T[10] + T[11];
+	const float a = x - cam.TM[3], b = y - cam.TM[7], c = z - cam.TM[11];
+	const float cx = a * cam.TM[0] + b * cam.TM[4] + c * cam.TM[8];
+	const float cy = a * cam.TM[1] + b * cam.TM[5] + c * cam.TM[9];
+	const float cz = a * cam.TM[2] + b * cam.TM[6] + c * cam.TM[10];
+	float u = FLT_MAX, v = FLT_MAX;
+	if (!((double)cz < 0.001)) { u = cx / cz * cam.K[0] + cam.K[2]; v = cy / cz * cam.K[1] + cam.K[3]; }
+	const float du = u - u0, dv = v - v0;
+	return du * du + dv * dv;
+}
+
+__device__ __forceinline__ void pose7_to_T(const float *pose, float *T) {   // pose already normalised: TransformMatrix::init
+	const float q0 = pose[0], q1 = pose[1], q2 = pose[2], q3 = pose[3];
+	T[0] = 1 - 2 * q1 * q1 - 2 * q2 * q2; T[1] = 2 * q0 * q1 - 2 * q3 * q2; T[2] = 2 * q0 * q2 + 2 * q3 * q1; T[3] = pose[4];
+	T[4] = 2 * q0 * q1 + 2 * q3 * q2; T[5] = 1 - 2 * q0 * q0 - 2 * q2 * q2; T[6] = 2 * q1 * q2 - 2 * q3 * q0; T[7] = pose[5];
+	T[8] = 2 * q0 * q2 - 2 * q3 * q1; T[9] = 2 * q1 * q2 + 2 * q3 * q0; T[10] = 1 - 2 * q0 * q0 - 2 * q1 * q1; T[11] = pose[6];
+}
+
+// inlier count of `pose` over a cluster's points by a lane group; optionally writes the mask
+template <int G>
+__device__ int count_inliers(const float *pose, int n, const float *xy, const float *xyz, const int32_t *image, const Camera *cams,
+                             float thr, unsigned mask, int lig, uint8_t *out_mask) {
+	float T[12];
+	pose7_to_T(pose, T);
+	int c = 0;
+	for (int i = lig; i < n; i += G) {
+		const float e = proj_err(T, cams[image[i]], xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], xy[2 * i], xy[2 * i + 1]);
+		const int in = e < thr;
+		if (out_mask) out_mask[i] = (uint8_t)in;
+		c += in;
+	}
+	return grp_sum_i<G>(c, mask);
+}
+
+// ---- the seedable LCG shared with the oracle (oracle/moped_oracle.c: mo_rand) with O(log k) jump-ahead ----
+__device__ __forceinline__ void lcg_jump(uint64_t k, uint64_t &A, uint64_t &C) {
+	uint64_t a = 6364136223846793005ULL, c = 1442695040888963407ULL;
+	A = 1; C = 0;
+	while (k) {
+		if (k & 1) { C = C * a + c; A = A * a; }
+		c = c * a + c; a = a * a;
+		k >>= 1;
+	}
+}
+__device__ __forceinline__ int lcg_out(uint64_t s) { return (int)((s >> 33) & 0x7fffffffULL); }
+
+// randSample + initPose for hypothesis h of a task (POSE_..._CPU.hpp:76-98,182-186): the task's LCG stream
+// hands draw h*(n+4)+i to cluster point i (key = (float)rand()) and the next four draws to the quaternion
+// (w first: g++ evaluates the arguments right to left). Points are taken in ascending (key, match index)
+// order, skipping repeated (image, coord2D). Lane group cooperative. Returns false if fewer than n_align
+// distinct points exist.
+template <int G>
+__device__ bool draw_sample(uint64_t seed, int h, int n, int n_align, const float *xy, const int32_t *image, const int32_t *tie,
+                            unsigned mask, int lig, int (&pos)[kMaxAlign], float (&quat)[4]) {
+	uint64_t A0, C0, AG, CG;
+	lcg_jump((uint64_t)h * (uint64_t)(n + 4) + (uint64_t)lig + 1, A0, C0);   // state after (index+1) steps
+	lcg_jump((uint64_t)G, AG, CG);
+	const uint64_t s_first = seed * A0 + C0;
+	float last_key = -1.f; int last_tie = -1;
+	int taken = 0;
+	for (int round = 0; round < n && taken < n_align; round++) {
+		// smallest (key, tie) strictly above the last popped one
+		float bk = CUDART_INF_F; int bt = 0x7fffffff, bp = -1;
+		uint64_t s = s_first;
+		for (int i = lig; i < n; i += G) {
+			const float key = (float)lcg_out(s);
+			const int t = tie ? tie[i] : i;
+			const bool above = key > last_key || (key == last_key && t > last_tie);
+			if (above && (key < bk || (key == bk && t < bt))) { bk = key; bt = t; bp = i; }
+			s = s * AG + CG;
+		}
+#pragma unroll
+		for (int o = G / 2; o; o >>= 1) {
+			const float ok = __shfl_xor_sync(mask, bk, o);
+			const int ot = __shfl_xor_sync(mask, bt, o), op = __shfl_xor_sync(mask, bp, o);
+			if (ok < bk || (ok == bk && ot < bt)) { bk = ok; bt = ot; bp = op; }
+		}
+		if (bp < 0) break;
+		last_key = bk; last_tie = bt;
+		bool dup = false;
+#pragma unroll
+		for (int j = 0; j < kMaxAlign; j++)
+			if (j < taken) {
+				const int sidx = pos[j];
+				dup = dup || (image[sidx] == image[bp] && xy[2 * sidx] == xy[2 * bp] && xy[2 * sidx + 1] == xy[2 * bp + 1]);
+			}
+		if (!dup) {
+#pragma unroll
+			for (int j = 0; j < kMaxAlign; j++) if (j == taken) pos[j] = bp;
+			taken++;
+		}
+	}
+	uint64_t Aq, Cq;
+	lcg_jump((uint64_t)h * (uint64_t)(n + 4) + (uint64_t)n + 1, Aq, Cq);
+	uint64_t s = seed * Aq + Cq;
+#pragma unroll
+	for (int j = 3; j >= 0; j--) {
+		quat[j] = (float)((lcg_out(s) & 255) / 256.);
+		s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+	}
+	return taken == n_align;
+}
+
+// sample fit + inlier count of one hypothesis by an 8-lane group. Returns #inliers or -1.
+__device__ int fit_and_score(const int (&pos)[kMaxAlign], int n_align, const float (&quat)[4], int n, const float *xy, const float *xyz,
+                             const int32_t *image, const Camera *cams, int max_lm, float thr, unsigned mask, int lig,
+                             float (&pose)[7], float &err, uint8_t *out_mask) {
+	LmPoint pts[1];
+	int mine = 0;
+#pragma unroll
+	for (int j = 0; j < kMaxAlign; j++) if (j == lig) mine = pos[j];
+	const int n_own = lig < n_align ? 1 : 0;
+	if (n_own) {
+		pts[0].u = xy[2 * mine]; pts[0].v = xy[2 * mine + 1];
+		pts[0].X = xyz[3 * mine]; pts[0].Y = xyz[3 * mine + 1]; pts[0].Z = xyz[3 * mine + 2];
+		pts[0].cam = image[mine];
+	} else { pts[0].u = pts[0].v = pts[0].X = pts[0].Y = pts[0].Z = 0.f; pts[0].cam = 0; }
+	pose[0] = quat[0]; pose[1] = quat[1]; pose[2] = quat[2]; pose[3] = quat[3];
+	pose[4] = 0.f; pose[5] = 0.f; pose[6] = 0.5f;
+	if (!optimize_camera<8, 1>(pose, max_lm, pts, n_own, cams, mask, err)) return -1;
+	return count_inliers<8>(pose, n, xy, xyz, image, cams, thr, mask, lig, out_mask);
+}
+
+// refit of `pose` on its inliers by a full warp (optimizeCamera(pose, consistent), :204-208).
+// list = per-warp shared scratch of kRefitCap ints. Returns false if LM failed (pose unchanged).
+template <int S>
+__device__ bool refit_S(float (&pose)[7], int n_inl, const int *list, const float *xy, const float *xyz, const int32_t *image,
+                        const Camera *cams, int max_lm, int lane, float &err) {
+	LmPoint pts[S];
+	int n_own = 0;
+#pragma unroll
+	for (int s = 0; s < S; s++) {
+		const int k = lane + 32 * s;
+		if (k < n_inl) {
+			const int i = list[k];
+			pts[s].u = xy[2 * i]; pts[s].v = xy[2 * i + 1];
+			pts[s].X = xyz[3 * i]; pts[s].Y = xyz[3 * i + 1]; pts[s].Z = xyz[3 * i + 2];
+			pts[s].cam = image[i];
+			n_own = s + 1;
+		} else { pts[s].u = pts[s].v = pts[s].X = pts[s].Y = pts[s].Z = 0.f; pts[s].cam = 0; }
+	}
+	return optimize_camera<32, S>(pose, max_lm, pts, n_own, cams, 0xffffffffu, err);
+}
+
+__device__ bool refit_warp(float (&pose)[7], int n, const float *xy, const float *xyz, const int32_t *image, const Camera *cams,
+                           float thr, int max_lm, int lane, int *list, float &err) {
+	// inliers of `pose` in cluster order -> list (the reference refits on `consistent` in cluster order)
+	float T[12];
+	pose7_to_T(pose, T);
+	int n_inl = 0;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + lane;
+		bool in = false;
+		if (i < n) in = proj_err(T, cams[image[i]], xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], xy[2 * i], xy[2 * i + 1]) < thr;
+		const unsigned m = __ballot_sync(0xffffffffu, in);
+		if (in) {
+			const int k = n_inl + __popc(m & ((1u << lane) - 1));
+			if (k < kRefitCap) list[k] = i;
+		}
+		n_inl += __popc(m);
+	}
+	__syncwarp();
+	if (n_inl > kRefitCap) n_inl = kRefitCap;
+	if (n_inl <= 32) return refit_S<1>(pose, n_inl, list, xy, xyz, image, cams, max_lm, lane, err);
+	if (n_inl <= 64) return refit_S<2>(pose, n_inl, list, xy, xyz, image, cams, max_lm, lane, err);
+	if (n_inl <= 128) return refit_S<4>(pose, n_inl, list, xy, xyz, image, cams, max_lm, lane, err);
+	if (n_inl <= 256) return refit_S<8>(pose, n_inl, list, xy, xyz, image, cams, max_lm, lane, err);
+	return refit_S<16>(pose, n_inl, list, xy, xyz, image, cams, max_lm, lane, err);
+}
+
+// ---- kernel A: explicit hypotheses, sample fit + inlier scoring; 4 hypotheses per warp ----
+constexpr int kPoseThreads = 256;
+__global__ void __launch_bounds__(kPoseThreads)
+k_pose_fit(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
+           const int32_t *__restrict__ image, const Camera *__restrict__ cams, const int32_t *__restrict__ hyp_cluster,
+           const int32_t *__restrict__ sample_pos, const float *__restrict__ init_quat, int n_hyp, int n_align, int max_lm, float thr,
+           const int64_t *__restrict__ mask_offsets, int32_t *__restrict__ n_inliers, float *__restrict__ pose_lm,
+           float *__restrict__ lm_err, uint8_t *__restrict__ inlier_mask) {
+	const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
+	const unsigned mask = 0xFFu << (8 * grp);
+	const int h = (blockIdx.x * (kPoseThreads / 32) + (threadIdx.x >> 5)) * 4 + grp;
+	if (h >= n_hyp) return;
+	const int c = hyp_cluster[h];
+	const int lo = cluster_offsets[c], n = cluster_offsets[c + 1] - lo;
+	int pos[kMaxAlign];
+#pragma unroll
+	for (int j = 0; j < kMaxAlign; j++) pos[j] = j < n_align ? sample_pos[(size_t)h * n_align + j] : 0;
+	float quat[4] = { init_quat[4 * h], init_quat[4 * h + 1], init_quat[4 * h + 2], init_quat[4 * h + 3] };
+	float pose[7], err;
+	uint8_t *om = inlier_mask ? inlier_mask + mask_offsets[h] : nullptr;
+	if (om) for (int i = lig; i < n; i += 8) om[i] = 0;
+	const int cnt = fit_and_score(pos, n_align, quat, n, xy + 2 * lo, xyz + 3 * lo, image + lo, cams, max_lm, thr, mask, lig, pose, err, om);
+	if (lig == 0) {
+		n_inliers[h] = cnt;
+		lm_err[2 * h] = err; lm_err[2 * h + 1] = -2.f;
+		for (int j = 0; j < 7; j++) pose_lm[7 * h + j] = cnt >= 0 ? pose[j] : 0.f;
+	}
+}
+
+// ---- kernel B: refit of every hypothesis with more than min_npts inliers; one warp per hypothesis ----
+__global__ void __launch_bounds__(kPoseThreads)
+k_pose_refit(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
+             const int32_t *__restrict__ image, const Camera *__restrict__ cams, const int32_t *__restrict__ hyp_cluster, int n_hyp,
+             int max_lm, float thr, int min_npts, const int32_t *__restrict__ n_inliers, const float *__restrict__ pose_lm,
+             float *__restrict__ pose_refit, float *__restrict__ lm_err) {
+	__shared__ int s_list[kPoseThreads / 32][kRefitCap];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int h = blockIdx.x * (kPoseThreads / 32) + w;
+	if (h >= n_hyp) return;
+	float pose[7];
+#pragma unroll
+	for (int j = 0; j < 7; j++) pose[j] = pose_lm[7 * h + j];
+	if (n_inliers[h] > min_npts) {
+		const int c = hyp_cluster[h];
+		const int lo = cluster_offsets[c], n = cluster_offsets[c + 1] - lo;
+		float err;
+		refit_warp(pose, n, xy + 2 * lo, xyz + 3 * lo, image + lo, cams, thr, max_lm, lane, s_list[w], err);
+		if (lane == 0) lm_err[2 * h + 1] = err;
+	}
+	if (lane == 0)
+		for (int j = 0; j < 7; j++) pose_refit[7 * h + j] = pose[j];
+}
+
+// ---- kernel C: full RANSAC, one CTA per (cluster, try) task; 32 hypotheses per round ----
+// Reference semantics (RANSAC(), :188-211): sequential tests, stop at the FIRST hypothesis whose inlier
+// count exceeds min_npts, refit it on its inliers. Here a round evaluates 32 consecutive hypotheses of the
+// task's stream in parallel and the lowest-numbered success of the round wins, which is the same hypothesis
+// the sequential loop would have stopped at.
+__global__ void __launch_bounds__(kPoseThreads)
+k_pose_ransac(const int32_t *__restrict__ cluster_offsets, const int32_t *__restrict__ n_clusters_p, int n_clusters_cap,
+              const float *__restrict__ xy, const float *__restrict__ xyz, const int32_t *__restrict__ image,
+              const int32_t *__restrict__ tie, const Camera *__restrict__ cams, int max_obj, int max_ransac, int max_lm, int n_align,
+              int min_npts, float thr, uint64_t seed, uint8_t *__restrict__ found, float *__restrict__ pose_out,
+              int32_t *__restrict__ n_tests) {
+	__shared__ int s_cnt[32];
+	__shared__ float s_pose[32][7];
+	__shared__ int s_list[kRefitCap];
+	__shared__ int s_winner, s_fail;
+	const int task = blockIdx.x;
+	const int n_clusters = n_clusters_p ? min(*n_clusters_p, n_clusters_cap) : n_clusters_cap;
+	const int c = task / max_obj;
+	if (c >= n_clusters) { if (threadIdx.x == 0) { found[task] = 0; n_tests[task] = 0; } return; }
+	const int lo = cluster_offsets[c], n = cluster_offsets[c + 1] - lo;
+	const float *cxy = xy + 2 * lo, *cxyz = xyz + 3 * lo;
+	const int32_t *cim = image + lo, *ctie = tie ? tie + lo : nullptr;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lig = lane & 7, grp = lane >> 3;
+	const unsigned mask = 0xFFu << (8 * grp);
+	const uint64_t task_seed = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(task + 1);
+	if (threadIdx.x == 0) { s_winner = -1; s_fail = 0; }
+	__syncthreads();
+	int tests = 0;
+	for (int base = 0; base < max_ransac; base += 32) {
+		const int slot = w * 4 + grp, h = base + slot;
+		int cnt = -1;
+		float pose[7] = { 0, 0, 0, 1, 0, 0, 0 }, err;
+		if (h < max_ransac) {
+			int pos[kMaxAlign]; float quat[4];
+#pragma unroll
+			for (int j = 0; j < kMaxAlign; j++) pos[j] = 0;
+			if (draw_sample<8>(task_seed, h, n, n_align, cxy, cim, ctie, mask, lig, pos, quat))
+				cnt = fit_and_score(pos, n_align, quat, n, cxy, cxyz, cim, cams, max_lm, thr, mask, lig, pose, err, nullptr);
+			else if (lig == 0) s_fail = 1;               // randSample fails for every hypothesis alike -> RANSAC returns false
+		}
+		if (lig == 0) {
+			s_cnt[slot] = cnt;
+			for (int j = 0; j < 7; j++) s_pose[slot][j] = pose[j];
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			for (int sl = 0; sl < 32; sl++)
+				if (s_cnt[sl] > min_npts) { s_winner = sl; break; }
+		}
+		__syncthreads();
+		const int winner = s_winner;
+		tests = min(base + 32, max_ransac);
+		if (winner >= 0) { tests = base + winner + 1; break; }
+		if (s_fail) { tests = 0; break; }
+		__syncthreads();
+	}
+	const int winner = s_winner;
+	if (winner >= 0 && w == 0) {
+		float pose[7], err;
+#pragma unroll
+		for (int j = 0; j < 7; j++) pose[j] = s_pose[winner][j];
+		refit_warp(pose, n, cxy, cxyz, cim, cams, thr, max_lm, lane, s_list, err);
+		if (lane == 0)
+			for (int j = 0; j < 7; j++) pose_out[7 * task + j] = pose[j];
+	}
+	if (threadIdx.x == 0) { found[task] = winner >= 0 ? 1 : 0; n_tests[task] = tests; }
+}
+
+// append the found poses to an object list in task order (device-side `objects->push_back`, :295-303)
+__global__ void k_pose_append(const int32_t *__restrict__ cluster_model, const int32_t *__restrict__ n_clusters_p, int n_clusters_cap,
+                              int max_obj, const uint8_t *__restrict__ found, const float *__restrict__ pose, int32_t *__restrict__ n_obj,
+                              int obj_cap, int32_t *__restrict__ obj_model, float *__restrict__ obj_pose) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const int n_clusters = n_clusters_p ? min(*n_clusters_p, n_clusters_cap) : n_clusters_cap;
+	int k = *n_obj;
+	for (int t = 0; t < n_clusters * max_obj; t++) {
+		if (!found[t] || k >= obj_cap) continue;
+		obj_model[k] = cluster_model[t / max_obj];
+		for (int j = 0; j < 7; j++) obj_pose[7 * k + j] = pose[7 * t + j];
+		k++;
+	}
+	*n_obj = k;
+}
+
+// ---- device entries ----
+mc_status pose_hypotheses_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, const float *d_xy, const float *d_xyz, const int32_t *d_image,
+                                 const int32_t *d_hyp_cluster, const int32_t *d_sample_pos, const float *d_init_quat, int n_hyp,
+                                 const mc_pose_params *pp, const int64_t *d_mask_offsets, int32_t *d_n_inliers, float *d_pose_lm,
+                                 float *d_pose_refit, float *d_lm_err, uint8_t *d_mask) {
+	if (!ctx->d_cams) { ctx->err = "pose: cameras not set (mc_set_cameras)"; return MC_ERR_STATE; }
+	if (pp->n_pts_align < 1 || pp->n_pts_align > kMaxAlign) { ctx->err = "pose: n_pts_align must be in 1..8"; return MC_ERR_ARG; }
+	if (n_hyp <= 0) return MC_OK;
+	const int wpb = kPoseThreads / 32;
+	k_pose_fit<<<(n_hyp + wpb * 4 - 1) / (wpb * 4), kPoseThreads, 0, ctx->stream>>>(d_cluster_offsets, d_xy, d_xyz, d_image, ctx->d_cams, d_hyp_cluster,
+	                                                                              d_sample_pos, d_init_quat, n_hyp, pp->n_pts_align, pp->max_lm_tests,
+	                                                                              pp->error_threshold, d_mask_offsets, d_n_inliers, d_pose_lm, d_lm_err, d_mask);
+	MC_LAUNCH_CHECK();
+	k_pose_refit<<<(n_hyp + wpb - 1) / wpb, kPoseThreads, 0, ctx->stream>>>(d_cluster_offsets, d_xy, d_xyz, d_image, ctx->d_cams, d_hyp_cluster, n_hyp,
+	                                                                      pp->max_lm_tests, pp->error_threshold, pp->min_npts_object, d_n_inliers,
+	                                                                      d_pose_lm, d_pose_refit, d_lm_err);
+	MC_LAUNCH_CHECK();
+	return MC_OK;
+}
+
+mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, const int32_t *d_n_clusters, int n_clusters_cap,
+                             const float *d_xy, const float *d_xyz, const int32_t *d_image, const int32_t *d_tie,
+                             const mc_pose_params *pp, uint8_t *d_found, float *d_pose, int32_t *d_n_tests) {
+	if (!ctx->d_cams) { ctx->err = "pose: cameras not set (mc_set_cameras)"; return MC_ERR_STATE; }
+	if (pp->n_pts_align < 1 || pp->n_pts_align > kMaxAlign) { ctx->err = "pose: n_pts_align must be in 1..8"; return MC_ERR_ARG; }
+	const int n_tasks = n_clusters_cap * pp->max_objects_per_cluster;
+	if (n_tasks <= 0) return MC_OK;
+	k_pose_ransac<<<n_tasks, kPoseThreads, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, d_tie, ctx->d_cams,
+	                                                       pp->max_objects_per_cluster, pp->max_ransac_tests, pp->max_lm_tests, pp->n_pts_align,
+	                                                       pp->min_npts_object, pp->error_threshold, pp->seed, d_found, d_pose, d_n_tests);
+	MC_LAUNCH_CHECK();
+	return MC_OK;
+}
+
+mc_status pose_append_device(mc_ctx *ctx, const int32_t *d_cluster_model, const int32_t *d_n_clusters, int n_clusters_cap, int max_obj,
+                             const uint8_t *d_found, const float *d_pose, int32_t *d_n_obj, int obj_cap, int32_t *d_obj_model, float *d_obj_pose) {
+	k_pose_append<<<1, 32, 0, ctx->stream>>>(d_cluster_model, d_n_clusters, n_clusters_cap, max_obj, d_found, d_pose, d_n_obj, obj_cap, d_obj_model, d_obj_pose);
+	MC_LAUNCH_CHECK();
+	return MC_OK;
+}
+
+} // namespace mc
