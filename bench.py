@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of MOPED's recognition core (MATCH..FILTER2) on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric): synthetic 1000-object database (~1M 128-d descriptors), one 640x480
+frame of 2000 features per step, the reference's default stage parameters (config.hpp:83-120).
+A step = one frame through MATCH -> CLUSTER -> POSE -> FILTER -> POSE2 -> FILTER2.
+
+ours:       value = frames/s with the frame's features resident in HBM; e2e = the same through the
+            host-buffer C ABI call (pinned host -> device copy of the features and device -> host read of
+            the objects inside the timed region). N > 1: database sharded by object, every rank matches all
+            queries against its shard, one NCCL all-gather of the per-query (row, distance) pairs, merge,
+            remaining stages on every rank (strong scaling: the job is fixed).
+reference:  the reference's own CPU stage classes (oracle/_ref, built from /root/reference) on the host
+            cores; a step is a bounded sample of the same frame (see `cpu_baseline.sample`).
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from moped_b200 import synth  # noqa: E402
+
+METRIC = "frames_per_s"
+UNIT = "frames/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops"]), float(d["hbm_gbs"]), "measured"
+    return 1590.0, 6650.0, "fallback"
+
+
+def host_norm_rows(x: np.ndarray) -> np.ndarray:
+    """Host-side L2 normalisation of descriptors (what the MATCH stage class does before upload,
+    MATCH_ANN_CPU.hpp:54-57,94,157)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = np.sqrt((x * x).sum(axis=1, dtype=np.float32)).astype(np.float32)
+    return (x * (np.float32(1.0) / n)[:, None]).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def shard_objects(n_pts: np.ndarray, world: int):
+    """Contiguous object ranges balanced by descriptor count."""
+    cum = np.concatenate([[0], np.cumsum(n_pts)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(cum, total * r / world)))
+    bounds.append(len(n_pts))
+    return [(bounds[r], bounds[r + 1], int(cum[bounds[r]]), int(cum[bounds[r + 1]])) for r in range(world)]
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------
+def reference_pl(frame):
+    planted = np.nonzero(frame["src_row"] >= 0)[0]
+    dis = np.nonzero(frame["src_row"] < 0)[0][:20]
+    return np.sort(np.concatenate([planted, dis]))
+
+
+def reference_setup(db, n_threads):
+    from oracle import ref
+    r = ref.Ref(n_threads)
+    r.set_models(db["n_pts"], db["xyz"], db["desc"])
+    r.set_images(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    t0 = time.time()
+    r.build_match(5.0, 0.8)          # kd-tree build: excluded from the timing like the GPU database upload
+    log(f"[reference] kd-tree build {time.time() - t0:.1f}s")
+    return r
+
+
+def reference_sample_step(r, frame, frac_inv, seed):
+    """One bounded sample of a frame: (a) MATCH_ANN_CPU (eps=5, the shipped default) on a uniformly random
+    1/frac_inv of the frame's features, time scaled x frac_inv (ANN matching is serial per query,
+    MATCH_ANN_CPU.hpp:155-162); (b) CLUSTER..FILTER2 on the matches of the planted features + 20 distractors,
+    i.e. on (all but a handful of) the matches the full frame produces.
+    Returns (seconds per full frame, per-stage seconds, #objects)."""
+    Q = len(frame["desc"])
+    rng = np.random.default_rng(seed)
+    uni = np.sort(rng.choice(Q, size=max(1, Q // frac_inv), replace=False))
+    pl = reference_pl(frame)
+    r.clear_frame()
+    r.set_features(frame["desc"][uni], frame["xy"][uni], frame["image_idx"][uni])
+    t_match = float(Q) / len(uni) * r.run_match(5.0, 0.8)
+    r.set_features(frame["desc"][pl], frame["xy"][pl], frame["image_idx"][pl])
+    n, times = r.run_pipeline(seed=seed)
+    stage = np.array(times)
+    stage[0] = t_match
+    return float(stage.sum()), stage, n
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        subprocess.call(["make", "-s", "-f", os.path.join(ROOT, "oracle", "Makefile"), "ref"])
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmoped_ref.so missing and /root/reference not present to build it"}))
+        return
+    cores = os.cpu_count() or 1
+    db = synth.make_db(args.objects, args.pts)
+    frames = [synth.make_frame(db, args.features, n_visible=8, frame_id=i) for i in range(4)]
+    r = reference_setup(db, cores)
+    # size the sample from a probe so that warmup + steps stay near two minutes of CPU work
+    s_probe, _, _ = reference_sample_step(r, frames[0], 32, seed=3)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    frac_inv = int(min(32, max(4, np.ceil(s_probe / budget))))
+    tot = 0.0
+    stages = np.zeros(6)
+    for i in range(args.warmup + args.steps):
+        s, st, n = reference_sample_step(r, frames[i % len(frames)], frac_inv, seed=11 + i)
+        if i >= args.warmup:
+            tot += s
+            stages += st
+        log(f"[reference] step {i}: {s:.2f}s/frame objects={n}")
+    sec = tot / args.steps
+    sample = (f"per step: MATCH_ANN_CPU(eps=5) on a uniform 1/{frac_inv} of the {args.features} features, time x{frac_inv}; "
+              "CLUSTER..FILTER2 on the planted features' matches; kd-tree build excluded")
+    out = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args, world),
+           "stage_ms": {k: float(v / args.steps * 1e3) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], stages)},
+           "cpu_baseline": {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+           "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def workload_config(args, world):
+    return {"workload": f"synthetic {args.objects}-object DB ({args.objects * args.pts} x 128-d SIFT-like descriptors), "
+                        f"{args.features} features/frame 640x480, MATCH..FILTER2 with config.hpp defaults",
+            "db_objects": args.objects, "db_descriptors": args.objects * args.pts, "features_per_frame": args.features,
+            "parallelism": f"db-sharded-by-object x{world}" if world > 1 else "single-gpu"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from moped_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmoped_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    db = synth.make_db(args.objects, args.pts)
+    n_frames = 8
+    frames = [synth.make_frame(db, args.features, n_visible=8, frame_id=i) for i in range(n_frames)]
+    dbn = host_norm_rows(db["desc"])
+    qn = [host_norm_rows(f["desc"]) for f in frames]
+    Q = args.features
+    shards = shard_objects(db["n_pts"], world)
+    o0, o1, r0, r1 = shards[rank]
+
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.db_upload(dbn[r0:r1], db["xyz"][r0:r1], db["model_of_row"][r0:r1], args.objects, row_base=r0)
+    if world > 1:
+        ctx.db_set_global_tables(db["xyz"], db["model_of_row"], args.objects)
+    ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    ctx.set_profiling(True)
+    params = ctx.default_params()
+
+    # device-resident copies (value leg) and pinned host copies (e2e leg)
+    d_q = [torch.from_numpy(q).to(dev) for q in qn]
+    d_xy = [torch.from_numpy(f["xy"]).to(dev) for f in frames]
+    d_img = [torch.from_numpy(f["image_idx"]).to(dev) for f in frames]
+    h_q = [torch.from_numpy(q).pin_memory() for q in qn]
+    h_xy = [torch.from_numpy(f["xy"]).pin_memory() for f in frames]
+    h_img = [torch.from_numpy(f["image_idx"]).pin_memory() for f in frames]
+    e_q = torch.empty((Q, 128), dtype=torch.float32, device=dev)
+    e_xy = torch.empty((Q, 2), dtype=torch.float32, device=dev)
+    e_img = torch.empty((Q,), dtype=torch.int32, device=dev)
+    nn_row = torch.empty((Q, 2), dtype=torch.int32, device=dev)
+    nn_dist = torch.empty((Q, 2), dtype=torch.float32, device=dev)
+    acc = torch.empty((Q,), dtype=torch.uint8, device=dev)
+    if world > 1:
+        all_row = torch.empty((world, Q, 2), dtype=torch.int32, device=dev)
+        all_dist = torch.empty((world, Q, 2), dtype=torch.float32, device=dev)
+    img_bytes = ((r1 - r0 + 127) // 128) * 32768
+    need_flush = img_bytes < 2 * L2_BYTES
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if need_flush else None
+
+    def matched_rest(q_ptr, xy_ptr, img_ptr):
+        """N > 1: shard-local match, all-gather, merge, remaining stages."""
+        ctx.match_dev(q_ptr, Q, params.match_ratio, params.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+        dist.all_gather_into_tensor(all_row, nn_row)
+        dist.all_gather_into_tensor(all_dist, nn_dist)
+        ctx.match_merge_dev(all_row.data_ptr(), all_dist.data_ptr(), world, Q, params.match_ratio, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+        return ctx.process_matched_dev(nn_row.data_ptr(), acc.data_ptr(), xy_ptr, img_ptr, Q, params)
+
+    def step_dev(i):
+        k = i % n_frames
+        if world == 1:
+            return ctx.process_frame_dev(d_q[k].data_ptr(), d_xy[k].data_ptr(), d_img[k].data_ptr(), Q, params)
+        return matched_rest(d_q[k].data_ptr(), d_xy[k].data_ptr(), d_img[k].data_ptr())
+
+    def step_e2e(i):
+        k = i % n_frames
+        if world == 1:
+            return ctx.process_frame(h_q[k].numpy(), h_xy[k].numpy(), h_img[k].numpy(), params)
+        e_q.copy_(h_q[k], non_blocking=True)
+        e_xy.copy_(h_xy[k], non_blocking=True)
+        e_img.copy_(h_img[k], non_blocking=True)
+        return matched_rest(e_q.data_ptr(), e_xy.data_ptr(), e_img.data_ptr())
+
+    def timed(step_fn, steps, warmup, collect_kernel=False):
+        for i in range(warmup):
+            step_fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kms, n_obj, n_match = [], 0, 0
+        l0 = ctx.launches
+        for i in range(steps):
+            if flush is not None:
+                flush.zero_()
+            ev[i][0].record(stream)
+            out = step_fn(warmup + i)
+            ev[i][1].record(stream)
+            n_obj += len(out["model"])
+            if collect_kernel:
+                kms.append(ctx.coarse_kernel_ms())
+        launches = ctx.launches - l0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kms, launches, n_obj
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, kms, launches, n_obj = timed(step_dev, args.steps, args.warmup, collect_kernel=True)
+    clocks = sampler.stop()
+    e2e_ms, _, _, n_obj_e = timed(step_e2e, args.steps, args.warmup)
+
+    # matches per frame (for matches/s) and per-stage device times, outside the timed region
+    ms_stage = np.zeros(6, np.float32)
+    if world == 1:
+        ctx.process_frame_dev(d_q[0].data_ptr(), d_xy[0].data_ptr(), d_img[0].data_ptr(), Q, params, times=ms_stage)
+    ctx.match_dev(d_q[0].data_ptr(), Q, params.match_ratio, params.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+    torch.cuda.synchronize()
+    n_acc_local = int(acc.sum().item())
+
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = measured_peaks()
+        ms_step = total_ms / args.steps
+        fps = 1e3 / ms_step
+        k_ms = float(np.mean(kms)) if kms else None
+        flops = 2.0 * Q * (r1 - r0) * 128
+        achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
+        out = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f16 tensor-core coarse pass + f32 exact re-rank/LM", "data": "synthetic",
+               "config": dict(workload_config(args, world), l2="db tile image > 2x L2, not flushed" if not need_flush else "L2 flushed between steps (256 MiB write)",
+                              frames_pool=n_frames),
+               "objects_per_frame": n_obj / args.steps,
+               "matches_per_s": None if world > 1 else n_acc_local * fps,
+               "stage_ms": None if world > 1 else {k: float(v) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], ms_stage)},
+               "gpu_launches": int(launches),
+               "clocks": clocks,
+               "e2e": {"value": 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(Q * (128 + 2 + 1) * 4),
+                       "d2h_bytes_per_step": int(8 + 4 + 36 * (n_obj_e / args.steps))},
+               "roofline": {"kernel": "k_match_coarse", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                            "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                            "peak_source": f"{peak_src} (MEASURED_PEAKS.json bf16_tflops, burst)", "kernel_ms": k_ms,
+                            "algorithmic_flops_per_launch": flops}}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
+                    cores = os.cpu_count() or 1
+                    r = reference_setup(db, cores)
+                    s, st, n = reference_sample_step(r, frames[0], 8, seed=5)
+                    out["cpu_baseline"] = {"value": 1.0 / s, "unit": UNIT, "cores": cores, "kind": "reference",
+                                           "sample": "1 frame: MATCH_ANN_CPU(eps=5) on a uniform 1/8 of the features, time x8 + CLUSTER..FILTER2 on the planted "
+                                                     "features' matches; kd-tree build excluded",
+                                           "stage_ms": {k: float(v * 1e3) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], st)},
+                                           "objects": int(n)}
+                else:
+                    out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+            except Exception as e:  # the GPU numbers stand on their own
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--objects", type=int, default=1000)
+    ap.add_argument("--pts", type=int, default=1000)
+    ap.add_argument("--features", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

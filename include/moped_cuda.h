@@ -62,6 +62,10 @@ mc_status mc_synchronize(mc_ctx *ctx);
 mc_status mc_db_upload(mc_ctx *ctx, const float *desc, const float *xyz, const int32_t *model_of_row,
                        int64_t n_rows, int desc_dim, int n_models, int64_t row_base);
 int64_t mc_db_rows(const mc_ctx *ctx);
+/* Object-sharded databases: descriptors stay sharded (mc_db_upload with row_base), but the stages after
+ * MATCH need coord3D and the model id of ANY global row, so every rank also holds these two small tables
+ * for the whole database (16 B per row). Call after mc_db_upload. */
+mc_status mc_db_set_global_tables(mc_ctx *ctx, const float *xyz_all, const int32_t *model_of_row_all, int64_t n_rows_all, int n_models_all);
 
 /* ---- cameras: FrameData::images[i]->{intrinsicLinearCalibration, cameraPose},
  *      moped2/libmoped/include/moped.hpp:226-241 --------------------------------------------- */
@@ -154,9 +158,19 @@ mc_status mc_process_frame_dev(mc_ctx *ctx, const float *q_desc_dev, const float
                                const mc_pipeline_params *params, int max_objects,
                                int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms);
 
+/* Stages after MATCH only (CLUSTER..FILTER2), from merged nearest neighbours already on the device: the
+ * multi-GPU path runs mc_match_dev per shard, all-gathers, mc_match_merge_dev, then this. */
+mc_status mc_process_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, const uint8_t *accepted_dev, const float *q_xy_dev,
+                                 const int32_t *q_image_dev, int n_queries, const mc_pipeline_params *params, int max_objects,
+                                 int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms);
+
 /* ---- introspection for tests and bench ------------------------------------------------------ */
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t mc_kernel_launches(const mc_ctx *ctx);
+/* when on, CUDA events are recorded on the context stream around the dominant kernel (the tcgen05 coarse
+ * matching kernel); mc_profile_read waits for the last such launch and returns its device time (ms) */
+mc_status mc_set_profiling(mc_ctx *ctx, int on);
+mc_status mc_profile_read(mc_ctx *ctx, float *coarse_kernel_ms);
 
 #ifdef __cplusplus
 }

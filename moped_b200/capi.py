@@ -48,6 +48,7 @@ SIGNATURES = {
     "mc_synchronize": (C.c_int, [C.c_void_p]),
     "mc_db_upload": (C.c_int, [C.c_void_p, _f32p, _f32p, _i32p, C.c_int64, C.c_int, C.c_int, C.c_int64]),
     "mc_db_rows": (C.c_int64, [C.c_void_p]),
+    "mc_db_set_global_tables": (C.c_int, [C.c_void_p, _f32p, _i32p, C.c_int64, C.c_int]),
     "mc_set_cameras": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int]),
     "mc_match": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_int, _i32p, _f32p, _u8p, C.c_void_p]),
     "mc_match_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -64,7 +65,11 @@ SIGNATURES = {
                                    _i32p, _f32p, _f32p, C.c_void_p]),
     "mc_process_frame_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PipelineParams), C.c_int,
                                        C.POINTER(C.c_int32), _i32p, _f32p, _f32p, C.c_void_p]),
+    "mc_process_matched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PipelineParams), C.c_int,
+                                         C.POINTER(C.c_int32), _i32p, _f32p, _f32p, C.c_void_p]),
     "mc_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "mc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "mc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
 }
 
 _lib = None
@@ -141,12 +146,25 @@ class Context:
     def launches(self) -> int:
         return int(self.L.mc_kernel_launches(self.h))
 
+    def set_profiling(self, on: bool):
+        self._check(self.L.mc_set_profiling(self.h, 1 if on else 0), "mc_set_profiling")
+
+    def coarse_kernel_ms(self) -> float:
+        v = C.c_float(0)
+        self._check(self.L.mc_profile_read(self.h, C.byref(v)), "mc_profile_read")
+        return float(v.value)
+
     # ---- database / cameras
     def db_upload(self, desc, xyz, model_of_row, n_models, row_base=0):
         desc, xyz, model_of_row = _f32(desc), _f32(xyz), _i32(model_of_row)
         self.D = desc.shape[1]
         self.n_models = int(n_models)
         self._check(self.L.mc_db_upload(self.h, desc, xyz, model_of_row, desc.shape[0], desc.shape[1], int(n_models), int(row_base)), "mc_db_upload")
+
+    def db_set_global_tables(self, xyz_all, model_of_row_all, n_models_all):
+        xyz_all, model_of_row_all = _f32(xyz_all), _i32(model_of_row_all)
+        self.n_models = int(n_models_all)
+        self._check(self.L.mc_db_set_global_tables(self.h, xyz_all, model_of_row_all, len(model_of_row_all), int(n_models_all)), "mc_db_set_global_tables")
 
     def set_cameras(self, K, cam_pose):
         K, cam_pose = _f32(K).reshape(-1, 4), _f32(cam_pose).reshape(-1, 7)
@@ -259,6 +277,17 @@ class Context:
         if want_times:
             out["stage_ms"] = ms
         return out
+
+    def process_matched_dev(self, nn_row_ptr, acc_ptr, xy_ptr, img_ptr, Q, params=None, max_objects=256, times=None):
+        p = params or self.default_params()
+        n = C.c_int32(0)
+        om = np.zeros(max_objects, np.int32)
+        op = np.zeros((max_objects, 7), np.float32)
+        os_ = np.zeros(max_objects, np.float32)
+        self._check(self.L.mc_process_matched_dev(self.h, nn_row_ptr, acc_ptr, xy_ptr, img_ptr, Q, C.byref(p), max_objects, C.byref(n), om, op, os_,
+                                                  times.ctypes.data if times is not None else None), "mc_process_matched_dev")
+        k = n.value
+        return dict(model=om[:k].copy(), pose=op[:k].copy(), score=os_[:k].copy())
 
     def process_frame_dev(self, q_ptr, xy_ptr, img_ptr, Q, params=None, max_objects=256, times=None):
         p = params or self.default_params()

@@ -23,7 +23,8 @@ mc_status filter_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32
                         uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets,
                         int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score);
 mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, int Q, const mc_pipeline_params *P,
-                               int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms);
+                               int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms,
+                               const int32_t *d_nn_row_in = nullptr, const uint8_t *d_accepted_in = nullptr);
 
 // bump allocator over one grow-only device buffer, for the temporaries of a host-buffer call
 struct Arena {
@@ -116,6 +117,23 @@ mc_status mc_synchronize(mc_ctx *ctx) {
 }
 
 int64_t mc_kernel_launches(const mc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+mc_status mc_set_profiling(mc_ctx *ctx, int on) {
+	if (!ctx) return MC_ERR_ARG;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	if (on && !ctx->ev_coarse[0]) { MC_CUDA(cudaEventCreate(&ctx->ev_coarse[0])); MC_CUDA(cudaEventCreate(&ctx->ev_coarse[1])); }
+	ctx->profile = on != 0; ctx->ev_valid = false;
+	return MC_OK;
+}
+
+mc_status mc_profile_read(mc_ctx *ctx, float *coarse_ms) {
+	if (!ctx || !coarse_ms) return MC_ERR_ARG;
+	*coarse_ms = 0.f;
+	if (!ctx->profile || !ctx->ev_valid) { ctx->err = "mc_profile_read: no profiled launch"; return MC_ERR_STATE; }
+	MC_CUDA(cudaEventSynchronize(ctx->ev_coarse[1]));
+	MC_CUDA(cudaEventElapsedTime(coarse_ms, ctx->ev_coarse[0], ctx->ev_coarse[1]));
+	return MC_OK;
+}
 int64_t mc_db_rows(const mc_ctx *ctx) { return ctx ? ctx->n_rows : 0; }
 
 mc_status mc_db_upload(mc_ctx *ctx, const float *desc, const float *xyz, const int32_t *model_of_row, int64_t n_rows, int desc_dim,
@@ -127,6 +145,7 @@ mc_status mc_db_upload(mc_ctx *ctx, const float *desc, const float *xyz, const i
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	free_db(ctx);
 	ctx->n_rows = n_rows; ctx->row_base = row_base; ctx->D = desc_dim; ctx->n_models = n_models;
+	ctx->table_base = row_base; ctx->table_rows = n_rows;
 	MC_CUDA(cudaMalloc(&ctx->d_db, sizeof(float) * (size_t)n_rows * desc_dim));
 	MC_CUDA(cudaMalloc(&ctx->d_xyz, sizeof(float) * 3 * (size_t)n_rows));
 	MC_CUDA(cudaMalloc(&ctx->d_model_of_row, sizeof(int32_t) * (size_t)n_rows));
@@ -135,6 +154,21 @@ mc_status mc_db_upload(mc_ctx *ctx, const float *desc, const float *xyz, const i
 	MC_CUDA(cudaMemcpyAsync(ctx->d_model_of_row, model_of_row, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyHostToDevice, ctx->stream));
 	MC_TRY(db_build_images(ctx));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+mc_status mc_db_set_global_tables(mc_ctx *ctx, const float *xyz_all, const int32_t *model_of_row_all, int64_t n_rows_all, int n_models_all) {
+	if (!ctx || !xyz_all || !model_of_row_all || n_rows_all <= 0 || n_models_all <= 0) { if (ctx) ctx->err = "mc_db_set_global_tables: bad argument"; return MC_ERR_ARG; }
+	if (!ctx->d_db) { ctx->err = "mc_db_set_global_tables: upload the shard first"; return MC_ERR_STATE; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_xyz); cudaFree(ctx->d_model_of_row);
+	ctx->d_xyz = nullptr; ctx->d_model_of_row = nullptr;
+	MC_CUDA(cudaMalloc(&ctx->d_xyz, sizeof(float) * 3 * (size_t)n_rows_all));
+	MC_CUDA(cudaMalloc(&ctx->d_model_of_row, sizeof(int32_t) * (size_t)n_rows_all));
+	MC_CUDA(cudaMemcpy(ctx->d_xyz, xyz_all, sizeof(float) * 3 * (size_t)n_rows_all, cudaMemcpyHostToDevice));
+	MC_CUDA(cudaMemcpy(ctx->d_model_of_row, model_of_row_all, sizeof(int32_t) * (size_t)n_rows_all, cudaMemcpyHostToDevice));
+	ctx->table_base = 0; ctx->table_rows = n_rows_all; ctx->n_models = n_models_all;
 	return MC_OK;
 }
 
@@ -365,6 +399,18 @@ mc_status mc_process_frame_dev(mc_ctx *ctx, const float *q_desc_dev, const float
 	}
 	MC_CUDA(cudaSetDevice(ctx->device));
 	return process_frame_device(ctx, q_desc_dev, q_xy_dev, q_image_dev, n_queries, params, max_objects, n_objects, obj_model, obj_pose, obj_score, stage_ms);
+}
+
+mc_status mc_process_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, const uint8_t *accepted_dev, const float *q_xy_dev,
+                                 const int32_t *q_image_dev, int n_queries, const mc_pipeline_params *params, int max_objects,
+                                 int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms) {
+	if (!ctx || !nn_row_dev || !accepted_dev || !q_xy_dev || !q_image_dev || !params || !n_objects || !obj_model || !obj_pose || !obj_score || max_objects <= 0) {
+		if (ctx) ctx->err = "mc_process_matched_dev: bad argument";
+		return MC_ERR_ARG;
+	}
+	MC_CUDA(cudaSetDevice(ctx->device));
+	return process_frame_device(ctx, nullptr, q_xy_dev, q_image_dev, n_queries, params, max_objects, n_objects, obj_model, obj_pose, obj_score, stage_ms,
+	                            nn_row_dev, accepted_dev);
 }
 
 mc_status mc_process_frame(mc_ctx *ctx, const float *q_desc, const float *q_xy, const int32_t *q_image, int Q, const mc_pipeline_params *params,

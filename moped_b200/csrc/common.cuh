@@ -44,8 +44,9 @@ struct mc_ctx {
 	int D = 0, n_models = 0;
 	float *d_db = nullptr;            // n_rows x D fp32, row-major (exact re-rank / exact scan)
 	__half *d_db_img = nullptr;       // n_tiles x 32 KiB pre-swizzled fp16 operand tiles (tcgen05 B operand)
-	float *d_xyz = nullptr;           // n_rows x 3
+	float *d_xyz = nullptr;           // table_rows x 3 (coord3D of rows table_base .. table_base+table_rows)
 	int32_t *d_model_of_row = nullptr;
+	int64_t table_base = 0, table_rows = 0;   // = this shard's rows unless mc_db_set_global_tables was called
 	float db_norm2_min = 1.f, db_norm2_max = 1.f;
 
 	// cameras
@@ -58,6 +59,9 @@ struct mc_ctx {
 	mc::DevBuf scratch[24];
 	void *h_pinned = nullptr; size_t h_pinned_cap = 0;
 	int last_stats[4] = {0, 0, 0, 0};
+	bool profile = false;             // record CUDA events around the dominant kernel (k_match_coarse)
+	cudaEvent_t ev_coarse[2] = {nullptr, nullptr};
+	bool ev_valid = false;
 };
 
 namespace mc {

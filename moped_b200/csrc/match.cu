@@ -636,10 +636,12 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 		k_pack_tiles<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_q, Q, (int64_t)n_mtiles * 2, (__half *)ctx->q_img.p, (float *)ctx->q_norm2.p);
 		MC_LAUNCH_CHECK();
 		dim3 grid(n_mtiles, n_splits);
+		if (ctx->profile) MC_CUDA(cudaEventRecord(ctx->ev_coarse[0], ctx->stream));
 		k_match_coarse<<<grid, kCoarseThreads, kCoarseSmemBytes, ctx->stream>>>((const __half *)ctx->q_img.p, ctx->d_db_img, ctx->n_tiles, ctx->n_rows,
 		                                                                       tiles_per_split, n_splits, (uint32_t *)ctx->tau.p,
 		                                                                       (float *)ctx->cand_score.p, (int32_t *)ctx->cand_row.p);
 		MC_LAUNCH_CHECK();
+		if (ctx->profile) { MC_CUDA(cudaEventRecord(ctx->ev_coarse[1], ctx->stream)); ctx->ev_valid = true; }
 		k_match_rerank<<<(Q + 7) / 8, 256, 0, ctx->stream>>>(d_q, (const float *)ctx->q_norm2.p, Q, ctx->d_db, (const float *)ctx->cand_score.p,
 		                                                    (const int32_t *)ctx->cand_row.p, n_cand, (const uint32_t *)ctx->tau.p,
 		                                                    ctx->db_norm2_min, ctx->db_norm2_max, ctx->row_base, d_nn_row, d_nn_dist,

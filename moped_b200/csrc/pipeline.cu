@@ -161,7 +161,8 @@ static mc_status carve(mc_ctx *ctx, FrameBufs &B, int Q, int n_models, int cl_ca
 
 // One frame, queries resident on the device. Results are copied to the host at the end (one sync).
 mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, int Q, const mc_pipeline_params *P,
-                               int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms) {
+                               int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms,
+                               const int32_t *d_nn_row_in, const uint8_t *d_accepted_in) {
 	if (!ctx->d_db) { ctx->err = "process_frame: no database uploaded"; return MC_ERR_STATE; }
 	if (!ctx->d_cams) { ctx->err = "process_frame: cameras not set"; return MC_ERR_STATE; }
 	if (Q <= 0) { *n_objects = 0; return MC_OK; }
@@ -178,9 +179,11 @@ mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy
 	MC_CUDA(cudaMemsetAsync(B.status, 0, 64, ctx->stream));
 	MC_CUDA(cudaMemsetAsync(B.n_obj, 0, 64, ctx->stream));
 	mark(0);
-	// MATCH
-	MC_TRY(match_device(ctx, d_q, Q, P->match_ratio, P->match_mode, B.nn_row, B.nn_dist, B.accepted));
-	k_match_compact<<<1, 1024, 0, ctx->stream>>>(B.nn_row, B.accepted, Q, ctx->row_base, ctx->d_model_of_row, ctx->d_xyz, d_qxy, d_qimg, ctx->n_models,
+	// MATCH (skipped when the caller already holds merged nearest neighbours of an object-sharded database)
+	const int32_t *nn_row = d_nn_row_in ? d_nn_row_in : B.nn_row;
+	const uint8_t *accepted = d_accepted_in ? d_accepted_in : B.accepted;
+	if (!d_nn_row_in) MC_TRY(match_device(ctx, d_q, Q, P->match_ratio, P->match_mode, B.nn_row, B.nn_dist, B.accepted));
+	k_match_compact<<<1, 1024, 0, ctx->stream>>>(nn_row, accepted, Q, ctx->table_base, ctx->d_model_of_row, ctx->d_xyz, d_qxy, d_qimg, ctx->n_models,
 	                                            B.acc_list, B.match_offsets, B.match_query, B.match_row, B.match_image, B.match_xy, B.match_xyz, B.status);
 	MC_LAUNCH_CHECK();
 	mark(1);
