@@ -229,7 +229,8 @@ def run_ours(args, rank, world, local_rank):
     o0, o1, r0, r1 = shards[rank]
 
     ctx = capi.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch, NCCL ordering and libmoped_cuda
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.db_upload(dbn[r0:r1], db["xyz"][r0:r1], db["model_of_row"][r0:r1], args.objects, row_base=r0)
     if world > 1:

@@ -17,7 +17,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmoped_cuda.so")
 SOURCES = ["api.cu", "match.cu", "cluster.cu", "pose.cu", "filter.cu", "pipeline.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + os.environ.get("MOPED_NVCC_FLAGS", "").split()
+LIB = os.environ.get("MOPED_LIB", LIB)
 # pose.cu flushes denormals like the reference process does
 PER_FILE = {"pose.cu": ["-ftz=true"]}
 

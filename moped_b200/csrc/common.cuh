@@ -16,7 +16,10 @@ constexpr int kD = 128;                 // descriptor length of the tcgen05 path
 constexpr int kTileRows = 128;          // DB rows / query rows per operand tile image
 constexpr int kTileBytes = kTileRows * kD * 2;   // 32 KiB: fp16, two 128B-swizzle K atoms of 64 elements
 constexpr int kMTile = 256;             // queries per CTA (two 128-row halves)
-constexpr int kTopK = 8;                // coarse candidates kept per (query, DB split)
+#ifndef MC_TOPK
+#define MC_TOPK 4
+#endif
+constexpr int kTopK = MC_TOPK;          // coarse candidates kept per (query, DB split)
 constexpr int kMaxSplits = 64;
 
 struct Camera {            // FrameData::images[i]: K=(fx,fy,cx,cy), TM = 3x4 of cameraPose (moped.hpp:226-241)

@@ -189,12 +189,23 @@ __device__ __forceinline__ void scan_chunk(const float (&r)[32], int row_base, f
 	float m3 = fmaxf(fmaxf(fmaxf(r[24], r[25]), fmaxf(r[26], r[27])), fmaxf(fmaxf(r[28], r[29]), fmaxf(r[30], r[31])));
 	float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 	if (m > tau) {
+		// stage only the groups that hold a survivor, remember which elements beat the threshold, and
+		// visit just those (typically one): the slow path must stay short, a warp pays it for all 32 queries
 		float buf[32];
-#pragma unroll
-		for (int j = 0; j < 32; j++) buf[j] = r[j];
-#pragma unroll 1
-		for (int j = 0; j < 32; j++) {
-			float v = buf[j];
+		unsigned mask = 0;
+#define MC_STAGE_GROUP(g, mg)                                                   \
+		if (mg > tau) {                                                         \
+			_Pragma("unroll") for (int j = 0; j < 8; j++) {                     \
+				buf[8 * g + j] = r[8 * g + j];                                  \
+				mask |= (r[8 * g + j] > tau) ? (1u << (8 * g + j)) : 0u;        \
+			}                                                                   \
+		}
+		MC_STAGE_GROUP(0, m0) MC_STAGE_GROUP(1, m1) MC_STAGE_GROUP(2, m2) MC_STAGE_GROUP(3, m3)
+#undef MC_STAGE_GROUP
+		while (mask) {
+			const int j = __ffs(mask) - 1;
+			mask &= mask - 1;
+			const float v = buf[j];
 			if (v > tau) {
 				topk_insert(ts, ti, v, row_base + j);
 				tau = fmaxf(tau, ts[kTopK - 1]);
@@ -300,12 +311,13 @@ k_match_coarse(const __half *__restrict__ q_img, const __half *__restrict__ db_i
 		float tau = -CUDART_INF_F;
 		float published = -CUDART_INF_F;
 		float ra[32], rb[32];
+		uint32_t og = 0;                                   // other CTAs' threshold for this query, fetched one tile ahead
 		for (int i = 0; i < ntiles; i++) {
 			const int s = i & 1;
-			const uint32_t og = __ldcg(&g_tau[qid]);       // other CTAs' threshold for this query
+			tau = fmaxf(tau, o2f(og));
+			og = __ldcg(&g_tau[qid]);                      // consumed at the top of the next tile: its L2 latency stays hidden
 			mbar_wait(bar_tfull(s), (i >> 1) & 1);
 			tc_fence_after();
-			tau = fmaxf(tau, o2f(og));
 			const int64_t row0 = (t0 + i) * kTileRows;
 			const bool tail = row0 + kTileRows > n_rows;
 			const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 256 + half * 128);
@@ -616,8 +628,9 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 		const int n_mtiles = (Q + kMTile - 1) / kMTile;
 		const int q_pad = n_mtiles * kMTile;
 		// DB splits: fill the SMs when there are few query tiles; one split when there are many
-		int n_splits = (ctx->num_sms + n_mtiles - 1) / n_mtiles;
-		if (n_mtiles >= ctx->num_sms) n_splits = 1;
+		// (floor: one CTA per SM in a single wave; a 149th CTA would run alone in a second wave)
+		int n_splits = ctx->num_sms / n_mtiles;
+		if (n_splits < 1) n_splits = 1;
 		if (n_splits > kMaxSplits) n_splits = kMaxSplits;
 		if ((int64_t)n_splits > ctx->n_tiles) n_splits = (int)ctx->n_tiles;
 		int tiles_per_split = (int)((ctx->n_tiles + n_splits - 1) / n_splits);
