@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from moped_b200 import synth  # noqa: E402
+from moped_b200.sharding import shard_objects  # noqa: E402
 
 METRIC = "frames_per_s"
 UNIT = "frames/s"
@@ -107,17 +108,6 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def shard_objects(n_pts: np.ndarray, world: int):
-    """Contiguous object ranges balanced by descriptor count."""
-    cum = np.concatenate([[0], np.cumsum(n_pts)])
-    total = cum[-1]
-    bounds = [0]
-    for r in range(1, world):
-        bounds.append(int(np.searchsorted(cum, total * r / world)))
-    bounds.append(len(n_pts))
-    return [(bounds[r], bounds[r + 1], int(cum[bounds[r]]), int(cum[bounds[r + 1]])) for r in range(world)]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,90 @@
+"""N > 1 host logic on CPU: object sharding + the all-gather exchange + the merge rule, world_size 2 over gloo.
+Each rank matches all queries against ITS shard (with the oracle — there is no GPU here), the per-query
+(global row, distance) pairs are all-gathered and merged exactly as k_match_merge does (smaller distance, then
+smaller global row id); the result must equal the single-shard answer bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def merge_top2(rows_all, dist_all):
+    """rows_all/dist_all: [shards, Q, 2] -> [Q, 2] each (test-side restatement of the merge rule)."""
+    S, Q, _ = rows_all.shape
+    rows = rows_all.transpose(1, 0, 2).reshape(Q, 2 * S)
+    dist = dist_all.transpose(1, 0, 2).reshape(Q, 2 * S)
+    out_r = np.empty((Q, 2), np.int32); out_d = np.empty((Q, 2), np.float32)
+    for q in range(Q):
+        valid = rows[q] >= 0
+        order = sorted(np.nonzero(valid)[0], key=lambda j: (dist[q, j], rows[q, j]))
+        for k in range(2):
+            out_r[q, k] = rows[q, order[k]] if k < len(order) else -1
+            out_d[q, k] = dist[q, order[k]] if k < len(order) else np.inf
+    return out_r, out_d
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from moped_b200 import synth
+    from moped_b200.sharding import shard_objects
+    from oracle import oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    db = synth.make_db(7, 150, seed=3, ragged=True)
+    fr = synth.make_frame(db, 200, n_visible=3, pts_visible=30, seed=3)
+    dbn, qn = oracle.norm_rows(db["desc"]), oracle.norm_rows(fr["desc"])
+    o0, o1, r0, r1 = shard_objects(db["n_pts"], world)[rank]
+    idx, d = oracle.match_2nn(dbn[r0:r1], qn)
+    idx = np.where(idx >= 0, idx + r0, -1).astype(np.int32)
+    rows_all = [torch.empty((len(qn), 2), dtype=torch.int32) for _ in range(world)]
+    dist_all = [torch.empty((len(qn), 2), dtype=torch.float32) for _ in range(world)]
+    dist.all_gather(rows_all, torch.from_numpy(idx))
+    dist.all_gather(dist_all, torch.from_numpy(d))
+    mr, md = merge_top2(torch.stack(rows_all).numpy(), torch.stack(dist_all).numpy())
+    fidx, fd = oracle.match_2nn(dbn, qn)
+    q.put((rank, bool(np.array_equal(mr, fidx)), bool(np.array_equal(md, fd)), (r0, r1)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_match_equals_single_shard():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] and r[2] for r in res), res
+    spans = sorted(r[3] for r in res)
+    assert spans[0][0] == 0 and spans[0][1] == spans[1][0]
+
+
+def test_shard_objects_partitions_everything():
+    from moped_b200.sharding import shard_objects
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        n_pts = rng.integers(600, 3000, size=1000)
+        sh = shard_objects(n_pts, world)
+        assert sh[0][0] == 0 and sh[-1][1] == 1000 and sh[-1][3] == n_pts.sum()
+        for a, b in zip(sh[:-1], sh[1:]):
+            assert a[1] == b[0] and a[3] == b[2]
+        sizes = np.array([s[3] - s[2] for s in sh])
+        assert sizes.max() - sizes.min() <= 3000 * 2
+
+
+def test_synth_is_deterministic():
+    from moped_b200 import synth
+    a, b = synth.make_db(3, 50, seed=9), synth.make_db(3, 50, seed=9)
+    assert np.array_equal(a["desc"], b["desc"]) and np.array_equal(a["xyz"], b["xyz"])
+    assert np.allclose(np.linalg.norm(a["desc"], axis=1), 1.0, atol=1e-5)
+    fa, fb = synth.make_frame(a, 100, n_visible=2, pts_visible=20), synth.make_frame(b, 100, n_visible=2, pts_visible=20)
+    assert np.array_equal(fa["desc"], fb["desc"]) and len(fa["desc"]) == 100
