@@ -382,7 +382,7 @@ __device__ __forceinline__ void top2_warp_reduce(Top2 &t) {
 	}
 }
 __device__ __forceinline__ Top2 top2_empty() {
-	Top2 t; t.d0 = t.d1 = CUDART_INF_F; t.i0 = t.i1 = -1; return t;
+	Top2 t; t.d0 = t.d1 = 3.402823466e+38f /* PQ_NULL_KEY = ANN_DIST_INF: a missing neighbour */; t.i0 = t.i1 = -1; return t;
 }
 
 // Exact re-rank of the coarse candidates; one warp per query.
@@ -530,7 +530,7 @@ __global__ void k_match_exact_decode(const int32_t *__restrict__ list, const int
 			unsigned long long k = nn_key[2 * (size_t)qi + j];
 			bool ok = k != ~0ull;
 			nn_row[2 * qi + j] = ok ? (int32_t)((int64_t)(uint32_t)(k & 0xffffffffull) + row_base) : -1;
-			nn_dist[2 * qi + j] = ok ? __uint_as_float((uint32_t)(k >> 32)) : CUDART_INF_F;
+			nn_dist[2 * qi + j] = ok ? __uint_as_float((uint32_t)(k >> 32)) : 3.402823466e+38f;
 		}
 	}
 }

@@ -108,7 +108,8 @@ def test_pose_ransac_heavy_config(gpu_ctx):
     assert found.all()
     for k in range(16):
         g = cl["gt_pose"][k]
-        assert np.abs(pose[k][4:] - g[4:]).max() < 5e-3 and quat_angle(pose[k][:4], g[:4]) < 2e-2
+        # vs the planted ground truth (0.5 px noise, 40 inliers): within 1 % of the depth and 2e-2 rad
+        assert np.abs(pose[k][4:] - g[4:]).max() < 0.01 * g[6] and quat_angle(pose[k][:4], g[:4]) < 2e-2
 
 
 def test_pose_too_few_distinct_points(gpu_ctx):
