@@ -65,3 +65,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+
+
+def build_stage_driver() -> str:
+    """tests/cpp/stages_main.cpp: the C++ stage classes driven through the plugin API (stand-alone build against
+    moped_b200/stages/moped_api.hpp). Host-only g++ build; links libmoped_cuda.so."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(LIBDIR, "stages_main")
+    src = os.path.join(root, "tests", "cpp", "stages_main.cpp")
+    deps = [src] + [os.path.join(HERE, "stages", f) for f in os.listdir(os.path.join(HERE, "stages"))]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(root, "include"), "-I" + os.path.join(HERE, "stages"),
+                           src, "-o", out, "-L" + LIBDIR, "-lmoped_cuda", "-Wl,-rpath,$ORIGIN"])
+    return out
