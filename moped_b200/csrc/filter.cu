@@ -38,12 +38,14 @@ __device__ __forceinline__ float reproj_err(const float *T, const Camera &cam, c
 	return du * du + dv * dv;
 }
 
-// in_cluster: n_objects x max_per_model bytes, row o covers the matches of model(o) (index j - lo)
+// in_cluster: n_objects x max_per_model bytes, row o covers the matches of model(o) (index j - lo).
+// One WARP per object: the reprojections run 32 at a time, then lane 0 adds the terms in match order
+// (`score += 1./(err+1.)` is a sequential fp32 <- double accumulation in the reference, :106).
 __global__ void k_filter_score(const int32_t *__restrict__ match_offsets, const int32_t *__restrict__ match_image,
                                const float *__restrict__ match_xy, const float *__restrict__ match_xyz, const Camera *__restrict__ cams,
                                const int32_t *__restrict__ obj_model, const float *__restrict__ obj_pose, const int32_t *__restrict__ n_obj_p,
                                int n_obj_cap, float feat_dist, int stride, uint8_t *__restrict__ in_cluster, float *__restrict__ score) {
-	const int o = blockIdx.x * blockDim.x + threadIdx.x;
+	const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
 	if (o >= n_obj) return;
 	const int m = obj_model[o];
@@ -51,13 +53,21 @@ __global__ void k_filter_score(const int32_t *__restrict__ match_offsets, const 
 	float T[12];
 	pose_matrix(obj_pose + 7 * o, obj_pose + 7 * o + 4, T);
 	float s = 0.f;
-	for (int j = lo; j < hi; j++) {
-		const float err = reproj_err(T, cams[match_image[j]], match_xyz + 3 * j, match_xy[2 * j], match_xy[2 * j + 1]);
-		const bool in = err < feat_dist;
-		in_cluster[(size_t)o * stride + (j - lo)] = in ? 1 : 0;
-		if (in) s = (float)((double)s + 1. / ((double)err + 1.));
+	for (int j0 = lo; j0 < hi; j0 += 32) {
+		const int j = j0 + lane;
+		float err = CUDART_INF_F;
+		if (j < hi) err = reproj_err(T, cams[match_image[j]], match_xyz + 3 * j, match_xy[2 * j], match_xy[2 * j + 1]);
+		const bool in = j < hi && err < feat_dist;
+		if (j < hi) in_cluster[(size_t)o * stride + (j - lo)] = in ? 1 : 0;
+		unsigned msk = __ballot_sync(0xffffffffu, in);
+		while (msk) {                                       // in-cluster terms in ascending match order
+			const int l = __ffs(msk) - 1;
+			msk &= msk - 1;
+			const float e = __shfl_sync(0xffffffffu, err, l);
+			s = (float)((double)s + 1. / ((double)e + 1.));
+		}
 	}
-	score[o] = s;
+	if (lane == 0) score[o] = s;
 }
 
 __device__ __forceinline__ bool better(float s, int m, int o, float bs, int bm, int bo) {
@@ -67,19 +77,21 @@ __device__ __forceinline__ bool better(float s, int m, int o, float bs, int bm, 
 	return o < bo;
 }
 
-// owner[j] = object owning match j's (coord2D, image) key, or -1
+// owner[j] = object owning match j's (coord2D, image) key, or -1. One CTA per match: the threads scan all
+// matches for the same key (usually only j itself), candidates are reduced by (score desc, visit order asc).
 __global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_models, const int32_t *__restrict__ match_image,
                              const float *__restrict__ match_xy, const int32_t *__restrict__ match_model,
                              const int32_t *__restrict__ obj_model, const int32_t *__restrict__ n_obj_p, int n_obj_cap, int stride,
                              const uint8_t *__restrict__ in_cluster, const float *__restrict__ score, int32_t *__restrict__ owner) {
+	__shared__ float s_bs[4]; __shared__ int s_bm[4], s_bo[4];
 	const int M = match_offsets[n_models];
-	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.x;
 	if (j >= M) return;
 	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
 	const float x = match_xy[2 * j], y = match_xy[2 * j + 1];
 	const int im = match_image[j];
 	float bs = 0.f; int bm = 0x7fffffff, bo = -1;
-	for (int j2 = 0; j2 < M; j2++) {
+	for (int j2 = threadIdx.x; j2 < M; j2 += blockDim.x) {
 		if (match_image[j2] != im || match_xy[2 * j2] != x || match_xy[2 * j2 + 1] != y) continue;
 		const int m2 = match_model[j2];
 		const int lo2 = match_offsets[m2];
@@ -90,7 +102,19 @@ __global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_mo
 			if (bo < 0 || better(s, m2, o, bs, bm, bo)) { bs = s; bm = m2; bo = o; }
 		}
 	}
-	owner[j] = bo;
+	for (int off = 16; off; off >>= 1) {
+		const float os = __shfl_xor_sync(0xffffffffu, bs, off);
+		const int om = __shfl_xor_sync(0xffffffffu, bm, off), oo = __shfl_xor_sync(0xffffffffu, bo, off);
+		if (oo >= 0 && (bo < 0 || better(os, om, oo, bs, bm, bo))) { bs = os; bm = om; bo = oo; }
+	}
+	const int w = threadIdx.x >> 5;
+	if ((threadIdx.x & 31) == 0) { s_bs[w] = bs; s_bm[w] = bm; s_bo[w] = bo; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int k = 1; k < (int)(blockDim.x >> 5); k++)
+			if (s_bo[k] >= 0 && (bo < 0 || better(s_bs[k], s_bm[k], s_bo[k], bs, bm, bo))) { bs = s_bs[k]; bm = s_bm[k]; bo = s_bo[k]; }
+		owner[j] = bo;
+	}
 }
 
 // per object: number of owned matches of its own model, keep flag
@@ -173,14 +197,14 @@ mc_status filter_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32
 	MC_TRY(reserve(ctx, b_owned, sizeof(int32_t) * (size_t)(cap + 1)));
 	MC_TRY(reserve(ctx, b_mm, sizeof(int32_t) * (size_t)(max_matches + 1)));
 	if (n_obj_cap > 0) {
-		k_filter_score<<<(n_obj_cap + 63) / 64, 64, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, d_match_xyz, ctx->d_cams, d_obj_model,
+		k_filter_score<<<(n_obj_cap * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, d_match_xyz, ctx->d_cams, d_obj_model,
 		                                                          d_obj_pose, d_n_obj, n_obj_cap, feat_dist, stride, (uint8_t *)b_in.p, d_score);
 		MC_LAUNCH_CHECK();
 	}
 	k_match_model_of<<<(n_models + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, n_models, (int32_t *)b_mm.p);
 	MC_LAUNCH_CHECK();
 	if (max_matches > 0) {
-		k_filter_own<<<(max_matches + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy, (const int32_t *)b_mm.p,
+		k_filter_own<<<max_matches, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy, (const int32_t *)b_mm.p,
 		                                                            d_obj_model, d_n_obj, n_obj_cap, stride, (const uint8_t *)b_in.p, d_score,
 		                                                            (int32_t *)b_owner.p);
 		MC_LAUNCH_CHECK();

@@ -163,8 +163,11 @@ __device__ bool lu_solve7(const float (&A)[28], float mu, const float (&b)[7], f
 // Jacobian (misc_core.c:135-168), Broyden rank-1 updates, K = 10 (lm_core.c:484-836). `pts` holds this
 // lane's correspondences (n_own of them). On return p is the solution (if >= 0 is returned) and err = ||e||^2.
 // Returns the iteration count or -1 (LM_ERROR, stop = 4).
+// `abort_if_below` (nullable): shared word holding the lowest hypothesis index that already succeeded; a group
+// working on a higher index gives up (its result could not be chosen any more).
 template <int G, int S>
-__device__ int lm_dif(float (&p)[7], int itmax, const LmPoint (&pts)[S], int n_own, const Camera *cams, unsigned mask, float &err) {
+__device__ int lm_dif(float (&p)[7], int itmax, const LmPoint (&pts)[S], int n_own, const Camera *cams, unsigned mask, float &err,
+                      const volatile int *abort_if_below = nullptr, int my_index = 0) {
 	const float tau = 1E-03f, eps1 = 1E-17f, eps2 = 1E-17f, eps2_sq = 1E-17f * 1E-17f, eps3 = 1E-17f, delta = 1E-06f;
 	float J[S][2][7], hx[S][2], wrk[S][2];
 	float jtj[28], jte[7], diag[7], Dp[7], pDp[7];
@@ -187,6 +190,7 @@ __device__ int lm_dif(float (&p)[7], int itmax, const LmPoint (&pts)[S], int n_o
 			for (int j = 0; j < 7; j++) J[i][r][j] = 0.f;
 
 	for (k = 0; k < itmax && !stop; ++k) {
+		if (abort_if_below && *abort_if_below < my_index) { stop = 4; break; }
 		if (p_eL2 <= eps3) { stop = 6; break; }
 
 		if ((updp && nu > 16) || updjac == K) {
@@ -306,11 +310,12 @@ __device__ int lm_dif(float (&p)[7], int itmax, const LmPoint (&pts)[S], int n_o
 // optimizeCamera (POSE_..._CPU.hpp:140-164): LM, then re-normalise the quaternion. Returns false on LM_ERROR
 // (pose untouched).
 template <int G, int S>
-__device__ bool optimize_camera(float (&pose)[7], int itmax, const LmPoint (&pts)[S], int n_own, const Camera *cams, unsigned mask, float &err) {
+__device__ bool optimize_camera(float (&pose)[7], int itmax, const LmPoint (&pts)[S], int n_own, const Camera *cams, unsigned mask, float &err,
+                                const volatile int *abort_if_below = nullptr, int my_index = 0) {
 	float p[7];
 #pragma unroll
 	for (int i = 0; i < 7; i++) p[i] = pose[i];
-	const int r = lm_dif<G, S>(p, itmax, pts, n_own, cams, mask, err);
+	const int r = lm_dif<G, S>(p, itmax, pts, n_own, cams, mask, err, abort_if_below, my_index);
 	if (r < 0) { err = -1.f; return false; }
 	float d = p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3];
 	d = 1.0f / sqrtf(d);
@@ -429,7 +434,7 @@ __device__ bool draw_sample(uint64_t seed, int h, int n, int n_align, const floa
 // sample fit + inlier count of one hypothesis by an 8-lane group. Returns #inliers or -1.
 __device__ int fit_and_score(const int (&pos)[kMaxAlign], int n_align, const float (&quat)[4], int n, const float *xy, const float *xyz,
                              const int32_t *image, const Camera *cams, int max_lm, float thr, unsigned mask, int lig,
-                             float (&pose)[7], float &err, uint8_t *out_mask) {
+                             float (&pose)[7], float &err, uint8_t *out_mask, const volatile int *abort_if_below = nullptr, int my_index = 0) {
 	LmPoint pts[1];
 	int mine = 0;
 #pragma unroll
@@ -442,7 +447,7 @@ __device__ int fit_and_score(const int (&pos)[kMaxAlign], int n_align, const flo
 	} else { pts[0].u = pts[0].v = pts[0].X = pts[0].Y = pts[0].Z = 0.f; pts[0].cam = 0; }
 	pose[0] = quat[0]; pose[1] = quat[1]; pose[2] = quat[2]; pose[3] = quat[3];
 	pose[4] = 0.f; pose[5] = 0.f; pose[6] = 0.5f;
-	if (!optimize_camera<8, 1>(pose, max_lm, pts, n_own, cams, mask, err)) return -1;
+	if (!optimize_camera<8, 1>(pose, max_lm, pts, n_own, cams, mask, err, abort_if_below, my_index)) return -1;
 	return count_inliers<8>(pose, n, xy, xyz, image, cams, thr, mask, lig, out_mask);
 }
 
@@ -546,21 +551,22 @@ k_pose_refit(const int32_t *__restrict__ cluster_offsets, const float *__restric
 		for (int j = 0; j < 7; j++) pose_refit[7 * h + j] = pose[j];
 }
 
-// ---- kernel C: full RANSAC, one CTA per (cluster, try) task; 32 hypotheses per round ----
+// ---- kernel C: full RANSAC, one CTA per (cluster, try) task ----
 // Reference semantics (RANSAC(), :188-211): sequential tests, stop at the FIRST hypothesis whose inlier
-// count exceeds min_npts, refit it on its inliers. Here a round evaluates 32 consecutive hypotheses of the
-// task's stream in parallel and the lowest-numbered success of the round wins, which is the same hypothesis
-// the sequential loop would have stopped at.
+// count exceeds min_npts, refit it on its inliers. Here a round evaluates consecutive hypotheses of the task's
+// stream in parallel and the lowest-numbered success wins, which is the same hypothesis the sequential loop
+// would have stopped at. Latency shaping: the first round runs ONE hypothesis per warp (8 per round: no
+// intra-warp divergence between hypotheses, and on real clusters hypothesis 0 usually succeeds); later rounds
+// pack four per warp (32 per round). A group whose index is above an already successful one aborts its LM.
 __global__ void __launch_bounds__(kPoseThreads)
 k_pose_ransac(const int32_t *__restrict__ cluster_offsets, const int32_t *__restrict__ n_clusters_p, int n_clusters_cap,
               const float *__restrict__ xy, const float *__restrict__ xyz, const int32_t *__restrict__ image,
               const int32_t *__restrict__ tie, const Camera *__restrict__ cams, int max_obj, int max_ransac, int max_lm, int n_align,
               int min_npts, float thr, uint64_t seed, uint8_t *__restrict__ found, float *__restrict__ pose_out,
               int32_t *__restrict__ n_tests) {
-	__shared__ int s_cnt[32];
 	__shared__ float s_pose[32][7];
 	__shared__ int s_list[kRefitCap];
-	__shared__ int s_winner, s_fail;
+	__shared__ int s_first, s_fail;
 	const int task = blockIdx.x;
 	const int n_clusters = n_clusters_p ? min(*n_clusters_p, n_clusters_cap) : n_clusters_cap;
 	const int c = task / max_obj;
@@ -571,47 +577,47 @@ k_pose_ransac(const int32_t *__restrict__ cluster_offsets, const int32_t *__rest
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lig = lane & 7, grp = lane >> 3;
 	const unsigned mask = 0xFFu << (8 * grp);
 	const uint64_t task_seed = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(task + 1);
-	if (threadIdx.x == 0) { s_winner = -1; s_fail = 0; }
+	if (threadIdx.x == 0) { s_first = 0x7fffffff; s_fail = 0; }
 	__syncthreads();
-	int tests = 0;
-	for (int base = 0; base < max_ransac; base += 32) {
-		const int slot = w * 4 + grp, h = base + slot;
-		int cnt = -1;
-		float pose[7] = { 0, 0, 0, 1, 0, 0, 0 }, err;
-		if (h < max_ransac) {
+	int tests = 0, base = 0;
+	while (base < max_ransac) {
+		const int hpw = base == 0 ? 1 : 4;                 // hypotheses per warp in this round
+		const int slot = w * hpw + grp, h = base + slot;
+		if (grp < hpw && h < max_ransac) {
+			int cnt = -1;
+			float pose[7] = { 0, 0, 0, 1, 0, 0, 0 }, err;
 			int pos[kMaxAlign]; float quat[4];
 #pragma unroll
 			for (int j = 0; j < kMaxAlign; j++) pos[j] = 0;
 			if (draw_sample<8>(task_seed, h, n, n_align, cxy, cim, ctie, mask, lig, pos, quat))
-				cnt = fit_and_score(pos, n_align, quat, n, cxy, cxyz, cim, cams, max_lm, thr, mask, lig, pose, err, nullptr);
+				cnt = fit_and_score(pos, n_align, quat, n, cxy, cxyz, cim, cams, max_lm, thr, mask, lig, pose, err, nullptr, &s_first, h);
 			else if (lig == 0) s_fail = 1;               // randSample fails for every hypothesis alike -> RANSAC returns false
-		}
-		if (lig == 0) {
-			s_cnt[slot] = cnt;
-			for (int j = 0; j < 7; j++) s_pose[slot][j] = pose[j];
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			for (int sl = 0; sl < 32; sl++)
-				if (s_cnt[sl] > min_npts) { s_winner = sl; break; }
+			if (lig == 0 && cnt > min_npts) {
+				for (int j = 0; j < 7; j++) s_pose[slot][j] = pose[j];
+				atomicMin(&s_first, h);
+			}
 		}
 		__syncthreads();
-		const int winner = s_winner;
-		tests = min(base + 32, max_ransac);
-		if (winner >= 0) { tests = base + winner + 1; break; }
+		const int first = s_first;
+		const int round_n = 8 * hpw;
+		tests = min(base + round_n, max_ransac);
+		if (first != 0x7fffffff) { tests = first + 1; break; }
 		if (s_fail) { tests = 0; break; }
+		base += round_n;
 		__syncthreads();
 	}
-	const int winner = s_winner;
-	if (winner >= 0 && w == 0) {
+	const int first = s_first;
+	const bool ok = first != 0x7fffffff;
+	if (ok && w == 0) {
+		const int slot = first - base;
 		float pose[7], err;
 #pragma unroll
-		for (int j = 0; j < 7; j++) pose[j] = s_pose[winner][j];
+		for (int j = 0; j < 7; j++) pose[j] = s_pose[slot][j];
 		refit_warp(pose, n, cxy, cxyz, cim, cams, thr, max_lm, lane, s_list, err);
 		if (lane == 0)
 			for (int j = 0; j < 7; j++) pose_out[7 * task + j] = pose[j];
 	}
-	if (threadIdx.x == 0) { found[task] = winner >= 0 ? 1 : 0; n_tests[task] = tests; }
+	if (threadIdx.x == 0) { found[task] = ok ? 1 : 0; n_tests[task] = tests; }
 }
 
 // append the found poses to an object list in task order (device-side `objects->push_back`, :295-303)
