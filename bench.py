@@ -4,15 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json metric): synthetic 1000-object database (~1M 128-d descriptors), one 640x480
-frame of 2000 features per step, the reference's default stage parameters (config.hpp:83-120).
-A step = one frame through MATCH -> CLUSTER -> POSE -> FILTER -> POSE2 -> FILTER2.
+Workload (BASELINE.json metric): synthetic 1000-object database (~1M 128-d descriptors), 640x480 frames of
+2000 features, the reference's default stage parameters (config.hpp:83-120). A step = one batch of --frames
+independent frames (a camera stream; BASELINE.json configs[4] batches frames the same way) through
+MATCH -> CLUSTER -> POSE -> FILTER -> POSE2 -> FILTER2; value = frames/s. The latency of a single frame
+(mc_process_frame) is reported beside it as `single_frame`.
 
-ours:       value = frames/s with the frame's features resident in HBM; e2e = the same through the
-            host-buffer C ABI call (pinned host -> device copy of the features and device -> host read of
-            the objects inside the timed region). N > 1: database sharded by object, every rank matches all
-            queries against its shard, one NCCL all-gather of the per-query (row, distance) pairs, merge,
-            remaining stages on every rank (strong scaling: the job is fixed).
+ours:       value = frames/s with the features resident in HBM (mc_process_frames_dev); e2e = the same through
+            the host-buffer C ABI call mc_process_frames (pinned host -> device copy of the features and
+            device -> host read of the objects inside the timed region). N > 1: database sharded by object, every
+            rank matches all queries of the batch against its shard, NCCL all-gather of the per-query
+            (row, distance) pairs, merge, then rank r runs CLUSTER..FILTER2 for its 1/N of the frames and the
+            per-frame results are all-gathered (strong scaling: the job — the batch and the database — is fixed).
 reference:  the reference's own CPU stage classes (oracle/_ref, built from /root/reference) on the host
             cores; a step is a bounded sample of the same frame (see `cpu_baseline.sample`).
 One JSON line on stdout (rank 0).
@@ -161,7 +164,7 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     db = synth.make_db(args.objects, args.pts)
-    frames = [synth.make_frame(db, args.features, n_visible=8, frame_id=i) for i in range(4)]
+    frames = [synth.make_frame(db, args.features, n_visible=8, frame_id=i) for i in range(4)]   # frames of our arm's first batch
     r = reference_setup(db, cores)
     # size the sample from a probe so that warmup + steps stay near two minutes of CPU work
     s_probe, _, _ = reference_sample_step(r, frames[0], 32, seed=3)
@@ -189,15 +192,18 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world):
     return {"workload": f"synthetic {args.objects}-object DB ({args.objects * args.pts} x 128-d SIFT-like descriptors), "
-                        f"{args.features} features/frame 640x480, MATCH..FILTER2 with config.hpp defaults",
+                        f"{args.features} features/frame 640x480, MATCH..FILTER2 with config.hpp defaults; "
+                        f"a step = a batch of {args.frames} independent frames",
             "db_objects": args.objects, "db_descriptors": args.objects * args.pts, "features_per_frame": args.features,
-            "parallelism": f"db-sharded-by-object x{world}" if world > 1 else "single-gpu"}
+            "frames_per_step": args.frames,
+            "parallelism": f"db-sharded-by-object x{world}, frames after MATCH partitioned x{world}" if world > 1 else "single-gpu"}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # the frame lanes are concurrent streams
     import torch
     import torch.distributed as dist
     from moped_b200 import capi
@@ -209,14 +215,17 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    B, Q = args.frames, args.features
+    if B % world:
+        raise SystemExit(f"bench.py: --frames {B} must be a multiple of the number of GPUs ({world})")
     db = synth.make_db(args.objects, args.pts)
-    n_frames = 8
-    frames = [synth.make_frame(db, args.features, n_visible=8, frame_id=i) for i in range(n_frames)]
+    n_pool = 2                                         # two different batches, alternated between steps
+    pool = [[synth.make_frame(db, Q, n_visible=8, frame_id=p * B + i) for i in range(B)] for p in range(n_pool)]
     dbn = host_norm_rows(db["desc"])
-    qn = [host_norm_rows(f["desc"]) for f in frames]
-    Q = args.features
     shards = shard_objects(db["n_pts"], world)
     o0, o1, r0, r1 = shards[rank]
+    fo = (np.arange(B + 1) * Q).astype(np.int32)
+    QT = B * Q
 
     ctx = capi.Context(local_rank)
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch, NCCL ordering and libmoped_cuda
@@ -227,50 +236,70 @@ def run_ours(args, rank, world, local_rank):
         ctx.db_set_global_tables(db["xyz"], db["model_of_row"], args.objects)
     ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
     ctx.set_profiling(True)
+    ctx.set_tuning(args.lanes, args.pose_warps, args.chunks)
     params = ctx.default_params()
+    MO = 64                                            # object slots per frame in the result arrays
 
-    # device-resident copies (value leg) and pinned host copies (e2e leg)
-    d_q = [torch.from_numpy(q).to(dev) for q in qn]
-    d_xy = [torch.from_numpy(f["xy"]).to(dev) for f in frames]
-    d_img = [torch.from_numpy(f["image_idx"]).to(dev) for f in frames]
-    h_q = [torch.from_numpy(q).pin_memory() for q in qn]
-    h_xy = [torch.from_numpy(f["xy"]).pin_memory() for f in frames]
-    h_img = [torch.from_numpy(f["image_idx"]).pin_memory() for f in frames]
-    e_q = torch.empty((Q, 128), dtype=torch.float32, device=dev)
-    e_xy = torch.empty((Q, 2), dtype=torch.float32, device=dev)
-    e_img = torch.empty((Q,), dtype=torch.int32, device=dev)
-    nn_row = torch.empty((Q, 2), dtype=torch.int32, device=dev)
-    nn_dist = torch.empty((Q, 2), dtype=torch.float32, device=dev)
-    acc = torch.empty((Q,), dtype=torch.uint8, device=dev)
+    # pinned host copies (e2e leg) and device-resident copies (value leg) of the two batches
+    h_q = [torch.from_numpy(np.concatenate([host_norm_rows(f["desc"]) for f in fr])).pin_memory() for fr in pool]
+    h_xy = [torch.from_numpy(np.concatenate([f["xy"] for f in fr])).pin_memory() for fr in pool]
+    h_img = [torch.from_numpy(np.concatenate([f["image_idx"] for f in fr])).pin_memory() for fr in pool]
+    d_q = [t.to(dev) for t in h_q]
+    d_xy = [t.to(dev) for t in h_xy]
+    d_img = [t.to(dev) for t in h_img]
     if world > 1:
-        all_row = torch.empty((world, Q, 2), dtype=torch.int32, device=dev)
-        all_dist = torch.empty((world, Q, 2), dtype=torch.float32, device=dev)
+        e_q = torch.empty((QT, 128), dtype=torch.float32, device=dev)
+        e_xy = torch.empty((QT, 2), dtype=torch.float32, device=dev)
+        e_img = torch.empty((QT,), dtype=torch.int32, device=dev)
+        nn_row = torch.empty((QT, 2), dtype=torch.int32, device=dev)
+        nn_dist = torch.empty((QT, 2), dtype=torch.float32, device=dev)
+        acc = torch.empty((QT,), dtype=torch.uint8, device=dev)
+        all_row = torch.empty((world, QT, 2), dtype=torch.int32, device=dev)
+        all_dist = torch.empty((world, QT, 2), dtype=torch.float32, device=dev)
+        Bl = B // world                                # frames of this rank after MATCH: [rank*Bl, (rank+1)*Bl)
+        # per-rank result block (int32 words): info[Bl,4] | model[Bl,MO] | score[Bl,MO] | pose[Bl,MO*7]; written in place by
+        # mc_process_frames_matched_dev, all-gathered as one tensor
+        o_info, o_model, o_score, o_pose = 0, Bl * 4, Bl * (4 + MO), Bl * (4 + 2 * MO)
+        REC = Bl * (4 + 9 * MO)
+        res_local = torch.zeros((REC,), dtype=torch.int32, device=dev)
+        res_all = torch.zeros((world, REC), dtype=torch.int32, device=dev)
+        res_host = torch.zeros((world, REC), dtype=torch.int32).pin_memory()
     img_bytes = ((r1 - r0 + 127) // 128) * 32768
     need_flush = img_bytes < 2 * L2_BYTES
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if need_flush else None
 
-    def matched_rest(q_ptr, xy_ptr, img_ptr):
-        """N > 1: shard-local match, all-gather, merge, remaining stages."""
-        ctx.match_dev(q_ptr, Q, params.match_ratio, params.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+    def sharded_step(q, xy, img):
+        """N > 1: shard-local MATCH of all B*Q queries, all-gather of the (row, distance) pairs, merge, this rank's
+        B/N frames through CLUSTER..FILTER2, all-gather of the per-frame results, read-back."""
+        ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
         dist.all_gather_into_tensor(all_row, nn_row)
         dist.all_gather_into_tensor(all_dist, nn_dist)
-        ctx.match_merge_dev(all_row.data_ptr(), all_dist.data_ptr(), world, Q, params.match_ratio, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
-        return ctx.process_matched_dev(nn_row.data_ptr(), acc.data_ptr(), xy_ptr, img_ptr, Q, params)
+        ctx.match_merge_dev(all_row.data_ptr(), all_dist.data_ptr(), world, QT, params.match_ratio, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+        ctx.process_frames_matched_dev(nn_row.data_ptr(), acc.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, rank * Bl, (rank + 1) * Bl, params, MO,
+                                       res_local.data_ptr() + 4 * o_info, res_local.data_ptr() + 4 * o_model, res_local.data_ptr() + 4 * o_pose,
+                                       res_local.data_ptr() + 4 * o_score)
+        dist.all_gather_into_tensor(res_all, res_local)
+        res_host.copy_(res_all, non_blocking=True)
+        stream.synchronize()
+        info = res_host[:, :Bl * 4].numpy().reshape(B, 4)
+        return int(info[:, 0].sum()), int(info[:, 2].sum())
 
     def step_dev(i):
-        k = i % n_frames
+        k = i % n_pool
         if world == 1:
-            return ctx.process_frame_dev(d_q[k].data_ptr(), d_xy[k].data_ptr(), d_img[k].data_ptr(), Q, params)
-        return matched_rest(d_q[k].data_ptr(), d_xy[k].data_ptr(), d_img[k].data_ptr())
+            out = ctx.process_frames_dev(d_q[k].data_ptr(), d_xy[k].data_ptr(), d_img[k].data_ptr(), fo, params, MO)
+            return sum(len(o["model"]) for o in out), sum(int(o["info"][2]) for o in out)
+        return sharded_step(d_q[k], d_xy[k], d_img[k])
 
     def step_e2e(i):
-        k = i % n_frames
+        k = i % n_pool
         if world == 1:
-            return ctx.process_frame(h_q[k].numpy(), h_xy[k].numpy(), h_img[k].numpy(), params)
+            out = ctx.process_frames(h_q[k].numpy(), h_xy[k].numpy(), h_img[k].numpy(), fo, params, MO)
+            return sum(len(o["model"]) for o in out), sum(int(o["info"][2]) for o in out)
         e_q.copy_(h_q[k], non_blocking=True)
         e_xy.copy_(h_xy[k], non_blocking=True)
         e_img.copy_(h_img[k], non_blocking=True)
-        return matched_rest(e_q.data_ptr(), e_xy.data_ptr(), e_img.data_ptr())
+        return sharded_step(e_q, e_xy, e_img)
 
     def timed(step_fn, steps, warmup, collect_kernel=False):
         for i in range(warmup):
@@ -285,9 +314,10 @@ def run_ours(args, rank, world, local_rank):
             if flush is not None:
                 flush.zero_()
             ev[i][0].record(stream)
-            out = step_fn(warmup + i)
+            no, nm = step_fn(warmup + i)
             ev[i][1].record(stream)
-            n_obj += len(out["model"])
+            n_obj += no
+            n_match += nm
             if collect_kernel:
                 kms.append(ctx.coarse_kernel_ms())
         launches = ctx.launches - l0
@@ -298,41 +328,50 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), kms, launches, n_obj
+        return float(t.item()), kms, launches, n_obj, n_match
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    total_ms, kms, launches, n_obj = timed(step_dev, args.steps, args.warmup, collect_kernel=True)
+    total_ms, kms, launches, n_obj, n_match = timed(step_dev, args.steps, args.warmup, collect_kernel=True)
     clocks = sampler.stop()
-    e2e_ms, _, _, n_obj_e = timed(step_e2e, args.steps, args.warmup)
+    e2e_ms, _, _, n_obj_e, _ = timed(step_e2e, args.steps, args.warmup)
 
-    # matches per frame (for matches/s) and per-stage device times, outside the timed region
-    ms_stage = np.zeros(6, np.float32)
+    # outside the timed region: device time of MATCH vs CLUSTER..FILTER2 for one batch, and the latency of a single frame
+    ms_batch = np.zeros(2, np.float32)
+    lat_ms, ms_stage = None, np.zeros(6, np.float32)
     if world == 1:
-        ctx.process_frame_dev(d_q[0].data_ptr(), d_xy[0].data_ptr(), d_img[0].data_ptr(), Q, params, times=ms_stage)
-    ctx.match_dev(d_q[0].data_ptr(), Q, params.match_ratio, params.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
-    torch.cuda.synchronize()
-    n_acc_local = int(acc.sum().item())
+        ctx.process_frames_dev(d_q[0].data_ptr(), d_xy[0].data_ptr(), d_img[0].data_ptr(), fo, params, MO, times=ms_batch)
+        ctx.set_tuning(0, 8, 0)
+        for _ in range(3):
+            ctx.process_frame_dev(d_q[0].data_ptr(), d_xy[0].data_ptr(), d_img[0].data_ptr(), Q, params, times=ms_stage)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ctx.process_frame_dev(d_q[0].data_ptr(), d_xy[0].data_ptr(), d_img[0].data_ptr(), Q, params)
+        lat_ms = (time.perf_counter() - t0) / 10 * 1e3
+        ctx.set_tuning(0, args.pose_warps, 0)
 
     if rank == 0:
         peak_tf, peak_gbs, peak_src = measured_peaks()
         ms_step = total_ms / args.steps
-        fps = 1e3 / ms_step
+        fps = B * 1e3 / ms_step
         k_ms = float(np.mean(kms)) if kms else None
-        flops = 2.0 * Q * (r1 - r0) * 128
+        launches_coarse = max(1, args.chunks if world == 1 else 1)
+        flops = 2.0 * (QT / launches_coarse) * (r1 - r0) * 128
         achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
         out = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f16 tensor-core coarse pass + f32 exact re-rank/LM", "data": "synthetic",
                "config": dict(workload_config(args, world), l2="db tile image > 2x L2, not flushed" if not need_flush else "L2 flushed between steps (256 MiB write)",
-                              frames_pool=n_frames),
-               "objects_per_frame": n_obj / args.steps,
-               "matches_per_s": None if world > 1 else n_acc_local * fps,
-               "stage_ms": None if world > 1 else {k: float(v) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], ms_stage)},
+                              batches_pool=n_pool, frame_lanes=args.lanes, pose_warps_per_task=args.pose_warps, match_chunks=args.chunks),
+               "objects_per_frame": n_obj / (args.steps * B),
+               "matches_per_s": n_match / (total_ms * 1e-3),
+               "query_descriptors_per_s": QT * args.steps / (total_ms * 1e-3),
+               "batch_ms": None if world > 1 else {"match": float(ms_batch[0]), "cluster_to_filter2": float(ms_batch[1])},
+               "single_frame": None if world > 1 else {"latency_ms": lat_ms, "stage_ms": {k: float(v) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], ms_stage)}},
                "gpu_launches": int(launches),
                "clocks": clocks,
-               "e2e": {"value": 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(Q * (128 + 2 + 1) * 4),
-                       "d2h_bytes_per_step": int(8 + 4 + 36 * (n_obj_e / args.steps))},
+               "e2e": {"value": B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(QT * (128 + 2 + 1) * 4),
+                       "d2h_bytes_per_step": int(B * (16 + 36 * MO))},
                "roofline": {"kernel": "k_match_coarse", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                             "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
                             "peak_source": f"{peak_src} (MEASURED_PEAKS.json bf16_tflops, burst)", "kernel_ms": k_ms,
@@ -343,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
                 if ref.available():
                     cores = os.cpu_count() or 1
                     r = reference_setup(db, cores)
-                    s, st, n = reference_sample_step(r, frames[0], 8, seed=5)
+                    s, st, n = reference_sample_step(r, pool[0][0], 8, seed=5)
                     out["cpu_baseline"] = {"value": 1.0 / s, "unit": UNIT, "cores": cores, "kind": "reference",
                                            "sample": "1 frame: MATCH_ANN_CPU(eps=5) on a uniform 1/8 of the features, time x8 + CLUSTER..FILTER2 on the planted "
                                                      "features' matches; kd-tree build excluded",
@@ -367,6 +406,10 @@ def main():
     ap.add_argument("--objects", type=int, default=1000)
     ap.add_argument("--pts", type=int, default=1000)
     ap.add_argument("--features", type=int, default=2000)
+    ap.add_argument("--frames", type=int, default=64, help="independent frames per step (batch)")
+    ap.add_argument("--lanes", type=int, default=32, help="concurrent frames after MATCH (mc_set_tuning)")
+    ap.add_argument("--pose-warps", type=int, default=2, help="warps per RANSAC task CTA (mc_set_tuning)")
+    ap.add_argument("--chunks", type=int, default=1, help="MATCH launches per batch (mc_set_tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

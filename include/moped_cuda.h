@@ -164,6 +164,39 @@ mc_status mc_process_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, const u
                                  const int32_t *q_image_dev, int n_queries, const mc_pipeline_params *params, int max_objects,
                                  int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms);
 
+/* ---- frame batches (BASELINE.json configs[4]: batched multi-camera stream) ----
+ * A batch is n_frames INDEPENDENT frames — what the reference does by calling Moped::processImages once per
+ * frame (moped2/libmoped/src/moped.cpp:166-194) — given as concatenated query arrays and frame_offsets
+ * (n_frames+1 ascending ints on the host, frame f owns queries [frame_offsets[f], frame_offsets[f+1])).
+ * MATCH runs once for all queries (one pass over the database); the stages after it run per frame on
+ * concurrent lanes (mc_set_tuning). Frame f's objects are exactly those mc_process_frame returns for it.
+ * Outputs: n_objects[f]; obj_model / obj_score [f*max_objects + i]; obj_pose [(f*max_objects + i)*7].
+ * frame_info (optional, n_frames x 4): {objects, status, accepted matches, clusters after CLUSTER}.
+ * stage_ms (optional, 2 floats): device time of MATCH and of CLUSTER..FILTER2 for the whole batch. */
+mc_status mc_process_frames(mc_ctx *ctx, const float *q_desc, const float *q_xy, const int32_t *q_image, const int32_t *frame_offsets,
+                            int n_frames, const mc_pipeline_params *params, int max_objects,
+                            int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, int32_t *frame_info, float *stage_ms);
+/* Same with the queries already resident in HBM. Results land on the host. */
+mc_status mc_process_frames_dev(mc_ctx *ctx, const float *q_desc_dev, const float *q_xy_dev, const int32_t *q_image_dev,
+                                const int32_t *frame_offsets, int n_frames, const mc_pipeline_params *params, int max_objects,
+                                int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, int32_t *frame_info, float *stage_ms);
+/* Stages after MATCH for frames [frame_begin, frame_end) of a batch whose merged nearest neighbours (all
+ * frames) are on the device — the multi-GPU path: every rank matches all queries against its shard, the
+ * (row, distance) pairs are all-gathered and merged (mc_match_merge_dev), then rank r runs its share of the
+ * frames here and the per-frame results are all-gathered. Asynchronous; outputs are DEVICE arrays with one
+ * slot per processed frame (slot = f - frame_begin): frame_info_dev 4 ints, obj_model_dev max_objects,
+ * obj_pose_dev 7*max_objects, obj_score_dev max_objects. */
+mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, const uint8_t *accepted_dev, const float *q_xy_dev,
+                                        const int32_t *q_image_dev, const int32_t *frame_offsets, int n_frames, int frame_begin, int frame_end,
+                                        const mc_pipeline_params *params, int max_objects, int32_t *frame_info_dev, int32_t *obj_model_dev,
+                                        float *obj_pose_dev, float *obj_score_dev);
+/* Scheduling knobs that never change results: frame_lanes = concurrent frames after MATCH in a batch (1..64,
+ * default 8); pose_warps_per_task = warps of a RANSAC task CTA (1..8, default 8: lowest single-frame latency;
+ * fewer warps let more tasks of a batch be resident per SM); match_chunks = MATCH launches per batch (1..16,
+ * default 1): with c > 1 the matching of chunk i+1 overlaps the latency-bound stages of chunk i.
+ * 0 keeps the current value. */
+mc_status mc_set_tuning(mc_ctx *ctx, int frame_lanes, int pose_warps_per_task, int match_chunks);
+
 /* ---- introspection for tests and bench ------------------------------------------------------ */
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t mc_kernel_launches(const mc_ctx *ctx);

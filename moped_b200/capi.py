@@ -67,6 +67,13 @@ SIGNATURES = {
                                        C.POINTER(C.c_int32), _i32p, _f32p, _f32p, C.c_void_p]),
     "mc_process_matched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PipelineParams), C.c_int,
                                          C.POINTER(C.c_int32), _i32p, _f32p, _f32p, C.c_void_p]),
+    "mc_process_frames": (C.c_int, [C.c_void_p, _f32p, _f32p, _i32p, _i32p, C.c_int, C.POINTER(PipelineParams), C.c_int,
+                                    _i32p, _i32p, _f32p, _f32p, C.c_void_p, C.c_void_p]),
+    "mc_process_frames_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32p, C.c_int, C.POINTER(PipelineParams), C.c_int,
+                                        _i32p, _i32p, _f32p, _f32p, C.c_void_p, C.c_void_p]),
+    "mc_process_frames_matched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int,
+                                                C.POINTER(PipelineParams), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mc_kernel_launches": (C.c_int64, [C.c_void_p]),
     "mc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -299,3 +306,55 @@ class Context:
                                                 times.ctypes.data if times is not None else None), "mc_process_frame_dev")
         k = n.value
         return dict(model=om[:k].copy(), pose=op[:k].copy(), score=os_[:k].copy())
+
+    # ---- frame batches
+    def set_tuning(self, frame_lanes=0, pose_warps_per_task=0, match_chunks=0):
+        self._check(self.L.mc_set_tuning(self.h, int(frame_lanes), int(pose_warps_per_task), int(match_chunks)), "mc_set_tuning")
+
+    @staticmethod
+    def _unpack_frames(n_frames, max_objects, n_obj, om, op, os_, info):
+        out = []
+        for f in range(n_frames):
+            k = int(n_obj[f])
+            out.append(dict(model=om[f, :k].copy(), pose=op[f, :k].copy(), score=os_[f, :k].copy(), info=info[f].copy()))
+        return out
+
+    def process_frames(self, q_desc, q_xy, q_image, frame_offsets, params=None, max_objects=64, times=None):
+        """Host-buffer batch call: list of per-frame dict(model, pose, score, info)."""
+        p = params or self.default_params()
+        fo = _i32(frame_offsets)
+        nf = len(fo) - 1
+        n_obj = np.zeros(nf, np.int32)
+        om = np.zeros((nf, max_objects), np.int32)
+        op = np.zeros((nf, max_objects, 7), np.float32)
+        os_ = np.zeros((nf, max_objects), np.float32)
+        info = np.zeros((nf, 4), np.int32)
+        q = _f32(q_desc).reshape(-1, self.D)
+        xy = _f32(q_xy).reshape(-1, 2)
+        img = _i32(q_image).reshape(-1)
+        if len(q) == 0:
+            q, xy, img = np.zeros((1, self.D), np.float32), np.zeros((1, 2), np.float32), np.zeros(1, np.int32)
+        self._check(self.L.mc_process_frames(self.h, q, xy, img, fo, nf, C.byref(p), max_objects, n_obj, om.reshape(-1), op.reshape(-1), os_.reshape(-1),
+                                             info.ctypes.data, times.ctypes.data if times is not None else None), "mc_process_frames")
+        return self._unpack_frames(nf, max_objects, n_obj, om, op, os_, info)
+
+    def process_frames_dev(self, q_ptr, xy_ptr, img_ptr, frame_offsets, params=None, max_objects=64, times=None):
+        p = params or self.default_params()
+        fo = _i32(frame_offsets)
+        nf = len(fo) - 1
+        n_obj = np.zeros(nf, np.int32)
+        om = np.zeros((nf, max_objects), np.int32)
+        op = np.zeros((nf, max_objects, 7), np.float32)
+        os_ = np.zeros((nf, max_objects), np.float32)
+        info = np.zeros((nf, 4), np.int32)
+        self._check(self.L.mc_process_frames_dev(self.h, q_ptr, xy_ptr, img_ptr, fo, nf, C.byref(p), max_objects, n_obj, om.reshape(-1), op.reshape(-1),
+                                                 os_.reshape(-1), info.ctypes.data, times.ctypes.data if times is not None else None),
+                    "mc_process_frames_dev")
+        return self._unpack_frames(nf, max_objects, n_obj, om, op, os_, info)
+
+    def process_frames_matched_dev(self, nn_row_ptr, acc_ptr, xy_ptr, img_ptr, frame_offsets, frame_begin, frame_end, params, max_objects,
+                                   info_ptr, model_ptr, pose_ptr, score_ptr):
+        fo = _i32(frame_offsets)
+        self._check(self.L.mc_process_frames_matched_dev(self.h, nn_row_ptr, acc_ptr, xy_ptr, img_ptr, fo, len(fo) - 1, int(frame_begin), int(frame_end),
+                                                         C.byref(params), int(max_objects), info_ptr, model_ptr, pose_ptr, score_ptr),
+                    "mc_process_frames_matched_dev")

@@ -25,6 +25,13 @@ mc_status filter_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32
 mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, int Q, const mc_pipeline_params *P,
                                int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms,
                                const int32_t *d_nn_row_in = nullptr, const uint8_t *d_accepted_in = nullptr);
+mc_status process_frames_device(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, const int32_t *frame_offsets,
+                                int f_begin, int f_end, const mc_pipeline_params *P, int max_objects, const int32_t *d_nn_row_in,
+                                const uint8_t *d_accepted_in, int32_t *d_out_info, int32_t *d_out_model, float *d_out_pose, float *d_out_score,
+                                cudaEvent_t *ev3);
+mc_status process_frames_host(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, const int32_t *frame_offsets, int n_frames,
+                              const mc_pipeline_params *P, int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score,
+                              int32_t *frame_info, float *stage_ms);
 
 // bump allocator over one grow-only device buffer, for the temporaries of a host-buffer call
 struct Arena {
@@ -83,19 +90,37 @@ static void free_db(mc_ctx *ctx) {
 	ctx->n_rows = 0; ctx->n_tiles = 0;
 }
 
+static void free_scratch(mc_ctx *ctx);
+
 void mc_destroy(mc_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	for (mc_ctx *lane : ctx->lanes) {          // lanes borrow the database and cameras: free only what they own
+		cudaStreamSynchronize(lane->stream);
+		free_scratch(lane);
+		if (lane->ev_done) cudaEventDestroy(lane->ev_done);
+		cudaStreamDestroy(lane->stream);
+		delete lane;
+	}
+	ctx->lanes.clear();
+	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	for (cudaEvent_t e : ctx->ev_chunk) cudaEventDestroy(e);
+	if (ctx->ev_coarse[0]) { cudaEventDestroy(ctx->ev_coarse[0]); cudaEventDestroy(ctx->ev_coarse[1]); }
 	free_db(ctx);
 	cudaFree(ctx->d_cams);
+	free_scratch(ctx);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+static void free_scratch(mc_ctx *ctx) {
 	DevBuf *named[] = { &ctx->q_desc, &ctx->q_img, &ctx->q_norm2, &ctx->tau, &ctx->cand_score, &ctx->cand_row, &ctx->flag_list, &ctx->flag_count,
 	                    &ctx->nn_key, &ctx->nn_row, &ctx->nn_dist, &ctx->accepted, &ctx->q_xy, &ctx->q_image };
 	for (DevBuf *b : named) cudaFree(b->p);
 	for (DevBuf &b : ctx->scratch) cudaFree(b.p);
+	cudaFree(ctx->batch_out.p);
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-	delete ctx;
 }
 
 const char *mc_last_error(const mc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -117,6 +142,15 @@ mc_status mc_synchronize(mc_ctx *ctx) {
 }
 
 int64_t mc_kernel_launches(const mc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+mc_status mc_set_tuning(mc_ctx *ctx, int frame_lanes, int pose_warps_per_task, int match_chunks) {
+	if (!ctx) return MC_ERR_ARG;
+	if (frame_lanes > 64 || pose_warps_per_task > 8 || match_chunks > 16) { ctx->err = "mc_set_tuning: at most 64 lanes, 8 warps per task, 16 chunks"; return MC_ERR_ARG; }
+	if (frame_lanes > 0) ctx->n_lanes_wanted = frame_lanes;
+	if (pose_warps_per_task > 0) ctx->pose_warps = pose_warps_per_task;
+	if (match_chunks > 0) ctx->match_chunks = match_chunks;
+	return MC_OK;
+}
 
 mc_status mc_set_profiling(mc_ctx *ctx, int on) {
 	if (!ctx) return MC_ERR_ARG;
@@ -427,6 +461,60 @@ mc_status mc_process_frame(mc_ctx *ctx, const float *q_desc, const float *q_xy, 
 	MC_TRY(h2d(ctx, (int32_t *)ctx->q_image.p, q_image, (size_t)Q));
 	return process_frame_device(ctx, (const float *)ctx->q_desc.p, (const float *)ctx->q_xy.p, (const int32_t *)ctx->q_image.p, Q, params, max_objects,
 	                            n_objects, obj_model, obj_pose, obj_score, stage_ms);
+}
+
+// ---- frame batches ------------------------------------------------------------------------------
+static mc_status check_frames(mc_ctx *ctx, const int32_t *frame_offsets, int n_frames, const char *who) {
+	if (!frame_offsets || n_frames <= 0 || frame_offsets[0] != 0) { ctx->err = std::string(who) + ": bad frame_offsets"; return MC_ERR_ARG; }
+	for (int f = 0; f < n_frames; f++)
+		if (frame_offsets[f + 1] < frame_offsets[f]) { ctx->err = std::string(who) + ": frame_offsets must ascend"; return MC_ERR_ARG; }
+	return MC_OK;
+}
+
+mc_status mc_process_frames_dev(mc_ctx *ctx, const float *q_desc_dev, const float *q_xy_dev, const int32_t *q_image_dev, const int32_t *frame_offsets,
+                                int n_frames, const mc_pipeline_params *params, int max_objects, int32_t *n_objects, int32_t *obj_model,
+                                float *obj_pose, float *obj_score, int32_t *frame_info, float *stage_ms) {
+	if (!ctx || !params || !n_objects || !obj_model || !obj_pose || !obj_score || max_objects <= 0) { if (ctx) ctx->err = "mc_process_frames_dev: bad argument"; return MC_ERR_ARG; }
+	MC_TRY(check_frames(ctx, frame_offsets, n_frames, "mc_process_frames_dev"));
+	if (frame_offsets[n_frames] > 0 && (!q_desc_dev || !q_xy_dev || !q_image_dev)) { ctx->err = "mc_process_frames_dev: null query pointer"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	return process_frames_host(ctx, q_desc_dev, q_xy_dev, q_image_dev, frame_offsets, n_frames, params, max_objects, n_objects, obj_model, obj_pose, obj_score,
+	                           frame_info, stage_ms);
+}
+
+mc_status mc_process_frames(mc_ctx *ctx, const float *q_desc, const float *q_xy, const int32_t *q_image, const int32_t *frame_offsets, int n_frames,
+                            const mc_pipeline_params *params, int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose,
+                            float *obj_score, int32_t *frame_info, float *stage_ms) {
+	if (!ctx || !params || !n_objects || !obj_model || !obj_pose || !obj_score || max_objects <= 0) { if (ctx) ctx->err = "mc_process_frames: bad argument"; return MC_ERR_ARG; }
+	MC_TRY(check_frames(ctx, frame_offsets, n_frames, "mc_process_frames"));
+	if (!ctx->d_db) { ctx->err = "mc_process_frames: no database uploaded"; return MC_ERR_STATE; }
+	const size_t Q = (size_t)frame_offsets[n_frames];
+	if (Q > 0 && (!q_desc || !q_xy || !q_image)) { ctx->err = "mc_process_frames: null query pointer"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	MC_TRY(reserve(ctx, ctx->q_desc, sizeof(float) * (Q + 1) * ctx->D));
+	MC_TRY(reserve(ctx, ctx->q_xy, sizeof(float) * 2 * (Q + 1)));
+	MC_TRY(reserve(ctx, ctx->q_image, sizeof(int32_t) * (Q + 1)));
+	MC_TRY(h2d(ctx, (float *)ctx->q_desc.p, q_desc, Q * ctx->D));
+	MC_TRY(h2d(ctx, (float *)ctx->q_xy.p, q_xy, 2 * Q));
+	MC_TRY(h2d(ctx, (int32_t *)ctx->q_image.p, q_image, Q));
+	return process_frames_host(ctx, (const float *)ctx->q_desc.p, (const float *)ctx->q_xy.p, (const int32_t *)ctx->q_image.p, frame_offsets, n_frames,
+	                           params, max_objects, n_objects, obj_model, obj_pose, obj_score, frame_info, stage_ms);
+}
+
+mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, const uint8_t *accepted_dev, const float *q_xy_dev,
+                                        const int32_t *q_image_dev, const int32_t *frame_offsets, int n_frames, int frame_begin, int frame_end,
+                                        const mc_pipeline_params *params, int max_objects, int32_t *frame_info_dev, int32_t *obj_model_dev,
+                                        float *obj_pose_dev, float *obj_score_dev) {
+	if (!ctx || !nn_row_dev || !accepted_dev || !q_xy_dev || !q_image_dev || !params || !frame_info_dev || !obj_model_dev || !obj_pose_dev ||
+	    !obj_score_dev || max_objects <= 0) {
+		if (ctx) ctx->err = "mc_process_frames_matched_dev: bad argument";
+		return MC_ERR_ARG;
+	}
+	MC_TRY(check_frames(ctx, frame_offsets, n_frames, "mc_process_frames_matched_dev"));
+	if (frame_begin < 0 || frame_end > n_frames || frame_begin > frame_end) { ctx->err = "mc_process_frames_matched_dev: bad frame range"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	return process_frames_device(ctx, nullptr, q_xy_dev, q_image_dev, frame_offsets, frame_begin, frame_end, params, max_objects, nn_row_dev, accepted_dev,
+	                             frame_info_dev, obj_model_dev, obj_pose_dev, obj_score_dev, nullptr);
 }
 
 } // extern "C"

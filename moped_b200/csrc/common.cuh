@@ -65,6 +65,19 @@ struct mc_ctx {
 	bool profile = false;             // record CUDA events around the dominant kernel (k_match_coarse)
 	cudaEvent_t ev_coarse[2] = {nullptr, nullptr};
 	bool ev_valid = false;
+
+	// frame batches (mc_process_frames*): the stages after MATCH of different frames run concurrently on
+	// "lanes" — child contexts with their own stream and scratch that borrow this context's database tables
+	// and cameras. A lane never owns the database.
+	mc_ctx *parent = nullptr;
+	std::vector<mc_ctx *> lanes;
+	int n_lanes_wanted = 8;           // mc_set_tuning
+	int pose_warps = 8;               // warps per RANSAC task CTA (mc_set_tuning); results do not depend on it
+	int match_chunks = 1;             // MATCH launches per batch (mc_set_tuning): chunk c+1 matches while chunk c runs its lanes
+	cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
+	std::vector<cudaEvent_t> ev_chunk;
+	mc::DevBuf batch_out;             // per-frame result slots of the running batch
+	int batch_stats[4] = {0, 0, 0, 0};   // {frames, accepted matches, objects, lanes used} of the last batch
 };
 
 namespace mc {

@@ -627,9 +627,21 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 	} else {
 		const int n_mtiles = (Q + kMTile - 1) / kMTile;
 		const int q_pad = n_mtiles * kMTile;
-		// DB splits: fill the SMs when there are few query tiles; one split when there are many
-		// (floor: one CTA per SM in a single wave; a 149th CTA would run alone in a second wave)
+		// DB splits. Work item = (query tile, DB split), all items equally long. Few query tiles (one frame): a
+		// single wave, floor(SMs / tiles) splits — a 149th CTA would run alone in a second wave. Many query tiles
+		// (frame batches): several waves; keep at least 8 splits so that every query has >= 32 coarse candidates
+		// (with fewer the exactness certificate starts to fail and queries fall to the exhaustive scan), and among
+		// 8..64 splits take the count that wastes the least of the last wave.
 		int n_splits = ctx->num_sms / n_mtiles;
+		if (n_splits < 8) {
+			double best = -1.0;
+			for (int sp = 8; sp <= kMaxSplits; sp++) {
+				const int64_t items = (int64_t)n_mtiles * sp;
+				const int64_t waves = (items + ctx->num_sms - 1) / ctx->num_sms;
+				const double eff = (double)items / (double)(waves * ctx->num_sms);
+				if (eff > best + 0.01) { best = eff; n_splits = sp; }
+			}
+		}
 		if (n_splits < 1) n_splits = 1;
 		if (n_splits > kMaxSplits) n_splits = kMaxSplits;
 		if ((int64_t)n_splits > ctx->n_tiles) n_splits = (int)ctx->n_tiles;

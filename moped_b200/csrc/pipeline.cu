@@ -5,6 +5,9 @@
 // host->device copy of the queries and one device->host copy of the objects.
 #include "common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace mc {
 
 mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
@@ -159,27 +162,30 @@ static mc_status carve(mc_ctx *ctx, FrameBufs &B, int Q, int n_models, int cl_ca
 	return MC_OK;
 }
 
-// One frame, queries resident on the device. Results are copied to the host at the end (one sync).
-mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, int Q, const mc_pipeline_params *P,
-                               int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms,
-                               const int32_t *d_nn_row_in, const uint8_t *d_accepted_in) {
-	if (!ctx->d_db) { ctx->err = "process_frame: no database uploaded"; return MC_ERR_STATE; }
-	if (!ctx->d_cams) { ctx->err = "process_frame: cameras not set"; return MC_ERR_STATE; }
-	if (Q <= 0) { *n_objects = 0; return MC_OK; }
+struct FrameCaps { int cl_cap, obj_cap, task_cap; };
+
+static FrameCaps frame_caps(int Q, const mc_pipeline_params *P) {
+	FrameCaps c;
 	const int min_pts = P->cluster_min_pts > 0 ? P->cluster_min_pts : 1;
-	const int cl_cap = Q / min_pts + 1;
+	c.cl_cap = Q / min_pts + 1;
 	const int max_obj_per = P->pose.max_objects_per_cluster > P->pose2.max_objects_per_cluster ? P->pose.max_objects_per_cluster : P->pose2.max_objects_per_cluster;
-	const int obj_cap = 2 * cl_cap * max_obj_per + 8;
-	const int task_cap = obj_cap * max_obj_per + 8;
-	FrameBufs B;
-	MC_TRY(carve(ctx, B, Q, ctx->n_models, cl_cap, task_cap, obj_cap));
-	cudaEvent_t ev[7];
-	if (stage_ms) for (int i = 0; i < 7; i++) MC_CUDA(cudaEventCreate(&ev[i]));
-	auto mark = [&](int i) { if (stage_ms) cudaEventRecord(ev[i], ctx->stream); };
+	c.obj_cap = 2 * c.cl_cap * max_obj_per + 8;
+	c.task_cap = c.obj_cap * max_obj_per + 8;
+	return c;
+}
+
+// Enqueue one frame on ctx->stream (ctx may be a lane of a batch): MATCH (unless the caller passes merged
+// nearest neighbours) -> CLUSTER -> POSE -> FILTER -> POSE2 -> FILTER2. No host synchronisation: cluster and
+// object counts stay on the device, grids are sized by upper bounds. The surviving objects end in
+// B.f_n / B.surv_*; `ev` (nullable, 7 events) brackets the six stages.
+static mc_status frame_enqueue(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, int Q, const mc_pipeline_params *P,
+                               FrameBufs &B, const FrameCaps &caps, cudaEvent_t *ev, const int32_t *d_nn_row_in, const uint8_t *d_accepted_in) {
+	const int cl_cap = caps.cl_cap, obj_cap = caps.obj_cap;
+	auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], ctx->stream); };
 	MC_CUDA(cudaMemsetAsync(B.status, 0, 64, ctx->stream));
 	MC_CUDA(cudaMemsetAsync(B.n_obj, 0, 64, ctx->stream));
 	mark(0);
-	// MATCH (skipped when the caller already holds merged nearest neighbours of an object-sharded database)
+	// MATCH (skipped when the caller already holds nearest neighbours: object-sharded databases, frame batches)
 	const int32_t *nn_row = d_nn_row_in ? d_nn_row_in : B.nn_row;
 	const uint8_t *accepted = d_accepted_in ? d_accepted_in : B.accepted;
 	if (!d_nn_row_in) MC_TRY(match_device(ctx, d_q, Q, P->match_ratio, P->match_mode, B.nn_row, B.nn_dist, B.accepted));
@@ -218,6 +224,23 @@ mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy
 	                     P->filter2_min_points, P->filter2_feature_distance, P->filter2_min_score, B.keep, B.obj_score, B.f_n, B.f_model, B.f_offsets,
 	                     B.f_members, B.surv_model, B.surv_pose, B.surv_score));
 	mark(6);
+	return MC_OK;
+}
+
+// One frame, queries resident on the device. Results are copied to the host at the end (one sync).
+mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, int Q, const mc_pipeline_params *P,
+                               int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score, float *stage_ms,
+                               const int32_t *d_nn_row_in, const uint8_t *d_accepted_in) {
+	if (!ctx->d_db) { ctx->err = "process_frame: no database uploaded"; return MC_ERR_STATE; }
+	if (!ctx->d_cams) { ctx->err = "process_frame: cameras not set"; return MC_ERR_STATE; }
+	if (Q <= 0) { *n_objects = 0; return MC_OK; }
+	const FrameCaps caps = frame_caps(Q, P);
+	const int obj_cap = caps.obj_cap;
+	FrameBufs B;
+	MC_TRY(carve(ctx, B, Q, ctx->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap));
+	cudaEvent_t ev[7];
+	if (stage_ms) for (int i = 0; i < 7; i++) MC_CUDA(cudaEventCreate(&ev[i]));
+	MC_TRY(frame_enqueue(ctx, d_q, d_qxy, d_qimg, Q, P, B, caps, stage_ms ? ev : nullptr, d_nn_row_in, d_accepted_in));
 	// results -> host
 	const size_t bytes = 64 + (size_t)max_objects * (4 + 28 + 4);
 	MC_TRY(pinned(ctx, bytes + 64));
@@ -243,6 +266,211 @@ mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy
 	memcpy(obj_pose, h_pose, 28ull * n);
 	memcpy(obj_score, h_score, 4ull * n);
 	return MC_OK;
+}
+
+// =============================================================================================
+// frame batches (BASELINE.json configs[4])
+// =============================================================================================
+// A batch is a list of independent frames (each its own FrameData in the reference: moped.cpp:166-194 runs
+// them one after the other). MATCH runs once for the queries of all frames — one pass over the database tile
+// images, query tiles of 256 may straddle frames — and the stages after it, which are latency-bound chains of
+// small kernels, run per frame on concurrent lanes. Every frame gives exactly the result of mc_process_frame.
+
+// frame result -> its slot of the batch output. info = {objects, status, accepted matches, clusters after CLUSTER}
+__global__ void k_export_objects(const int32_t *__restrict__ f_n, const int32_t *__restrict__ status, const int32_t *__restrict__ match_offsets,
+                                 int n_models, const int32_t *__restrict__ cl_n, const int32_t *__restrict__ surv_model,
+                                 const float *__restrict__ surv_pose, const float *__restrict__ surv_score, int max_objects,
+                                 int32_t *__restrict__ out_info, int32_t *__restrict__ out_model, float *__restrict__ out_pose,
+                                 float *__restrict__ out_score) {
+	const int n = f_n[0];
+	const int m = n < max_objects ? n : max_objects;
+	for (int i = threadIdx.x; i < m; i += blockDim.x) { out_model[i] = surv_model[i]; out_score[i] = surv_score[i]; }
+	for (int i = threadIdx.x; i < 7 * m; i += blockDim.x) out_pose[i] = surv_pose[i];
+	if (threadIdx.x == 0) { out_info[0] = n; out_info[1] = status[0]; out_info[2] = match_offsets[n_models]; out_info[3] = cl_n[0]; }
+}
+
+__global__ void k_export_empty(int32_t *__restrict__ out_info) {
+	if (threadIdx.x < 4) out_info[threadIdx.x] = 0;
+}
+
+static void lane_borrow(mc_ctx *ctx, mc_ctx *lane) {
+	lane->device = ctx->device; lane->num_sms = ctx->num_sms;
+	lane->n_rows = ctx->n_rows; lane->row_base = ctx->row_base; lane->n_tiles = ctx->n_tiles; lane->D = ctx->D; lane->n_models = ctx->n_models;
+	lane->d_db = ctx->d_db; lane->d_db_img = ctx->d_db_img; lane->d_xyz = ctx->d_xyz; lane->d_model_of_row = ctx->d_model_of_row;
+	lane->table_base = ctx->table_base; lane->table_rows = ctx->table_rows;
+	lane->db_norm2_min = ctx->db_norm2_min; lane->db_norm2_max = ctx->db_norm2_max;
+	lane->d_cams = ctx->d_cams; lane->n_images = ctx->n_images;
+	lane->pose_warps = ctx->pose_warps;
+}
+
+static mc_status ensure_lanes(mc_ctx *ctx, int n) {
+	if (!ctx->ev_fork) MC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+	while ((int)ctx->lanes.size() < n) {
+		mc_ctx *lane = new mc_ctx;
+		lane->parent = ctx;
+		if (cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&lane->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+			delete lane;
+			ctx->err = "process_frames: cannot create a lane stream";
+			return MC_ERR_CUDA;
+		}
+		lane->own_stream = true;
+		ctx->lanes.push_back(lane);
+	}
+	for (mc_ctx *lane : ctx->lanes) lane_borrow(ctx, lane);
+	return MC_OK;
+}
+
+// Frames [f_begin, f_end) of a batch whose queries (all frames, concatenated) are resident on the device.
+// d_nn_row_in / d_accepted_in (nullable, all frames): merged nearest neighbours of an object-sharded database;
+// otherwise MATCH runs here for the queries of frames [f_begin, f_end). Outputs are DEVICE arrays with one slot
+// per processed frame: out_info 4 ints, out_model max_objects, out_pose 7*max_objects, out_score max_objects.
+// Asynchronous: returns with the work enqueued and ctx->stream ordered after all lanes.
+mc_status process_frames_device(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, const int32_t *frame_offsets,
+                                int f_begin, int f_end, const mc_pipeline_params *P, int max_objects, const int32_t *d_nn_row_in,
+                                const uint8_t *d_accepted_in, int32_t *d_out_info, int32_t *d_out_model, float *d_out_pose, float *d_out_score,
+                                cudaEvent_t *ev3) {
+	if (!ctx->d_db) { ctx->err = "process_frames: no database uploaded"; return MC_ERR_STATE; }
+	if (!ctx->d_cams) { ctx->err = "process_frames: cameras not set"; return MC_ERR_STATE; }
+	const int nf = f_end - f_begin;
+	if (nf <= 0) return MC_OK;
+	const int q_lo = frame_offsets[f_begin], q_hi = frame_offsets[f_end];
+	const int Qb = q_hi - q_lo;
+	if (ev3) MC_CUDA(cudaEventRecord(ev3[0], ctx->stream));
+	const int32_t *nn_row = d_nn_row_in;
+	const uint8_t *accepted = d_accepted_in;
+	const bool do_match = !d_nn_row_in && Qb > 0;
+	if (do_match) {
+		MC_TRY(reserve(ctx, ctx->nn_row, sizeof(int32_t) * 2 * (size_t)Qb));
+		MC_TRY(reserve(ctx, ctx->nn_dist, sizeof(float) * 2 * (size_t)Qb));
+		MC_TRY(reserve(ctx, ctx->accepted, (size_t)Qb));
+		// the batch-local arrays are indexed by global query id below
+		nn_row = (const int32_t *)ctx->nn_row.p - 2 * (size_t)q_lo;
+		accepted = (const uint8_t *)ctx->accepted.p - (size_t)q_lo;
+	}
+	int n_lanes = ctx->n_lanes_wanted < nf ? ctx->n_lanes_wanted : nf;
+	if (n_lanes < 1) n_lanes = 1;
+	MC_TRY(ensure_lanes(ctx, n_lanes));
+	// Chunks: MATCH of chunk c+1 (ctx->stream, tensor-bound, one CTA per SM) overlaps the latency-bound stages
+	// of chunk c (lanes), whose small CTAs fit beside a matching CTA on the same SM.
+	int n_chunks = do_match ? ctx->match_chunks : 1;
+	if (n_chunks > nf) n_chunks = nf;
+	if (n_chunks < 1) n_chunks = 1;
+	while ((int)ctx->ev_chunk.size() < n_chunks) {
+		cudaEvent_t e;
+		MC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		ctx->ev_chunk.push_back(e);
+	}
+	static const bool trace = getenv("MOPED_CUDA_TRACE") != nullptr;     // debugging aid: per-frame stage timeline on stderr
+	std::vector<cudaEvent_t> tev;
+	cudaEvent_t t0 = nullptr;
+	if (trace) {
+		tev.resize(7 * (size_t)nf);
+		for (auto &e : tev) cudaEventCreate(&e);
+		cudaEventCreate(&t0);
+		cudaEventRecord(t0, ctx->stream);
+	}
+	for (int c = 0; c < n_chunks; c++) {
+		const int fb = f_begin + (int)((int64_t)nf * c / n_chunks), fe = f_begin + (int)((int64_t)nf * (c + 1) / n_chunks);
+		const int cq_lo = frame_offsets[fb], cq = frame_offsets[fe] - cq_lo;
+		if (do_match && cq > 0)
+			MC_TRY(match_device(ctx, d_q + (size_t)cq_lo * ctx->D, cq, P->match_ratio, P->match_mode, (int32_t *)nn_row + 2 * (size_t)cq_lo,
+			                    (float *)ctx->nn_dist.p + 2 * (size_t)(cq_lo - q_lo), (uint8_t *)accepted + cq_lo));
+		if (ev3 && c == n_chunks - 1) MC_CUDA(cudaEventRecord(ev3[1], ctx->stream));
+		MC_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
+		const int used = (fe - fb) < n_lanes ? (fe - fb) : n_lanes;
+		for (int l = 0; l < used; l++) MC_CUDA(cudaStreamWaitEvent(ctx->lanes[(fb - f_begin + l) % n_lanes]->stream, ctx->ev_chunk[c], 0));
+		for (int f = fb; f < fe; f++) {
+			const int s = f - f_begin;
+			mc_ctx *lane = ctx->lanes[s % n_lanes];
+			const int q0 = frame_offsets[f], Q = frame_offsets[f + 1] - q0;
+			int32_t *o_info = d_out_info + 4 * (size_t)s;
+			mc_status st = MC_OK;
+			if (Q <= 0) {
+				k_export_empty<<<1, 32, 0, lane->stream>>>(o_info);
+				lane->launches++;
+			} else {
+				const FrameCaps caps = frame_caps(Q, P);
+				FrameBufs B;
+				st = carve(lane, B, Q, lane->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap);
+				if (st == MC_OK) st = frame_enqueue(lane, nullptr, d_qxy + 2 * (size_t)q0, d_qimg + q0, Q, P, B, caps, trace ? &tev[7 * (size_t)s] : nullptr, nn_row + 2 * (size_t)q0, accepted + q0);
+				if (st == MC_OK) {
+					k_export_objects<<<1, 128, 0, lane->stream>>>(B.f_n, B.status, B.match_offsets, lane->n_models, B.cl_n, B.surv_model, B.surv_pose, B.surv_score,
+					                                             max_objects, o_info, d_out_model + (size_t)s * max_objects,
+					                                             d_out_pose + 7 * (size_t)s * max_objects, d_out_score + (size_t)s * max_objects);
+					lane->launches++;
+					if (cudaGetLastError() != cudaSuccess) { lane->err = "process_frames: export launch failed"; st = MC_ERR_CUDA; }
+				}
+			}
+			if (st != MC_OK) { ctx->err = lane->err; return st; }
+		}
+	}
+	for (int l = 0; l < n_lanes; l++) {
+		mc_ctx *lane = ctx->lanes[l];
+		MC_CUDA(cudaEventRecord(lane->ev_done, lane->stream));
+		MC_CUDA(cudaStreamWaitEvent(ctx->stream, lane->ev_done, 0));
+		ctx->launches += lane->launches; lane->launches = 0;
+	}
+	if (ev3) MC_CUDA(cudaEventRecord(ev3[2], ctx->stream));
+	if (trace) {
+		cudaStreamSynchronize(ctx->stream);
+		for (int s = 0; s < nf; s++) {
+			if (frame_offsets[f_begin + s + 1] - frame_offsets[f_begin + s] <= 0) continue;
+			fprintf(stderr, "[trace] frame %3d:", f_begin + s);
+			for (int i = 0; i < 7; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, t0, tev[7 * (size_t)s + i]); fprintf(stderr, " %7.3f", ms); }
+			fprintf(stderr, "  (ms since batch start: begin, compact, cluster, pose, filter, pose2, filter2)\n");
+		}
+		for (auto &e : tev) cudaEventDestroy(e);
+		cudaEventDestroy(t0);
+	}
+	ctx->batch_stats[0] = nf; ctx->batch_stats[3] = n_lanes;
+	return MC_OK;
+}
+
+// Host-facing tail: batch outputs -> host arrays (one copy, one synchronisation).
+mc_status process_frames_host(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, const int32_t *frame_offsets, int n_frames,
+                              const mc_pipeline_params *P, int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score,
+                              int32_t *frame_info, float *stage_ms) {
+	const size_t per = 16 + (size_t)max_objects * 36;
+	const size_t bytes = per * (size_t)n_frames;
+	MC_TRY(reserve(ctx, ctx->batch_out, bytes + 256));
+	MC_TRY(pinned(ctx, bytes + 256));
+	char *d = (char *)ctx->batch_out.p;
+	int32_t *d_info = (int32_t *)d;
+	int32_t *d_model = (int32_t *)(d + 16ull * n_frames);
+	float *d_pose = (float *)(d + (16ull + 4ull * max_objects) * n_frames);
+	float *d_score = (float *)(d + (16ull + 32ull * max_objects) * n_frames);
+	cudaEvent_t ev[3];
+	if (stage_ms) for (int i = 0; i < 3; i++) MC_CUDA(cudaEventCreate(&ev[i]));
+	MC_TRY(process_frames_device(ctx, d_q, d_qxy, d_qimg, frame_offsets, 0, n_frames, P, max_objects, nullptr, nullptr, d_info, d_model, d_pose, d_score,
+	                             stage_ms ? ev : nullptr));
+	char *h = (char *)ctx->h_pinned;
+	MC_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (stage_ms) {
+		cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
+		cudaEventElapsedTime(&stage_ms[1], ev[1], ev[2]);
+		for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
+	}
+	const int32_t *h_info = (const int32_t *)h;
+	const int32_t *h_model = (const int32_t *)(h + 16ull * n_frames);
+	const float *h_pose = (const float *)(h + (16ull + 4ull * max_objects) * n_frames);
+	const float *h_score = (const float *)(h + (16ull + 32ull * max_objects) * n_frames);
+	mc_status st = MC_OK;
+	int tot_m = 0, tot_o = 0;
+	for (int f = 0; f < n_frames; f++) {
+		const int n = h_info[4 * f];
+		if (frame_info) memcpy(frame_info + 4 * f, h_info + 4 * f, 16);
+		n_objects[f] = n;
+		tot_m += h_info[4 * f + 2]; tot_o += n;
+		if (h_info[4 * f + 1]) { ctx->err = "process_frames: more than 8192 accepted matches in one frame"; st = MC_ERR_CAPACITY; continue; }
+		if (n > max_objects) { ctx->err = "process_frames: object buffer too small"; st = MC_ERR_CAPACITY; continue; }
+		memcpy(obj_model + (size_t)f * max_objects, h_model + (size_t)f * max_objects, 4ull * n);
+		memcpy(obj_pose + 7 * (size_t)f * max_objects, h_pose + 7 * (size_t)f * max_objects, 28ull * n);
+		memcpy(obj_score + (size_t)f * max_objects, h_score + (size_t)f * max_objects, 4ull * n);
+	}
+	ctx->batch_stats[1] = tot_m; ctx->batch_stats[2] = tot_o;
+	return st;
 }
 
 } // namespace mc

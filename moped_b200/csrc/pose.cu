@@ -558,6 +558,8 @@ k_pose_refit(const int32_t *__restrict__ cluster_offsets, const float *__restric
 // would have stopped at. Latency shaping: the first round runs ONE hypothesis per warp (8 per round: no
 // intra-warp divergence between hypotheses, and on real clusters hypothesis 0 usually succeeds); later rounds
 // pack four per warp (32 per round). A group whose index is above an already successful one aborts its LM.
+// blockDim = 32 x (warps per task, 1..8; mc_set_tuning): fewer warps per task trade the latency of one task for
+// more resident tasks per SM when a frame batch brings hundreds of them. The winner does not depend on it.
 __global__ void __launch_bounds__(kPoseThreads)
 k_pose_ransac(const int32_t *__restrict__ cluster_offsets, const int32_t *__restrict__ n_clusters_p, int n_clusters_cap,
               const float *__restrict__ xy, const float *__restrict__ xyz, const int32_t *__restrict__ image,
@@ -575,6 +577,7 @@ k_pose_ransac(const int32_t *__restrict__ cluster_offsets, const int32_t *__rest
 	const float *cxy = xy + 2 * lo, *cxyz = xyz + 3 * lo;
 	const int32_t *cim = image + lo, *ctie = tie ? tie + lo : nullptr;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lig = lane & 7, grp = lane >> 3;
+	const int nw = blockDim.x >> 5;
 	const unsigned mask = 0xFFu << (8 * grp);
 	const uint64_t task_seed = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(task + 1);
 	if (threadIdx.x == 0) { s_first = 0x7fffffff; s_fail = 0; }
@@ -599,7 +602,7 @@ k_pose_ransac(const int32_t *__restrict__ cluster_offsets, const int32_t *__rest
 		}
 		__syncthreads();
 		const int first = s_first;
-		const int round_n = 8 * hpw;
+		const int round_n = nw * hpw;
 		tests = min(base + round_n, max_ransac);
 		if (first != 0x7fffffff) { tests = first + 1; break; }
 		if (s_fail) { tests = 0; break; }
@@ -663,7 +666,8 @@ mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, cons
 	if (pp->n_pts_align < 1 || pp->n_pts_align > kMaxAlign) { ctx->err = "pose: n_pts_align must be in 1..8"; return MC_ERR_ARG; }
 	const int n_tasks = n_clusters_cap * pp->max_objects_per_cluster;
 	if (n_tasks <= 0) return MC_OK;
-	k_pose_ransac<<<n_tasks, kPoseThreads, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, d_tie, ctx->d_cams,
+	const int warps = ctx->pose_warps < 1 ? 1 : (ctx->pose_warps > kPoseThreads / 32 ? kPoseThreads / 32 : ctx->pose_warps);
+	k_pose_ransac<<<n_tasks, 32 * warps, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, d_tie, ctx->d_cams,
 	                                                       pp->max_objects_per_cluster, pp->max_ransac_tests, pp->max_lm_tests, pp->n_pts_align,
 	                                                       pp->min_npts_object, pp->error_threshold, pp->seed, d_found, d_pose, d_n_tests);
 	MC_LAUNCH_CHECK();

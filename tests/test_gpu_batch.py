@@ -1,0 +1,125 @@
+"""Frame batches through the C ABI (mc_process_frames*, BASELINE.json configs[4]): every frame of a batch must give
+exactly the objects mc_process_frame gives for it alone — the batch only changes scheduling (one MATCH pass for all
+queries, concurrent lanes after it), never results. Covers ragged and empty frames and every tuning setting."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def batch_case(oracle_mod):
+    from moped_b200 import synth
+    db = synth.make_db(30, 1000)
+    sizes = [2000, 700, 0, 1500, 2000, 256, 1, 2000, 1234]
+    frames = [synth.make_frame(db, q, n_visible=(4 if q >= 700 else 1), frame_id=10 + i) if q > 0 else None for i, q in enumerate(sizes)]
+    dbn = oracle_mod.norm_rows(db["desc"])
+    qn = [oracle_mod.norm_rows(f["desc"]) if f is not None else np.zeros((0, 128), np.float32) for f in frames]
+    xy = [f["xy"] if f is not None else np.zeros((0, 2), np.float32) for f in frames]
+    img = [f["image_idx"] if f is not None else np.zeros(0, np.int32) for f in frames]
+    return dict(db=db, dbn=dbn, frames=frames, qn=qn, xy=xy, img=img, sizes=sizes)
+
+
+@pytest.fixture()
+def ctx30(gpu_ctx, batch_case):
+    from moped_b200 import synth
+    c = batch_case
+    gpu_ctx.db_upload(c["dbn"], c["db"]["xyz"], c["db"]["model_of_row"], 30)
+    gpu_ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    gpu_ctx.set_tuning(8, 8, 1)
+    return gpu_ctx
+
+
+def _single(ctx, c):
+    out = []
+    for q, xy, img in zip(c["qn"], c["xy"], c["img"]):
+        if len(q) == 0:
+            out.append(dict(model=np.zeros(0, np.int32), pose=np.zeros((0, 7), np.float32), score=np.zeros(0, np.float32)))
+        else:
+            out.append(ctx.process_frame(q, xy, img, max_objects=64))
+    return out
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for f, (x, y) in enumerate(zip(a, b)):
+        assert np.array_equal(x["model"], y["model"]), f
+        assert np.array_equal(x["pose"], y["pose"]), f            # bit-identical: same kernels, same seeds
+        assert np.array_equal(x["score"], y["score"]), f
+
+
+@pytest.mark.parametrize("lanes,warps,chunks", [(1, 8, 1), (4, 2, 2), (8, 1, 3), (16, 4, 16)])
+def test_batch_equals_single_frames(ctx30, batch_case, lanes, warps, chunks):
+    c = batch_case
+    ctx30.set_tuning(8, 8, 1)
+    single = _single(ctx30, c)
+    assert sum(len(s["model"]) for s in single) >= 12          # the planted objects are found
+    ctx30.set_tuning(lanes, warps, chunks)
+    fo = np.concatenate([[0], np.cumsum(c["sizes"])]).astype(np.int32)
+    batch = ctx30.process_frames(np.concatenate(c["qn"]), np.concatenate(c["xy"]), np.concatenate(c["img"]), fo, max_objects=64)
+    _same(batch, single)
+    for f, b in enumerate(batch):
+        assert b["info"][0] == len(b["model"]) and b["info"][1] == 0
+        if c["sizes"][f] == 0:
+            assert b["info"].tolist() == [0, 0, 0, 0]
+    ctx30.set_tuning(8, 8, 1)
+
+
+def test_batch_objects_match_ground_truth(ctx30, batch_case):
+    c = batch_case
+    fo = np.concatenate([[0], np.cumsum(c["sizes"])]).astype(np.int32)
+    batch = ctx30.process_frames(np.concatenate(c["qn"]), np.concatenate(c["xy"]), np.concatenate(c["img"]), fo, max_objects=64)
+    for f, fr in enumerate(c["frames"]):
+        if fr is None or c["sizes"][f] < 700:
+            continue
+        assert sorted(batch[f]["model"].tolist()) == sorted(fr["gt_model"].tolist()), f
+        for m, p in zip(batch[f]["model"], batch[f]["pose"]):
+            g = fr["gt_pose"][list(fr["gt_model"]).index(m)]
+            assert np.abs(p[4:] - g[4:]).max() < 0.01
+
+
+def test_batch_device_entry_and_frame_range(ctx30, batch_case):
+    """mc_process_frames_dev (queries resident) and mc_process_frames_matched_dev on a frame sub-range (the
+    multi-GPU split of the stages after MATCH) give the same frames."""
+    import torch
+    c = batch_case
+    dev = torch.device("cuda", 0)
+    fo = np.concatenate([[0], np.cumsum(c["sizes"])]).astype(np.int32)
+    Q = int(fo[-1])
+    q = torch.from_numpy(np.concatenate(c["qn"])).to(dev)
+    xy = torch.from_numpy(np.concatenate(c["xy"])).to(dev)
+    img = torch.from_numpy(np.concatenate(c["img"])).to(dev)
+    ref = ctx30.process_frames_dev(q.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, max_objects=64)
+    _same(ref, _single(ctx30, c))
+    # matched entry: nearest neighbours of all queries from mc_match_dev, then frames [3, 8)
+    p = ctx30.default_params()
+    nn_row = torch.empty((Q, 2), dtype=torch.int32, device=dev)
+    nn_dist = torch.empty((Q, 2), dtype=torch.float32, device=dev)
+    acc = torch.empty((Q,), dtype=torch.uint8, device=dev)
+    ctx30.match_dev(q.data_ptr(), Q, p.match_ratio, p.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+    nf, mo = 5, 64
+    info = torch.zeros((nf, 4), dtype=torch.int32, device=dev)
+    om = torch.zeros((nf, mo), dtype=torch.int32, device=dev)
+    op = torch.zeros((nf, mo, 7), dtype=torch.float32, device=dev)
+    osc = torch.zeros((nf, mo), dtype=torch.float32, device=dev)
+    ctx30.process_frames_matched_dev(nn_row.data_ptr(), acc.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, 3, 8, p, mo,
+                                     info.data_ptr(), om.data_ptr(), op.data_ptr(), osc.data_ptr())
+    ctx30.synchronize()
+    torch.cuda.synchronize()
+    info, om, op, osc = info.cpu().numpy(), om.cpu().numpy(), op.cpu().numpy(), osc.cpu().numpy()
+    for s in range(nf):
+        k = int(info[s, 0])
+        assert np.array_equal(om[s, :k], ref[3 + s]["model"])
+        assert np.array_equal(op[s, :k], ref[3 + s]["pose"])
+        assert np.array_equal(osc[s, :k], ref[3 + s]["score"])
+
+
+def test_batch_argument_errors(ctx30, batch_case):
+    from moped_b200 import capi
+    c = batch_case
+    with pytest.raises(capi.MopedCudaError):
+        ctx30.process_frames(c["qn"][0], c["xy"][0], c["img"][0], np.array([0, 100, 50], np.int32))
+    with pytest.raises(capi.MopedCudaError):
+        ctx30.process_frames(c["qn"][0], c["xy"][0], c["img"][0], np.array([5, 100], np.int32))
+    with pytest.raises(capi.MopedCudaError):
+        ctx30.set_tuning(65, 0, 0)
