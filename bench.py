@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from moped_b200 import synth  # noqa: E402
-from moped_b200.sharding import shard_objects  # noqa: E402
+from moped_b200.sharding import ResultBlock, frame_range, shard_objects  # noqa: E402
 
 METRIC = "frames_per_s"
 UNIT = "frames/s"
@@ -256,11 +256,10 @@ def run_ours(args, rank, world, local_rank):
         acc = torch.empty((QT,), dtype=torch.uint8, device=dev)
         all_row = torch.empty((world, QT, 2), dtype=torch.int32, device=dev)
         all_dist = torch.empty((world, QT, 2), dtype=torch.float32, device=dev)
-        Bl = B // world                                # frames of this rank after MATCH: [rank*Bl, (rank+1)*Bl)
-        # per-rank result block (int32 words): info[Bl,4] | model[Bl,MO] | score[Bl,MO] | pose[Bl,MO*7]; written in place by
-        # mc_process_frames_matched_dev, all-gathered as one tensor
-        o_info, o_model, o_score, o_pose = 0, Bl * 4, Bl * (4 + MO), Bl * (4 + 2 * MO)
-        REC = Bl * (4 + 9 * MO)
+        f_lo, f_hi = frame_range(B, world, rank)       # frames of this rank after MATCH
+        Bl = f_hi - f_lo
+        blk = ResultBlock(Bl, MO)                      # written in place by mc_process_frames_matched_dev, all-gathered as one tensor
+        REC = blk.words
         res_local = torch.zeros((REC,), dtype=torch.int32, device=dev)
         res_all = torch.zeros((world, REC), dtype=torch.int32, device=dev)
         res_host = torch.zeros((world, REC), dtype=torch.int32).pin_memory()
@@ -275,9 +274,9 @@ def run_ours(args, rank, world, local_rank):
         dist.all_gather_into_tensor(all_row, nn_row)
         dist.all_gather_into_tensor(all_dist, nn_dist)
         ctx.match_merge_dev(all_row.data_ptr(), all_dist.data_ptr(), world, QT, params.match_ratio, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
-        ctx.process_frames_matched_dev(nn_row.data_ptr(), acc.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, rank * Bl, (rank + 1) * Bl, params, MO,
-                                       res_local.data_ptr() + 4 * o_info, res_local.data_ptr() + 4 * o_model, res_local.data_ptr() + 4 * o_pose,
-                                       res_local.data_ptr() + 4 * o_score)
+        ctx.process_frames_matched_dev(nn_row.data_ptr(), acc.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, f_lo, f_hi, params, MO,
+                                       res_local.data_ptr() + 4 * blk.o_info, res_local.data_ptr() + 4 * blk.o_model,
+                                       res_local.data_ptr() + 4 * blk.o_pose, res_local.data_ptr() + 4 * blk.o_score)
         dist.all_gather_into_tensor(res_all, res_local)
         res_host.copy_(res_all, non_blocking=True)
         stream.synchronize()

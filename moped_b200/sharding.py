@@ -18,3 +18,41 @@ def shard_objects(n_pts: np.ndarray, world: int):
         bounds.append(min(max(b, bounds[-1]), len(n_pts)))
     bounds.append(len(n_pts))
     return [(bounds[r], bounds[r + 1], int(cum[bounds[r]]), int(cum[bounds[r + 1]])) for r in range(world)]
+
+
+def frame_range(n_frames: int, world: int, rank: int):
+    """Frames of a batch that rank `rank` runs through CLUSTER..FILTER2 after the merged MATCH: contiguous blocks
+    of n_frames / world (so that the all-gathered per-rank result blocks are in frame order)."""
+    if n_frames % world:
+        raise ValueError(f"{n_frames} frames do not split evenly over {world} ranks")
+    per = n_frames // world
+    return rank * per, (rank + 1) * per
+
+
+class ResultBlock:
+    """Layout of one rank's result block for `frames` frames with `max_objects` slots each, in int32 words:
+    info[frames,4] | model[frames,MO] | score[frames,MO] (f32 bits) | pose[frames,MO*7] (f32 bits).
+    mc_process_frames_matched_dev writes the four regions in place; one all-gather moves the block."""
+
+    def __init__(self, frames: int, max_objects: int):
+        self.frames, self.mo = frames, max_objects
+        self.o_info = 0
+        self.o_model = frames * 4
+        self.o_score = frames * (4 + max_objects)
+        self.o_pose = frames * (4 + 2 * max_objects)
+        self.words = frames * (4 + 9 * max_objects)
+
+    def unpack(self, blocks: np.ndarray):
+        """blocks: [world, words] int32 (the all-gathered blocks) -> list of per-frame dict(model, pose, score, info)
+        in frame order."""
+        blocks = np.asarray(blocks, dtype=np.int32).reshape(-1, self.words)
+        out = []
+        for b in blocks:
+            info = b[self.o_info:self.o_model].reshape(self.frames, 4)
+            model = b[self.o_model:self.o_score].reshape(self.frames, self.mo)
+            score = b[self.o_score:self.o_pose].view(np.float32).reshape(self.frames, self.mo)
+            pose = b[self.o_pose:self.words].view(np.float32).reshape(self.frames, self.mo, 7)
+            for f in range(self.frames):
+                k = min(int(info[f, 0]), self.mo)
+                out.append(dict(model=model[f, :k].copy(), pose=pose[f, :k].copy(), score=score[f, :k].copy(), info=info[f].copy()))
+        return out

@@ -123,3 +123,53 @@ def test_batch_argument_errors(ctx30, batch_case):
         ctx30.process_frames(c["qn"][0], c["xy"][0], c["img"][0], np.array([5, 100], np.int32))
     with pytest.raises(capi.MopedCudaError):
         ctx30.set_tuning(65, 0, 0)
+
+
+def test_sharded_batch_equals_single_context(ctx30, batch_case):
+    """The N = 2 data path of bench.py on one GPU: two contexts hold the two object shards (+ the global coord3D /
+    model tables), each matches ALL queries of the batch against its shard, the (row, distance) pairs are stacked
+    (= the all-gather) and merged, then "rank" r runs CLUSTER..FILTER2 for its half of the frames and writes its
+    result block; the unpacked blocks must equal the single-context batch bit for bit."""
+    import torch
+    from moped_b200 import capi, synth
+    from moped_b200.sharding import ResultBlock, frame_range, shard_objects
+    c = batch_case
+    sizes = [2000, 700, 0, 1500, 2000, 256, 1, 2000]          # 8 frames -> 4 per rank
+    fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    Q = int(fo[-1])
+    qn, xy, img = np.concatenate(c["qn"][:8]), np.concatenate(c["xy"][:8]), np.concatenate(c["img"][:8])
+    ref = ctx30.process_frames(qn, xy, img, fo, max_objects=32)
+    dev = torch.device("cuda", 0)
+    dq, dxy, dimg = torch.from_numpy(qn).to(dev), torch.from_numpy(xy).to(dev), torch.from_numpy(img).to(dev)
+    world, MO = 2, 32
+    rows_all = torch.empty((world, Q, 2), dtype=torch.int32, device=dev)
+    dist_all = torch.empty((world, Q, 2), dtype=torch.float32, device=dev)
+    acc = torch.empty(Q, dtype=torch.uint8, device=dev)
+    ctxs = []
+    for r, (o0, o1, r0, r1) in enumerate(shard_objects(c["db"]["n_pts"], world)):
+        cx = capi.Context(0)
+        cx.db_upload(c["dbn"][r0:r1], c["db"]["xyz"][r0:r1], c["db"]["model_of_row"][r0:r1], 30, row_base=r0)
+        cx.db_set_global_tables(c["db"]["xyz"], c["db"]["model_of_row"], 30)
+        cx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+        cx.set_tuning(4, 2, 1)
+        cx.match_dev(dq.data_ptr(), Q, 0.8, capi.MATCH_TENSOR, rows_all[r].data_ptr(), dist_all[r].data_ptr(), acc.data_ptr())
+        cx.synchronize()
+        ctxs.append(cx)
+    blocks = []
+    p = ctxs[0].default_params()
+    for r, cx in enumerate(ctxs):
+        nn_row = torch.empty((Q, 2), dtype=torch.int32, device=dev); nn_dist = torch.empty((Q, 2), dtype=torch.float32, device=dev)
+        a = torch.empty(Q, dtype=torch.uint8, device=dev)
+        cx.match_merge_dev(rows_all.data_ptr(), dist_all.data_ptr(), world, Q, 0.8, nn_row.data_ptr(), nn_dist.data_ptr(), a.data_ptr())
+        lo, hi = frame_range(8, world, r)
+        blk = ResultBlock(hi - lo, MO)
+        buf = torch.zeros(blk.words, dtype=torch.int32, device=dev)
+        cx.process_frames_matched_dev(nn_row.data_ptr(), a.data_ptr(), dxy.data_ptr(), dimg.data_ptr(), fo, lo, hi, p, MO,
+                                      buf.data_ptr() + 4 * blk.o_info, buf.data_ptr() + 4 * blk.o_model, buf.data_ptr() + 4 * blk.o_pose,
+                                      buf.data_ptr() + 4 * blk.o_score)
+        cx.synchronize()
+        blocks.append(buf.cpu().numpy())
+    got = blk.unpack(np.stack(blocks))
+    _same(got, ref)
+    for cx in ctxs:
+        cx.close()

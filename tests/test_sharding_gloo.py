@@ -88,3 +88,56 @@ def test_synth_is_deterministic():
     assert np.allclose(np.linalg.norm(a["desc"], axis=1), 1.0, atol=1e-5)
     fa, fb = synth.make_frame(a, 100, n_visible=2, pts_visible=20), synth.make_frame(b, 100, n_visible=2, pts_visible=20)
     assert np.array_equal(fa["desc"], fb["desc"]) and len(fa["desc"]) == 100
+
+
+def _worker_frames(rank, world, port, q):
+    """Frame partition of a batch + the all-gather of the per-rank result blocks (what bench.py does over NCCL)."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from moped_b200.sharding import ResultBlock, frame_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, MO = 6, 5
+    lo, hi = frame_range(B, world, rank)
+    blk = ResultBlock(hi - lo, MO)
+    buf = np.zeros(blk.words, np.int32)
+    # frame f "finds" f % 4 objects: model id 100 + f, pose = f + slot/10, score = f
+    for s, f in enumerate(range(lo, hi)):
+        k = f % 4
+        buf[blk.o_info + 4 * s:blk.o_info + 4 * s + 4] = [k, 0, 10 * f, f]
+        buf[blk.o_model + MO * s:blk.o_model + MO * s + k] = 100 + f
+        buf[blk.o_score + MO * s:blk.o_score + MO * s + k] = np.full(k, f, np.float32).view(np.int32)
+        buf[blk.o_pose + 7 * MO * s:blk.o_pose + 7 * MO * s + 7 * k] = (f + np.arange(7 * k) // 7 / 10).astype(np.float32).view(np.int32)
+    out = [torch.empty(blk.words, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(out, torch.from_numpy(buf))
+    frames = blk.unpack(torch.stack(out).numpy())
+    ok = len(frames) == B
+    for f, fr in enumerate(frames):
+        k = f % 4
+        ok = ok and fr["info"].tolist() == [k, 0, 10 * f, f] and fr["model"].tolist() == [100 + f] * k
+        ok = ok and np.allclose(fr["score"], f) and fr["pose"].shape == (k, 7) and np.allclose(fr["pose"][:, 0], f + np.arange(k) / 10)
+    q.put((rank, bool(ok), (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_frame_partition_and_result_gather():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_frames, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    assert sorted(r[2] for r in res) == [(0, 3), (3, 6)]
+
+
+def test_frame_range_rejects_uneven_split():
+    from moped_b200.sharding import frame_range
+    with pytest.raises(ValueError):
+        frame_range(7, 2, 0)
+    assert [frame_range(8, 4, r) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
