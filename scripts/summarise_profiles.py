@@ -17,7 +17,7 @@ if os.path.exists(launches):
         per[name] = per.get(name, 0.0) + us; n_per[name] += 1
     tot = sum(per.values())
     with open(os.path.join(ROOT, "profiles", f"launches_{tag}_summary.md"), "w") as f:
-        f.write(f"# Launch list summary ({tag})\n\nCommand: `ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n"
+        f.write(f"# Launch list summary ({tag})\n\nCommand: `" + os.environ.get("LAUNCH_CMD", "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline") + "`\n"
                 "(B200, per-launch times are cold-cache and serialised: compare SHARES). Includes the database upload kernels of the setup.\n\n"
                 "| kernel | launches | total us | share | us / launch |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(per.items(), key=lambda x: -x[1]):
@@ -34,8 +34,8 @@ if os.path.exists(rep):
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
             "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic"]
     with open(os.path.join(ROOT, "profiles", f"ncu_k_match_coarse_{tag}.md"), "w") as f:
-        f.write(f"# ncu --set full, k_match_coarse ({tag})\n\nCommand: `ncu --set full --clock-control none --import-source on -k regex:k_match_coarse -s 2 -c 1 python scripts/gpu_match_bench.py` "
-                "(1 M descriptors x 2000 queries, k=4, B200). Times under the profiler are not bench values.\n\n| metric | value | unit |\n|---|---:|---|\n")
+        f.write(f"# ncu --set full, k_match_coarse ({tag})\n\nCommand: `" + os.environ.get("FULL_CMD", "ncu --set full --clock-control none --import-source on -k regex:k_match_coarse -s 2 -c 1 python scripts/gpu_match_bench.py") + "` "
+                "(" + os.environ.get("FULL_WHAT", "1 M descriptors x 2000 queries") + ", k=4, B200). Times under the profiler are not bench values.\n\n| metric | value | unit |\n|---|---:|---|\n")
         for k in keys:
             if k in d: f.write(f"| {k} | {d[k][0]} | {d[k][1]} |\n")
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
