@@ -56,6 +56,28 @@ def measured_peaks():
     return 1590.0, 6650.0, "fallback"
 
 
+def measured_sustained_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return None
+
+
+def measured_traffic(kernel, **cfg):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this configuration, or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            for e in json.load(f).get(kernel, []):
+                if all(cfg.get(k) == v for k, v in e["when"].items()):
+                    return {"bytes": e["dram_bytes_read"] + e["dram_bytes_write"], "source": e["source"]}
+    except Exception:
+        pass
+    return None
+
+
 def host_norm_rows(x: np.ndarray) -> np.ndarray:
     """Host-side L2 normalisation of descriptors (what the MATCH stage class does before upload,
     MATCH_ANN_CPU.hpp:54-57,94,157)."""
@@ -351,6 +373,8 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak_tf, peak_gbs, peak_src = measured_peaks()
+        peak_sus = measured_sustained_tflops()
+        traffic = measured_traffic("k_match_coarse", db_descriptors=args.objects * args.pts, features_per_frame=Q, frames_per_step=B, n_gpus=world)
         ms_step = total_ms / args.steps
         fps = B * 1e3 / ms_step
         k_ms = float(np.mean(kms)) if kms else None
@@ -372,9 +396,12 @@ def run_ours(args, rank, world, local_rank):
                "e2e": {"value": B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(QT * (128 + 2 + 1) * 4),
                        "d2h_bytes_per_step": int(B * (16 + 36 * MO))},
                "roofline": {"kernel": "k_match_coarse", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                            "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                            "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic["bytes"] if traffic else None,
+                            "traffic_source": traffic["source"] if traffic else None,
                             "peak_source": f"{peak_src} (MEASURED_PEAKS.json bf16_tflops, burst)", "kernel_ms": k_ms,
-                            "algorithmic_flops_per_launch": flops}}
+                            "peak_sustained": peak_sus, "frac_of_sustained": (achieved / peak_sus) if achieved and peak_sus else None,
+                            "algorithmic_flops_per_launch": flops,
+                            "algorithmic_bytes_per_launch": int((r1 - r0 + 127) // 128 * 32768 + QT * 256)}}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref
@@ -396,6 +423,174 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: RANSAC-heavy — 64 clusters x 2048 explicit hypotheses with LM refinement
+# ------------------------------------------------------------------------------------------------
+RANSAC_PARAMS = (600, 200, 1, 5, 6, 10.0)    # POSE defaults (config.hpp:105): LM itmax 200, 5-point samples, > 6 inliers, 10 px^2
+
+
+def ransac_config(args, world):
+    return {"workload": f"RANSAC-heavy (BASELINE configs[3]): {args.clusters} clusters x {args.hyp} explicit hypotheses, 80 points/cluster, 50% outliers, "
+                        "sample fit (LM itmax 200) + inlier scoring + refit on inliers",
+            "clusters": args.clusters, "hypotheses_per_cluster": args.hyp,
+            "parallelism": f"clusters round-robin over {world} GPUs, no data-path collective" if world > 1 else "single-gpu"}
+
+
+def run_ransac_reference(args, rank, world):
+    """--impl reference --workload ransac: the reference's optimizeCamera/testAllPoints/refit per hypothesis (oracle/_ref) on all host
+    cores, a bounded sample of the hypotheses of every cluster per step."""
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmoped_ref.so missing"}))
+        return
+    cores = os.cpu_count() or 1
+    cl = synth.make_ransac_clusters(args.clusters, 80, 0.5)
+    hy = synth.make_hypotheses(cl, args.hyp, 5)
+    per = max(8, min(args.hyp, 32768 // args.clusters))       # hypotheses per cluster per step
+    r = ransac_reference_setup(cl, cores)
+    tot, nh = 0.0, 0
+    for i in range(args.warmup + args.steps):
+        s, n = ransac_reference_step(r, cl, hy, args, per, i)
+        if i >= args.warmup:
+            tot += s
+            nh += n
+        log(f"[reference] step {i}: {n / s:.0f} hypotheses/s")
+    v = nh / tot
+    out = {"impl": "reference", "metric": "hypotheses_per_s", "value": v, "unit": "hypotheses/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": ransac_config(args, world),
+           "cpu_baseline": {"value": v, "unit": "hypotheses/s", "cores": cores, "kind": "reference",
+                            "sample": f"per step: {per} of the {args.hyp} hypotheses of each of the {args.clusters} clusters, OpenMP over hypotheses"},
+           "e2e": {"value": v, "unit": "hypotheses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def ransac_reference_setup(cl, cores):
+    from oracle import ref
+    n_clusters = len(cl["offsets"]) - 1
+    r = ref.Ref(cores)
+    # one model per cluster; the cluster's correspondences are that model's matches
+    n_pts = np.diff(cl["offsets"]).astype(np.int32)
+    r.set_models(n_pts, cl["xyz"], np.zeros((len(cl["xyz"]), 128), np.float32) + np.float32(0.1))
+    r.set_images(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    r.set_matches(dict(offsets=cl["offsets"], image=cl["image"], xy=cl["xy"], xyz=cl["xyz"]))
+    return r
+
+
+def ransac_reference_step(r, cl, hy, args, per, step):
+    sec, n = 0.0, 0
+    for c in range(args.clusters):
+        lo = c * args.hyp + (step * per) % max(1, args.hyp - per + 1)
+        members = np.arange(cl["offsets"][c + 1] - cl["offsets"][c], dtype=np.int32)
+        s, _, _ = r.hypotheses_batch(c, members, hy["sample_pos"][lo:lo + per], hy["init_quat"][lo:lo + per],
+                                     RANSAC_PARAMS[1], RANSAC_PARAMS[5], RANSAC_PARAMS[4])
+        sec += s
+        n += per
+    return sec, n
+
+
+def run_ransac_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from moped_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmoped_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cl = synth.make_ransac_clusters(args.clusters, 80, 0.5)
+    hy = synth.make_hypotheses(cl, args.hyp, 5)
+    mine = np.nonzero(hy["hyp_cluster"] % world == rank)[0]            # clusters round-robin over the ranks
+    H = len(mine)
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    pp = capi.PoseParams.of(RANSAC_PARAMS)
+    h_in = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
+            (cl["offsets"], cl["xy"], cl["xyz"], cl["image"], hy["hyp_cluster"][mine], hy["sample_pos"][mine], hy["init_quat"][mine])]
+    d_in = [t.to(dev) for t in h_in]
+    e_in = [torch.empty_like(t, device=dev) for t in h_in]
+    d_out = [torch.zeros(H, dtype=torch.int32, device=dev), torch.zeros((H, 7), dtype=torch.float32, device=dev),
+             torch.zeros((H, 7), dtype=torch.float32, device=dev), torch.zeros((H, 2), dtype=torch.float32, device=dev)]
+    h_out = [torch.zeros(H, dtype=torch.int32).pin_memory(), torch.zeros((H, 7), dtype=torch.float32).pin_memory()]
+
+    def launch(bufs):
+        ctx.pose_hypotheses_dev(*[t.data_ptr() for t in bufs], H, pp, *[t.data_ptr() for t in d_out])
+
+    def step_dev(i):
+        launch(d_in)
+
+    def step_e2e(i):
+        for e, h in zip(e_in, h_in):
+            e.copy_(h, non_blocking=True)
+        launch(e_in)
+        h_out[0].copy_(d_out[0], non_blocking=True)
+        h_out[1].copy_(d_out[2], non_blocking=True)
+        stream.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launches - l0
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, launches = timed(step_dev, args.steps, args.warmup)
+    clocks = sampler.stop()
+    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
+    n_in = d_out[0].cpu().numpy()
+    if rank == 0:
+        Htot = args.clusters * args.hyp
+        ms_step = total_ms / args.steps
+        out = {"metric": "hypotheses_per_s", "value": Htot * 1e3 / ms_step, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": dict(ransac_config(args, world), l2="working set (a few hundred KB) is cache resident by nature; not flushed"),
+               "accepted_fraction_rank0": float((n_in > RANSAC_PARAMS[4]).mean()), "lm_failed_fraction_rank0": float((n_in < 0).mean()),
+               "gpu_launches": int(launches), "clocks": clocks,
+               "e2e": {"value": Htot * 1e3 / (e2e_ms / args.steps), "unit": "hypotheses/s",
+                       "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_in)),
+                       "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_out))},
+               "roofline": {"kernel": "k_pose_fit", "bound": "fp32-issue/divergence (latency-shaped; see profiles/ for the ncu issue-slot figures)",
+                            "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None}}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                from oracle import ref
+                if ref.available():
+                    cores = os.cpu_count() or 1
+                    r = ransac_reference_setup(cl, cores)
+                    per = max(8, min(args.hyp, 32768 // args.clusters))
+                    ransac_reference_step(r, cl, hy, args, per, 0)
+                    s, n = ransac_reference_step(r, cl, hy, args, per, 1)
+                    out["cpu_baseline"] = {"value": n / s, "unit": "hypotheses/s", "cores": cores, "kind": "reference",
+                                           "sample": f"{per} of the {args.hyp} hypotheses of each cluster, OpenMP over hypotheses"}
+            except Exception as e:
+                out["cpu_baseline"] = {"value": None, "unit": "hypotheses/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,11 +605,21 @@ def main():
     ap.add_argument("--pose-warps", type=int, default=2, help="warps per RANSAC task CTA (mc_set_tuning)")
     ap.add_argument("--chunks", type=int, default=1, help="MATCH launches per batch (mc_set_tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="frames", choices=["frames", "ransac"],
+                    help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s")
+    ap.add_argument("--clusters", type=int, default=64)
+    ap.add_argument("--hyp", type=int, default=2048, help="hypotheses per cluster (ransac workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "ransac":
+        if args.impl == "reference":
+            run_ransac_reference(args, rank, world)
+        else:
+            args.warmup = max(args.warmup, 3)
+            run_ransac_ours(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         args.warmup = max(args.warmup, 3)

@@ -121,6 +121,13 @@ mc_status mc_pose_hypotheses(mc_ctx *ctx, const int32_t *cluster_offsets, int n_
                              const mc_pose_params *params,
                              int32_t *n_inliers, float *pose_lm, float *pose_refit, float *lm_err, uint8_t *inlier_mask);
 
+/* The same with every array resident on the device (no inlier masks); asynchronous on the context's stream.
+ * The entry BASELINE.json configs[3] (64 clusters x 2048 hypotheses) is measured through. */
+mc_status mc_pose_hypotheses_dev(mc_ctx *ctx, const int32_t *cluster_offsets_dev, const float *pt_xy_dev, const float *pt_xyz_dev,
+                                 const int32_t *pt_image_dev, const int32_t *hyp_cluster_dev, const int32_t *sample_pos_dev,
+                                 const float *init_quat_dev, int n_hyp, const mc_pose_params *params,
+                                 int32_t *n_inliers_dev, float *pose_lm_dev, float *pose_refit_dev, float *lm_err_dev);
+
 /* Full RANSAC per (cluster, try): tasks = clusters x max_objects_per_cluster; each task tests up to
  * max_ransac_tests hypotheses (own counter-based RNG) and returns the FIRST successful one in hypothesis
  * order, refitted on its inliers. Outputs (host): found[t], pose[t*7], n_tests[t] (hypotheses consumed). */
@@ -196,6 +203,35 @@ mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, 
  * default 1): with c > 1 the matching of chunk i+1 overlaps the latency-bound stages of chunk i.
  * 0 keeps the current value. */
 mc_status mc_set_tuning(mc_ctx *ctx, int frame_lanes, int pose_warps_per_task, int match_chunks);
+
+/* ---- model-database loader: replaces sXML + Moped::addModel,
+ *      moped2/libmoped/include/sXML.hpp:55-127, moped2/libmoped/src/moped.cpp:100-158 ---------- */
+typedef struct mc_model_db mc_model_db;
+mc_status mc_model_db_create(mc_model_db **db);
+void mc_model_db_destroy(mc_model_db *db);
+const char *mc_model_db_last_error(const mc_model_db *db);
+/* Parse `.moped.xml` model files (the format MopedModeling.py / sfm_export_xml.m write) and add them in list order;
+ * a model whose name already exists replaces it in place and — as in the reference, whose `found` flag only remembers
+ * the last list entry — is also appended unless it was the last model (moped.cpp:138-149). Files are parsed by n_threads host
+ * threads (0 = all cores); if any file fails nothing is added. */
+mc_status mc_model_db_add_xml_file(mc_model_db *db, const char *path);
+mc_status mc_model_db_add_xml_files(mc_model_db *db, const char *const *paths, int n_files, int n_threads);
+mc_status mc_model_db_add_xml_buffer(mc_model_db *db, const char *data, int64_t len);
+mc_status mc_model_db_remove(mc_model_db *db, const char *name);           /* Moped::removeModel */
+int mc_model_db_n_models(const mc_model_db *db);
+const char *mc_model_db_model_name(const mc_model_db *db, int i);
+mc_status mc_model_db_model_bbox(const mc_model_db *db, int i, float *bbox6 /* min xyz, max xyz */);
+/* Rows of one descriptor type in the matcher's numbering (models in order, points in file order,
+ * MATCH_ANN_CPU.hpp:85-100); the first desc_size values of each descriptor, L2-normalised over the whole stored
+ * descriptor when normalise != 0 (:54-57,94). The returned arrays belong to the database object and stay valid
+ * until it changes. */
+mc_status mc_model_db_pack(mc_model_db *db, const char *desc_type, int desc_size, int normalise, int64_t *n_rows, const float **desc,
+                           const float **xyz, const int32_t **model_of_row, const int32_t **n_pts_per_model);
+/* pack (normalised) + mc_db_upload: what modelsUpdated() -> MATCH::Update() amounts to on this path */
+mc_status mc_model_db_upload(mc_model_db *db, mc_ctx *ctx, const char *desc_type, int desc_size);
+/* binary cache of the parsed models (all descriptor types, unnormalised): parse the XML text once */
+mc_status mc_model_db_save(const mc_model_db *db, const char *path);
+mc_status mc_model_db_load(mc_model_db *db, const char *path);
 
 /* ---- introspection for tests and bench ------------------------------------------------------ */
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmoped_cuda.so")
-SOURCES = ["api.cu", "match.cu", "cluster.cu", "pose.cu", "filter.cu", "pipeline.cu"]
+SOURCES = ["api.cu", "match.cu", "cluster.cu", "pose.cu", "filter.cu", "pipeline.cu", "model_db.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + os.environ.get("MOPED_NVCC_FLAGS", "").split()
 LIB = os.environ.get("MOPED_LIB", LIB)
@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(LIBDIR, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc(), *ARCH, *COMMON, *PER_FILE.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -57,9 +57,25 @@ SIGNATURES = {
                                        C.POINTER(C.c_int32), _i32p, _i32p, _i32p]),
     "mc_pose_hypotheses": (C.c_int, [C.c_void_p, _i32p, C.c_int, _f32p, _f32p, _i32p, _i32p, _i32p, _f32p, C.c_int, C.POINTER(PoseParams),
                                      _i32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "mc_pose_hypotheses_dev": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.POINTER(PoseParams)] + [C.c_void_p] * 4),
     "mc_pose_ransac": (C.c_int, [C.c_void_p, _i32p, C.c_int, _f32p, _f32p, _i32p, C.POINTER(PoseParams), _u8p, _f32p, _i32p]),
     "mc_filter_projection": (C.c_int, [C.c_void_p, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float,
                                        _u8p, _f32p, C.POINTER(C.c_int32), _i32p, _i32p]),
+    "mc_model_db_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "mc_model_db_destroy": (None, [C.c_void_p]),
+    "mc_model_db_last_error": (C.c_char_p, [C.c_void_p]),
+    "mc_model_db_add_xml_file": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mc_model_db_add_xml_files": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int]),
+    "mc_model_db_add_xml_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "mc_model_db_remove": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mc_model_db_n_models": (C.c_int, [C.c_void_p]),
+    "mc_model_db_model_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "mc_model_db_model_bbox": (C.c_int, [C.c_void_p, C.c_int, _f32p]),
+    "mc_model_db_pack": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "mc_model_db_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]),
+    "mc_model_db_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mc_model_db_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mc_pipeline_default_params": (None, [C.POINTER(PipelineParams)]),
     "mc_process_frame": (C.c_int, [C.c_void_p, _f32p, _f32p, _i32p, C.c_int, C.POINTER(PipelineParams), C.c_int, C.POINTER(C.c_int32),
                                    _i32p, _f32p, _f32p, C.c_void_p]),
@@ -231,6 +247,12 @@ class Context:
             masks = [mask[o[h]:o[h + 1]].astype(bool) for h in range(n_hyp)]
         return n_in, pose_lm, pose_refit, err, masks
 
+    def pose_hypotheses_dev(self, co_ptr, xy_ptr, xyz_ptr, img_ptr, hc_ptr, sp_ptr, iq_ptr, n_hyp, params, n_in_ptr, pose_lm_ptr, pose_refit_ptr, err_ptr):
+        """Device-pointer variant (asynchronous on the context's stream)."""
+        pp = params if isinstance(params, PoseParams) else PoseParams.of(params)
+        self._check(self.L.mc_pose_hypotheses_dev(self.h, co_ptr, xy_ptr, xyz_ptr, img_ptr, hc_ptr, sp_ptr, iq_ptr, n_hyp, C.byref(pp),
+                                                  n_in_ptr, pose_lm_ptr, pose_refit_ptr, err_ptr), "mc_pose_hypotheses_dev")
+
     def pose_ransac(self, cluster_offsets, pt_xy, pt_xyz, pt_image, params, seed=1):
         co = _i32(cluster_offsets)
         pp = params if isinstance(params, PoseParams) else PoseParams.of(params, seed)
@@ -358,3 +380,75 @@ class Context:
         self._check(self.L.mc_process_frames_matched_dev(self.h, nn_row_ptr, acc_ptr, xy_ptr, img_ptr, fo, len(fo) - 1, int(frame_begin), int(frame_end),
                                                          C.byref(params), int(max_objects), info_ptr, model_ptr, pose_ptr, score_ptr),
                     "mc_process_frames_matched_dev")
+
+
+class ModelDB:
+    """ctypes view of the model-database loader (mc_model_db_*): `.moped.xml` files -> packed rows -> device."""
+
+    def __init__(self):
+        self.L = load()
+        h = C.c_void_p()
+        st = self.L.mc_model_db_create(C.byref(h))
+        if st != 0:
+            raise MopedCudaError("mc_model_db_create failed")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mc_model_db_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, what):
+        if st != 0:
+            raise MopedCudaError(f"{what}: status {st}: {self.L.mc_model_db_last_error(self.h).decode()}")
+
+    def add_xml_file(self, path):
+        self._check(self.L.mc_model_db_add_xml_file(self.h, os.fsencode(path)), "mc_model_db_add_xml_file")
+
+    def add_xml_files(self, paths, n_threads=0):
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        self._check(self.L.mc_model_db_add_xml_files(self.h, arr, len(paths), n_threads), "mc_model_db_add_xml_files")
+
+    def add_xml_buffer(self, data: bytes):
+        self._check(self.L.mc_model_db_add_xml_buffer(self.h, data, len(data)), "mc_model_db_add_xml_buffer")
+
+    def remove(self, name):
+        self._check(self.L.mc_model_db_remove(self.h, name.encode()), "mc_model_db_remove")
+
+    def names(self):
+        return [self.L.mc_model_db_model_name(self.h, i).decode() for i in range(self.L.mc_model_db_n_models(self.h))]
+
+    def bbox(self, i):
+        b = np.zeros(6, np.float32)
+        self._check(self.L.mc_model_db_model_bbox(self.h, i, b), "mc_model_db_model_bbox")
+        return b
+
+    def pack(self, desc_type="SIFT", desc_size=128, normalise=True):
+        """Copies of the packed rows: dict(desc[N,D], xyz[N,3], model_of_row[N], n_pts[n_models])."""
+        n = C.c_int64()
+        pd, px, pm, pn = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.L.mc_model_db_pack(self.h, desc_type.encode(), desc_size, 1 if normalise else 0, C.byref(n), C.byref(pd), C.byref(px),
+                                            C.byref(pm), C.byref(pn)), "mc_model_db_pack")
+        N, M = n.value, self.L.mc_model_db_n_models(self.h)
+
+        def view(ptr, ctype, count, shape):
+            if count == 0:
+                return np.zeros(shape, dtype=np.dtype(ctype))
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).reshape(shape).copy()
+        return dict(desc=view(pd, C.c_float, N * desc_size, (N, desc_size)), xyz=view(px, C.c_float, N * 3, (N, 3)),
+                    model_of_row=view(pm, C.c_int32, N, (N,)), n_pts=view(pn, C.c_int32, M, (M,)))
+
+    def upload(self, ctx: "Context", desc_type="SIFT", desc_size=128):
+        self._check(self.L.mc_model_db_upload(self.h, ctx.h, desc_type.encode(), desc_size), "mc_model_db_upload")
+
+    def save(self, path):
+        self._check(self.L.mc_model_db_save(self.h, os.fsencode(path)), "mc_model_db_save")
+
+    def load(self, path):
+        self._check(self.L.mc_model_db_load(self.h, os.fsencode(path)), "mc_model_db_load")

@@ -124,3 +124,22 @@ def make_ransac_clusters(n_clusters: int = 64, pts: int = 80, outlier_frac: floa
     offsets = (np.arange(n_clusters + 1) * pts).astype(np.int32)
     return dict(offsets=offsets, xy=np.concatenate(xy).astype(np.float32), xyz=np.concatenate(xyz).astype(np.float32),
                 image=np.zeros(n_clusters * pts, dtype=np.int32), gt_pose=np.stack(poses).astype(np.float32))
+
+
+def make_hypotheses(cl, n_hyp_per_cluster: int = 2048, n_pts_align: int = 5, seed: int = BASE_SEED):
+    """Explicit RANSAC hypotheses for `make_ransac_clusters` output: per cluster n_hyp_per_cluster sample sets of
+    n_pts_align DISTINCT point positions and an initial quaternion with components k/256 (what initPose draws,
+    POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:182-186). Inputs only: the parity tests draw their sets with the
+    oracle's RNG stream instead. Returns dict(hyp_cluster[int32 H], sample_pos[int32 H,n], init_quat[H,4])."""
+    rng = np.random.default_rng(seed + 15485863)
+    n_clusters = len(cl["offsets"]) - 1
+    hc, sp = [], []
+    for c in range(n_clusters):
+        n = int(cl["offsets"][c + 1] - cl["offsets"][c])
+        keys = rng.random((n_hyp_per_cluster, n))
+        sp.append(np.argsort(keys, axis=1)[:, :n_pts_align].astype(np.int32))
+        hc.append(np.full(n_hyp_per_cluster, c, np.int32))
+    H = n_clusters * n_hyp_per_cluster
+    quat = (rng.integers(0, 256, size=(H, 4)) / 256.0).astype(np.float32)
+    quat[(quat == 0).all(axis=1)] = np.array([0, 0, 0, 0.5], np.float32)
+    return dict(hyp_cluster=np.concatenate(hc), sample_pos=np.ascontiguousarray(np.concatenate(sp)), init_quat=quat)

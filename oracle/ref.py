@@ -56,6 +56,14 @@ def _load():
         "ref_draw_samples": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, C.c_int, C.c_uint64, C.c_int, _i32p, _f32p]),
         "ref_hypothesis": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _f32p, C.c_int, C.c_float, C.c_int,
                                      _f32p, _f32p, _f32p, _u8p]),
+        "ref_hypotheses_batch": (C.c_double, [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_int,
+                                              _i32p, _f32p]),
+        "ref_add_model_xml": (C.c_int, [C.c_void_p, C.c_char_p]),
+        "ref_model_count": (C.c_int, [C.c_void_p]),
+        "ref_model_name": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
+        "ref_model_bbox": (None, [C.c_void_p, C.c_int, _f32p]),
+        "ref_model_points": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_long)]),
+        "ref_get_model_points": (None, [C.c_void_p, C.c_int, C.c_char_p, _f32p, _i32p, _f32p]),
         "ref_ransac": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint64, _f32p]),
         "ref_project": (None, [C.c_void_p, _f32p, _f32p, _i32p, C.c_int, _f32p]),
         "ref_run_pipeline": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f64p]),
@@ -128,6 +136,34 @@ class Ref:
         self.n_models = len(n_pts)
         self.N = desc.shape[0]
         self.L.ref_set_models(self.h, len(n_pts), n_pts, xyz, desc, self.D)
+
+    # ---- model files through the reference's sXML reader + addModel loop
+    def add_model_xml(self, path):
+        return self.L.ref_add_model_xml(self.h, os.fsencode(path))
+
+    def model_names(self):
+        out = []
+        for i in range(self.L.ref_model_count(self.h)):
+            buf = C.create_string_buffer(4096)
+            self.L.ref_model_name(self.h, i, buf, 4096)
+            out.append(buf.value.decode())
+        return out
+
+    def model_bbox(self, i):
+        b = np.zeros(6, np.float32)
+        self.L.ref_model_bbox(self.h, i, b)
+        return b
+
+    def model_points(self, i, desc_type="SIFT"):
+        """(xyz[n,3], desc_len[n], desc_values[sum]) of model i as the reference parsed them."""
+        nv = C.c_long()
+        n = self.L.ref_model_points(self.h, i, desc_type.encode(), C.byref(nv))
+        xyz = np.zeros((n, 3), np.float32)
+        ln = np.zeros(n, np.int32)
+        vals = np.zeros(nv.value, np.float32)
+        if n:
+            self.L.ref_get_model_points(self.h, i, desc_type.encode(), xyz, ln, vals)
+        return xyz, ln, vals
 
     def model_desc(self):
         out = np.empty((self.N, self.D), np.float32)
@@ -240,6 +276,16 @@ class Ref:
         r = self.L.ref_hypothesis(self.h, model, members, len(members), sample_pos, len(sample_pos), init_quat,
                                   max_lm, err_thr, min_npts, pose_lm, pose_refit, err, mask)
         return r, pose_lm, pose_refit, err, mask
+
+    def hypotheses_batch(self, model, members, sample_pos, init_quat, max_lm, err_thr, min_npts):
+        """Many explicit hypotheses of one cluster on the OpenMP team. Returns (seconds, n_inliers, pose)."""
+        members, sample_pos, init_quat = _i32(members), _i32(sample_pos), _f32(init_quat)
+        n_hyp, n_samples = sample_pos.shape
+        n_inl = np.zeros(n_hyp, np.int32)
+        pose = np.zeros((n_hyp, 7), np.float32)
+        sec = self.L.ref_hypotheses_batch(self.h, model, members, len(members), sample_pos, n_samples, init_quat, n_hyp,
+                                          max_lm, err_thr, min_npts, n_inl, pose)
+        return sec, n_inl, pose
 
     def ransac(self, model, members, params, seed):
         members = _i32(members)

@@ -33,6 +33,7 @@
 #include <util.hpp>
 #include <ANN.h>
 #include <lm.h>
+#include <sXML.hpp>
 
 /* ---- seedable stand-in for libc rand() (31-bit output like glibc; RAND_MAX = 2^31-1) ---- */
 static __thread uint64_t g_rng_state = 0x9E3779B97F4A7C15ULL;
@@ -133,6 +134,80 @@ void ref_set_models(void *h, int n_models, const int *n_pts, const float *xyz, c
 		c->models.push_back(mod);
 	}
 	if (c->match) { delete c->match; c->match = NULL; }
+}
+
+/* Model load through the reference's OWN sXML reader (include/sXML.hpp) followed by the loop of
+ * MopedPimpl::addModel(sXML&) and addModel(SP_Model&) (moped.cpp:100-149). MopedPimpl itself cannot be compiled here
+ * (moped.cpp includes config.hpp, hence every FEAT_* stage and OpenCV), so those fifteen lines of glue are repeated
+ * verbatim in behaviour: last <Points> child, every child of it is a point, `istringstream >>` for p3d and desc,
+ * replace-by-name. Returns 1 if a model was added/replaced, 0 if the file has no Points (addModel returns ""),
+ * -1 if sXML::fromFile fails. */
+int ref_add_model_xml(void *h, const char *path) {
+	RefCtx *c = (RefCtx *)h;
+	sXML sxml;
+	string fileName(path);
+	if (!sxml.fromFile(fileName)) return -1;
+	SP_Model m(new Model);
+	m->name = sxml["name"];
+	m->boundingBox[0].init(10E10, 10E10, 10E10);
+	m->boundingBox[1].init(-10E10, -10E10, -10E10);
+	sXML *points = NULL;
+	foreach (pts, sxml.children)
+		if (pts.name == "Points") points = &pts;
+	if (points == NULL) return 0;
+	foreach (pt, points->children) {
+		Model::IP ip;
+		ip.coord3D.init(0, 0, 0);                 /* the reference leaves it uninitialised; files under test always give p3d */
+		std::istringstream iss(pt["p3d"]);
+		iss >> ip.coord3D;
+		m->boundingBox[0].min(ip.coord3D);
+		m->boundingBox[1].max(ip.coord3D);
+		std::istringstream jss(pt["desc"]);
+		Float f;
+		while (jss >> f) ip.descriptor.push_back(f);
+		m->IPs[pt["desc_type"]].push_back(ip);
+	}
+	int found = false;
+	foreach (mm, c->models)
+		if ((found = (mm->name == m->name))) mm = m;
+	if (!found) c->models.push_back(m);
+	if (c->match) { delete c->match; c->match = NULL; }
+	return 1;
+}
+
+int ref_model_count(void *h) { return (int)((RefCtx *)h)->models.size(); }
+
+int ref_model_name(void *h, int i, char *buf, int cap) {
+	RefCtx *c = (RefCtx *)h;
+	snprintf(buf, cap, "%s", c->models[i]->name.c_str());
+	return (int)c->models[i]->name.size();
+}
+
+void ref_model_bbox(void *h, int i, float *bbox6) {
+	RefCtx *c = (RefCtx *)h;
+	for (int k = 0; k < 3; k++) { bbox6[k] = c->models[i]->boundingBox[0][k]; bbox6[3 + k] = c->models[i]->boundingBox[1][k]; }
+}
+
+/* #points of model i under desc_type, and the total number of descriptor values they hold */
+int ref_model_points(void *h, int i, const char *desc_type, long *n_values) {
+	RefCtx *c = (RefCtx *)h;
+	map<string, vector<Model::IP> >::iterator it = c->models[i]->IPs.find(desc_type);
+	if (it == c->models[i]->IPs.end()) { if (n_values) *n_values = 0; return 0; }
+	long v = 0;
+	for (size_t k = 0; k < it->second.size(); k++) v += (long)it->second[k].descriptor.size();
+	if (n_values) *n_values = v;
+	return (int)it->second.size();
+}
+
+void ref_get_model_points(void *h, int i, const char *desc_type, float *xyz, int *desc_len, float *desc_values) {
+	RefCtx *c = (RefCtx *)h;
+	vector<Model::IP> &ips = c->models[i]->IPs[desc_type];
+	long v = 0;
+	for (size_t k = 0; k < ips.size(); k++) {
+		for (int j = 0; j < 3; j++) xyz[3 * k + j] = ips[k].coord3D[j];
+		desc_len[k] = (int)ips[k].descriptor.size();
+		for (size_t j = 0; j < ips[k].descriptor.size(); j++) desc_values[v++] = ips[k].descriptor[j];
+	}
 }
 
 /* Descriptors as the reference holds them now (MATCH normalises the Model in place). */
@@ -441,6 +516,36 @@ int ref_hypothesis(void *h, int model, const int *members, int n, const int *sam
 	if ((int)consistent.size() > minNPts) lm_err[1] = alg.optimizeCamera(pose, consistent, maxLM);
 	for (int j = 0; j < 7; j++) pose_refit[j] = pose[j];
 	return (int)consistent.size();
+}
+
+/* The same iteration body for MANY explicit hypotheses of one cluster (BASELINE.json configs[3]), spread over the
+ * OpenMP team the way process() spreads its tasks (`#pragma omp parallel for`, POSE_..._CPU.hpp:282). Only
+ * #inliers and the final pose are kept. Returns the wall-clock seconds of the loop. */
+double ref_hypotheses_batch(void *h, int model, const int *members, int n, const int *sample_pos, int n_samples, const float *init_quat,
+                            int n_hyp, int maxLM, float errThr, int minNPts, int *n_inliers, float *pose_out) {
+	FtzGuard ftz_guard;
+	RefCtx *c = (RefCtx *)h;
+	POSE_T alg(1, maxLM, 1, n_samples, minNPts, errThr);
+	HypCtx hc; build_cluster(c, alg, hc, model, members, n);
+	double t0 = now_s();
+	#pragma omp parallel for schedule(dynamic, 8)
+	for (int k = 0; k < n_hyp; k++) {
+		vector<POSE_T::LmData *> samples;
+		for (int j = 0; j < n_samples; j++) samples.push_back(hc.cl[sample_pos[k * n_samples + j]]);
+		Pose pose;
+		pose.rotation.init(init_quat[4 * k], init_quat[4 * k + 1], init_quat[4 * k + 2], init_quat[4 * k + 3]);
+		pose.translation.init(0., 0., 0.5);
+		Float r = alg.optimizeCamera(pose, samples, maxLM);
+		n_inliers[k] = -1;
+		for (int j = 0; j < 7; j++) pose_out[7 * k + j] = 0;
+		if ((int)r == -1) continue;
+		vector<POSE_T::LmData *> consistent;
+		alg.testAllPoints(consistent, pose, hc.cl, errThr);
+		if ((int)consistent.size() > minNPts) alg.optimizeCamera(pose, consistent, maxLM);
+		n_inliers[k] = (int)consistent.size();
+		for (int j = 0; j < 7; j++) pose_out[7 * k + j] = pose[j];
+	}
+	return now_s() - t0;
 }
 
 /* Whole RANSAC() on one cluster with the seeded RNG; returns found (0/1). */

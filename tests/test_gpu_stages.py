@@ -224,3 +224,44 @@ def test_sharded_match_merge_equals_single(gpu_ctx, small_case):
     assert np.array_equal(acc.cpu().numpy().astype(bool), a_full)
     for cx in ctxs:
         cx.close()
+
+
+@pytest.mark.gpu
+def test_pose_hypotheses_dev_ransac_heavy_shape(gpu_ctx, oracle_mod):
+    """BASELINE configs[3] shape (clusters of 80 points, 50 % outliers, explicit 5-point hypotheses): the
+    device-pointer entry gives exactly what the host entry gives, and agrees with the oracle's per-hypothesis
+    evaluation on the same sets (same gates as test_pose_hypotheses_golden)."""
+    import torch
+    from moped_b200 import synth
+    cl = synth.make_ransac_clusters(8, 80, 0.5)
+    hy = synth.make_hypotheses(cl, 64, 5)
+    P = (600, 200, 1, 5, 6, 10.0)
+    gpu_ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    n_in, plm, prf, err, _ = gpu_ctx.pose_hypotheses(cl["offsets"], cl["xy"], cl["xyz"], cl["image"], hy["hyp_cluster"], hy["sample_pos"],
+                                                     hy["init_quat"], P, want_mask=False)
+    dev = torch.device("cuda", 0)
+    d_in = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in
+            (cl["offsets"], cl["xy"], cl["xyz"], cl["image"], hy["hyp_cluster"], hy["sample_pos"], hy["init_quat"])]
+    H = len(hy["hyp_cluster"])
+    d_out = [torch.zeros(H, dtype=torch.int32, device=dev), torch.zeros((H, 7), device=dev), torch.zeros((H, 7), device=dev), torch.zeros((H, 2), device=dev)]
+    torch.cuda.synchronize()
+    gpu_ctx.pose_hypotheses_dev(*[t.data_ptr() for t in d_in], H, P, *[t.data_ptr() for t in d_out])
+    gpu_ctx.synchronize()
+    assert np.array_equal(d_out[0].cpu().numpy(), n_in)
+    assert np.array_equal(d_out[1].cpu().numpy(), plm) and np.array_equal(d_out[2].cpu().numpy(), prf)
+    # against the oracle
+    cams = oracle_mod.cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    o_in = np.zeros(H, np.int32)
+    o_pose = np.zeros((H, 7), np.float32)
+    for h in range(H):
+        c = hy["hyp_cluster"][h]
+        s = slice(cl["offsets"][c], cl["offsets"][c + 1])
+        r = oracle_mod.hypothesis(cl["xy"][s], cl["xyz"][s], cl["image"][s], cams, hy["sample_pos"][h], hy["init_quat"][h], 200, 10.0, 6)
+        o_in[h], o_pose[h] = r[0], r[2]
+    assert ((n_in > 6) == (o_in > 6)).mean() >= 0.95
+    both = (n_in > 6) & (o_in > 6)
+    assert both.sum() >= 8
+    dt = np.abs(prf[both, 4:] - o_pose[both, 4:]).max(1)
+    dr = np.array([quat_angle(a[:4], b[:4]) for a, b in zip(prf[both], o_pose[both])])
+    assert np.median(dt) < 1e-4 and np.median(dr) < 1e-3, (np.median(dt), np.median(dr))
+    assert (dt < 5e-4).mean() >= 0.9 and (dr < 2e-3).mean() >= 0.9

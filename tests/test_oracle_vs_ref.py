@@ -96,3 +96,26 @@ def test_sample_failure_when_too_few_distinct_points(ref_mod, oracle_mod):
     img = np.zeros(7, np.int32)
     ok, pos, quat = oracle_mod.draw_samples(xy, img, None, 5, 3, 2)
     assert ok == 0
+
+
+def test_hypotheses_batch_equals_single_calls(ref_mod):
+    """bench.py's configs[3] CPU baseline (ref_hypotheses_batch, OpenMP over hypotheses) is the same computation as
+    the per-hypothesis entry the parity tests use."""
+    from moped_b200 import synth
+    cl = synth.make_ransac_clusters(2, 80, 0.5)
+    hy = synth.make_hypotheses(cl, 24, 5)
+    assert hy["sample_pos"].shape == (48, 5) and all(len(set(r)) == 5 for r in hy["sample_pos"].tolist())
+    r = ref_mod.Ref(2)
+    r.set_models(np.diff(cl["offsets"]).astype(np.int32), cl["xyz"], np.full((len(cl["xyz"]), 128), 0.1, np.float32))
+    r.set_images(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    r.set_matches(dict(offsets=cl["offsets"], image=cl["image"], xy=cl["xy"], xyz=cl["xyz"]))
+    members = np.arange(80, dtype=np.int32)
+    for c in range(2):
+        sel = slice(24 * c, 24 * (c + 1))
+        sec, n_in, pose = r.hypotheses_batch(c, members, hy["sample_pos"][sel], hy["init_quat"][sel], 200, 10.0, 6)
+        assert sec > 0
+        for k in range(24):
+            ni, _, prf, _, _ = r.hypothesis(c, members, hy["sample_pos"][24 * c + k], hy["init_quat"][24 * c + k], 200, 10.0, 6)
+            assert ni == n_in[k]
+            if ni >= 0:
+                assert np.array_equal(prf, pose[k])
