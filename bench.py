@@ -602,7 +602,7 @@ def main():
     ap.add_argument("--features", type=int, default=2000)
     ap.add_argument("--frames", type=int, default=64, help="independent frames per step (batch)")
     ap.add_argument("--lanes", type=int, default=32, help="concurrent frames after MATCH (mc_set_tuning)")
-    ap.add_argument("--pose-warps", type=int, default=2, help="warps per RANSAC task CTA (mc_set_tuning)")
+    ap.add_argument("--pose-warps", type=int, default=4, help="first-round hypotheses per RANSAC task (mc_set_tuning)")
     ap.add_argument("--chunks", type=int, default=1, help="MATCH launches per batch (mc_set_tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="frames", choices=["frames", "ransac"],

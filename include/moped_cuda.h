@@ -198,9 +198,10 @@ mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, 
                                         const mc_pipeline_params *params, int max_objects, int32_t *frame_info_dev, int32_t *obj_model_dev,
                                         float *obj_pose_dev, float *obj_score_dev);
 /* Scheduling knobs that never change results: frame_lanes = concurrent frames after MATCH in a batch (1..64,
- * default 8); pose_warps_per_task = warps of a RANSAC task CTA (1..8, default 8: lowest single-frame latency;
- * fewer warps let more tasks of a batch be resident per SM); match_chunks = MATCH launches per batch (1..16,
- * default 1): with c > 1 the matching of chunk i+1 overlaps the latency-bound stages of chunk i.
+ * default 8); pose_warps_per_task = hypotheses of EVERY RANSAC task tested by the first RANSAC kernel (1..8, default
+ * 8: lowest single-frame latency when a task's first hypotheses fail; 1 packs the first hypothesis of four tasks into
+ * one warp and wastes nothing when it succeeds — the setting for frame batches); match_chunks = MATCH launches per batch
+ * (1..16, default 1): with c > 1 the matching of chunk i+1 overlaps the latency-bound stages of chunk i.
  * 0 keeps the current value. */
 mc_status mc_set_tuning(mc_ctx *ctx, int frame_lanes, int pose_warps_per_task, int match_chunks);
 
@@ -232,6 +233,13 @@ mc_status mc_model_db_upload(mc_model_db *db, mc_ctx *ctx, const char *desc_type
 /* binary cache of the parsed models (all descriptor types, unnormalised): parse the XML text once */
 mc_status mc_model_db_save(const mc_model_db *db, const char *path);
 mc_status mc_model_db_load(mc_model_db *db, const char *path);
+
+/* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
+ *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
+ *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)
+ *   "ransac_fused"         != 0: mc_pose_ransac / the frame pipeline use the single one-CTA-per-task RANSAC kernel
+ *                          instead of the staged kernels (same results; kept for A/B measurements) */
+mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value);
 
 /* ---- introspection for tests and bench ------------------------------------------------------ */
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mc_model_db_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]),
     "mc_model_db_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mc_model_db_load": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mc_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "mc_pipeline_default_params": (None, [C.POINTER(PipelineParams)]),
     "mc_process_frame": (C.c_int, [C.c_void_p, _f32p, _f32p, _i32p, C.c_int, C.POINTER(PipelineParams), C.c_int, C.POINTER(C.c_int32),
                                    _i32p, _f32p, _f32p, C.c_void_p]),
@@ -330,6 +331,9 @@ class Context:
         return dict(model=om[:k].copy(), pose=op[:k].copy(), score=os_[:k].copy())
 
     # ---- frame batches
+    def set_option(self, key: str, value: int):
+        self._check(self.L.mc_set_option(self.h, key.encode(), int(value)), "mc_set_option")
+
     def set_tuning(self, frame_lanes=0, pose_warps_per_task=0, match_chunks=0):
         self._check(self.L.mc_set_tuning(self.h, int(frame_lanes), int(pose_warps_per_task), int(match_chunks)), "mc_set_tuning")
 

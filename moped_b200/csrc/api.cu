@@ -152,6 +152,16 @@ mc_status mc_set_tuning(mc_ctx *ctx, int frame_lanes, int pose_warps_per_task, i
 	return MC_OK;
 }
 
+mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
+	if (!ctx || !key) return MC_ERR_ARG;
+	const std::string k(key);
+	if (k == "pose_fit_thread_min") ctx->fit_thread_min = value < 1 ? 1 : value;
+	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
+	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }
+	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; }
+	return MC_OK;
+}
+
 mc_status mc_set_profiling(mc_ctx *ctx, int on) {
 	if (!ctx) return MC_ERR_ARG;
 	MC_CUDA(cudaSetDevice(ctx->device));

@@ -301,6 +301,7 @@ static void lane_borrow(mc_ctx *ctx, mc_ctx *lane) {
 	lane->db_norm2_min = ctx->db_norm2_min; lane->db_norm2_max = ctx->db_norm2_max;
 	lane->d_cams = ctx->d_cams; lane->n_images = ctx->n_images;
 	lane->pose_warps = ctx->pose_warps;
+	lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused;
 }
 
 static mc_status ensure_lanes(mc_ctx *ctx, int n) {

@@ -16,6 +16,8 @@ dbn = norm(db["desc"])
 ctx = capi.Context(0)
 ctx.db_upload(dbn, db["xyz"], db["model_of_row"], n_obj)
 ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+if os.environ.get("FUSED"):
+    ctx.set_option("ransac_fused", 1)
 dev = torch.device("cuda", 0)
 NF = int(os.environ.get("NF", 64))
 frames = [synth.make_frame(db, 2000, n_visible=8, frame_id=i) for i in range(NF)]
@@ -24,7 +26,8 @@ xy = torch.from_numpy(np.concatenate([f["xy"] for f in frames])).to(dev)
 img = torch.from_numpy(np.concatenate([f["image_idx"] for f in frames])).to(dev)
 for B in [int(x) for x in os.environ.get("BATCHES", "64").split(",")]:
     fo = (np.arange(B + 1) * 2000).astype(np.int32)
-    for lanes, warps, chunks in ((32, 2, 1), (32, 2, 2), (32, 2, 4), (32, 2, 8), (64, 2, 1), (64, 2, 4), (64, 1, 4), (32, 1, 4), (16, 2, 4), (32, 4, 4), (32, 2, 16)):
+    cfgs = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("CONFIGS", "32:1:1,32:2:1,32:4:1,64:1:1,32:1:2,32:1:4,16:1:1").split(",")]
+    for lanes, warps, chunks in cfgs:
         if lanes > B and lanes != 1:
             continue
         ctx.set_tuning(lanes, warps, chunks)

@@ -265,3 +265,78 @@ def test_pose_hypotheses_dev_ransac_heavy_shape(gpu_ctx, oracle_mod):
     dr = np.array([quat_angle(a[:4], b[:4]) for a, b in zip(prf[both], o_pose[both])])
     assert np.median(dt) < 1e-4 and np.median(dr) < 1e-3, (np.median(dt), np.median(dr))
     assert (dt < 5e-4).mean() >= 0.9 and (dr < 2e-3).mean() >= 0.9
+
+
+@pytest.mark.gpu
+def test_pose_fit_thread_per_hypothesis_kernel(gpu_ctx, oracle_mod):
+    """The one-thread-per-hypothesis shape of the explicit-hypothesis entry (used from 16384 hypotheses up, forced here)
+    against the oracle on the same sets, same gates as the lane-group kernel; and against the lane-group kernel."""
+    from moped_b200 import synth
+    cl = synth.make_ransac_clusters(8, 80, 0.5, seed=77)
+    hy = synth.make_hypotheses(cl, 96, 5, seed=77)
+    P = (600, 200, 1, 5, 6, 10.0)
+    gpu_ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    args = (cl["offsets"], cl["xy"], cl["xyz"], cl["image"], hy["hyp_cluster"], hy["sample_pos"], hy["init_quat"], P)
+    g_in, g_plm, g_prf, _, _ = gpu_ctx.pose_hypotheses(*args, want_mask=False)
+    gpu_ctx.set_option("pose_fit_thread_min", 1)
+    try:
+        t_in, t_plm, t_prf, t_err, _ = gpu_ctx.pose_hypotheses(*args, want_mask=False)
+    finally:
+        gpu_ctx.set_option("pose_fit_thread_min", 16384)
+    H = len(t_in)
+    cams = oracle_mod.cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    o_in = np.zeros(H, np.int32)
+    o_pose = np.zeros((H, 7), np.float32)
+    for h in range(H):
+        c = hy["hyp_cluster"][h]
+        s = slice(cl["offsets"][c], cl["offsets"][c + 1])
+        r = oracle_mod.hypothesis(cl["xy"][s], cl["xyz"][s], cl["image"][s], cams, hy["sample_pos"][h], hy["init_quat"][h], 200, 10.0, 6)
+        o_in[h], o_pose[h] = r[0], r[2]
+    for name, ref_in, ref_pose in (("oracle", o_in, o_pose), ("lane-group kernel", g_in, g_prf)):
+        assert ((t_in > 6) == (ref_in > 6)).mean() >= 0.95, name
+        both = (t_in > 6) & (ref_in > 6)
+        assert both.sum() >= 8, name
+        dt = np.abs(t_prf[both, 4:] - ref_pose[both, 4:]).max(1)
+        dr = np.array([quat_angle(a[:4], b[:4]) for a, b in zip(t_prf[both], ref_pose[both])])
+        assert np.median(dt) < 1e-4 and np.median(dr) < 1e-3, (name, np.median(dt), np.median(dr))
+        assert (dt < 5e-4).mean() >= 0.9 and (dr < 2e-3).mean() >= 0.9, name
+    assert (np.abs(np.linalg.norm(t_prf[t_in > 6, :4], axis=1) - 1) < 1e-5).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first_round", [1, 2, 8])
+def test_staged_ransac_equals_one_cta_per_task_kernel(gpu_ctx, first_round):
+    """The staged RANSAC kernels pick the same hypothesis (n_tests) and give the same pose, bit for bit, as the
+    one-CTA-per-task kernel, for easy clusters, 50 %-outlier clusters, a hopeless cluster (all tests fail) and a
+    cluster with too few distinct points; MaxRANSACTests small, 36-boundary and large."""
+    from moped_b200 import synth
+    easy = synth.make_ransac_clusters(6, 40, 0.1, seed=5)
+    hard = synth.make_ransac_clusters(6, 80, 0.6, seed=6)
+    rng = np.random.default_rng(9)
+    junk_xy = np.stack([rng.uniform(0, 640, 30), rng.uniform(0, 480, 30)], 1).astype(np.float32)
+    junk_xyz = rng.uniform(-0.1, 0.1, (30, 3)).astype(np.float32)
+    few_xy = np.array([[10, 10]] * 4 + [[20, 20]] * 3, np.float32)
+    xy = np.concatenate([easy["xy"], hard["xy"], junk_xy, few_xy])
+    xyz = np.concatenate([easy["xyz"], hard["xyz"], junk_xyz, np.zeros((7, 3), np.float32)])
+    sizes = [40] * 6 + [80] * 6 + [30, 7]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    img = np.zeros(len(xy), np.int32)
+    gpu_ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    try:
+        for max_ransac in (3, 36, 37, 200):
+            P = (max_ransac, 200, 4, 5, 6, 10.0)
+            gpu_ctx.set_option("ransac_fused", 1)
+            gpu_ctx.set_tuning(0, 8, 0)
+            f0, p0, n0 = gpu_ctx.pose_ransac(off, xy, xyz, img, P, seed=11)
+            gpu_ctx.set_option("ransac_fused", 0)
+            gpu_ctx.set_tuning(0, first_round, 0)
+            f1, p1, n1 = gpu_ctx.pose_ransac(off, xy, xyz, img, P, seed=11)
+            assert np.array_equal(f0, f1), max_ransac
+            assert np.array_equal(n0, n1), (max_ransac, n0, n1)
+            assert np.array_equal(p0[f0], p1[f1]), max_ransac
+            assert not f1[-4:].any() and (n1[-4:] == 0).all()            # too few distinct points
+            assert (n1[-8:-4] == max_ransac).all() or f1[-8:-4].any()     # the junk cluster normally exhausts its tests
+        assert f1[:24].all()
+    finally:
+        gpu_ctx.set_option("ransac_fused", 0)
+        gpu_ctx.set_tuning(0, 8, 0)
