@@ -238,7 +238,9 @@ mc_status mc_model_db_load(mc_model_db *db, const char *path);
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)
  *   "ransac_fused"         != 0: mc_pose_ransac / the frame pipeline use the single one-CTA-per-task RANSAC kernel
- *                          instead of the staged kernels (same results; kept for A/B measurements) */
+ *                          instead of the staged kernels (same results; kept for A/B measurements)
+ *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
+ *                          MATCH instead of ~40 kernel launches (same kernels, same results) */
 mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value);
 
 /* ---- introspection for tests and bench ------------------------------------------------------ */

@@ -120,6 +120,9 @@ static void free_scratch(mc_ctx *ctx) {
 	for (DevBuf *b : named) cudaFree(b->p);
 	for (DevBuf &b : ctx->scratch) cudaFree(b.p);
 	cudaFree(ctx->batch_out.p);
+	cudaFree(ctx->frame_desc.p);
+	for (auto &g : ctx->fgraphs) cudaGraphExecDestroy(g.exec);
+	ctx->fgraphs.clear();
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
 }
 
@@ -157,8 +160,9 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	const std::string k(key);
 	if (k == "pose_fit_thread_min") ctx->fit_thread_min = value < 1 ? 1 : value;
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
+	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
 	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }
-	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; }
+	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs; }
 	return MC_OK;
 }
 

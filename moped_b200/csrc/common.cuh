@@ -27,6 +27,16 @@ struct Camera {            // FrameData::images[i]: K=(fx,fy,cx,cy), TM = 3x4 of
 	float TM[12];
 };
 
+struct FrameDesc {         // what differs between the frames of a stream: read by the stage chain through ONE indirection,
+	const int32_t *nn_row;      // so that the chain itself (a CUDA graph per lane) never changes
+	const uint8_t *accepted;
+	const float *q_xy;
+	const int32_t *q_image;
+	int32_t *out_info, *out_model;
+	float *out_pose, *out_score;
+	int Q, max_objects;
+};
+
 struct DevBuf {            // grow-only device scratch
 	void *p = nullptr;
 	size_t cap = 0;
@@ -79,6 +89,12 @@ struct mc_ctx {
 	cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
 	std::vector<cudaEvent_t> ev_chunk;
 	mc::DevBuf batch_out;             // per-frame result slots of the running batch
+	// per-lane CUDA graph of the stage chain CLUSTER..FILTER2 (+ compaction and export): replayed once per frame
+	mc::DevBuf frame_desc;            // device copy of the current frame's FrameDesc
+	struct FrameGraph { uint64_t cfg, ptr_key; cudaGraphExec_t exec; int nodes; };
+	std::vector<FrameGraph> fgraphs;  // one per configuration seen on this lane (sizes, parameters), most recent last
+	bool capturing = false;           // reserve() must not allocate while the lane's stream is being captured
+	bool frame_graphs = true;         // mc_set_option "frame_graphs"
 	int batch_stats[4] = {0, 0, 0, 0};   // {frames, accepted matches, objects, lanes used} of the last batch
 };
 
@@ -111,6 +127,7 @@ namespace mc {
 
 inline mc_status reserve(mc_ctx *ctx, DevBuf &b, size_t bytes) {
 	if (bytes <= b.cap && b.p) return MC_OK;
+	if (ctx->capturing) { ctx->err = "scratch allocation requested during graph capture"; return MC_ERR_STATE; }
 	if (b.p) { MC_CUDA(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
 	size_t cap = bytes < 256 ? 256 : bytes + bytes / 4;
 	MC_CUDA(cudaMalloc(&b.p, cap));

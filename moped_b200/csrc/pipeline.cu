@@ -30,13 +30,19 @@ constexpr int kCompactCap = 8192;    // accepted matches per frame handled by th
 // (`matches[correspModel[nx[0]]].push_back(...)` in query order, MATCH_ANN_CPU.hpp:165-176; the order matters:
 // mean-shift is order dependent). Single CTA: stable compaction of the accepted queries, then a bitonic sort
 // of (model << 13 | rank) keys in shared memory.
+__global__ void k_set_desc(FrameDesc *dst, FrameDesc v) { *dst = v; }
+
 __global__ void __launch_bounds__(1024)
-k_match_compact(const int32_t *__restrict__ nn_row, const uint8_t *__restrict__ accepted, int Q, int64_t row_base,
-                const int32_t *__restrict__ model_of_row, const float *__restrict__ db_xyz, const float *__restrict__ q_xy,
-                const int32_t *__restrict__ q_image, int n_models, int32_t *__restrict__ acc_list,
+k_match_compact(const FrameDesc *__restrict__ fd, int64_t row_base,
+                const int32_t *__restrict__ model_of_row, const float *__restrict__ db_xyz, int n_models, int32_t *__restrict__ acc_list,
                 int32_t *__restrict__ match_offsets, int32_t *__restrict__ match_query, int32_t *__restrict__ match_row,
                 int32_t *__restrict__ match_image, float *__restrict__ match_xy, float *__restrict__ match_xyz,
                 int32_t *__restrict__ status) {
+	const int32_t *__restrict__ nn_row = fd->nn_row;
+	const uint8_t *__restrict__ accepted = fd->accepted;
+	const float *__restrict__ q_xy = fd->q_xy;
+	const int32_t *__restrict__ q_image = fd->q_image;
+	const int Q = fd->Q;
 	__shared__ uint32_t keys[kCompactCap];
 	__shared__ int s_warp[32];
 	__shared__ int s_base;
@@ -124,6 +130,23 @@ __global__ void k_copy_objects(const int32_t *__restrict__ n_p, const int32_t *_
 	if (threadIdx.x == 0) *dst_n = n;
 }
 
+__global__ void k_export_objects(const FrameDesc *__restrict__ fd, const int32_t *__restrict__ f_n, const int32_t *__restrict__ status,
+                                 const int32_t *__restrict__ match_offsets, int n_models, const int32_t *__restrict__ cl_n,
+                                 const int32_t *__restrict__ surv_model, const float *__restrict__ surv_pose, const float *__restrict__ surv_score) {
+	const int max_objects = fd->max_objects;
+	int32_t *out_info = fd->out_info, *out_model = fd->out_model;
+	float *out_pose = fd->out_pose, *out_score = fd->out_score;
+	const int n = f_n[0];
+	const int m = n < max_objects ? n : max_objects;
+	for (int i = threadIdx.x; i < m; i += blockDim.x) { out_model[i] = surv_model[i]; out_score[i] = surv_score[i]; }
+	for (int i = threadIdx.x; i < 7 * m; i += blockDim.x) out_pose[i] = surv_pose[i];
+	if (threadIdx.x == 0) { out_info[0] = n; out_info[1] = status[0]; out_info[2] = match_offsets[n_models]; out_info[3] = cl_n[0]; }
+}
+
+__global__ void k_export_empty(int32_t *__restrict__ out_info) {
+	if (threadIdx.x < 4) out_info[threadIdx.x] = 0;
+}
+
 struct FrameBufs {
 	int32_t *nn_row; float *nn_dist; uint8_t *accepted;
 	int32_t *acc_list, *match_offsets, *match_query, *match_row, *match_image; float *match_xy, *match_xyz;
@@ -174,22 +197,23 @@ static FrameCaps frame_caps(int Q, const mc_pipeline_params *P) {
 	return c;
 }
 
-// Enqueue one frame on ctx->stream (ctx may be a lane of a batch): MATCH (unless the caller passes merged
-// nearest neighbours) -> CLUSTER -> POSE -> FILTER -> POSE2 -> FILTER2. No host synchronisation: cluster and
-// object counts stay on the device, grids are sized by upper bounds. The surviving objects end in
-// B.f_n / B.surv_*; `ev` (nullable, 7 events) brackets the six stages.
-static mc_status frame_enqueue(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, int Q, const mc_pipeline_params *P,
-                               FrameBufs &B, const FrameCaps &caps, cudaEvent_t *ev, const int32_t *d_nn_row_in, const uint8_t *d_accepted_in) {
+// Enqueue one frame on ctx->stream (ctx may be a lane of a batch): MATCH (only when d_q is given; otherwise the
+// descriptor already points at nearest neighbours: object-sharded databases, frame batches) -> CLUSTER -> POSE ->
+// FILTER -> POSE2 -> FILTER2 (-> export into the descriptor's output slots when `do_export`). No host
+// synchronisation: cluster and object counts stay on the device, grids are sized by upper bounds derived from Q (an
+// upper bound of the frame's feature count; the true count is read from the descriptor). Everything that differs
+// between frames is read through ctx->frame_desc, so the enqueued chain can be captured once and replayed.
+// The surviving objects end in B.f_n / B.surv_*; `ev` (nullable, 7 events) brackets the six stages.
+static mc_status frame_enqueue(mc_ctx *ctx, const float *d_q, int Q, const mc_pipeline_params *P,
+                               FrameBufs &B, const FrameCaps &caps, cudaEvent_t *ev, bool do_export) {
+	const FrameDesc *fd = (const FrameDesc *)ctx->frame_desc.p;
 	const int cl_cap = caps.cl_cap, obj_cap = caps.obj_cap;
 	auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], ctx->stream); };
 	MC_CUDA(cudaMemsetAsync(B.status, 0, 64, ctx->stream));
 	MC_CUDA(cudaMemsetAsync(B.n_obj, 0, 64, ctx->stream));
 	mark(0);
-	// MATCH (skipped when the caller already holds nearest neighbours: object-sharded databases, frame batches)
-	const int32_t *nn_row = d_nn_row_in ? d_nn_row_in : B.nn_row;
-	const uint8_t *accepted = d_accepted_in ? d_accepted_in : B.accepted;
-	if (!d_nn_row_in) MC_TRY(match_device(ctx, d_q, Q, P->match_ratio, P->match_mode, B.nn_row, B.nn_dist, B.accepted));
-	k_match_compact<<<1, 1024, 0, ctx->stream>>>(nn_row, accepted, Q, ctx->table_base, ctx->d_model_of_row, ctx->d_xyz, d_qxy, d_qimg, ctx->n_models,
+	if (d_q) MC_TRY(match_device(ctx, d_q, Q, P->match_ratio, P->match_mode, B.nn_row, B.nn_dist, B.accepted));
+	k_match_compact<<<1, 1024, 0, ctx->stream>>>(fd, ctx->table_base, ctx->d_model_of_row, ctx->d_xyz, ctx->n_models,
 	                                            B.acc_list, B.match_offsets, B.match_query, B.match_row, B.match_image, B.match_xy, B.match_xyz, B.status);
 	MC_LAUNCH_CHECK();
 	mark(1);
@@ -224,6 +248,96 @@ static mc_status frame_enqueue(mc_ctx *ctx, const float *d_q, const float *d_qxy
 	                     P->filter2_min_points, P->filter2_feature_distance, P->filter2_min_score, B.keep, B.obj_score, B.f_n, B.f_model, B.f_offsets,
 	                     B.f_members, B.surv_model, B.surv_pose, B.surv_score));
 	mark(6);
+	if (do_export) {
+		k_export_objects<<<1, 128, 0, ctx->stream>>>(fd, B.f_n, B.status, B.match_offsets, ctx->n_models, B.cl_n, B.surv_model, B.surv_pose, B.surv_score);
+		MC_LAUNCH_CHECK();
+	}
+	return MC_OK;
+}
+
+static mc_status set_frame_desc(mc_ctx *ctx, const FrameDesc &d) {
+	MC_TRY(reserve(ctx, ctx->frame_desc, 256));
+	k_set_desc<<<1, 1, 0, ctx->stream>>>((FrameDesc *)ctx->frame_desc.p, d);
+	MC_LAUNCH_CHECK();
+	return MC_OK;
+}
+
+static uint64_t fnv(uint64_t h, const void *p, size_t n) {
+	const unsigned char *b = (const unsigned char *)p;
+	for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+	return h;
+}
+
+// The stage chain of one frame of a batch on a lane (the descriptor is already set): compaction, CLUSTER .. FILTER2,
+// export. Replayed from a CUDA graph of the lane when one exists for this configuration (feature-count bucket, stage
+// parameters, database) and the lane's scratch buffers have not moved since it was captured; otherwise the chain is
+// captured, instantiated and launched. If the capture finds that a scratch buffer has to grow (reserve() refuses to
+// allocate while capturing) the frame runs eagerly instead — that run makes the reservations and the next frame captures.
+// ~40 kernel launches per frame become one graph launch: with 64 frames per batch the host was the bottleneck of the
+// stages after MATCH (2000 launches x ~3.3 us against ~3 ms of device work).
+static mc_status frame_chain(mc_ctx *lane, int Q, const mc_pipeline_params *P, cudaEvent_t *ev) {
+	mc_ctx *ctx = lane;
+	const int q_cap = (Q + 511) & ~511;                  // grids and buffers are sized by upper bounds: a few sizes serve all frames
+	const FrameCaps caps = frame_caps(q_cap, P);
+	FrameBufs B;
+	if (!lane->frame_graphs || ev) {
+		MC_TRY(carve(lane, B, q_cap, lane->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap));
+		return frame_enqueue(lane, nullptr, q_cap, P, B, caps, ev, true);
+	}
+	uint64_t cfg = fnv(1469598103934665603ULL, &q_cap, sizeof q_cap);
+	cfg = fnv(cfg, P, sizeof *P);
+	const int64_t ints[] = { lane->n_models, lane->n_images, lane->table_base, lane->pose_warps, lane->ransac_fused, (int64_t)lane->num_sms };
+	cfg = fnv(cfg, ints, sizeof ints);
+	const void *ptrs[] = { lane->d_cams, lane->d_xyz, lane->d_model_of_row };
+	cfg = fnv(cfg, ptrs, sizeof ptrs);
+	auto ptr_key = [&]() {
+		uint64_t k = 1469598103934665603ULL;
+		for (const DevBuf &b : lane->scratch) k = fnv(k, &b.p, sizeof b.p);
+		return fnv(k, &lane->frame_desc.p, sizeof lane->frame_desc.p);
+	};
+	for (size_t i = 0; i < lane->fgraphs.size(); i++) {
+		mc_ctx::FrameGraph &g = lane->fgraphs[i];
+		if (g.cfg != cfg) continue;
+		if (g.ptr_key == ptr_key()) {
+			MC_CUDA(cudaGraphLaunch(g.exec, lane->stream));
+			lane->launches += g.nodes;
+			return MC_OK;
+		}
+		cudaGraphExecDestroy(g.exec);                    // a scratch buffer moved: the captured addresses are stale
+		lane->fgraphs.erase(lane->fgraphs.begin() + (long)i);
+		break;
+	}
+	const int64_t l0 = lane->launches;
+	MC_CUDA(cudaStreamBeginCapture(lane->stream, cudaStreamCaptureModeRelaxed));
+	lane->capturing = true;
+	mc_status st = carve(lane, B, q_cap, lane->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap);
+	if (st == MC_OK) st = frame_enqueue(lane, nullptr, q_cap, P, B, caps, nullptr, true);
+	lane->capturing = false;
+	cudaGraph_t graph = nullptr;
+	const cudaError_t e_end = cudaStreamEndCapture(lane->stream, &graph);
+	const int nodes = (int)(lane->launches - l0);
+	lane->launches = l0;
+	if (st == MC_ERR_STATE) {                            // a reservation is missing: run this frame eagerly (it allocates)
+		if (graph) cudaGraphDestroy(graph);
+		cudaGetLastError();
+		MC_TRY(carve(lane, B, q_cap, lane->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap));
+		return frame_enqueue(lane, nullptr, q_cap, P, B, caps, nullptr, true);
+	}
+	if (st != MC_OK || e_end != cudaSuccess || !graph) {
+		if (graph) cudaGraphDestroy(graph);
+		cudaGetLastError();
+		if (st == MC_OK) { lane->err = std::string("graph capture: ") + cudaGetErrorString(e_end); st = MC_ERR_CUDA; }
+		return st;
+	}
+	mc_ctx::FrameGraph g;
+	g.cfg = cfg; g.ptr_key = ptr_key(); g.nodes = nodes; g.exec = nullptr;
+	const cudaError_t e_inst = cudaGraphInstantiate(&g.exec, graph, 0);
+	cudaGraphDestroy(graph);
+	if (e_inst != cudaSuccess) { lane->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e_inst); return MC_ERR_CUDA; }
+	if (lane->fgraphs.size() >= 8) { cudaGraphExecDestroy(lane->fgraphs.front().exec); lane->fgraphs.erase(lane->fgraphs.begin()); }
+	lane->fgraphs.push_back(g);
+	MC_CUDA(cudaGraphLaunch(g.exec, lane->stream));
+	lane->launches += g.nodes;
 	return MC_OK;
 }
 
@@ -240,7 +354,12 @@ mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy
 	MC_TRY(carve(ctx, B, Q, ctx->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap));
 	cudaEvent_t ev[7];
 	if (stage_ms) for (int i = 0; i < 7; i++) MC_CUDA(cudaEventCreate(&ev[i]));
-	MC_TRY(frame_enqueue(ctx, d_q, d_qxy, d_qimg, Q, P, B, caps, stage_ms ? ev : nullptr, d_nn_row_in, d_accepted_in));
+	FrameDesc d;
+	d.nn_row = d_nn_row_in ? d_nn_row_in : B.nn_row; d.accepted = d_accepted_in ? d_accepted_in : B.accepted;
+	d.q_xy = d_qxy; d.q_image = d_qimg; d.Q = Q; d.max_objects = max_objects;
+	d.out_info = nullptr; d.out_model = nullptr; d.out_pose = nullptr; d.out_score = nullptr;
+	MC_TRY(set_frame_desc(ctx, d));
+	MC_TRY(frame_enqueue(ctx, d_nn_row_in ? nullptr : d_q, Q, P, B, caps, stage_ms ? ev : nullptr, false));
 	// results -> host
 	const size_t bytes = 64 + (size_t)max_objects * (4 + 28 + 4);
 	MC_TRY(pinned(ctx, bytes + 64));
@@ -277,22 +396,6 @@ mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy
 // small kernels, run per frame on concurrent lanes. Every frame gives exactly the result of mc_process_frame.
 
 // frame result -> its slot of the batch output. info = {objects, status, accepted matches, clusters after CLUSTER}
-__global__ void k_export_objects(const int32_t *__restrict__ f_n, const int32_t *__restrict__ status, const int32_t *__restrict__ match_offsets,
-                                 int n_models, const int32_t *__restrict__ cl_n, const int32_t *__restrict__ surv_model,
-                                 const float *__restrict__ surv_pose, const float *__restrict__ surv_score, int max_objects,
-                                 int32_t *__restrict__ out_info, int32_t *__restrict__ out_model, float *__restrict__ out_pose,
-                                 float *__restrict__ out_score) {
-	const int n = f_n[0];
-	const int m = n < max_objects ? n : max_objects;
-	for (int i = threadIdx.x; i < m; i += blockDim.x) { out_model[i] = surv_model[i]; out_score[i] = surv_score[i]; }
-	for (int i = threadIdx.x; i < 7 * m; i += blockDim.x) out_pose[i] = surv_pose[i];
-	if (threadIdx.x == 0) { out_info[0] = n; out_info[1] = status[0]; out_info[2] = match_offsets[n_models]; out_info[3] = cl_n[0]; }
-}
-
-__global__ void k_export_empty(int32_t *__restrict__ out_info) {
-	if (threadIdx.x < 4) out_info[threadIdx.x] = 0;
-}
-
 static void lane_borrow(mc_ctx *ctx, mc_ctx *lane) {
 	lane->device = ctx->device; lane->num_sms = ctx->num_sms;
 	lane->n_rows = ctx->n_rows; lane->row_base = ctx->row_base; lane->n_tiles = ctx->n_tiles; lane->D = ctx->D; lane->n_models = ctx->n_models;
@@ -301,7 +404,7 @@ static void lane_borrow(mc_ctx *ctx, mc_ctx *lane) {
 	lane->db_norm2_min = ctx->db_norm2_min; lane->db_norm2_max = ctx->db_norm2_max;
 	lane->d_cams = ctx->d_cams; lane->n_images = ctx->n_images;
 	lane->pose_warps = ctx->pose_warps;
-	lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused;
+	lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs;
 }
 
 static mc_status ensure_lanes(mc_ctx *ctx, int n) {
@@ -391,17 +494,13 @@ mc_status process_frames_device(mc_ctx *ctx, const float *d_q, const float *d_qx
 				k_export_empty<<<1, 32, 0, lane->stream>>>(o_info);
 				lane->launches++;
 			} else {
-				const FrameCaps caps = frame_caps(Q, P);
-				FrameBufs B;
-				st = carve(lane, B, Q, lane->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap);
-				if (st == MC_OK) st = frame_enqueue(lane, nullptr, d_qxy + 2 * (size_t)q0, d_qimg + q0, Q, P, B, caps, trace ? &tev[7 * (size_t)s] : nullptr, nn_row + 2 * (size_t)q0, accepted + q0);
-				if (st == MC_OK) {
-					k_export_objects<<<1, 128, 0, lane->stream>>>(B.f_n, B.status, B.match_offsets, lane->n_models, B.cl_n, B.surv_model, B.surv_pose, B.surv_score,
-					                                             max_objects, o_info, d_out_model + (size_t)s * max_objects,
-					                                             d_out_pose + 7 * (size_t)s * max_objects, d_out_score + (size_t)s * max_objects);
-					lane->launches++;
-					if (cudaGetLastError() != cudaSuccess) { lane->err = "process_frames: export launch failed"; st = MC_ERR_CUDA; }
-				}
+				FrameDesc d;
+				d.nn_row = nn_row + 2 * (size_t)q0; d.accepted = accepted + q0; d.q_xy = d_qxy + 2 * (size_t)q0; d.q_image = d_qimg + q0;
+				d.Q = Q; d.max_objects = max_objects;
+				d.out_info = o_info; d.out_model = d_out_model + (size_t)s * max_objects;
+				d.out_pose = d_out_pose + 7 * (size_t)s * max_objects; d.out_score = d_out_score + (size_t)s * max_objects;
+				st = set_frame_desc(lane, d);
+				if (st == MC_OK) st = frame_chain(lane, Q, P, trace ? &tev[7 * (size_t)s] : nullptr);
 			}
 			if (st != MC_OK) { ctx->err = lane->err; return st; }
 		}

@@ -173,3 +173,40 @@ def test_sharded_batch_equals_single_context(ctx30, batch_case):
     _same(got, ref)
     for cx in ctxs:
         cx.close()
+
+
+def test_frame_graphs_equal_eager_launches(ctx30, batch_case):
+    """mc_process_frames replays one CUDA graph per frame for the stages after MATCH (captured per lane and per
+    feature-count bucket). Replays, re-captures after a bucket change and the eager path give identical results,
+    also when the same context then processes a second, different batch."""
+    c = batch_case
+    order = [0, 4, 7, 3, 8, 1, 5, 6, 2, 0, 4, 7, 7, 4]                  # repeated buckets on few lanes -> replays
+    q = np.concatenate([c["qn"][i] for i in order])
+    xy = np.concatenate([c["xy"][i] for i in order])
+    img = np.concatenate([c["img"][i] for i in order])
+    fo = np.concatenate([[0], np.cumsum([c["sizes"][i] for i in order])]).astype(np.int32)
+    try:
+        ctx30.set_tuning(2, 4, 1)
+        ctx30.set_option("frame_graphs", 0)
+        eager = ctx30.process_frames(q, xy, img, fo, max_objects=64)
+        l0 = ctx30.launches
+        eager2 = ctx30.process_frames(q, xy, img, fo, max_objects=64)
+        n_eager = ctx30.launches - l0
+        ctx30.set_option("frame_graphs", 1)
+        for _ in range(3):                                               # first pass captures, later passes only replay
+            l0 = ctx30.launches
+            graph = ctx30.process_frames(q, xy, img, fo, max_objects=64)
+            n_graph = ctx30.launches - l0
+            _same(graph, eager)
+        _same(eager2, eager)
+        assert n_graph == n_eager                                        # replays are counted kernel by kernel
+        assert sum(len(g["model"]) for g in graph) >= 20
+        # a different batch on the same context (other buckets first)
+        rev = order[::-1]
+        q2 = np.concatenate([c["qn"][i] for i in rev]); xy2 = np.concatenate([c["xy"][i] for i in rev]); img2 = np.concatenate([c["img"][i] for i in rev])
+        fo2 = np.concatenate([[0], np.cumsum([c["sizes"][i] for i in rev])]).astype(np.int32)
+        g2 = ctx30.process_frames(q2, xy2, img2, fo2, max_objects=64)
+        _same(g2, eager[::-1])
+    finally:
+        ctx30.set_option("frame_graphs", 1)
+        ctx30.set_tuning(8, 8, 1)
