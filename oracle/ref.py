@@ -58,6 +58,8 @@ def _load():
                                      _f32p, _f32p, _f32p, _u8p]),
         "ref_hypotheses_batch": (C.c_double, [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_int,
                                               _i32p, _f32p]),
+        "ref_sift": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int]),
+        "ref_sift_get": (None, [_f32p, _f32p]),
         "ref_add_model_xml": (C.c_int, [C.c_void_p, C.c_char_p]),
         "ref_model_count": (C.c_int, [C.c_void_p]),
         "ref_model_name": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
@@ -108,6 +110,17 @@ def pipeline_param_vector(p=DEFAULT_PARAMS, quality=None):
                     dtype=np.float32)
 
 
+def sift(gray_u8, double_size=True):
+    """The reference's FEAT_SIFT_CPU (libsiftfast) on one grayscale image: (xy[n,2], desc[n,128])."""
+    g = np.ascontiguousarray(gray_u8, dtype=np.uint8)
+    n = lib().ref_sift(g, g.shape[0], g.shape[1], 1 if double_size else 0)
+    xy = np.zeros((n, 2), np.float32)
+    desc = np.zeros((n, 128), np.float32)
+    if n:
+        lib().ref_sift_get(xy, desc)
+    return xy, desc
+
+
 class Ref:
     """One reference pipeline context (models + cameras + one frame's FrameData)."""
 
@@ -139,7 +152,11 @@ class Ref:
 
     # ---- model files through the reference's sXML reader + addModel loop
     def add_model_xml(self, path):
-        return self.L.ref_add_model_xml(self.h, os.fsencode(path))
+        st = self.L.ref_add_model_xml(self.h, os.fsencode(path))
+        # row count of the SIFT-128 database the matcher will build (model_desc() sizes its output from it)
+        self.D = 128
+        self.N = sum(self.L.ref_model_points(self.h, i, b"SIFT", None) for i in range(self.L.ref_model_count(self.h)))
+        return st
 
     def model_names(self):
         out = []

@@ -53,6 +53,7 @@ extern "C" void ref_srand(uint64_t seed) { g_rng_state = seed; }
 #include <cluster/CLUSTER_MEAN_SHIFT_CPU.hpp>
 #include <pose/POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp>
 #include <filter/FILTER_PROJECTION_CPU.hpp>
+#include <feat/FEAT_SIFT_CPU.hpp>
 #undef class
 #undef rand
 
@@ -207,6 +208,35 @@ void ref_get_model_points(void *h, int i, const char *desc_type, float *xyz, int
 		for (int j = 0; j < 3; j++) xyz[3 * k + j] = ips[k].coord3D[j];
 		desc_len[k] = (int)ips[k].descriptor.size();
 		for (size_t j = 0; j < ips[k].descriptor.size(); j++) desc_values[v++] = ips[k].descriptor[j];
+	}
+}
+
+/* ---- feature extraction with the reference's own step 1 (FEAT_SIFT_CPU over the vendored libsiftfast 1.1), used
+ * only to turn the reference's shipped test images into real descriptors for the parity fixtures of the hot path
+ * (SURVEY.md 8d "real-image config"). ScaleOrigin "-1" doubles the image like config.hpp:72; "0" does not. ---- */
+static vector<FrameData::DetectedFeature> g_sift_out;
+
+int ref_sift(const unsigned char *gray, int height, int width, int double_size) {
+	FEAT_SIFT_CPU alg(double_size ? "-1" : "0");
+	map<string, string> cfg;
+	alg.getConfig(cfg);
+	alg.setConfig(cfg);                       /* sets libsiftfast's DoubleImSize from ScaleOrigin (FEAT_SIFT_CPU.hpp:69-76) */
+	SP_Image im(new Image);
+	im->name = "img"; im->width = width; im->height = height;
+	im->data.assign(gray, gray + (size_t)width * height);
+	FrameData fd;
+	fd.images.push_back(im);
+	alg.process(fd);
+	g_sift_out.clear();
+	for (map<string, vector<FrameData::DetectedFeature> >::iterator it = fd.detectedFeatures.begin(); it != fd.detectedFeatures.end(); ++it)
+		g_sift_out.insert(g_sift_out.end(), it->second.begin(), it->second.end());
+	return (int)g_sift_out.size();
+}
+
+void ref_sift_get(float *xy, float *desc) {
+	for (size_t i = 0; i < g_sift_out.size(); i++) {
+		xy[2 * i] = g_sift_out[i].coord2D[0]; xy[2 * i + 1] = g_sift_out[i].coord2D[1];
+		memcpy(desc + 128 * i, &g_sift_out[i].descriptor[0], 128 * sizeof(float));
 	}
 }
 
