@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from moped_b200 import synth  # noqa: E402
-from moped_b200.sharding import ResultBlock, frame_range, shard_objects  # noqa: E402
+from moped_b200.sharding import ResultBlock, cluster_partition, frame_range, shard_objects  # noqa: E402
 
 METRIC = "frames_per_s"
 UNIT = "frames/s"
@@ -504,7 +504,7 @@ def run_ransac_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     cl = synth.make_ransac_clusters(args.clusters, 80, 0.5)
     hy = synth.make_hypotheses(cl, args.hyp, 5)
-    mine = np.nonzero(hy["hyp_cluster"] % world == rank)[0]            # clusters round-robin over the ranks
+    mine = cluster_partition(hy["hyp_cluster"], world, rank)           # clusters round-robin over the ranks
     H = len(mine)
     ctx = capi.Context(local_rank)
     stream = torch.cuda.Stream()

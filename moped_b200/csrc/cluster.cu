@@ -5,8 +5,10 @@
 // The reference algorithm is order-dependent (canopies are merged by pointer chasing in list order), so
 // the kernel keeps the list order and the floating-point summation order of the reference:
 //   (i)   aggregate of every live canopy: all threads, each walking the live list in order (O(n^2/threads));
-//   (ii)  merge redirection in list order: one warp tests 32 earlier canopies at a time (ballot) and
-//         lane 0 applies the qualifying redirections in ascending order;
+//   (ii)  merge redirection in list order: the "aggregates closer than Merge" predicate of every (canopy, earlier canopy)
+//         pair does not depend on the redirections, so all warps evaluate it 64 list rows at a time into a bit matrix
+//         in shared memory (one ballot = one word) and one thread then applies the set bits in ascending (row, column)
+//         order — the order of the reference's double loop;
 //   (iii) folding of redirected canopies into their targets in list order: one thread (O(n)).
 // One CTA per model, images in sequence; working set staged in shared memory (<= kCap points per group,
 // larger groups use the same code on a global-memory scratch area).
@@ -14,8 +16,11 @@
 
 namespace mc {
 
-constexpr int kClusterThreads = 128;
+constexpr int kClusterThreads = 256;
 constexpr int kCap = 1024;       // points per (model, image) group held in shared memory
+constexpr int kBitRows = 64;     // list rows of the merge predicate evaluated per round
+constexpr int kBitWords = kCap / 32;
+constexpr size_t kClusterSmem = sizeof(float) * 4 * kCap + sizeof(int) * 7 * kCap + sizeof(unsigned) * kBitRows * kBitWords;
 
 struct MsArrays {
 	float *cx, *cy, *ax, *ay;
@@ -24,8 +29,8 @@ struct MsArrays {
 
 __device__ void meanshift_group(const MsArrays &A, int n, float sq_radius, float sq_merge, int min_pts, int max_iter,
                                 const int *pid, int *out_count, int *out_sizes, int *out_members, int &n_clusters, int &n_members,
-                                int *sh_n_alive, int *sh_done) {
-	const int tid = threadIdx.x, lane = tid & 31;
+                                int *sh_n_alive, int *sh_done, unsigned *bits) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
 	for (int i = tid; i < n; i += blockDim.x) {
 		A.size[i] = 1; A.target[i] = i; A.alive[i] = i; A.head[i] = i; A.tail[i] = i; A.next[i] = -1;
 	}
@@ -58,8 +63,45 @@ __device__ void meanshift_group(const MsArrays &A, int n, float sq_radius, float
 			A.ay[c] = __fdiv_rn(sy, (float)touch);
 		}
 		__syncthreads();
-		// (ii) redirections, in list order (:122-132); warp 0 only
-		if (tid < 32) {
+		// (ii) redirections, in list order (:122-132)
+		if (n_alive <= kCap) {
+			for (int a0 = 1; a0 < n_alive; a0 += kBitRows) {
+				const int a1 = a0 + kBitRows < n_alive ? a0 + kBitRows : n_alive;
+				for (int a = a0 + warp; a < a1; a += n_warps) {           // predicate bits of rows [a0, a1): one warp per row
+					const int c = A.alive[a];
+					const float acx = A.ax[c], acy = A.ay[c];
+					const int nw = (a + 31) >> 5;
+					for (int w = 0; w < nw; w++) {
+						const int b = (w << 5) + lane;
+						bool close = false;
+						if (b < a) {
+							const int o = A.alive[b];
+							const float dx = __fsub_rn(A.ax[o], acx), dy = __fsub_rn(A.ay[o], acy);
+							close = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < sq_merge;
+						}
+						const unsigned m = __ballot_sync(0xffffffffu, close);
+						if (lane == 0) bits[(a - a0) * kBitWords + w] = m;
+					}
+				}
+				__syncthreads();
+				if (tid == 0) {                                           // apply in ascending (row, column) order
+					for (int a = a0; a < a1; a++) {
+						const int c = A.alive[a];
+						const int nw = (a + 31) >> 5;
+						for (int w = 0; w < nw; w++) {
+							unsigned m = bits[(a - a0) * kBitWords + w];
+							while (m) {
+								const int o = A.alive[(w << 5) + __ffs(m) - 1];
+								m &= m - 1;
+								A.target[A.target[o]] = c;
+								A.target[o] = c;
+							}
+						}
+					}
+				}
+				__syncthreads();
+			}
+		} else if (tid < 32) {                                            // groups beyond the shared-memory capacity: one warp, 32 at a time
 			for (int a = 1; a < n_alive; a++) {
 				const int c = A.alive[a];
 				const float acx = A.ax[c], acy = A.ay[c];
@@ -131,8 +173,10 @@ k_meanshift(const int32_t *__restrict__ match_offsets, const int32_t *__restrict
             int n_images, float radius, float merge, int min_pts, int max_iter,
             int32_t *__restrict__ model_count, int32_t *__restrict__ sizes, int32_t *__restrict__ members,
             float *__restrict__ gscratch_f, int32_t *__restrict__ gscratch_i) {
-	__shared__ float s_f[4 * kCap];
-	__shared__ int s_i[7 * kCap];
+	extern __shared__ __align__(16) unsigned char s_dyn[];
+	float *s_f = reinterpret_cast<float *>(s_dyn);
+	int *s_i = reinterpret_cast<int *>(s_f + 4 * kCap);
+	unsigned *s_bits = reinterpret_cast<unsigned *>(s_i + 7 * kCap);
 	__shared__ int sh_n, sh_n_alive, sh_done;
 	const int m = blockIdx.x, tid = threadIdx.x;
 	const int lo = match_offsets[m], hi = match_offsets[m + 1], cnt = hi - lo;
@@ -174,7 +218,7 @@ k_meanshift(const int32_t *__restrict__ match_offsets, const int32_t *__restrict
 		const int n = sh_n;
 		if (n == 0) continue;
 		meanshift_group(A, n, sq_radius, sq_merge, min_pts, max_iter, pid, &model_count[m], sizes + lo, members + lo, n_clusters, n_members,
-		                &sh_n_alive, &sh_done);
+		                &sh_n_alive, &sh_done, s_bits);
 	}
 }
 
@@ -234,7 +278,12 @@ mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int3
 	MC_TRY(reserve(ctx, b_members, sizeof(int32_t) * (max_matches + 1)));
 	MC_TRY(reserve(ctx, b_f, sizeof(float) * 4 * (size_t)(max_matches + 1)));
 	MC_TRY(reserve(ctx, b_i, sizeof(int32_t) * 7 * (size_t)(max_matches + 1)));
-	k_meanshift<<<n_models, kClusterThreads, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, n_images, radius, merge, min_pts, max_iter,
+	static bool attr_set = false;
+	if (!attr_set) {
+		MC_CUDA(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+		attr_set = true;
+	}
+	k_meanshift<<<n_models, kClusterThreads, kClusterSmem, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, n_images, radius, merge, min_pts, max_iter,
 	                                                         (int32_t *)b_count.p, (int32_t *)b_sizes.p, (int32_t *)b_members.p,
 	                                                         (float *)b_f.p, (int32_t *)b_i.p);
 	MC_LAUNCH_CHECK();

@@ -17,6 +17,12 @@
 
 #include <math_constants.h>
 
+// MC_COARSE_DBG (experiments only, never in the shipped library): 1 = the epilogue hands the accumulator stage back without
+// reading it (MMA + TMA pace alone), 2 = the epilogue reads TMEM but skips the top-k scan (adds the TMEM-read pace)
+#ifndef MC_COARSE_DBG
+#define MC_COARSE_DBG 0
+#endif
+
 namespace mc {
 
 // =============================================================================================
@@ -321,6 +327,23 @@ k_match_coarse(const __half *__restrict__ q_img, const __half *__restrict__ db_i
 			const int64_t row0 = (t0 + i) * kTileRows;
 			const bool tail = row0 + kTileRows > n_rows;
 			const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 256 + half * 128);
+#if MC_COARSE_DBG == 1
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_tempty(s));
+			(void)taddr; (void)tail; (void)ra; (void)rb;
+#elif MC_COARSE_DBG == 2
+			tmem_ld32(taddr, ra); tmem_ld_wait();
+			tmem_ld32(taddr + 32, rb); tmem_ld_wait();
+			tau = fmaxf(tau, ra[0] + rb[31]);
+			tmem_ld32(taddr + 64, ra); tmem_ld_wait();
+			tmem_ld32(taddr + 96, rb); tmem_ld_wait();
+			tau = fmaxf(tau, ra[0] + rb[31]);
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_tempty(s));
+			(void)tail;
+#else
 			tmem_ld32(taddr, ra);
 			tmem_ld_wait();
 			tmem_ld32(taddr + 32, rb);
@@ -341,6 +364,7 @@ k_match_coarse(const __half *__restrict__ q_img, const __half *__restrict__ db_i
 			if (lane == 0) mbar_arrive(bar_tempty(s));
 			if (tail) mask_tail(rb, row0 + 96, n_rows);
 			scan_chunk(rb, (int)row0 + 96, tau, ts, ti);
+#endif
 			if (ts[kTopK - 1] > published) {               // publish this CTA's k-th best (a valid global lower bound)
 				published = ts[kTopK - 1];
 				atomicMax(&g_tau[qid], f2o(published));

@@ -56,3 +56,10 @@ class ResultBlock:
                 k = min(int(info[f, 0]), self.mo)
                 out.append(dict(model=model[f, :k].copy(), pose=pose[f, :k].copy(), score=score[f, :k].copy(), info=info[f].copy()))
         return out
+
+
+def cluster_partition(hyp_cluster: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """RANSAC work distributed by cluster (north_star; BASELINE configs[3]): cluster c belongs to rank c % world, so a
+    rank owns every hypothesis of its clusters and no data-path collective is needed. Returns the indices (ascending)
+    of the hypotheses rank `rank` evaluates; the union over ranks is a partition of range(len(hyp_cluster))."""
+    return np.nonzero(np.asarray(hyp_cluster) % world == rank)[0]

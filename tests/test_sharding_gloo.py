@@ -141,3 +141,59 @@ def test_frame_range_rejects_uneven_split():
     with pytest.raises(ValueError):
         frame_range(7, 2, 0)
     assert [frame_range(8, 4, r) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 8)]
+
+
+def _ransac_rank(rank, world, port, q):
+    import torch.distributed as dist
+    from moped_b200 import synth
+    from moped_b200.sharding import cluster_partition
+    from oracle import oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cl = synth.make_ransac_clusters(5, 40, 0.3, seed=3)
+    hy = synth.make_hypotheses(cl, 6, 5, seed=3)
+    mine = cluster_partition(hy["hyp_cluster"], world, rank)
+    cams = oracle.cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    n_in = np.full(len(hy["hyp_cluster"]), -7, np.int32)
+    for h in mine:                                       # the per-rank work: its clusters' hypotheses, nothing else
+        c = hy["hyp_cluster"][h]
+        s = slice(cl["offsets"][c], cl["offsets"][c + 1])
+        n_in[h] = oracle.hypothesis(cl["xy"][s], cl["xyz"][s], cl["image"][s], cams, hy["sample_pos"][h], hy["init_quat"][h], 200, 10.0, 6)[0]
+    import torch
+    t = torch.from_numpy(n_in)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)             # test-only gather of the disjoint results
+    if rank == 0:
+        q.put((mine.tolist(), t.numpy().tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_cluster_partition_covers_every_hypothesis_once():
+    """RANSAC-heavy configuration over 2 ranks (gloo): every hypothesis is evaluated by exactly one rank (the owner of
+    its cluster) and the union equals the single-process evaluation."""
+    import torch.multiprocessing as mp
+    from moped_b200 import synth
+    from moped_b200.sharding import cluster_partition
+    from oracle import oracle
+    cl = synth.make_ransac_clusters(5, 40, 0.3, seed=3)
+    hy = synth.make_hypotheses(cl, 6, 5, seed=3)
+    parts = [cluster_partition(hy["hyp_cluster"], 2, r) for r in range(2)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(30))
+    assert set(hy["hyp_cluster"][parts[0]]) == {0, 2, 4} and set(hy["hyp_cluster"][parts[1]]) == {1, 3}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_ransac_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    mine0, merged = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert mine0 == parts[0].tolist()
+    cams = oracle.cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    single = []
+    for h in range(30):
+        c = hy["hyp_cluster"][h]
+        s = slice(cl["offsets"][c], cl["offsets"][c + 1])
+        single.append(oracle.hypothesis(cl["xy"][s], cl["xyz"][s], cl["image"][s], cams, hy["sample_pos"][h], hy["init_quat"][h], 200, 10.0, 6)[0])
+    assert merged == single
