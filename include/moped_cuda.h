@@ -234,6 +234,27 @@ mc_status mc_model_db_upload(mc_model_db *db, mc_ctx *ctx, const char *desc_type
 mc_status mc_model_db_save(const mc_model_db *db, const char *path);
 mc_status mc_model_db_load(mc_model_db *db, const char *path);
 
+/* ---- feature extraction: replaces FEAT_SIFT_CPU::process,
+ *      moped2/libmoped/src/feat/FEAT_SIFT_CPU.hpp:78-112, i.e. GetKeypoints of the vendored libsiftfast 1.1
+ *      (moped2/libmoped/libs/libs.tgz!libsiftfast-1.1-src/libsiftfast.cpp:301-361) ------------------------------ */
+/* gray: n_images images of height x width bytes each (Image::data of a 1-channel image, FEAT_SIFT_CPU.hpp:88), all the
+ * same size — a camera rig or a stream batch; one set of kernel launches serves the whole batch.
+ * double_size != 0 is ScaleOrigin "-1" (DoubleImSize=1, FEAT_SIFT_CPU.hpp:69-76).
+ * Outputs, one block of max_keypoints slots per image (image f, keypoint i at slot f*max_keypoints + i), in the order
+ * FEAT_SIFT_CPU appends detectedFeatures: counts[f] = keypoints FOUND in image f; xy = coord2D = (col, row) in input
+ * pixels; scale_ori (optional) = (scale, orientation); desc = 128 floats (unit length, clamped at 0.2 like the
+ * reference's). If an image has more than max_keypoints keypoints the call returns MC_ERR_CAPACITY: counts[f] still holds
+ * the number found, the slots hold max_keypoints of them (an unspecified subset). */
+mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_images, int height, int width, int double_size,
+                          int max_keypoints, int32_t *counts, float *xy, float *scale_ori, float *desc);
+/* Same with every array on the device, asynchronous on the context's stream: desc_dev blocks feed mc_match_dev /
+ * mc_process_frames_dev without leaving HBM. counts_dev may exceed max_keypoints (see above). */
+mc_status mc_sift_extract_dev(mc_ctx *ctx, const uint8_t *gray_dev, int n_images, int height, int width, int double_size,
+                              int max_keypoints, float *xy_dev, float *scale_ori_dev, float *desc_dev, int32_t *counts_dev);
+/* test/bench introspection: one plane of the scale-space left by the last extraction (stack 0 Gaussian 0..5, 1 DoG 0..4,
+ * 2 gradient magnitude 0..2, 3 orientation 0..2); out may be NULL to query the octave's size. */
+mc_status mc_sift_read_plane(mc_ctx *ctx, int frame, int octave, int stack, int index, float *out, int32_t *rows, int32_t *cols);
+
 /* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)

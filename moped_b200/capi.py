@@ -76,6 +76,9 @@ SIGNATURES = {
     "mc_model_db_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]),
     "mc_model_db_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mc_model_db_load": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mc_sift_extract": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _f32p, C.c_void_p, _f32p]),
+    "mc_sift_extract_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_sift_read_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mc_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "mc_pipeline_default_params": (None, [C.POINTER(PipelineParams)]),
     "mc_process_frame": (C.c_int, [C.c_void_p, _f32p, _f32p, _i32p, C.c_int, C.POINTER(PipelineParams), C.c_int, C.POINTER(C.c_int32),
@@ -291,6 +294,33 @@ class Context:
         p = PipelineParams()
         self.L.mc_pipeline_default_params(C.byref(p))
         return p
+
+    def sift(self, gray, double_size=True, max_keypoints=8192):
+        """FEAT step on a batch of equally sized grayscale images [B,H,W] (or one [H,W]) -> list of (xy, scale_ori, desc)."""
+        g = np.ascontiguousarray(gray, dtype=np.uint8)
+        single = g.ndim == 2
+        if single:
+            g = g[None]
+        B, H, W = g.shape
+        counts = np.zeros(B, np.int32)
+        xy = np.zeros((B, max_keypoints, 2), np.float32)
+        so = np.zeros((B, max_keypoints, 2), np.float32)
+        desc = np.zeros((B, max_keypoints, 128), np.float32)
+        self._check(self.L.mc_sift_extract(self.h, g.reshape(-1), B, H, W, 1 if double_size else 0, max_keypoints, counts, xy.reshape(-1),
+                                           so.ctypes.data, desc.reshape(-1)), "mc_sift_extract")
+        out = [(xy[f, :counts[f]].copy(), so[f, :counts[f]].copy(), desc[f, :counts[f]].copy()) for f in range(B)]
+        return out[0] if single else out
+
+    def sift_dev(self, gray_ptr, B, H, W, double_size, max_keypoints, xy_ptr, so_ptr, desc_ptr, counts_ptr):
+        self._check(self.L.mc_sift_extract_dev(self.h, gray_ptr, B, H, W, 1 if double_size else 0, max_keypoints, xy_ptr, so_ptr, desc_ptr,
+                                               counts_ptr), "mc_sift_extract_dev")
+
+    def sift_plane(self, frame, octave, stack, index):
+        r, c = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.mc_sift_read_plane(self.h, frame, octave, stack, index, None, C.byref(r), C.byref(c)), "mc_sift_read_plane")
+        out = np.zeros((r.value, c.value), np.float32)
+        self._check(self.L.mc_sift_read_plane(self.h, frame, octave, stack, index, out.ctypes.data, None, None), "mc_sift_read_plane")
+        return out
 
     def process_frame(self, q_desc, q_xy, q_image, params=None, max_objects=256, want_times=False):
         p = params or self.default_params()

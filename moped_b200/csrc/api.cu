@@ -108,6 +108,7 @@ void mc_destroy(mc_ctx *ctx) {
 	for (cudaEvent_t e : ctx->ev_chunk) cudaEventDestroy(e);
 	if (ctx->ev_coarse[0]) { cudaEventDestroy(ctx->ev_coarse[0]); cudaEventDestroy(ctx->ev_coarse[1]); }
 	free_db(ctx);
+	sift_free(ctx);
 	cudaFree(ctx->d_cams);
 	free_scratch(ctx);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

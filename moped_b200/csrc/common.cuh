@@ -96,6 +96,7 @@ struct mc_ctx {
 	bool capturing = false;           // reserve() must not allocate while the lane's stream is being captured
 	bool frame_graphs = true;         // mc_set_option "frame_graphs"
 	int batch_stats[4] = {0, 0, 0, 0};   // {frames, accepted matches, objects, lanes used} of the last batch
+	void *sift_state = nullptr;          // feature extraction (sift.cu): scale-space plan and buffers, created on first use
 };
 
 namespace mc {
@@ -146,6 +147,9 @@ inline mc_status pinned(mc_ctx *ctx, size_t bytes) {
 
 // ---- stage entry points implemented in the .cu files (device pointers, async on ctx->stream) ----
 mc_status db_build_images(mc_ctx *ctx);
+void sift_free(mc_ctx *ctx);
+mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, int W, int dbl, int max_kp,
+                              float *d_xy, float *d_so, float *d_desc, int32_t *d_counts);
 mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mode,
                        int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted);
 mc_status match_merge_device(mc_ctx *ctx, const int32_t *rows_all, const float *dist_all, int n_shards, int Q, float ratio,

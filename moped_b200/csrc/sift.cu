@@ -1,0 +1,674 @@
+// sift.cu — step 1 of MOPED's pipeline (feature extraction) on the device: the producer on the input side of MATCH
+// (SURVEY.md §8f row 3). Replaces FEAT_SIFT_CPU::process (moped2/libmoped/src/feat/FEAT_SIFT_CPU.hpp:78-112) over the
+// vendored libsiftfast 1.1 (libs.tgz!libsiftfast-1.1-src/libsiftfast.cpp; the vendored copy #undef's __SSE*__ at :40-42,
+// so the reference runs its scalar branches — those are the ones followed here).
+//
+// Design (B200): a BATCH of equally sized images per call; every kernel has the frame as a grid dimension, so one
+// set of ~100 launches serves all frames of a camera rig / stream batch. The scale-space of a 640x480 frame
+// (1278x958 after doubling, 7 octaves) is ~110 MB and stays L2/HBM resident; the pyramid kernels are HBM/L2-bound
+// streaming kernels, the keypoint kernels (one warp / one CTA per keypoint) are latency-bound and small.
+//
+// Arithmetic: compiled with -fmad=false; sums are in the reference's source order with separate multiply and add,
+// '/' and sqrtf are IEEE, so the pyramid, the DoG extrema, the sub-pixel fit and hence the keypoint SET are
+// bit-identical to the C restatement (oracle/moped_sift_oracle.c). Only expf/atan2f/sinf/cosf/powf differ from
+// glibc's by an ulp or two. Histogram and descriptor bins are accumulated in 64-bit fixed point (2^-40 units) with
+// shared-memory atomics: order-independent, hence deterministic, and closer to the exact sum than a float chain.
+//
+// Output order = the order FEAT_SIFT_CPU emits with one OpenMP thread: the reverse of creation order
+// (libsiftfast.cpp:941-951,1423), i.e. octave descending, then DoG index / row / column descending, then
+// orientation peak descending.
+#include "common.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace mc {
+
+constexpr int kSiftScales = 3;
+constexpr int kSiftMaxOct = 16;
+constexpr float kSiftInitSigma = 1.6f;
+#define SIFT_PI 3.141592654f
+#define SIFT_SQRT2 1.4142136f
+
+struct GaussK { float k[64]; int ksize; };
+
+struct SiftOct {
+	int rows, cols;
+	size_t plane;                 // rows*cols
+	float *gauss, *dog, *grad, *ori;   // [frame][6|5|3|3][plane]
+	int32_t *claim;               // [frame][plane]: smallest scan id that reached this pixel (duplicate suppression)
+};
+
+struct SiftCand { int frame, oct, index, row, col, scan_id; float X[3]; };
+struct SiftKp { int frame, oct, index; float frow, fcol, fsize, ori; unsigned long long key; int slot; };
+
+struct SiftState {
+	int B = 0, H = 0, W = 0, dbl = -1, n_oct = 0, max_kp = 0, cap_cand = 0;
+	SiftOct oct[kSiftMaxOct];
+	DevBuf pyr, tmp, gray, cand, kp, counters, lut;
+	GaussK k_init, k_oct[kSiftScales + 2];
+	bool has_init = false;
+};
+
+// GaussianBlur's kernel (libsiftfast.cpp:470-508): ksize+1 weights enter the sum, ksize are normalised (host, glibc expf)
+static void make_kernel(float fblur, GaussK &g) {
+	const float GaussTruncate = 4.0f;
+	int ksize = (int)(2.0f * GaussTruncate * fblur + 1.0f);
+	if (ksize < 3) ksize = 3;
+	ksize += !(ksize & 1);
+	double faccum = 0;
+	int width = ksize >> 1;
+	memset(g.k, 0, sizeof(g.k));
+	for (int i = 0; i <= ksize; ++i) {
+		float fweight = expf(-(float)(i - width) * (i - width) / (2.0f * fblur * fblur));
+		faccum += (double)fweight;
+		g.k[i] = fweight;
+	}
+	for (int i = 0; i < ksize; ++i) g.k[i] /= (float)faccum;
+	g.k[ksize] = 0.f;
+	g.ksize = ksize;
+}
+
+// ---- pyramid kernels -------------------------------------------------------------------------------------------
+
+// FEAT_SIFT_CPU.hpp:86-90 (pixel = (float)(g * 1./255.), a 256-entry table computed on the host in double) followed by
+// SiftDoubleSize (libsiftfast.cpp:363-380) or SiftCopyImage (:382-388)
+__global__ void k_sift_base(const uint8_t *__restrict__ gray, const float *__restrict__ lut, int H, int W, int dbl,
+                            float *__restrict__ dst, int rows, int cols) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z;
+	if (c >= cols) return;
+	const uint8_t *g = gray + (size_t)f * H * W;
+	float v;
+	if (!dbl) v = lut[g[(size_t)r * W + c]];
+	else {
+		int i = r >> 1, j = c >> 1;
+		float p00 = lut[g[(size_t)i * W + j]], p01 = lut[g[(size_t)i * W + j + 1]];
+		float p10 = lut[g[(size_t)(i + 1) * W + j]], p11 = lut[g[(size_t)(i + 1) * W + j + 1]];
+		if (!(r & 1)) v = (c & 1) ? 0.5f * (p00 + p01) : p00;
+		else v = (c & 1) ? 0.25f * (p00 + p01 + p10 + p11) : 0.5f * (p00 + p10);
+	}
+	dst[(size_t)f * rows * cols + (size_t)r * cols + c] = v;
+}
+
+// ConvHorizontal + ConvBuffer (libsiftfast.cpp:523-546,573-581): replicate padding, taps summed in order j = 0..ksize-1.
+// src/dst frames are fstride_src / fstride_dst floats apart.
+__global__ void k_sift_blur_h(const float *__restrict__ src, size_t fstride_src, float *__restrict__ dst, size_t fstride_dst,
+                              int rows, int cols, const __grid_constant__ GaussK gk) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z;
+	if (c >= cols) return;
+	const float *p = src + (size_t)f * fstride_src + (size_t)r * cols;
+	const int ksize = gk.ksize, width = ksize >> 1;
+	float acc = 0.f;
+	for (int j = 0; j < ksize; ++j) {
+		int x = c + j - width;
+		x = x < 0 ? 0 : (x >= cols ? cols - 1 : x);
+		acc += __ldg(p + x) * gk.k[j];
+	}
+	dst[(size_t)f * fstride_dst + (size_t)r * cols + c] = acc;
+}
+
+// ConvVertical (:548-571) fused with SubtractImage (:460-464): dst = blur_v(src); if dog: dog = prev - dst
+// (prev = the previous Gaussian image, same frame stride as dst; the DoG stack has its own frame stride)
+__global__ void k_sift_blur_v(const float *__restrict__ src, size_t fstride_src, float *__restrict__ dst, size_t fstride_dst,
+                              const float *__restrict__ prev, float *__restrict__ dog, size_t fstride_dog, int rows, int cols,
+                              const __grid_constant__ GaussK gk) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z;
+	if (c >= cols) return;
+	const float *p = src + (size_t)f * fstride_src + c;
+	const int ksize = gk.ksize, width = ksize >> 1;
+	float acc = 0.f;
+	for (int j = 0; j < ksize; ++j) {
+		int y = r + j - width;
+		y = y < 0 ? 0 : (y >= rows ? rows - 1 : y);
+		acc += __ldg(p + (size_t)y * cols) * gk.k[j];
+	}
+	size_t o = (size_t)r * cols + c;
+	dst[(size_t)f * fstride_dst + o] = acc;
+	if (dog) dog[(size_t)f * fstride_dog + o] = prev[(size_t)f * fstride_dst + o] - acc;
+}
+
+// HalfImageSize (:390-408)
+__global__ void k_sift_half(const float *__restrict__ src, size_t fstride_src, int cols, float *__restrict__ dst, size_t fstride_dst,
+                            int nrows, int ncols) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z;
+	if (c >= ncols) return;
+	dst[(size_t)f * fstride_dst + (size_t)r * ncols + c] = src[(size_t)f * fstride_src + (size_t)(2 * r) * cols + 2 * c];
+}
+
+// GradOriImages (:959-992) of the Gaussian images 1..3 (blockIdx.z = frame*3 + (index-1))
+__global__ void k_sift_gradori(const float *__restrict__ gauss, float *__restrict__ grad, float *__restrict__ ori, int rows, int cols) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, f = blockIdx.z / kSiftScales, s = blockIdx.z % kSiftScales;
+	if (j >= cols) return;
+	size_t plane = (size_t)rows * cols;
+	const float *p = gauss + ((size_t)f * (kSiftScales + 3) + s + 1) * plane + (size_t)i * cols;
+	float fdiffc, fdiffr;
+	if (j == 0) fdiffc = 2.0f * (p[1] - p[0]);
+	else if (j == cols - 1) fdiffc = 2.0f * (p[j] - p[j - 1]);
+	else fdiffc = p[j + 1] - p[j - 1];
+	if (i == 0) fdiffr = 2.0f * (p[j] - p[cols + j]);
+	else if (i == rows - 1) fdiffr = 2.0f * (p[-cols + j] - p[j]);
+	else fdiffr = p[-cols + j] - p[cols + j];
+	size_t o = ((size_t)f * kSiftScales + s) * plane + (size_t)i * cols + j;
+	grad[o] = sqrtf(fdiffc * fdiffc + fdiffr * fdiffr);
+	ori[o] = atan2f(fdiffr, fdiffc);
+}
+
+// ---- extrema ---------------------------------------------------------------------------------------------------
+
+// LocalMaxMin (:1126-1147)
+__device__ __forceinline__ bool local_max_min(float fval, const float *d, int cols, int r, int c) {
+	for (int row = r - 1; row <= r + 1; ++row) {
+		const float *pf = d + (size_t)row * cols + c - 1;
+		if (fval > 0) { if (pf[0] > fval || pf[1] > fval || pf[2] > fval) return false; }
+		else { if (fval > pf[0] || fval > pf[1] || fval > pf[2]) return false; }
+	}
+	return true;
+}
+
+// NotOnEdge (:1149-1162)
+__device__ __forceinline__ bool not_on_edge(const float *d, int s, int row, int col) {
+	const float *p = d + (size_t)row * s;
+	float f1 = p[-s + col] - p[col] * 2 + p[s + col];
+	float f2 = p[col - 1] - p[col] * 2 + p[col + 1];
+	float f3 = p[s + col + 1] - p[s + col - 1];
+	float f4 = p[-s + col + 1] - p[-s + col - 1];
+	float f5 = (f3 - f4) * 0.25f;
+	float f6 = f1 * f2 - f5 * f5;
+	float f8 = f1 + f2;
+	return f6 * 11 * 11 > f8 * f8 * 10;
+}
+
+// SolveLinearSystem (:1235-1274) for dim 3
+__device__ void solve3(float *Y, float *H) {
+	const int dim = 3;
+	int bestj = 0;
+	for (int i = 0; i < dim - 1; ++i) {
+		float fmax = -1;
+		for (int j = i; j < dim; ++j) {
+			float f = H[j * dim + i];
+			if (f < 0) f = -f;
+			if (f > fmax) { fmax = f; bestj = j; }
+		}
+		if (bestj != i) {
+			for (int j = 0; j < dim; ++j) { float t = H[bestj * dim + j]; H[bestj * dim + j] = H[i * dim + j]; H[i * dim + j] = t; }
+			float t = Y[bestj]; Y[bestj] = Y[i]; Y[i] = t;
+		}
+		for (int j = i + 1; j < dim; ++j) {
+			float f = H[j * dim + i] / H[i * dim + i];
+			for (int k = i; k < dim; ++k) H[j * dim + k] -= f * H[i * dim + k];
+			Y[j] -= Y[i] * f;
+		}
+	}
+	for (int i = dim - 1; i >= 0; --i) {
+		for (int j = dim - 1; j > i; --j) Y[i] -= Y[j] * H[i * dim + j];
+		Y[i] /= H[i * dim + i];
+	}
+}
+
+// FitQuadratic (:1208-1231)
+__device__ float fit_quadratic(float *X, const float *d0, const float *d1, const float *d2, int s, int r, int c) {
+	float H[9], Y[3];
+	const float *p0 = d0 + (size_t)r * s, *p1 = d1 + (size_t)r * s, *p2 = d2 + (size_t)r * s;
+	Y[0] = 0.5f * (p2[c] - p0[c]);
+	Y[1] = 0.5f * (p1[s + c] - p1[-s + c]);
+	Y[2] = 0.5f * (p1[c + 1] - p1[c - 1]);
+	H[0] = p0[c] - 2.0f * p1[c] + p2[c];
+	H[4] = p1[-s + c] - 2.0f * p1[c] + p1[s + c];
+	H[8] = p1[c - 1] - 2.0f * p1[c] + p1[c + 1];
+	H[3] = H[1] = 0.25f * ((p2[s + c] - p2[-s + c]) - (p0[s + c] - p0[-s + c]));
+	H[6] = H[2] = 0.25f * ((p2[c + 1] - p2[c - 1]) - (p0[c + 1] - p0[c - 1]));
+	H[7] = H[5] = 0.25f * ((p1[s + c + 1] - p1[s + c - 1]) - (p1[-s + c + 1] - p1[-s + c - 1]));
+	X[0] = -Y[0]; X[1] = -Y[1]; X[2] = -Y[2];
+	solve3(X, H);
+	return p1[c] + 0.5f * (X[0] * Y[0] + X[1] * Y[1] + X[2] * Y[2]);
+}
+
+// FindMaxMin's scan (:898-939) + InterpKeyPoint (:1164-1205) up to the duplicate test. The reference marks
+// s_MaxMinArray[row, col] when the FIRST extremum in scan order arrives there; here every extremum that passes the
+// tests bids its scan id with atomicMin and k_sift_orient keeps the winner — the same survivor.
+__global__ void k_sift_detect(const float *__restrict__ dog, int32_t *__restrict__ claim, int rows, int cols, int oct, float peak_thresh,
+                              SiftCand *__restrict__ cand, int *__restrict__ n_cand, int cap_cand) {
+	int c0 = blockIdx.x * blockDim.x + threadIdx.x + 5, r0 = blockIdx.y + 5;
+	int f = blockIdx.z / kSiftScales, index = blockIdx.z % kSiftScales + 1;
+	if (c0 >= cols - 5) return;
+	size_t plane = (size_t)rows * cols;
+	const float *d1 = dog + ((size_t)f * (kSiftScales + 2) + index) * plane;
+	float fval = d1[(size_t)r0 * cols + c0];
+	if (!(fabsf(fval) > peak_thresh * 0.8f)) return;
+	const float *d0 = d1 - plane, *d2 = d1 + plane;
+	if (!(local_max_min(fval, d1, cols, r0, c0) && local_max_min(fval, d0, cols, r0, c0) && local_max_min(fval, d2, cols, r0, c0) &&
+	      not_on_edge(d1, cols, r0, c0)))
+		return;
+	int rowstart = r0, colstart = c0, steps = 5;
+	float X[3], fquad;
+	for (;;) {
+		fquad = fit_quadratic(X, d0, d1, d2, cols, rowstart, colstart);
+		int newrow = rowstart, newcol = colstart;
+		if (X[1] > 0.6f && rowstart < rows - 3) newrow++;
+		if (X[1] < -0.6f && rowstart > 3) newrow--;
+		if (X[2] > 0.6f && colstart < cols - 3) newcol++;
+		if (X[2] < -0.6f && colstart > 3) newcol--;
+		if (steps > 0 && (newrow != rowstart || newcol != colstart)) { rowstart = newrow; colstart = newcol; steps--; continue; }
+		break;
+	}
+	if (fabsf(X[0]) <= 1.5f && fabsf(X[1]) <= 1.5f && fabsf(X[2]) <= 1.5f && fabsf(fquad) >= peak_thresh) {
+		int scan_id = ((index - 1) * rows + r0) * cols + c0;
+		atomicMin(&claim[(size_t)f * plane + (size_t)rowstart * cols + colstart], scan_id);
+		int slot = atomicAdd(n_cand, 1);
+		if (slot < cap_cand) {
+			SiftCand k;
+			k.frame = f; k.oct = oct; k.index = index; k.row = rowstart; k.col = colstart; k.scan_id = scan_id;
+			k.X[0] = X[0]; k.X[1] = X[1]; k.X[2] = X[2];
+			cand[slot] = k;
+		}
+	}
+}
+
+// ---- orientation: AssignOriHist (:1276-1382), one warp per surviving extremum ---------------------------------
+
+struct SiftOctView { int rows, cols; const float *grad, *ori; const int32_t *claim; };
+struct SiftOctViews { SiftOctView o[kSiftMaxOct]; float fscale0; };
+
+__device__ __forceinline__ void smooth_histogram(float *phist) {       // SmoothHistogram (:1395-1407)
+	const int numbins = 36;
+	float ffirst = phist[0];
+	float fprev = phist[numbins - 1];
+	for (int i = 0; i < numbins - 1; ++i) {
+		float forg = phist[i];
+		phist[i] = (fprev + forg + phist[i + 1]) * 0.33333333f;
+		fprev = forg;
+	}
+	phist[numbins - 1] = (fprev + phist[numbins - 1] + ffirst) * 0.3333333f;
+}
+
+constexpr float kFix = 1099511627776.f;        // 2^40
+constexpr float kFixInv = 1.f / 1099511627776.f;
+
+__global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict__ cand, const int *__restrict__ n_cand, int cap_cand,
+                                                     const __grid_constant__ SiftOctViews views, SiftKp *__restrict__ kp,
+                                                     int *__restrict__ kp_count, int max_kp) {
+	__shared__ unsigned long long s_hist[4][36];
+	__shared__ float s_h[4][36];
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n = min(*n_cand, cap_cand);
+	for (int i = blockIdx.x * 4 + w; i < n; i += gridDim.x * 4) {
+	SiftCand k = cand[i];
+	const SiftOctView v = views.o[k.oct];
+	const int rows = v.rows, cols = v.cols;
+	const size_t plane = (size_t)rows * cols;
+	if (v.claim[(size_t)k.frame * plane + (size_t)k.row * cols + k.col] != k.scan_id) continue;
+	const float *grad = v.grad + ((size_t)k.frame * kSiftScales + (k.index - 1)) * plane;
+	const float *orim = v.ori + ((size_t)k.frame * kSiftScales + (k.index - 1)) * plane;
+	float fscale = views.fscale0;
+	for (int o = 0; o < k.oct; ++o) fscale += fscale;
+	const float fSize = kSiftInitSigma * powf(2.0f, ((float)k.index + k.X[0]) / (float)kSiftScales);
+	const float frowstart = (float)k.row + k.X[1], fcolstart = (float)k.col + k.X[2];
+	const int rowstart = (int)(frowstart + 0.5f), colstart = (int)(fcolstart + 0.5f);
+	const float fexpmult = -1.0f / (2.0f * 1.5f * 1.5f * fSize * fSize);
+	const float fbinmult = 36.0f / (2 * SIFT_PI);
+	const float fbinadd = (float)(SIFT_PI + 0.001f) * fbinmult;
+	const int windowsize = (int)(fSize * 1.5f * 3.0f);
+	for (int b = lane; b < 36; b += 32) s_hist[w][b] = 0ull;
+	__syncwarp();
+	const int side = 2 * windowsize + 1;
+	for (int t = lane; t < side * side; t += 32) {
+		int rowcur = rowstart - windowsize + t / side, colcur = colstart - windowsize + t % side;
+		if (rowcur < 0 || rowcur >= rows - 2 || colcur < 0 || colcur >= cols - 2) continue;
+		float fdx = grad[(size_t)rowcur * cols + colcur];
+		if (fdx > 0) {
+			float fdrow = (float)rowcur - frowstart, fdcol = (float)colcur - fcolstart;
+			float fradius2 = fdrow * fdrow + fdcol * fdcol;
+			if ((float)(windowsize * windowsize) + 0.5f > fradius2) {
+				float fweight = expf(fradius2 * fexpmult);
+				int binindex = (int)(orim[(size_t)rowcur * cols + colcur] * fbinmult + fbinadd);
+				if (binindex > 36) binindex = 0;
+				if (binindex == 36) binindex = 35;
+				if (binindex < 0) binindex = 0;
+				atomicAdd(&s_hist[w][binindex], (unsigned long long)__float2ll_rn(fdx * fweight * kFix));
+			}
+		}
+	}
+	__syncwarp();
+	for (int b = lane; b < 36; b += 32) s_h[w][b] = __ll2float_rn((long long)s_hist[w][b]) * kFixInv;
+	__syncwarp();
+	if (lane != 0) continue;
+	float hists[36];
+	for (int b = 0; b < 36; ++b) hists[b] = s_h[w][b];
+	for (int it = 0; it < 6; ++it) smooth_histogram(hists);
+	float fmaxval = 0;
+	for (int b = 0; b < 36; ++b) if (hists[b] > fmaxval) fmaxval = hists[b];
+	fmaxval *= 0.8f;
+	const float foriadd = 0.5f * 2 * SIFT_PI / 36.0f - SIFT_PI, forimult = 2 * SIFT_PI / 36.0f;
+	int previndex = 35;
+	for (int index = 0; index < 36; ++index) {
+		if (index != 0) previndex = index - 1;
+		int nextindex = 0;
+		if (index != 35) nextindex = index + 1;
+		if (hists[index] <= hists[previndex] || hists[index] <= hists[nextindex] || hists[index] < fmaxval) continue;
+		float f0 = hists[previndex], f1 = hists[index], f2 = hists[nextindex];
+		if (f1 < 0) { f0 = -f0; f1 = -f1; f2 = -f2; }
+		float fpeak = 0.5f * (f0 - f2) / (f0 - 2.0f * f1 + f2);
+		float forient = (index + fpeak) * forimult + foriadd;
+		int slot = atomicAdd(&kp_count[k.frame], 1);
+		if (slot < max_kp) {
+			SiftKp q;
+			q.frame = k.frame; q.oct = k.oct; q.index = k.index; q.frow = frowstart; q.fcol = fcolstart; q.fsize = fSize; q.ori = forient;
+			q.key = ((unsigned long long)k.oct << 40) | ((unsigned long long)(unsigned)k.scan_id << 6) | (unsigned long long)index;
+			q.slot = -1;
+			kp[(size_t)k.frame * max_kp + slot] = q;
+		}
+	}
+	}
+}
+
+// output slot of every keypoint = number of keypoints of its frame with a larger key (reverse creation order)
+__global__ void k_sift_rank(SiftKp *__restrict__ kp, const int *__restrict__ kp_count, int max_kp) {
+	int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+	int n = min(kp_count[f], max_kp);
+	if (i >= n) return;
+	SiftKp *base = kp + (size_t)f * max_kp;
+	unsigned long long key = base[i].key;
+	int rank = 0;
+	for (int j = 0; j < n; ++j) rank += base[j].key > key;
+	base[i].slot = rank;
+}
+
+// ---- descriptor: MakeKeypoint / KeySample / AddSample / PlaceInIndex (:1409-1668), one CTA per keypoint -----------
+__global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict__ kp, const int *__restrict__ kp_count, int max_kp, int n_frames,
+                                                       const __grid_constant__ SiftOctViews views,
+                                                       float *__restrict__ out_xy, float *__restrict__ out_so, float *__restrict__ out_desc) {
+	__shared__ unsigned long long s_acc[128];
+	__shared__ float s_d[128];
+	__shared__ float s_scale;
+	__shared__ int s_clamped;
+	for (int item = blockIdx.x; item < n_frames * max_kp; item += gridDim.x) {
+	const int f = item / max_kp, i = item % max_kp;
+	if (i >= min(kp_count[f], max_kp)) continue;      // empty slot (block-uniform)
+	const SiftKp q = kp[(size_t)f * max_kp + i];
+	__syncthreads();
+	const SiftOctView v = views.o[q.oct];
+	const int rows = v.rows, cols = v.cols;
+	const size_t plane = (size_t)rows * cols;
+	const float *grad = v.grad + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
+	const float *orim = v.ori + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
+	s_acc[threadIdx.x] = 0ull;
+	__syncthreads();
+	const float fSize = q.fsize, frowstart = q.frow, fcolstart = q.fcol, keyori = q.ori;
+	const int rowstart = (int)(frowstart + 0.5f), colstart = (int)(fcolstart + 0.5f);
+	const float sinang = sinf(keyori), cosang = cosf(keyori);
+	const float fdrow = frowstart - (float)rowstart, fdcol = fcolstart - (float)colstart;
+	const float frealsize = 3.0f * fSize;
+	const float firealsize = 1.0f / (3.0f * fSize);
+	const int windowsize = (int)(frealsize * SIFT_SQRT2 * 5.0f * 0.5f + 0.5f);
+	const float fsr = sinang * firealsize, fcr = cosang * firealsize, fdrr = -fdrow * firealsize, fdcr = -fdcol * firealsize;
+	const int side = 2 * windowsize + 1;
+	for (int t = threadIdx.x; t < side * side; t += blockDim.x) {
+		int row = t / side - windowsize, col = t % side - windowsize;
+		float frow = (float)row, fcol = (float)col;     // the reference's running fcol takes exactly these integer values
+		float rpos = fsr * fcol + fcr * frow + fdrr;
+		float cpos = fcr * fcol - fsr * frow + fdcr;
+		float rx = rpos + (2.0f - 0.5f);
+		float cx = cpos + (2.0f - 0.5f);
+		if (!(rx > -0.9999f && rx < 3.9999f && cx > -0.9999f && cx < 3.9999f)) continue;
+		int r = rowstart + row, c = colstart + col;
+		if (r < 0 || r >= rows || c < 0 || c >= cols) continue;
+		float mag = grad[(size_t)r * cols + c] * expf(-0.125f * (rpos * rpos + cpos * cpos));
+		float fo = orim[(size_t)r * cols + c] - keyori;
+		while (fo > 2 * SIFT_PI) fo -= 2 * SIFT_PI;
+		while (fo < 0) fo += 2 * SIFT_PI;
+		// PlaceInIndex
+		float oribin = fo * (8.0f / (2 * (float)SIFT_PI));
+		int newrow = rx < 0 ? (int)(rx - 1) : (int)rx;
+		float rfrac = rx - (float)newrow;
+		int newcol = cx < 0 ? (int)(cx - 1) : (int)cx;
+		float cfrac = cx - (float)newcol;
+		int neworient = oribin < 0 ? (int)(oribin - 1) : (int)oribin;
+		float ofrac = oribin - (float)neworient;
+		for (int a = 0; a < 2; ++a) {
+			if ((unsigned)(a + newrow) >= 4) continue;
+			float frowgrad = a == 0 ? mag * (1 - rfrac) : mag * rfrac;
+			for (int b = 0; b < 2; ++b) {
+				if ((unsigned)(b + newcol) >= 4) continue;
+				float fcolgrad = b == 0 ? frowgrad * (1 - cfrac) : frowgrad * cfrac;
+				int basebin = 8 * (4 * (a + newrow) + b + newcol);
+				for (int e = 0; e < 2; ++e) {
+					float forigrad = e == 0 ? fcolgrad * (1 - ofrac) : fcolgrad * ofrac;
+					atomicAdd(&s_acc[basebin + ((neworient + e) & 7)], (unsigned long long)__float2ll_rn(forigrad * kFix));
+				}
+			}
+		}
+	}
+	__syncthreads();
+	s_d[threadIdx.x] = __ll2float_rn((long long)s_acc[threadIdx.x]) * kFixInv;
+	__syncthreads();
+	// scalar normalisation branch (:1503-1516): NormalizeVec, clamp at 0.2, NormalizeVec again if anything was clamped
+	if (threadIdx.x == 0) {
+		float faccum = 0;
+		for (int j = 0; j < 128; ++j) faccum += s_d[j] * s_d[j];
+		s_scale = 1 / sqrtf(faccum);
+		s_clamped = 0;
+	}
+	__syncthreads();
+	float d = s_d[threadIdx.x] * s_scale;
+	if (d > 0.2f) { d = 0.2f; s_clamped = 1; }
+	s_d[threadIdx.x] = d;
+	__syncthreads();
+	if (s_clamped) {
+		if (threadIdx.x == 0) {
+			float faccum = 0;
+			for (int j = 0; j < 128; ++j) faccum += s_d[j] * s_d[j];
+			s_scale = 1 / sqrtf(faccum);
+		}
+		__syncthreads();
+		d = d * s_scale;
+	}
+	size_t o = (size_t)f * max_kp + q.slot;
+	out_desc[o * 128 + threadIdx.x] = d;
+	if (threadIdx.x == 0) {
+		float fscale = views.fscale0;
+		for (int k = 0; k < q.oct; ++k) fscale += fscale;
+		out_xy[2 * o] = fscale * fcolstart; out_xy[2 * o + 1] = fscale * frowstart;      // coord2D = (col, row), FEAT_SIFT_CPU.hpp:102-103
+		if (out_so) { out_so[2 * o] = fscale * fSize; out_so[2 * o + 1] = keyori; }
+	}
+	}
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+
+static SiftState *state(mc_ctx *ctx) {
+	if (!ctx->sift_state) ctx->sift_state = new SiftState();
+	return (SiftState *)ctx->sift_state;
+}
+
+void sift_free(mc_ctx *ctx) {
+	SiftState *s = (SiftState *)ctx->sift_state;
+	if (!s) return;
+	DevBuf *bufs[] = { &s->pyr, &s->tmp, &s->gray, &s->cand, &s->kp, &s->counters, &s->lut };
+	for (DevBuf *b : bufs) cudaFree(b->p);
+	delete s;
+	ctx->sift_state = nullptr;
+}
+
+// (re)plans the scale-space for a batch shape: octave sizes like GetKeypoints' loop (libsiftfast.cpp:344-348)
+static mc_status sift_plan(mc_ctx *ctx, SiftState *s, int B, int H, int W, int dbl, int max_kp) {
+	if (s->B == B && s->H == H && s->W == W && s->dbl == dbl && s->max_kp == max_kp) return MC_OK;
+	int rows = dbl ? 2 * H - 2 : H, cols = dbl ? 2 * W - 2 : W;
+	int n = 0;
+	size_t total = 0;
+	const int per_px = (kSiftScales + 3) + (kSiftScales + 2) + 2 * kSiftScales + 1;   // gauss, dog, grad, ori, claim
+	int r = rows, c = cols;
+	while (r > 12 && c > 12 && n < kSiftMaxOct) {
+		s->oct[n].rows = r; s->oct[n].cols = c; s->oct[n].plane = (size_t)r * c;
+		total += (size_t)r * c * per_px * B;
+		r >>= 1; c >>= 1; n++;
+	}
+	s->n_oct = n;
+	MC_TRY(reserve(ctx, s->pyr, total * sizeof(float) + 256));
+	MC_TRY(reserve(ctx, s->tmp, (size_t)rows * cols * B * sizeof(float) + 256));
+	float *p = (float *)s->pyr.p;
+	for (int o = 0; o < n; ++o) {
+		SiftOct &q = s->oct[o];
+		size_t pl = q.plane * B;
+		q.gauss = p; p += pl * (kSiftScales + 3);
+		q.dog = p; p += pl * (kSiftScales + 2);
+		q.grad = p; p += pl * kSiftScales;
+		q.ori = p; p += pl * kSiftScales;
+		q.claim = (int32_t *)p; p += pl;
+	}
+	s->cap_cand = B * (max_kp > 8192 ? max_kp : 8192) * 2;
+	MC_TRY(reserve(ctx, s->cand, (size_t)s->cap_cand * sizeof(SiftCand)));
+	MC_TRY(reserve(ctx, s->kp, (size_t)B * max_kp * sizeof(SiftKp)));
+	MC_TRY(reserve(ctx, s->counters, (size_t)(B + 1) * sizeof(int)));
+	if (!s->lut.p) {
+		MC_TRY(reserve(ctx, s->lut, 256 * sizeof(float)));
+		float lut[256];
+		for (int g = 0; g < 256; ++g) lut[g] = (float)(((float)g) * 1. / 255.);
+		MC_CUDA(cudaMemcpyAsync(s->lut.p, lut, sizeof(lut), cudaMemcpyHostToDevice, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	// GetKeypoints (:326-332) and OctaveKeypoints (:414-430)
+	float fnewscale = dbl ? 1.0f : 0.5f;
+	s->has_init = kSiftInitSigma > fnewscale;
+	if (s->has_init) make_kernel(sqrtf(kSiftInitSigma * kSiftInitSigma - fnewscale * fnewscale), s->k_init);
+	float fwidth = powf(2.0f, 1.0f / (float)kSiftScales);
+	float fincsigma = sqrtf(fwidth * fwidth - 1.0f);
+	float sigma = kSiftInitSigma;
+	for (int i = 1; i < kSiftScales + 3; ++i) { make_kernel(fincsigma * sigma, s->k_oct[i - 1]); sigma *= fwidth; }
+	s->B = B; s->H = H; s->W = W; s->dbl = dbl; s->max_kp = max_kp;
+	return MC_OK;
+}
+
+static inline dim3 grid2(int cols, int rows, int z, int bx) { return dim3((cols + bx - 1) / bx, rows, z); }
+
+mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, int W, int dbl, int max_kp,
+                              float *d_xy, float *d_so, float *d_desc, int32_t *d_counts) {
+	if (B < 1 || H < 8 || W < 8 || max_kp < 1 || (size_t)B * 3 * kSiftScales > 65535) { ctx->err = "mc_sift: bad batch shape"; return MC_ERR_ARG; }
+	SiftState *s = state(ctx);
+	MC_TRY(sift_plan(ctx, s, B, H, W, dbl ? 1 : 0, max_kp));
+	cudaStream_t st = ctx->stream;
+	const int TB = 128;
+	const float peak_thresh = 0.04f / (float)kSiftScales;
+	int *n_cand = (int *)s->counters.p, *kp_count = n_cand + 1;
+	MC_CUDA(cudaMemsetAsync(s->counters.p, 0, (size_t)(B + 1) * sizeof(int), st));
+	for (int o = 0; o < s->n_oct; ++o) MC_CUDA(cudaMemsetAsync(s->oct[o].claim, 0x7f, s->oct[o].plane * B * sizeof(int32_t), st));
+
+	SiftOct &o0 = s->oct[0];
+	const size_t gstride0 = o0.plane * (kSiftScales + 3);
+	if (s->n_oct > 0) {
+		float *base = s->has_init ? (float *)s->tmp.p : o0.gauss;
+		size_t bstride = s->has_init ? o0.plane : gstride0;
+		k_sift_base<<<grid2(o0.cols, o0.rows, B, TB), TB, 0, st>>>(d_gray, (const float *)s->lut.p, H, W, dbl ? 1 : 0, base, o0.rows, o0.cols);
+		MC_LAUNCH_CHECK();
+		if (s->has_init) {
+			// in-place blur of the reference = horizontal pass into a second buffer, vertical pass back (gauss[1] is free here)
+			float *t2 = o0.gauss + o0.plane;
+			k_sift_blur_h<<<grid2(o0.cols, o0.rows, B, TB), TB, 0, st>>>(base, bstride, t2, gstride0, o0.rows, o0.cols, s->k_init);
+			MC_LAUNCH_CHECK();
+			k_sift_blur_v<<<grid2(o0.cols, o0.rows, B, TB), TB, 0, st>>>(t2, gstride0, o0.gauss, gstride0, nullptr, nullptr, 0, o0.rows, o0.cols, s->k_init);
+			MC_LAUNCH_CHECK();
+		}
+	}
+	SiftOctViews views;
+	memset(&views, 0, sizeof(views));
+	views.fscale0 = dbl ? 0.5f : 1.0f;
+	for (int o = 0; o < s->n_oct; ++o) {
+		SiftOct &q = s->oct[o];
+		const size_t gstride = q.plane * (kSiftScales + 3), dstride = q.plane * (kSiftScales + 2);
+		dim3 g = grid2(q.cols, q.rows, B, TB);
+		for (int i = 1; i < kSiftScales + 3; ++i) {
+			k_sift_blur_h<<<g, TB, 0, st>>>(q.gauss + (size_t)(i - 1) * q.plane, gstride, (float *)s->tmp.p, q.plane, q.rows, q.cols, s->k_oct[i - 1]);
+			MC_LAUNCH_CHECK();
+			k_sift_blur_v<<<g, TB, 0, st>>>((const float *)s->tmp.p, q.plane, q.gauss + (size_t)i * q.plane, gstride,
+			                                q.gauss + (size_t)(i - 1) * q.plane, q.dog + (size_t)(i - 1) * q.plane, dstride, q.rows, q.cols, s->k_oct[i - 1]);
+			MC_LAUNCH_CHECK();
+		}
+		k_sift_gradori<<<grid2(q.cols, q.rows, B * kSiftScales, TB), TB, 0, st>>>(q.gauss, q.grad, q.ori, q.rows, q.cols);
+		MC_LAUNCH_CHECK();
+		if (q.rows > 10 && q.cols > 10) {
+			k_sift_detect<<<grid2(q.cols - 10, q.rows - 10, B * kSiftScales, TB), TB, 0, st>>>(q.dog, q.claim, q.rows, q.cols, o, peak_thresh,
+			                                                                                 (SiftCand *)s->cand.p, n_cand, s->cap_cand);
+			MC_LAUNCH_CHECK();
+		}
+		if (o + 1 < s->n_oct) {
+			SiftOct &nx = s->oct[o + 1];
+			k_sift_half<<<grid2(nx.cols, nx.rows, B, TB), TB, 0, st>>>(q.gauss + (size_t)kSiftScales * q.plane, gstride, q.cols, nx.gauss,
+			                                                           nx.plane * (kSiftScales + 3), nx.rows, nx.cols);
+			MC_LAUNCH_CHECK();
+		}
+		views.o[o].rows = q.rows; views.o[o].cols = q.cols; views.o[o].grad = q.grad; views.o[o].ori = q.ori; views.o[o].claim = q.claim;
+	}
+	// the numbers of extrema / keypoints are only known on the device: persistent grids loop over what is there
+	const int pgrid = ctx->num_sms * 8;
+	k_sift_orient<<<pgrid, 128, 0, st>>>((const SiftCand *)s->cand.p, n_cand, s->cap_cand, views, (SiftKp *)s->kp.p, kp_count, max_kp);
+	MC_LAUNCH_CHECK();
+	k_sift_rank<<<dim3((max_kp + 127) / 128, B), 128, 0, st>>>((SiftKp *)s->kp.p, kp_count, max_kp);
+	MC_LAUNCH_CHECK();
+	k_sift_describe<<<pgrid, 128, 0, st>>>((const SiftKp *)s->kp.p, kp_count, max_kp, B, views, d_xy, d_so, d_desc);
+	MC_LAUNCH_CHECK();
+	MC_CUDA(cudaMemcpyAsync(d_counts, kp_count, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+	return MC_OK;
+}
+
+} // namespace mc
+
+using namespace mc;
+
+extern "C" mc_status mc_sift_extract_dev(mc_ctx *ctx, const uint8_t *gray_dev, int n_images, int height, int width, int double_size,
+                                         int max_keypoints, float *xy_dev, float *scale_ori_dev, float *desc_dev, int32_t *counts_dev) {
+	if (!ctx) return MC_ERR_ARG;
+	if (!gray_dev || !xy_dev || !desc_dev || !counts_dev) { ctx->err = "mc_sift_extract_dev: null pointer"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	return sift_extract_device(ctx, gray_dev, n_images, height, width, double_size, max_keypoints, xy_dev, scale_ori_dev, desc_dev, counts_dev);
+}
+
+extern "C" mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_images, int height, int width, int double_size,
+                                     int max_keypoints, int32_t *counts, float *xy, float *scale_ori, float *desc) {
+	if (!ctx) return MC_ERR_ARG;
+	if (!gray || !counts || !xy || !desc) { ctx->err = "mc_sift_extract: null pointer"; return MC_ERR_ARG; }
+	if (n_images < 1 || max_keypoints < 1) { ctx->err = "mc_sift_extract: bad sizes"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	SiftState *s = state(ctx);
+	const size_t npx = (size_t)n_images * height * width, nk = (size_t)n_images * max_keypoints;
+	MC_TRY(reserve(ctx, s->gray, npx + nk * (2 + 2 + 128) * sizeof(float) + (size_t)n_images * sizeof(int32_t) + 1024));
+	uint8_t *d_gray = (uint8_t *)s->gray.p;
+	float *d_xy = (float *)(d_gray + ((npx + 255) & ~(size_t)255));
+	float *d_so = d_xy + nk * 2, *d_desc = d_so + nk * 2;
+	int32_t *d_counts = (int32_t *)(d_desc + nk * 128);
+	MC_CUDA(cudaMemcpyAsync(d_gray, gray, npx, cudaMemcpyHostToDevice, ctx->stream));
+	MC_TRY(sift_extract_device(ctx, d_gray, n_images, height, width, double_size, max_keypoints, d_xy, d_so, d_desc, d_counts));
+	MC_CUDA(cudaMemcpyAsync(counts, d_counts, (size_t)n_images * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	mc_status rc = MC_OK;
+	for (int f = 0; f < n_images; ++f) {
+		int n = counts[f];
+		if (n > max_keypoints) { n = max_keypoints; ctx->err = "mc_sift_extract: more keypoints than max_keypoints (counts[] holds the number found)"; rc = MC_ERR_CAPACITY; }
+		if (!n) continue;
+		size_t o = (size_t)f * max_keypoints;
+		MC_CUDA(cudaMemcpyAsync(xy + o * 2, d_xy + o * 2, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+		if (scale_ori) MC_CUDA(cudaMemcpyAsync(scale_ori + o * 2, d_so + o * 2, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaMemcpyAsync(desc + o * 128, d_desc + o * 128, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return rc;
+}
+
+/* test/bench introspection: one plane of the scale-space of the LAST mc_sift_extract* call.
+ * stack: 0 Gaussian (index 0..5), 1 DoG (0..4), 2 gradient magnitude (0..2 = Gaussian 1..3), 3 orientation (0..2) */
+extern "C" mc_status mc_sift_read_plane(mc_ctx *ctx, int frame, int octave, int stack, int index, float *out, int32_t *rows, int32_t *cols) {
+	if (!ctx) return MC_ERR_ARG;
+	SiftState *s = (SiftState *)ctx->sift_state;
+	if (!s || s->B == 0) { ctx->err = "mc_sift_read_plane: no extraction has run"; return MC_ERR_STATE; }
+	const int depth[4] = { kSiftScales + 3, kSiftScales + 2, kSiftScales, kSiftScales };
+	if (frame < 0 || frame >= s->B || octave < 0 || octave >= s->n_oct || stack < 0 || stack > 3 || index < 0 || index >= depth[stack]) {
+		ctx->err = "mc_sift_read_plane: bad index"; return MC_ERR_ARG;
+	}
+	const SiftOct &q = s->oct[octave];
+	if (rows) *rows = q.rows;
+	if (cols) *cols = q.cols;
+	if (!out) return MC_OK;
+	const float *base = stack == 0 ? q.gauss : stack == 1 ? q.dog : stack == 2 ? q.grad : q.ori;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	MC_CUDA(cudaMemcpyAsync(out, base + ((size_t)frame * depth[stack] + index) * q.plane, q.plane * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}

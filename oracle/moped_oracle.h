@@ -52,6 +52,14 @@ int mo_filter(int n_models, const int *match_offsets, const int *match_image, co
               const mo_camera *cams, int n_obj, const int *obj_model, const float *obj_pose, int min_points, float feat_dist,
               float min_score, unsigned char *keep, float *score, int *cluster_offsets, int *members);
 
+/* FEAT (SIFT) — moped_sift_oracle.c -------------------------------------------- */
+typedef struct { int octave, index, scan_row, scan_col, row, col; float X[3]; float fsize; int first_kp; } mo_sift_trace;
+int mo_sift_gauss_kernel(float fblur, float *kernel /* >= 64 floats */);
+int mo_sift(const uint8_t *gray, int height, int width, int double_size, int max_kp,
+            float *xy /* (col,row) */, float *scale_ori, float *desc /* x128 */);
+int mo_sift_debug(const uint8_t *gray, int height, int width, int double_size, int dbg_octave, float *dbg_gauss /* 6 images */,
+                  float *dbg_dog /* 5 images */, int max_trace, mo_sift_trace *trace, int *n_trace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,9 @@ def _load():
                                     _f32p, _f32p, _f32p, _u8p]),
         "mo_ransac": (C.c_int, [_u64p, C.c_int, _f32p, _f32p, _i32p, C.c_void_p, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 _f32p, C.POINTER(C.c_int)]),
+        "mo_sift": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]),
+        "mo_sift_debug": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+        "mo_sift_gauss_kernel": (C.c_int, [C.c_float, _f32p]),
         "mo_filter": (C.c_int, [C.c_int, _i32p, _i32p, _f32p, _f32p, camp, C.c_int, _i32p, _f32p, C.c_int, C.c_float, C.c_float,
                                 _u8p, _f32p, _i32p, _i32p]),
     }
@@ -202,3 +205,41 @@ def filter_objects(matches, cams, obj_model, obj_pose, params=(5, 4096.0, 2.0)):
     ns = lib().mo_filter(len(off) - 1, off, _i32(matches["image"]), _f32(matches["xy"]), _f32(matches["xyz"]), cams, n,
                          obj_model, obj_pose, params[0], params[1], params[2], keep, score, co, mem)
     return dict(keep=keep[:n].astype(bool), score=score[:n].copy(), offsets=co[:ns + 1].copy(), members=mem[:co[ns]].copy())
+
+
+SIFT_TRACE = np.dtype([("octave", np.int32), ("index", np.int32), ("scan_row", np.int32), ("scan_col", np.int32), ("row", np.int32),
+                       ("col", np.int32), ("X", np.float32, 3), ("fsize", np.float32), ("first_kp", np.int32)])
+
+
+def sift(gray_u8, double_size=True, max_kp=65536):
+    """FEAT_SIFT_CPU / libsiftfast restated (moped_sift_oracle.c): xy[n,2]=(col,row), scale_ori[n,2], desc[n,128], in the
+    order FEAT_SIFT_CPU emits them with one OpenMP thread."""
+    g = np.ascontiguousarray(gray_u8, dtype=np.uint8)
+    xy = np.zeros((max_kp, 2), np.float32)
+    so = np.zeros((max_kp, 2), np.float32)
+    desc = np.zeros((max_kp, 128), np.float32)
+    n = lib().mo_sift(g, g.shape[0], g.shape[1], 1 if double_size else 0, max_kp, xy, so, desc)
+    n = min(n, max_kp)
+    return xy[:n].copy(), so[:n].copy(), desc[:n].copy()
+
+
+def sift_octave_dims(height, width, double_size=True):
+    r, c = (2 * height - 2, 2 * width - 2) if double_size else (height, width)
+    dims = []
+    while r > 12 and c > 12:
+        dims.append((r, c))
+        r, c = r >> 1, c >> 1
+    return dims
+
+
+def sift_debug(gray_u8, double_size=True, octave=0, max_trace=65536):
+    """Gaussian (6) and DoG (5) images of one octave plus the accepted-extremum trace (creation order)."""
+    g = np.ascontiguousarray(gray_u8, dtype=np.uint8)
+    r, c = sift_octave_dims(g.shape[0], g.shape[1], double_size)[octave]
+    gauss = np.zeros((6, r, c), np.float32)
+    dog = np.zeros((5, r, c), np.float32)
+    trace = np.zeros(max_trace, SIFT_TRACE)
+    nt = C.c_int(0)
+    lib().mo_sift_debug(g, g.shape[0], g.shape[1], 1 if double_size else 0, octave, gauss.ctypes.data, dog.ctypes.data, max_trace,
+                        trace.ctypes.data, C.byref(nt))
+    return gauss, dog, trace[:min(nt.value, max_trace)].copy()
