@@ -261,7 +261,9 @@ mc_status mc_sift_read_plane(mc_ctx *ctx, int frame, int octave, int stack, int 
  *   "ransac_fused"         != 0: mc_pose_ransac / the frame pipeline use the single one-CTA-per-task RANSAC kernel
  *                          instead of the staged kernels (same results; kept for A/B measurements)
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
- *                          MATCH instead of ~40 kernel launches (same kernels, same results) */
+ *                          MATCH instead of ~40 kernel launches (same kernels, same results)
+ *   "sift_two_pass"        != 0: mc_sift_extract* blur with the separate row / column kernels instead of the fused
+ *                          shared-memory kernel (same bits; kept for A/B measurements) */
 mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value);
 
 /* ---- introspection for tests and bench ------------------------------------------------------ */

@@ -148,6 +148,7 @@ inline mc_status pinned(mc_ctx *ctx, size_t bytes) {
 // ---- stage entry points implemented in the .cu files (device pointers, async on ctx->stream) ----
 mc_status db_build_images(mc_ctx *ctx);
 void sift_free(mc_ctx *ctx);
+mc_status sift_set_two_pass(mc_ctx *ctx, int on);
 mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, int W, int dbl, int max_kp,
                               float *d_xy, float *d_so, float *d_desc, int32_t *d_counts);
 mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mode,

@@ -8,9 +8,11 @@
 // (1278x958 after doubling, 7 octaves) is ~110 MB and stays L2/HBM resident; the pyramid kernels are HBM/L2-bound
 // streaming kernels, the keypoint kernels (one warp / one CTA per keypoint) are latency-bound and small.
 //
-// Arithmetic: compiled with -fmad=false; sums are in the reference's source order with separate multiply and add,
-// '/' and sqrtf are IEEE, so the pyramid, the DoG extrema, the sub-pixel fit and hence the keypoint SET are
-// bit-identical to the C restatement (oracle/moped_sift_oracle.c). Only expf/atan2f/sinf/cosf/powf differ from
+// Arithmetic: sums are in the reference's source order; the convolution taps accumulate with explicit fused
+// multiply-add in tap order (one of the roundings -ffast-math leaves to the reference's compiler, see the oracle's
+// header), everything else is compiled with -fmad=false (separate multiply and add); '/' and sqrtf are IEEE. So the
+// pyramid, the DoG extrema, the sub-pixel fit and hence the keypoint SET are bit-identical to the C restatement
+// (oracle/moped_sift_oracle.c). Only expf/atan2f/sinf/cosf/powf differ from
 // glibc's by an ulp or two. Histogram and descriptor bins are accumulated in 64-bit fixed point (2^-40 units) with
 // shared-memory atomics: order-independent, hence deterministic, and closer to the exact sum than a float chain.
 //
@@ -45,9 +47,10 @@ struct SiftKp { int frame, oct, index; float frow, fcol, fsize, ori; unsigned lo
 struct SiftState {
 	int B = 0, H = 0, W = 0, dbl = -1, n_oct = 0, max_kp = 0, cap_cand = 0;
 	SiftOct oct[kSiftMaxOct];
-	DevBuf pyr, tmp, gray, cand, kp, counters, lut;
+	DevBuf pyr, tmp, tmp2, gray, cand, kp, counters, lut;
 	GaussK k_init, k_oct[kSiftScales + 2];
 	bool has_init = false;
+	bool two_pass = false;        // mc_set_option("sift_two_pass"): the unfused blur kernels (A/B aid, same bits)
 };
 
 // GaussianBlur's kernel (libsiftfast.cpp:470-508): ksize+1 weights enter the sum, ksize are normalised (host, glibc expf)
@@ -102,15 +105,15 @@ __global__ void k_sift_blur_h(const float *__restrict__ src, size_t fstride_src,
 	for (int j = 0; j < ksize; ++j) {
 		int x = c + j - width;
 		x = x < 0 ? 0 : (x >= cols ? cols - 1 : x);
-		acc += __ldg(p + x) * gk.k[j];
+		acc = __fmaf_rn(__ldg(p + x), gk.k[j], acc);
 	}
 	dst[(size_t)f * fstride_dst + (size_t)r * cols + c] = acc;
 }
 
 // ConvVertical (:548-571) fused with SubtractImage (:460-464): dst = blur_v(src); if dog: dog = prev - dst
-// (prev = the previous Gaussian image, same frame stride as dst; the DoG stack has its own frame stride)
+// (prev = the image being blurred; every stack has its own frame stride)
 __global__ void k_sift_blur_v(const float *__restrict__ src, size_t fstride_src, float *__restrict__ dst, size_t fstride_dst,
-                              const float *__restrict__ prev, float *__restrict__ dog, size_t fstride_dog, int rows, int cols,
+                              const float *__restrict__ prev, size_t fstride_prev, float *__restrict__ dog, size_t fstride_dog, int rows, int cols,
                               const __grid_constant__ GaussK gk) {
 	int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z;
 	if (c >= cols) return;
@@ -120,11 +123,93 @@ __global__ void k_sift_blur_v(const float *__restrict__ src, size_t fstride_src,
 	for (int j = 0; j < ksize; ++j) {
 		int y = r + j - width;
 		y = y < 0 ? 0 : (y >= rows ? rows - 1 : y);
-		acc += __ldg(p + (size_t)y * cols) * gk.k[j];
+		acc = __fmaf_rn(__ldg(p + (size_t)y * cols), gk.k[j], acc);
 	}
 	size_t o = (size_t)r * cols + c;
 	dst[(size_t)f * fstride_dst + o] = acc;
-	if (dog) dog[(size_t)f * fstride_dog + o] = prev[(size_t)f * fstride_dst + o] - acc;
+	if (dog) dog[(size_t)f * fstride_dog + o] = prev[(size_t)f * fstride_prev + o] - acc;
+}
+
+// GaussianBlur (:470-521) as ONE kernel: a CTA loads a 64x64 output tile plus its halo (replicate-clamped at the image
+// border like ConvHorizontal/ConvVertical's padded line buffers), runs the horizontal pass into shared memory (also for
+// the halo rows the vertical pass needs), then the vertical pass, and writes the Gaussian image and — SubtractImage
+// (:460-464) fused — the DoG image = (centre of the input tile) - result. Per output pixel the taps are summed in the
+// reference's order j = 0..ksize-1 exactly as in the two-pass kernels above, so the result is bit-identical to them.
+// Register blocking: a thread produces 8 consecutive outputs from one sliding window of ksize+7 shared-memory loads;
+// in the horizontal pass the lanes of a warp span ROWS (odd pitches -> conflict-free), in the vertical pass columns.
+// HBM traffic per blur: 1 plane read (+halo from L2), 2 planes written, instead of 6 plane passes unfused.
+template <int KS>
+__global__ void __launch_bounds__(256) k_sift_blur(const float *__restrict__ src, size_t fstride_src, float *__restrict__ dst, size_t fstride_dst,
+                                                   float *__restrict__ dog, size_t fstride_dog, int rows, int cols, const __grid_constant__ GaussK gk) {
+	constexpr int W = KS / 2, TW = 64, TH = 64, IH = TH + 2 * W, IW = TW + 2 * W, PIN = IW + 1, PMID = TW + 1, G = 8;
+	extern __shared__ float sm[];
+	float *s_in = sm, *s_mid = sm + IH * PIN;
+	const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH, f = blockIdx.z;
+	const float *p = src + (size_t)f * fstride_src;
+	for (int idx = threadIdx.x; idx < IH * IW; idx += 256) {
+		int i = idx / IW, j = idx - i * IW;
+		int y = r0 - W + i, x = c0 - W + j;
+		y = y < 0 ? 0 : (y >= rows ? rows - 1 : y);
+		x = x < 0 ? 0 : (x >= cols ? cols - 1 : x);
+		s_in[i * PIN + j] = __ldg(p + (size_t)y * cols + x);
+	}
+	__syncthreads();
+	for (int item = threadIdx.x; item < IH * (TW / G); item += 256) {
+		int row = item % IH, g = item / IH;
+		const float *in = s_in + row * PIN + g * G;
+		float v[KS + G - 1], acc[G];
+#pragma unroll
+		for (int t = 0; t < KS + G - 1; ++t) v[t] = in[t];
+#pragma unroll
+		for (int k = 0; k < G; ++k) acc[k] = 0.f;
+#pragma unroll
+		for (int j = 0; j < KS; ++j)
+#pragma unroll
+			for (int k = 0; k < G; ++k) acc[k] = __fmaf_rn(v[k + j], gk.k[j], acc[k]);
+#pragma unroll
+		for (int k = 0; k < G; ++k) s_mid[row * PMID + g * G + k] = acc[k];
+	}
+	__syncthreads();
+	for (int item = threadIdx.x; item < TW * (TH / G); item += 256) {
+		int col = item % TW, h = item / TW;
+		const float *in = s_mid + (h * G) * PMID + col;
+		float v[KS + G - 1], acc[G];
+#pragma unroll
+		for (int t = 0; t < KS + G - 1; ++t) v[t] = in[t * PMID];
+#pragma unroll
+		for (int k = 0; k < G; ++k) acc[k] = 0.f;
+#pragma unroll
+		for (int j = 0; j < KS; ++j)
+#pragma unroll
+			for (int k = 0; k < G; ++k) acc[k] = __fmaf_rn(v[k + j], gk.k[j], acc[k]);
+		const int x = c0 + col;
+		if (x < cols) {
+#pragma unroll
+			for (int k = 0; k < G; ++k) {
+				int y = r0 + h * G + k;
+				if (y < rows) {
+					size_t o = (size_t)y * cols + x;
+					dst[(size_t)f * fstride_dst + o] = acc[k];
+					if (dog) dog[(size_t)f * fstride_dog + o] = s_in[(h * G + k + W) * PIN + col + W] - acc[k];
+				}
+			}
+		}
+	}
+}
+
+template <int KS>
+static mc_status launch_blur_t(mc_ctx *ctx, const float *src, size_t fs_src, float *dst, size_t fs_dst, float *dog, size_t fs_dog,
+                               int rows, int cols, int B, const GaussK &gk) {
+	constexpr int W = KS / 2, IH = 64 + 2 * W, IW = 64 + 2 * W;
+	constexpr size_t smem = ((size_t)IH * (IW + 1) + (size_t)IH * 65) * sizeof(float);
+	static bool configured = false;
+	if (!configured) {
+		MC_CUDA(cudaFuncSetAttribute(k_sift_blur<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		configured = true;
+	}
+	k_sift_blur<KS><<<dim3((cols + 63) / 64, (rows + 63) / 64, B), 256, smem, ctx->stream>>>(src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, gk);
+	MC_LAUNCH_CHECK();
+	return MC_OK;
 }
 
 // HalfImageSize (:390-408)
@@ -483,7 +568,7 @@ static SiftState *state(mc_ctx *ctx) {
 void sift_free(mc_ctx *ctx) {
 	SiftState *s = (SiftState *)ctx->sift_state;
 	if (!s) return;
-	DevBuf *bufs[] = { &s->pyr, &s->tmp, &s->gray, &s->cand, &s->kp, &s->counters, &s->lut };
+	DevBuf *bufs[] = { &s->pyr, &s->tmp, &s->tmp2, &s->gray, &s->cand, &s->kp, &s->counters, &s->lut };
 	for (DevBuf *b : bufs) cudaFree(b->p);
 	delete s;
 	ctx->sift_state = nullptr;
@@ -505,6 +590,7 @@ static mc_status sift_plan(mc_ctx *ctx, SiftState *s, int B, int H, int W, int d
 	s->n_oct = n;
 	MC_TRY(reserve(ctx, s->pyr, total * sizeof(float) + 256));
 	MC_TRY(reserve(ctx, s->tmp, (size_t)rows * cols * B * sizeof(float) + 256));
+	MC_TRY(reserve(ctx, s->tmp2, (size_t)rows * cols * B * sizeof(float) + 256));
 	float *p = (float *)s->pyr.p;
 	for (int o = 0; o < n; ++o) {
 		SiftOct &q = s->oct[o];
@@ -538,6 +624,29 @@ static mc_status sift_plan(mc_ctx *ctx, SiftState *s, int B, int H, int W, int d
 	return MC_OK;
 }
 
+// dst = GaussianBlur(src) (+ dog = src - dst): the fused kernel for the tap counts the reference's sigmas produce
+// (11, 13, 17, 21, 25), the two-pass kernels through `tmp` for anything else. src and dst must be different buffers.
+static mc_status blur(mc_ctx *ctx, SiftState *s, const float *src, size_t fs_src, float *dst, size_t fs_dst, float *dog, size_t fs_dog,
+                      int rows, int cols, size_t plane, int B, const GaussK &gk) {
+	if (!s->two_pass) {
+		switch (gk.ksize) {
+		case 11: return launch_blur_t<11>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 13: return launch_blur_t<13>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 17: return launch_blur_t<17>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 21: return launch_blur_t<21>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 25: return launch_blur_t<25>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		default: break;
+		}
+	}
+	const int TB = 128;
+	dim3 g((cols + TB - 1) / TB, rows, B);
+	k_sift_blur_h<<<g, TB, 0, ctx->stream>>>(src, fs_src, (float *)s->tmp2.p, plane, rows, cols, gk);
+	MC_LAUNCH_CHECK();
+	k_sift_blur_v<<<g, TB, 0, ctx->stream>>>((const float *)s->tmp2.p, plane, dst, fs_dst, src, fs_src, dog, fs_dog, rows, cols, gk);
+	MC_LAUNCH_CHECK();
+	return MC_OK;
+}
+
 static inline dim3 grid2(int cols, int rows, int z, int bx) { return dim3((cols + bx - 1) / bx, rows, z); }
 
 mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, int W, int dbl, int max_kp,
@@ -559,14 +668,8 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 		size_t bstride = s->has_init ? o0.plane : gstride0;
 		k_sift_base<<<grid2(o0.cols, o0.rows, B, TB), TB, 0, st>>>(d_gray, (const float *)s->lut.p, H, W, dbl ? 1 : 0, base, o0.rows, o0.cols);
 		MC_LAUNCH_CHECK();
-		if (s->has_init) {
-			// in-place blur of the reference = horizontal pass into a second buffer, vertical pass back (gauss[1] is free here)
-			float *t2 = o0.gauss + o0.plane;
-			k_sift_blur_h<<<grid2(o0.cols, o0.rows, B, TB), TB, 0, st>>>(base, bstride, t2, gstride0, o0.rows, o0.cols, s->k_init);
-			MC_LAUNCH_CHECK();
-			k_sift_blur_v<<<grid2(o0.cols, o0.rows, B, TB), TB, 0, st>>>(t2, gstride0, o0.gauss, gstride0, nullptr, nullptr, 0, o0.rows, o0.cols, s->k_init);
-			MC_LAUNCH_CHECK();
-		}
+		if (s->has_init)       // the reference blurs in place; here: base image in `tmp` -> gauss[0]
+			MC_TRY(blur(ctx, s, base, bstride, o0.gauss, gstride0, nullptr, 0, o0.rows, o0.cols, o0.plane, B, s->k_init));
 	}
 	SiftOctViews views;
 	memset(&views, 0, sizeof(views));
@@ -574,14 +677,9 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 	for (int o = 0; o < s->n_oct; ++o) {
 		SiftOct &q = s->oct[o];
 		const size_t gstride = q.plane * (kSiftScales + 3), dstride = q.plane * (kSiftScales + 2);
-		dim3 g = grid2(q.cols, q.rows, B, TB);
-		for (int i = 1; i < kSiftScales + 3; ++i) {
-			k_sift_blur_h<<<g, TB, 0, st>>>(q.gauss + (size_t)(i - 1) * q.plane, gstride, (float *)s->tmp.p, q.plane, q.rows, q.cols, s->k_oct[i - 1]);
-			MC_LAUNCH_CHECK();
-			k_sift_blur_v<<<g, TB, 0, st>>>((const float *)s->tmp.p, q.plane, q.gauss + (size_t)i * q.plane, gstride,
-			                                q.gauss + (size_t)(i - 1) * q.plane, q.dog + (size_t)(i - 1) * q.plane, dstride, q.rows, q.cols, s->k_oct[i - 1]);
-			MC_LAUNCH_CHECK();
-		}
+		for (int i = 1; i < kSiftScales + 3; ++i)      // gauss[i] = blur(gauss[i-1]); dog[i-1] = gauss[i-1] - gauss[i]
+			MC_TRY(blur(ctx, s, q.gauss + (size_t)(i - 1) * q.plane, gstride, q.gauss + (size_t)i * q.plane, gstride,
+			            q.dog + (size_t)(i - 1) * q.plane, dstride, q.rows, q.cols, q.plane, B, s->k_oct[i - 1]));
 		k_sift_gradori<<<grid2(q.cols, q.rows, B * kSiftScales, TB), TB, 0, st>>>(q.gauss, q.grad, q.ori, q.rows, q.cols);
 		MC_LAUNCH_CHECK();
 		if (q.rows > 10 && q.cols > 10) {
@@ -651,6 +749,8 @@ extern "C" mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_ima
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	return rc;
 }
+
+mc_status mc::sift_set_two_pass(mc_ctx *ctx, int on) { state(ctx)->two_pass = on != 0; return MC_OK; }
 
 /* test/bench introspection: one plane of the scale-space of the LAST mc_sift_extract* call.
  * stack: 0 Gaussian (index 0..5), 1 DoG (0..4), 2 gradient magnitude (0..2 = Gaussian 1..3), 3 orientation (0..2) */

@@ -10,10 +10,14 @@
  * branches: ConvHorizontal/ConvVertical/ConvBuffer (:523-581), GradOriImages with libm atan2f (:959-992), the
  * scalar descriptor normalisation (:1503-1516). Those are what this file follows.
  *
- * Arithmetic: every sum is written in the reference's source order with separate multiply and add (this file is
- * compiled with -ffp-contract=off). The reference itself is built with -ffast-math, so ITS sums may be
- * re-associated/vectorised by the compiler: parity against oracle/_ref is to tolerance (tests/test_sift_oracle.py
- * states it), parity CUDA-vs-this-file is exact up to the libm calls (expf, atan2f, sinf, cosf, powf).
+ * Arithmetic: every sum is written in the reference's source order. The convolution taps (ConvBuffer) accumulate with
+ * fused multiply-add in tap order; everything else uses separate multiply and add (this file is compiled with
+ * -ffp-contract=off). The reference itself is built with -ffast-math -march=native: its compiler may re-associate,
+ * vectorise and contract the sums (the x86-64-v3 build in oracle/_ref has 8-lane partial sums and a mix of vfmadd and
+ * vmul/vadd in ConvBuffer), so there is no single "reference rounding"; both variants of this file were measured to be
+ * equally close to oracle/_ref (same keypoint lists, mean |d coord2D| 3e-5 px). Parity against oracle/_ref is therefore
+ * to tolerance (tests/test_sift_oracle.py states it); parity CUDA-vs-this-file is exact up to the libm calls (expf,
+ * atan2f, sinf, cosf, powf).
  *
  * Keypoint order: the reference prepends to a linked list (libsiftfast.cpp:941-951,1423); with one OpenMP thread
  * the list FEAT_SIFT_CPU walks is the exact reverse of creation order. With several threads the row order and the
@@ -60,7 +64,7 @@ int mo_sift_gauss_kernel(float fblur, float *kernel /* >= 64 */) {
 static void conv_line(const float *buf, const float *kernel, int n, int ksize, float *out, int ostride) {
 	for (int i = 0; i < n; ++i) {
 		float faccum = 0;
-		for (int j = 0; j < ksize; ++j) faccum += buf[i + j] * kernel[j];
+		for (int j = 0; j < ksize; ++j) faccum = fmaf(buf[i + j], kernel[j], faccum);
 		out[(size_t)i * ostride] = faccum;
 	}
 }

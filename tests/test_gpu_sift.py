@@ -95,3 +95,20 @@ def test_capacity_and_degenerate_inputs(gpu_ctx, gold):
     assert len(gpu_ctx.sift(np.zeros((12, 40), np.uint8), False)[0]) == 0       # no octave at all (rows <= 12)
     xy, so, desc = gpu_ctx.sift(im, True)                                        # the context still works afterwards
     assert len(xy) == len(gold["bag0_crop_double/xy"]) or abs(len(xy) - len(gold["bag0_crop_double/xy"])) <= 2
+
+
+def test_fused_blur_equals_two_pass_kernels(gpu_ctx, gold):
+    """The shared-memory fused Gaussian kernel and the separate row/column kernels sum the taps in the same order."""
+    im = gold["ex2_odd_double/image"]
+    try:
+        fused = gpu_ctx.sift(im, True)
+        planes = [gpu_ctx.sift_plane(0, o, 1, 4) for o in (0, 2)]
+        gpu_ctx.set_option("sift_two_pass", 1)
+        two = gpu_ctx.sift(im, True)
+        planes2 = [gpu_ctx.sift_plane(0, o, 1, 4) for o in (0, 2)]
+    finally:
+        gpu_ctx.set_option("sift_two_pass", 0)
+    for a, b in zip(fused, two):
+        assert np.array_equal(a, b)
+    for a, b in zip(planes, planes2):
+        assert np.array_equal(a, b)
