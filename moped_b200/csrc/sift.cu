@@ -220,22 +220,30 @@ __global__ void k_sift_half(const float *__restrict__ src, size_t fstride_src, i
 	dst[(size_t)f * fstride_dst + (size_t)r * ncols + c] = src[(size_t)f * fstride_src + (size_t)(2 * r) * cols + 2 * c];
 }
 
-// GradOriImages (:959-992) of the Gaussian images 1..3 (blockIdx.z = frame*3 + (index-1))
-__global__ void k_sift_gradori(const float *__restrict__ gauss, float *__restrict__ grad, float *__restrict__ ori, int rows, int cols) {
-	int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, f = blockIdx.z / kSiftScales, s = blockIdx.z % kSiftScales;
+// GradOriImages (:959-992) of the Gaussian images 1..3 (blockIdx.z = frame*3 + (index-1)); a block covers 128 columns x 8 rows
+constexpr int kRowsPerBlock = 8;
+__global__ void __launch_bounds__(128) k_sift_gradori(const float *__restrict__ gauss, float *__restrict__ grad, float *__restrict__ ori, int rows, int cols) {
+	const int j = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.z / kSiftScales, s = blockIdx.z % kSiftScales;
 	if (j >= cols) return;
-	size_t plane = (size_t)rows * cols;
-	const float *p = gauss + ((size_t)f * (kSiftScales + 3) + s + 1) * plane + (size_t)i * cols;
-	float fdiffc, fdiffr;
-	if (j == 0) fdiffc = 2.0f * (p[1] - p[0]);
-	else if (j == cols - 1) fdiffc = 2.0f * (p[j] - p[j - 1]);
-	else fdiffc = p[j + 1] - p[j - 1];
-	if (i == 0) fdiffr = 2.0f * (p[j] - p[cols + j]);
-	else if (i == rows - 1) fdiffr = 2.0f * (p[-cols + j] - p[j]);
-	else fdiffr = p[-cols + j] - p[cols + j];
-	size_t o = ((size_t)f * kSiftScales + s) * plane + (size_t)i * cols + j;
-	grad[o] = sqrtf(fdiffc * fdiffc + fdiffr * fdiffr);
-	ori[o] = atan2f(fdiffr, fdiffc);
+	const size_t plane = (size_t)rows * cols;
+	const float *img = gauss + ((size_t)f * (kSiftScales + 3) + s + 1) * plane;
+	const int i0 = blockIdx.y * kRowsPerBlock;
+#pragma unroll
+	for (int k = 0; k < kRowsPerBlock; ++k) {
+		const int i = i0 + k;
+		if (i >= rows) break;
+		const float *p = img + (size_t)i * cols;
+		float fdiffc, fdiffr;
+		if (j == 0) fdiffc = 2.0f * (p[1] - p[0]);
+		else if (j == cols - 1) fdiffc = 2.0f * (p[j] - p[j - 1]);
+		else fdiffc = p[j + 1] - p[j - 1];
+		if (i == 0) fdiffr = 2.0f * (p[j] - p[cols + j]);
+		else if (i == rows - 1) fdiffr = 2.0f * (p[-cols + j] - p[j]);
+		else fdiffr = p[-cols + j] - p[cols + j];
+		size_t o = ((size_t)f * kSiftScales + s) * plane + (size_t)i * cols + j;
+		grad[o] = sqrtf(fdiffc * fdiffc + fdiffr * fdiffr);
+		ori[o] = atan2f(fdiffr, fdiffc);
+	}
 }
 
 // ---- extrema ---------------------------------------------------------------------------------------------------
@@ -313,17 +321,35 @@ __device__ float fit_quadratic(float *X, const float *d0, const float *d1, const
 // tests bids its scan id with atomicMin and k_sift_orient keeps the winner — the same survivor.
 __global__ void k_sift_detect(const float *__restrict__ dog, int32_t *__restrict__ claim, int rows, int cols, int oct, float peak_thresh,
                               SiftCand *__restrict__ cand, int *__restrict__ n_cand, int cap_cand) {
-	int c0 = blockIdx.x * blockDim.x + threadIdx.x + 5, r0 = blockIdx.y + 5;
-	int f = blockIdx.z / kSiftScales, index = blockIdx.z % kSiftScales + 1;
-	if (c0 >= cols - 5) return;
-	size_t plane = (size_t)rows * cols;
+	const int cx = blockIdx.x * blockDim.x + threadIdx.x + 5;
+	const int f = blockIdx.z / kSiftScales, index = blockIdx.z % kSiftScales + 1;
+	const bool valid = cx < cols - 5;                  // no early exit: every lane takes part in the shuffles below
+	const int c0 = valid ? cx : cols - 6;
+	const size_t plane = (size_t)rows * cols;
 	const float *d1 = dog + ((size_t)f * (kSiftScales + 2) + index) * plane;
-	float fval = d1[(size_t)r0 * cols + c0];
-	if (!(fabsf(fval) > peak_thresh * 0.8f)) return;
 	const float *d0 = d1 - plane, *d2 = d1 + plane;
+	// the thread walks down its column keeping (up, centre, down) in registers and gets (left, right) from its warp
+	// neighbours: four of the 26 neighbour comparisons cost no extra load and reject most threshold passers before
+	// the full test (which repeats them, so the outcome is exactly LocalMaxMin x3 + NotOnEdge)
+	const int rbeg = blockIdx.y * kRowsPerBlock + 5, rend = min(rbeg + kRowsPerBlock, rows - 5);
+	const int lane = threadIdx.x & 31;
+	float up = d1[(size_t)(rbeg - 1) * cols + c0], fval = d1[(size_t)rbeg * cols + c0];
+	for (int r0 = rbeg; r0 < rend; ++r0) {
+	const float down = d1[(size_t)(r0 + 1) * cols + c0];
+	const float cur = fval;
+	const float left = __shfl_up_sync(0xffffffffu, cur, 1), right = __shfl_down_sync(0xffffffffu, cur, 1);
+	bool go = valid && fabsf(cur) > peak_thresh * 0.8f;
+	if (go) {
+		if (cur > 0) go = !(up > cur || down > cur || (lane > 0 && left > cur) || (lane < 31 && c0 + 1 < cols - 5 && right > cur));
+		else go = !(cur > up || cur > down || (lane > 0 && cur > left) || (lane < 31 && c0 + 1 < cols - 5 && cur > right));
+	}
+	up = cur; fval = down;
+	if (!go) continue;
+	{ const float fval = cur;
 	if (!(local_max_min(fval, d1, cols, r0, c0) && local_max_min(fval, d0, cols, r0, c0) && local_max_min(fval, d2, cols, r0, c0) &&
 	      not_on_edge(d1, cols, r0, c0)))
-		return;
+		continue;
+	}
 	int rowstart = r0, colstart = c0, steps = 5;
 	float X[3], fquad;
 	for (;;) {
@@ -347,6 +373,7 @@ __global__ void k_sift_detect(const float *__restrict__ dog, int32_t *__restrict
 			cand[slot] = k;
 		}
 	}
+	}
 }
 
 // ---- orientation: AssignOriHist (:1276-1382), one warp per surviving extremum ---------------------------------
@@ -369,10 +396,26 @@ __device__ __forceinline__ void smooth_histogram(float *phist) {       // Smooth
 constexpr float kFix = 1099511627776.f;        // 2^40
 constexpr float kFixInv = 1.f / 1099511627776.f;
 
+// 64-bit fixed-point accumulator in shared memory as (lo, hi) 32-bit words: a 64-bit atomicAdd on shared memory
+// compiles to a compare-and-swap spin loop (ATOMS.CAST.SPIN.64), two native 32-bit ATOMS.ADD do not. The carry out
+// of the low word is recovered from the value the first atomic returns; integer addition commutes, so the final
+// (hi, lo) pair is the exact sum whatever the order of arrival.
+struct Fix64 { unsigned int lo, hi; };
+__device__ __forceinline__ void fix_add(Fix64 *a, float v) {
+	unsigned long long q = (unsigned long long)__float2ll_rn(v * kFix);
+	unsigned int lo = (unsigned int)q, hi = (unsigned int)(q >> 32);
+	unsigned int old = atomicAdd(&a->lo, lo);
+	hi += (old + lo) < old;
+	if (hi) atomicAdd(&a->hi, hi);
+}
+__device__ __forceinline__ float fix_read(const Fix64 &a) {
+	return __ll2float_rn((long long)(((unsigned long long)a.hi << 32) | a.lo)) * kFixInv;
+}
+
 __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict__ cand, const int *__restrict__ n_cand, int cap_cand,
                                                      const __grid_constant__ SiftOctViews views, SiftKp *__restrict__ kp,
                                                      int *__restrict__ kp_count, int max_kp) {
-	__shared__ unsigned long long s_hist[4][36];
+	__shared__ Fix64 s_hist[4][36];
 	__shared__ float s_h[4][36];
 	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int n = min(*n_cand, cap_cand);
@@ -393,7 +436,7 @@ __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict_
 	const float fbinmult = 36.0f / (2 * SIFT_PI);
 	const float fbinadd = (float)(SIFT_PI + 0.001f) * fbinmult;
 	const int windowsize = (int)(fSize * 1.5f * 3.0f);
-	for (int b = lane; b < 36; b += 32) s_hist[w][b] = 0ull;
+	for (int b = lane; b < 36; b += 32) s_hist[w][b] = Fix64{0u, 0u};
 	__syncwarp();
 	const int side = 2 * windowsize + 1;
 	for (int t = lane; t < side * side; t += 32) {
@@ -409,12 +452,12 @@ __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict_
 				if (binindex > 36) binindex = 0;
 				if (binindex == 36) binindex = 35;
 				if (binindex < 0) binindex = 0;
-				atomicAdd(&s_hist[w][binindex], (unsigned long long)__float2ll_rn(fdx * fweight * kFix));
+				fix_add(&s_hist[w][binindex], fdx * fweight);
 			}
 		}
 	}
 	__syncwarp();
-	for (int b = lane; b < 36; b += 32) s_h[w][b] = __ll2float_rn((long long)s_hist[w][b]) * kFixInv;
+	for (int b = lane; b < 36; b += 32) s_h[w][b] = fix_read(s_hist[w][b]);
 	__syncwarp();
 	if (lane != 0) continue;
 	float hists[36];
@@ -462,7 +505,7 @@ __global__ void k_sift_rank(SiftKp *__restrict__ kp, const int *__restrict__ kp_
 __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict__ kp, const int *__restrict__ kp_count, int max_kp, int n_frames,
                                                        const __grid_constant__ SiftOctViews views,
                                                        float *__restrict__ out_xy, float *__restrict__ out_so, float *__restrict__ out_desc) {
-	__shared__ unsigned long long s_acc[128];
+	__shared__ Fix64 s_acc[128];
 	__shared__ float s_d[128];
 	__shared__ float s_scale;
 	__shared__ int s_clamped;
@@ -476,7 +519,7 @@ __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict_
 	const size_t plane = (size_t)rows * cols;
 	const float *grad = v.grad + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
 	const float *orim = v.ori + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
-	s_acc[threadIdx.x] = 0ull;
+	s_acc[threadIdx.x] = Fix64{0u, 0u};
 	__syncthreads();
 	const float fSize = q.fsize, frowstart = q.frow, fcolstart = q.fcol, keyori = q.ori;
 	const int rowstart = (int)(frowstart + 0.5f), colstart = (int)(fcolstart + 0.5f);
@@ -518,13 +561,13 @@ __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict_
 				int basebin = 8 * (4 * (a + newrow) + b + newcol);
 				for (int e = 0; e < 2; ++e) {
 					float forigrad = e == 0 ? fcolgrad * (1 - ofrac) : fcolgrad * ofrac;
-					atomicAdd(&s_acc[basebin + ((neworient + e) & 7)], (unsigned long long)__float2ll_rn(forigrad * kFix));
+					fix_add(&s_acc[basebin + ((neworient + e) & 7)], forigrad);
 				}
 			}
 		}
 	}
 	__syncthreads();
-	s_d[threadIdx.x] = __ll2float_rn((long long)s_acc[threadIdx.x]) * kFixInv;
+	s_d[threadIdx.x] = fix_read(s_acc[threadIdx.x]);
 	__syncthreads();
 	// scalar normalisation branch (:1503-1516): NormalizeVec, clamp at 0.2, NormalizeVec again if anything was clamped
 	if (threadIdx.x == 0) {
@@ -680,10 +723,10 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 		for (int i = 1; i < kSiftScales + 3; ++i)      // gauss[i] = blur(gauss[i-1]); dog[i-1] = gauss[i-1] - gauss[i]
 			MC_TRY(blur(ctx, s, q.gauss + (size_t)(i - 1) * q.plane, gstride, q.gauss + (size_t)i * q.plane, gstride,
 			            q.dog + (size_t)(i - 1) * q.plane, dstride, q.rows, q.cols, q.plane, B, s->k_oct[i - 1]));
-		k_sift_gradori<<<grid2(q.cols, q.rows, B * kSiftScales, TB), TB, 0, st>>>(q.gauss, q.grad, q.ori, q.rows, q.cols);
+		k_sift_gradori<<<grid2(q.cols, (q.rows + kRowsPerBlock - 1) / kRowsPerBlock, B * kSiftScales, TB), TB, 0, st>>>(q.gauss, q.grad, q.ori, q.rows, q.cols);
 		MC_LAUNCH_CHECK();
 		if (q.rows > 10 && q.cols > 10) {
-			k_sift_detect<<<grid2(q.cols - 10, q.rows - 10, B * kSiftScales, TB), TB, 0, st>>>(q.dog, q.claim, q.rows, q.cols, o, peak_thresh,
+			k_sift_detect<<<grid2(q.cols - 10, (q.rows - 10 + kRowsPerBlock - 1) / kRowsPerBlock, B * kSiftScales, TB), TB, 0, st>>>(q.dog, q.claim, q.rows, q.cols, o, peak_thresh,
 			                                                                                 (SiftCand *)s->cand.p, n_cand, s->cap_cand);
 			MC_LAUNCH_CHECK();
 		}

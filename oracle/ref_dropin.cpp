@@ -26,8 +26,10 @@
 #include <cluster/CLUSTER_MEAN_SHIFT_CPU.hpp>
 #include <pose/POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp>
 #include <filter/FILTER_PROJECTION_CPU.hpp>
+#include <feat/FEAT_SIFT_CPU.hpp>
 
 #include <pipeline_cuda.hpp>
+#include <FEAT_SIFT_CUDA.hpp>
 
 using namespace MopedNS;
 
@@ -72,8 +74,54 @@ static bool same_matches(const FrameData &a, const FrameData &b) {
 }
 static bool same_clusters(const FrameData &a, const FrameData &b) { return a.clusters == b.clusters; }
 
+/* `moped_dropin --sift case.bin`: step 1 side by side. case.bin = int32 {height, width, n_images, double_size} + pixels.
+ * FEAT_SIFT_CPU and FEAT_SIFT_CUDA are registered under the step name "SIFT" in two reference MopedPipelines and run
+ * on the same FrameData::images; the detectedFeatures lists are compared entry by entry (same imageIdx, coord2D and
+ * descriptor within the printed tolerances, same order). */
+static int sift_side_by_side(const char *path) {
+	FILE *f = fopen(path, "rb");
+	if (!f) return 2;
+	vector<int> hdr = readi(f, 4);
+	const int H = hdr[0], W = hdr[1], nImages = hdr[2], dbl = hdr[3];
+	vector<SP_Image> images;
+	for (int i = 0; i < nImages; i++) {
+		SP_Image im(new Image);
+		im->width = W; im->height = H;
+		im->data.resize((size_t)W * H);
+		if (fread(&im->data[0], 1, (size_t)W * H, f) != (size_t)W * H) return 3;
+		images.push_back(im);
+	}
+	fclose(f);
+	omp_set_num_threads(1);                      /* the reference's list order and duplicate suppression race otherwise */
+	MopedPipeline cpu, gpu;
+	cpu.addAlg( "SIFT", new FEAT_SIFT_CPU( dbl ? "-1" : "0" ) );
+	gpu.addAlg( "SIFT", new FEAT_SIFT_CUDA( dbl ? "-1" : "0" ) );
+	map<string,string> cfg;
+	list<MopedAlg *> ca = cpu.getAlgs(true), ga = gpu.getAlgs(true);
+	foreach( alg, ga ) alg->getConfig(cfg);
+	foreach( kv, cfg ) printf("CONFIG %s=%s\n", kv.first.c_str(), kv.second.c_str());
+	foreach( alg, ca ) { alg->getConfig(cfg); alg->setConfig(cfg); }     /* FEAT_SIFT_CPU sets libsiftfast's DoubleImSize here (:69-76) */
+	FrameData fdCpu, fdGpu;
+	fdCpu.images = images; fdGpu.images = images;
+	try {
+		foreach( alg, ca ) alg->process(fdCpu);
+		foreach( alg, ga ) alg->process(fdGpu);
+	} catch (string &e) { fprintf(stderr, "ERROR %s\n", e.c_str()); return 1; }
+	vector<FrameData::DetectedFeature> &a = fdCpu.detectedFeatures["SIFT"], &b = fdGpu.detectedFeatures["SIFT"];
+	size_t n = a.size() < b.size() ? a.size() : b.size(), same = 0;
+	float maxdxy = 0, maxdd = 0;
+	for (size_t i = 0; i < n; i++) {
+		float dxy = fmaxf(fabsf(a[i].coord2D[0] - b[i].coord2D[0]), fabsf(a[i].coord2D[1] - b[i].coord2D[1])), dd = 0;
+		for (int k = 0; k < 128; k++) dd = fmaxf(dd, fabsf(a[i].descriptor[k] - b[i].descriptor[k]));
+		if (a[i].imageIdx == b[i].imageIdx && dxy < 0.02f && dd < 5e-3f) { same++; maxdxy = fmaxf(maxdxy, dxy); maxdd = fmaxf(maxdd, dd); }
+	}
+	printf("SIFT cpu=%d gpu=%d same_in_order=%d max_dxy=%g max_ddesc=%g\n", (int)a.size(), (int)b.size(), (int)same, maxdxy, maxdd);
+	return 0;
+}
+
 int main(int argc, char **argv) {
 	if (argc < 2) return 2;
+	if (argc >= 3 && !strcmp(argv[1], "--sift")) return sift_side_by_side(argv[2]);
 	FILE *f = fopen(argv[1], "rb");
 	if (!f) return 2;
 	vector<int> hdr = readi(f, 4);

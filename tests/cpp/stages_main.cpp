@@ -6,14 +6,55 @@
 #include <cstdlib>
 #include <moped_api.hpp>
 #include <pipeline_cuda.hpp>
+#include <FEAT_SIFT_CUDA.hpp>
+#include <cstring>
 
 using namespace MopedNS;
 
 static std::vector<float> readf(FILE *f, size_t n) { std::vector<float> v(n); if (n && fread(&v[0], 4, n, f) != n) exit(3); return v; }
 static std::vector<int> readi(FILE *f, size_t n) { std::vector<int> v(n); if (n && fread(&v[0], 4, n, f) != n) exit(3); return v; }
 
+// `stages_main --sift case.bin out.bin`: FEAT_SIFT_CUDA through the plugin API. case.bin = int32 {height, width, n_images,
+// double_size} + pixels; out.bin = int32 n, then per feature {int32 imageIdx, float x, float y, float desc[128]}.
+static int sift_mode(const char *path, const char *out) {
+	FILE *f = fopen(path, "rb");
+	if (!f) return 2;
+	std::vector<int> hdr = readi(f, 4);
+	FrameData fd;
+	for (int i = 0; i < hdr[2]; i++) {
+		SP_Image im(new Image);
+		im->width = hdr[1]; im->height = hdr[0];
+		im->data.resize((size_t)hdr[0] * hdr[1]);
+		if (fread(&im->data[0], 1, im->data.size(), f) != im->data.size()) return 3;
+		fd.images.push_back(im);
+	}
+	fclose(f);
+	MopedPipeline pipeline;
+	pipeline.addAlg("SIFT", new FEAT_SIFT_CUDA(hdr[3] ? "-1" : "0"));
+	std::map<std::string, std::string> config;
+	std::list<MopedAlg *> algs = pipeline.getAlgs(true);
+	for (std::list<MopedAlg *>::iterator a = algs.begin(); a != algs.end(); ++a) (*a)->getConfig(config);
+	for (std::map<std::string, std::string>::iterator c = config.begin(); c != config.end(); ++c) printf("CONFIG %s=%s\n", c->first.c_str(), c->second.c_str());
+	try {
+		for (std::list<MopedAlg *>::iterator a = algs.begin(); a != algs.end(); ++a) (*a)->process(fd);
+	} catch (std::string &e) { fprintf(stderr, "ERROR %s\n", e.c_str()); return 1; }
+	std::vector<FrameData::DetectedFeature> &feats = fd.detectedFeatures["SIFT"];
+	FILE *o = fopen(out, "wb");
+	if (!o) return 2;
+	int n = (int)feats.size();
+	fwrite(&n, 4, 1, o);
+	for (int i = 0; i < n; i++) {
+		float xy[2] = { feats[i].coord2D[0], feats[i].coord2D[1] };
+		fwrite(&feats[i].imageIdx, 4, 1, o); fwrite(xy, 4, 2, o); fwrite(&feats[i].descriptor[0], 4, 128, o);
+	}
+	fclose(o);
+	printf("SIFT features %d\n", n);
+	return 0;
+}
+
 int main(int argc, char **argv) {
 	if (argc < 2) return 2;
+	if (argc >= 4 && !strcmp(argv[1], "--sift")) return sift_mode(argv[2], argv[3]);
 	FILE *f = fopen(argv[1], "rb");
 	if (!f) return 2;
 	std::vector<int> hdr = readi(f, 4);                   // n_models, N, Q, D

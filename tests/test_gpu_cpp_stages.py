@@ -73,3 +73,57 @@ def test_dropin_inside_reference_api(case):
     for name, pose in gpu:
         ref_pose = [p for n, p in cpu if n == name][0]
         assert np.abs(pose[4:] - ref_pose[4:]).max() < 2e-3       # independent RANSAC streams: same optimum up to LM tolerance
+
+
+# ---- step 1 (feature extraction): FEAT_SIFT_CUDA behind the plugin API ---------------------------
+
+def _write_sift_case(path, frames, double_size):
+    with open(path, "wb") as f:
+        np.array([frames.shape[1], frames.shape[2], frames.shape[0], int(double_size)], np.int32).tofile(f)
+        frames.astype(np.uint8).tofile(f)
+
+
+@pytest.fixture(scope="module")
+def sift_case(tmp_path_factory):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sift_golden.npz"))
+    im = g["bag0_crop_double/image"]
+    frames = np.stack([im, np.ascontiguousarray(im[::-1])])           # a two-camera frame: images of one size = one device batch
+    path = str(tmp_path_factory.mktemp("sift") / "sift_case.bin")
+    _write_sift_case(path, frames, True)
+    return path, frames, g
+
+
+def test_standalone_feat_sift_cuda(sift_case, tmp_path):
+    from moped_b200 import build
+    from sift_util import assert_same_keypoints
+    exe = build.build_stage_driver()
+    path, frames, g = sift_case
+    out = str(tmp_path / "feats.bin")
+    r = subprocess.run([exe, "--sift", path, out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "CONFIG SIFT:0:FEAT_SIFT_CUDA/ScaleOrigin=-1" in r.stdout, r.stdout
+    raw = np.fromfile(out, np.uint8)
+    n = int(raw[:4].view(np.int32)[0])
+    rec = raw[4:].view(np.dtype([("image", np.int32), ("xy", np.float32, 2), ("desc", np.float32, 128)]))
+    assert len(rec) == n and n > 400
+    assert np.all(np.diff(rec["image"]) >= 0) and set(rec["image"]) == {0, 1}       # appended image by image
+    first = rec[rec["image"] == 0]
+    assert_same_keypoints(first["xy"], first["desc"], g["bag0_crop_double/xy"], g["bag0_crop_double/desc"])   # the reference's output
+
+
+def test_dropin_feat_sift_inside_reference_api(sift_case):
+    """FEAT_SIFT_CPU and FEAT_SIFT_CUDA registered in two reference MopedPipelines, same FrameData::images."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "moped_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/moped_dropin not built (needs /root/reference at build time)")
+    path, frames, g = sift_case
+    r = subprocess.run([exe, "--sift", path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"SIFT cpu=(\d+) gpu=(\d+) same_in_order=(\d+) max_dxy=(\S+) max_ddesc=(\S+)", r.stdout)
+    assert m, r.stdout
+    cpu, gpu, same = int(m.group(1)), int(m.group(2)), int(m.group(3))
+    assert cpu > 400 and abs(cpu - gpu) <= 2
+    # an extremum on a threshold may exist on one side only (the reference is -ffast-math): entries after it shift by one
+    assert same >= 0.5 * cpu
+    if cpu == gpu:
+        assert same >= 0.99 * cpu
