@@ -591,6 +591,179 @@ def run_ransac_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# --workload sift: feature extraction, frames/s of FEAT on 640x480 frames
+# ------------------------------------------------------------------------------------------------
+def sift_config(args, world):
+    return {"workload": f"feature extraction (step 1, FEAT_SIFT): synthetic 640x480 grey frames (~2k SIFT keypoints each), ScaleOrigin -1 "
+                        f"(doubled image, 7 octaves x 3 scales); a step = a batch of {args.frames} frames",
+            "frames_per_step": args.frames, "image": "640x480 u8", "parallelism": "single-gpu" if world == 1 else f"frames partitioned x{world}"}
+
+
+def sift_images(n, first=0):
+    return np.stack([synth.make_image(first + i) for i in range(n)])
+
+
+def run_sift_reference(args, rank, world):
+    """--impl reference --workload sift: the reference's FEAT_SIFT_CPU/libsiftfast (oracle/_ref) with all host threads
+    (libsiftfast parallelises inside an image with OpenMP) on a bounded sample of the step's frames."""
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmoped_ref.so missing and /root/reference not present to build it"}))
+        return
+    cores = os.cpu_count() or 1
+    per = max(1, min(args.frames, 4))
+    imgs = sift_images(per)
+    tot, nk = 0.0, 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        k = sum(len(ref.sift(im, True)[0]) for im in imgs)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            tot += dt
+            nk += k
+        log(f"[reference] sift step {i}: {dt / per * 1e3:.1f} ms/frame, {k // per} keypoints/frame")
+    fps = per * args.steps / tot
+    out = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": tot / args.steps / per * args.frames * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": sift_config(args, world), "keypoints_per_frame": nk / (per * args.steps),
+           "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": f"{per} of the {args.frames} frames of a step per step; libsiftfast's own OpenMP parallelism (OMP default threads)"},
+           "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def run_sift_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from moped_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmoped_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lo, hi = rank * args.frames // world, (rank + 1) * args.frames // world      # frames are independent: partition, no collective
+    B = hi - lo
+    pool = [sift_images(B, first=1000 * p + lo) for p in range(2)]               # two different batches, alternated
+    H, W = pool[0].shape[1:]
+    max_kp = 4096
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    h_gray = [torch.from_numpy(p).pin_memory() for p in pool]
+    d_gray = [t.to(dev) for t in h_gray]
+    e_gray = torch.empty_like(d_gray[0])
+    d_xy = torch.zeros((B, max_kp, 2), dtype=torch.float32, device=dev)
+    d_so = torch.zeros((B, max_kp, 2), dtype=torch.float32, device=dev)
+    d_desc = torch.zeros((B, max_kp, 128), dtype=torch.float32, device=dev)
+    d_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_xy = torch.zeros((B, max_kp, 2), dtype=torch.float32).pin_memory()
+    h_desc = torch.zeros((B, max_kp, 128), dtype=torch.float32).pin_memory()
+    d2h = [0]
+
+    def extract(gray):
+        ctx.sift_dev(gray.data_ptr(), B, H, W, True, max_kp, d_xy.data_ptr(), d_so.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr())
+
+    def step_dev(i):
+        extract(d_gray[i % 2])
+
+    def step_e2e(i):
+        # the call a user makes, spelled out with pinned buffers: images up, features (counts, coord2D, descriptors) down
+        e_gray.copy_(h_gray[i % 2], non_blocking=True)
+        extract(e_gray)
+        h_cnt.copy_(d_cnt, non_blocking=True)
+        stream.synchronize()
+        n = 0
+        for f in range(B):
+            k = min(int(h_cnt[f]), max_kp)
+            h_xy[f, :k].copy_(d_xy[f, :k], non_blocking=True)
+            h_desc[f, :k].copy_(d_desc[f, :k], non_blocking=True)
+            n += k
+        stream.synchronize()
+        d2h[0] = 4 * B + n * (2 + 128) * 4
+
+    blur_ms, blur_bytes = [], [0.0]
+
+    def timed(fn, steps, warmup, collect=False):
+        for i in range(warmup):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+            if collect:
+                ms, by = ctx.sift_profile_read()
+                blur_ms.append(ms)
+                blur_bytes[0] = by
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launches - l0
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, launches = timed(step_dev, args.steps, args.warmup)
+    clocks = sampler.stop()
+    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
+    ctx.set_profiling(True)                       # separate pass: the event pairs sit between the kernels of the step
+    timed(step_dev, min(args.steps, 10), 1, collect=True)
+    ctx.set_profiling(False)
+    kp = int(d_cnt.sum().item())
+    if rank == 0:
+        ms_step = total_ms / args.steps
+        _, hbm_peak, src = measured_peaks()
+        kms = float(np.mean(blur_ms)) / 5.0                      # five octave-0 Gaussian+DoG launches per step
+        ach = blur_bytes[0] / 5.0 / (kms * 1e-3) / 1e9
+        plane_mb = B * (2 * H - 2) * (2 * W - 2) * 4 / 1e6
+        # the working set of a batch (scale-space of all frames) is far larger than L2 for B >= 2; for B = 1 it is L2 resident
+        l2 = (f"scale-space of a batch = {19 * 1.33 * plane_mb:.0f} MB > 126 MB L2, and two different batches alternate: not flushed"
+              if 19 * 1.33 * plane_mb > 2 * L2_BYTES / 1e6 else "scale-space fits L2 at this batch size (latency case); not flushed")
+        out = {"metric": METRIC, "value": args.frames * 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32 (u8 pixels in)", "data": "synthetic", "config": dict(sift_config(args, world), l2=l2, max_keypoints=max_kp),
+               "keypoints_per_frame_rank0": kp / B, "keypoints_per_s": kp / B * args.frames * 1e3 / ms_step,
+               "gpu_launches": int(launches), "clocks": clocks,
+               "e2e": {"value": args.frames * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(B * H * W), "d2h_bytes_per_step": int(d2h[0])},
+               "roofline": {"kernel": "k_sift_blur (fused Gaussian + DoG, octave 0)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": ach / hbm_peak, "traffic": (measured_traffic("k_sift_blur", frames=B) or {}).get("bytes"),
+                            "traffic_source": (measured_traffic("k_sift_blur", frames=B) or {}).get("source"),
+                            "peak_source": f"{src} (MEASURED_PEAKS.json hbm_gbs)", "kernel_ms": kms,
+                            "algorithmic_bytes_per_launch": blur_bytes[0] / 5.0,
+                            "algorithmic_bytes": "per launch and frame: 1 plane read + Gaussian plane + DoG plane written, plane = 1278 x 958 x 4 B"}}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                from oracle import ref
+                if ref.available():
+                    cores = os.cpu_count() or 1
+                    imgs = pool[0][:4]
+                    ref.sift(imgs[0], True)
+                    t0 = time.perf_counter()
+                    k = sum(len(ref.sift(im, True)[0]) for im in imgs)
+                    dt = time.perf_counter() - t0
+                    out["cpu_baseline"] = {"value": len(imgs) / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                                           "sample": f"{len(imgs)} frames of the step, FEAT_SIFT_CPU/libsiftfast with its own OpenMP parallelism",
+                                           "keypoints_per_frame": k / len(imgs)}
+            except Exception as e:
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -605,8 +778,9 @@ def main():
     ap.add_argument("--pose-warps", type=int, default=4, help="first-round hypotheses per RANSAC task (mc_set_tuning)")
     ap.add_argument("--chunks", type=int, default=1, help="MATCH launches per batch (mc_set_tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="frames", choices=["frames", "ransac"],
-                    help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s")
+    ap.add_argument("--workload", default="frames", choices=["frames", "ransac", "sift"],
+                    help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s; "
+                         "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1")
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--hyp", type=int, default=2048, help="hypotheses per cluster (ransac workload)")
     args = ap.parse_args()
@@ -619,6 +793,12 @@ def main():
         else:
             args.warmup = max(args.warmup, 3)
             run_ransac_ours(args, rank, world, local_rank)
+    elif args.workload == "sift":
+        if args.impl == "reference":
+            run_sift_reference(args, rank, world)
+        else:
+            args.warmup = max(args.warmup, 3)
+            run_sift_ours(args, rank, world, local_rank)
     elif args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -251,6 +251,14 @@ mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_images, int he
  * mc_process_frames_dev without leaving HBM. counts_dev may exceed max_keypoints (see above). */
 mc_status mc_sift_extract_dev(mc_ctx *ctx, const uint8_t *gray_dev, int n_images, int height, int width, int double_size,
                               int max_keypoints, float *xy_dev, float *scale_ori_dev, float *desc_dev, int32_t *counts_dev);
+/* Images in, objects out: FEAT chained to MATCH..FILTER2 for a batch of n_frames single-camera frames of one size (each
+ * frame is what Moped::processImages gets with one image, moped2/libmoped/src/moped.cpp:166-194; camera 0 of
+ * mc_set_cameras applies to every frame). Descriptors stay in HBM between the steps, normalised on the device with the
+ * MATCH stage's expression. Outputs like mc_process_frames; n_features (optional) = keypoints per frame;
+ * stage_ms (optional, 3 floats) = device time of FEAT (incl. the image upload), MATCH, CLUSTER..FILTER2. */
+mc_status mc_process_images(mc_ctx *ctx, const uint8_t *gray, int n_frames, int height, int width, int double_size, int max_keypoints,
+                            const mc_pipeline_params *params, int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose,
+                            float *obj_score, int32_t *n_features, int32_t *frame_info, float *stage_ms);
 /* test/bench introspection: one plane of the scale-space left by the last extraction (stack 0 Gaussian 0..5, 1 DoG 0..4,
  * 2 gradient magnitude 0..2, 3 orientation 0..2); out may be NULL to query the octave's size. */
 mc_status mc_sift_read_plane(mc_ctx *ctx, int frame, int octave, int stack, int index, float *out, int32_t *rows, int32_t *cols);
@@ -273,6 +281,9 @@ int64_t mc_kernel_launches(const mc_ctx *ctx);
  * matching kernel); mc_profile_read waits for the last such launch and returns its device time (ms) */
 mc_status mc_set_profiling(mc_ctx *ctx, int on);
 mc_status mc_profile_read(mc_ctx *ctx, float *coarse_kernel_ms);
+/* same for feature extraction: summed device time of the five octave-0 Gaussian+DoG launches (the dominant kernel of
+ * mc_sift_extract*) of the last extraction, and their algorithmic bytes (1 plane read + 2 planes written per launch) */
+mc_status mc_sift_profile_read(mc_ctx *ctx, float *blur_ms, double *algorithmic_bytes);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,9 @@ struct SiftState {
 	DevBuf pyr, tmp, tmp2, gray, cand, kp, counters, lut;
 	GaussK k_init, k_oct[kSiftScales + 2];
 	bool has_init = false;
+	cudaEvent_t ev[2 * (kSiftScales + 2)] = {};   // mc_set_profiling: around the five octave-0 Gaussian+DoG launches
+	bool ev_valid = false;
+	double ev_bytes = 0;
 	bool two_pass = false;        // mc_set_option("sift_two_pass"): the unfused blur kernels (A/B aid, same bits)
 };
 
@@ -490,8 +493,13 @@ __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict_
 }
 
 // output slot of every keypoint = number of keypoints of its frame with a larger key (reverse creation order)
-__global__ void k_sift_rank(SiftKp *__restrict__ kp, const int *__restrict__ kp_count, int max_kp) {
+__global__ void k_sift_rank(SiftKp *__restrict__ kp, const int *__restrict__ kp_count, int max_kp, int32_t *__restrict__ offsets, int n_frames) {
 	int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (offsets && f == 0 && i == 0) {            // compact output: frame f's keypoints start at offsets[f]
+		int acc = 0;
+		for (int k = 0; k < n_frames; ++k) { offsets[k] = acc; acc += min(kp_count[k], max_kp); }
+		offsets[n_frames] = acc;
+	}
 	int n = min(kp_count[f], max_kp);
 	if (i >= n) return;
 	SiftKp *base = kp + (size_t)f * max_kp;
@@ -503,6 +511,7 @@ __global__ void k_sift_rank(SiftKp *__restrict__ kp, const int *__restrict__ kp_
 
 // ---- descriptor: MakeKeypoint / KeySample / AddSample / PlaceInIndex (:1409-1668), one CTA per keypoint -----------
 __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict__ kp, const int *__restrict__ kp_count, int max_kp, int n_frames,
+                                                       const int32_t *__restrict__ offsets, int match_normalise,
                                                        const __grid_constant__ SiftOctViews views,
                                                        float *__restrict__ out_xy, float *__restrict__ out_so, float *__restrict__ out_desc) {
 	__shared__ Fix64 s_acc[128];
@@ -590,7 +599,22 @@ __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict_
 		__syncthreads();
 		d = d * s_scale;
 	}
-	size_t o = (size_t)f * max_kp + q.slot;
+	if (match_normalise) {
+		// what the MATCH stage does to every query first (MATCH_ANN_CPU.hpp:54-57,157; the expression of
+		// MATCH_CUDA::normalise): sequential sum of squares, inv = (float)(1. / sqrtf(ss)), scale — done here so
+		// that the descriptors can go to the matcher without leaving HBM
+		__syncthreads();
+		s_d[threadIdx.x] = d;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			float ss = 0;
+			for (int j = 0; j < 128; ++j) ss += s_d[j] * s_d[j];
+			s_scale = (float)(1. / (double)sqrtf(ss));
+		}
+		__syncthreads();
+		d = d * s_scale;
+	}
+	size_t o = offsets ? (size_t)offsets[f] + q.slot : (size_t)f * max_kp + q.slot;
 	out_desc[o * 128 + threadIdx.x] = d;
 	if (threadIdx.x == 0) {
 		float fscale = views.fscale0;
@@ -611,6 +635,7 @@ static SiftState *state(mc_ctx *ctx) {
 void sift_free(mc_ctx *ctx) {
 	SiftState *s = (SiftState *)ctx->sift_state;
 	if (!s) return;
+	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
 	DevBuf *bufs[] = { &s->pyr, &s->tmp, &s->tmp2, &s->gray, &s->cand, &s->kp, &s->counters, &s->lut };
 	for (DevBuf *b : bufs) cudaFree(b->p);
 	delete s;
@@ -693,7 +718,7 @@ static mc_status blur(mc_ctx *ctx, SiftState *s, const float *src, size_t fs_src
 static inline dim3 grid2(int cols, int rows, int z, int bx) { return dim3((cols + bx - 1) / bx, rows, z); }
 
 mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, int W, int dbl, int max_kp,
-                              float *d_xy, float *d_so, float *d_desc, int32_t *d_counts) {
+                              float *d_xy, float *d_so, float *d_desc, int32_t *d_counts, int32_t *d_offsets, int match_normalise) {
 	if (B < 1 || H < 8 || W < 8 || max_kp < 1 || (size_t)B * 3 * kSiftScales > 65535) { ctx->err = "mc_sift: bad batch shape"; return MC_ERR_ARG; }
 	SiftState *s = state(ctx);
 	MC_TRY(sift_plan(ctx, s, B, H, W, dbl ? 1 : 0, max_kp));
@@ -720,9 +745,17 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 	for (int o = 0; o < s->n_oct; ++o) {
 		SiftOct &q = s->oct[o];
 		const size_t gstride = q.plane * (kSiftScales + 3), dstride = q.plane * (kSiftScales + 2);
-		for (int i = 1; i < kSiftScales + 3; ++i)      // gauss[i] = blur(gauss[i-1]); dog[i-1] = gauss[i-1] - gauss[i]
+		const bool prof = ctx->profile && o == 0;      // bench.py's roofline: the dominant kernel timed on its own stream
+		for (int i = 1; i < kSiftScales + 3; ++i) {    // gauss[i] = blur(gauss[i-1]); dog[i-1] = gauss[i-1] - gauss[i]
+			if (prof) {
+				if (!s->ev[2 * i - 2]) { MC_CUDA(cudaEventCreate(&s->ev[2 * i - 2])); MC_CUDA(cudaEventCreate(&s->ev[2 * i - 1])); }
+				MC_CUDA(cudaEventRecord(s->ev[2 * i - 2], st));
+			}
 			MC_TRY(blur(ctx, s, q.gauss + (size_t)(i - 1) * q.plane, gstride, q.gauss + (size_t)i * q.plane, gstride,
 			            q.dog + (size_t)(i - 1) * q.plane, dstride, q.rows, q.cols, q.plane, B, s->k_oct[i - 1]));
+			if (prof) MC_CUDA(cudaEventRecord(s->ev[2 * i - 1], st));
+		}
+		if (prof) { s->ev_valid = true; s->ev_bytes = 3.0 * sizeof(float) * (double)q.plane * B * (kSiftScales + 2); }
 		k_sift_gradori<<<grid2(q.cols, (q.rows + kRowsPerBlock - 1) / kRowsPerBlock, B * kSiftScales, TB), TB, 0, st>>>(q.gauss, q.grad, q.ori, q.rows, q.cols);
 		MC_LAUNCH_CHECK();
 		if (q.rows > 10 && q.cols > 10) {
@@ -742,9 +775,9 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 	const int pgrid = ctx->num_sms * 8;
 	k_sift_orient<<<pgrid, 128, 0, st>>>((const SiftCand *)s->cand.p, n_cand, s->cap_cand, views, (SiftKp *)s->kp.p, kp_count, max_kp);
 	MC_LAUNCH_CHECK();
-	k_sift_rank<<<dim3((max_kp + 127) / 128, B), 128, 0, st>>>((SiftKp *)s->kp.p, kp_count, max_kp);
+	k_sift_rank<<<dim3((max_kp + 127) / 128, B), 128, 0, st>>>((SiftKp *)s->kp.p, kp_count, max_kp, d_offsets, B);
 	MC_LAUNCH_CHECK();
-	k_sift_describe<<<pgrid, 128, 0, st>>>((const SiftKp *)s->kp.p, kp_count, max_kp, B, views, d_xy, d_so, d_desc);
+	k_sift_describe<<<pgrid, 128, 0, st>>>((const SiftKp *)s->kp.p, kp_count, max_kp, B, d_offsets, match_normalise, views, d_xy, d_so, d_desc);
 	MC_LAUNCH_CHECK();
 	MC_CUDA(cudaMemcpyAsync(d_counts, kp_count, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
 	return MC_OK;
@@ -759,7 +792,7 @@ extern "C" mc_status mc_sift_extract_dev(mc_ctx *ctx, const uint8_t *gray_dev, i
 	if (!ctx) return MC_ERR_ARG;
 	if (!gray_dev || !xy_dev || !desc_dev || !counts_dev) { ctx->err = "mc_sift_extract_dev: null pointer"; return MC_ERR_ARG; }
 	MC_CUDA(cudaSetDevice(ctx->device));
-	return sift_extract_device(ctx, gray_dev, n_images, height, width, double_size, max_keypoints, xy_dev, scale_ori_dev, desc_dev, counts_dev);
+	return sift_extract_device(ctx, gray_dev, n_images, height, width, double_size, max_keypoints, xy_dev, scale_ori_dev, desc_dev, counts_dev, nullptr, 0);
 }
 
 extern "C" mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_images, int height, int width, int double_size,
@@ -776,7 +809,7 @@ extern "C" mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_ima
 	float *d_so = d_xy + nk * 2, *d_desc = d_so + nk * 2;
 	int32_t *d_counts = (int32_t *)(d_desc + nk * 128);
 	MC_CUDA(cudaMemcpyAsync(d_gray, gray, npx, cudaMemcpyHostToDevice, ctx->stream));
-	MC_TRY(sift_extract_device(ctx, d_gray, n_images, height, width, double_size, max_keypoints, d_xy, d_so, d_desc, d_counts));
+	MC_TRY(sift_extract_device(ctx, d_gray, n_images, height, width, double_size, max_keypoints, d_xy, d_so, d_desc, d_counts, nullptr, 0));
 	MC_CUDA(cudaMemcpyAsync(counts, d_counts, (size_t)n_images * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	mc_status rc = MC_OK;
@@ -791,6 +824,67 @@ extern "C" mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_ima
 	}
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	return rc;
+}
+
+/* Images in, objects out (SURVEY.md 8f rows 1+3 chained): FEAT -> MATCH -> CLUSTER -> POSE -> FILTER -> POSE2 -> FILTER2 for a
+ * batch of single-camera frames. The descriptors never leave HBM: the describe kernel writes them compacted and already
+ * normalised the way MATCH normalises its queries; only the per-frame keypoint counts (4 B each) come back to the host
+ * before MATCH is launched, because the frame partition of the query list is host-side state of the batch driver. */
+extern "C" mc_status mc_process_images(mc_ctx *ctx, const uint8_t *gray, int n_frames, int height, int width, int double_size, int max_keypoints,
+                                       const mc_pipeline_params *params, int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose,
+                                       float *obj_score, int32_t *n_features, int32_t *frame_info, float *stage_ms) {
+	if (!ctx) return MC_ERR_ARG;
+	if (!gray || !params || !n_objects || !obj_model || !obj_pose || !obj_score || n_frames < 1 || max_keypoints < 1 || max_objects < 1) {
+		ctx->err = "mc_process_images: bad argument"; return MC_ERR_ARG;
+	}
+	if (!ctx->d_db) { ctx->err = "mc_process_images: no database uploaded"; return MC_ERR_STATE; }
+	if (ctx->D != 128) { ctx->err = "mc_process_images: the database does not hold 128-d descriptors"; return MC_ERR_STATE; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	SiftState *s = state(ctx);
+	const size_t npx = (size_t)n_frames * height * width, nk = (size_t)n_frames * max_keypoints;
+	MC_TRY(reserve(ctx, s->gray, ((npx + 255) & ~(size_t)255) + nk * (2 + 128 + 1) * sizeof(float) + (size_t)(2 * n_frames + 2) * sizeof(int32_t) + 1024));
+	uint8_t *d_gray = (uint8_t *)s->gray.p;
+	float *d_xy = (float *)(d_gray + ((npx + 255) & ~(size_t)255));
+	float *d_desc = d_xy + nk * 2;
+	int32_t *d_qimg = (int32_t *)(d_desc + nk * 128);
+	int32_t *d_counts = d_qimg + nk, *d_offsets = d_counts + n_frames;
+	MC_TRY(pinned(ctx, (size_t)(2 * n_frames + 2) * sizeof(int32_t)));
+	cudaEvent_t ev[2];
+	if (stage_ms) { MC_CUDA(cudaEventCreate(&ev[0])); MC_CUDA(cudaEventCreate(&ev[1])); MC_CUDA(cudaEventRecord(ev[0], ctx->stream)); }
+	MC_CUDA(cudaMemcpyAsync(d_gray, gray, npx, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_qimg, 0, nk * sizeof(int32_t), ctx->stream));           // one camera per frame: imageIdx = 0
+	MC_TRY(sift_extract_device(ctx, d_gray, n_frames, height, width, double_size, max_keypoints, d_xy, nullptr, d_desc, d_counts, d_offsets, 1));
+	int32_t *h = (int32_t *)ctx->h_pinned;
+	MC_CUDA(cudaMemcpyAsync(h, d_counts, (size_t)(2 * n_frames + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	if (stage_ms) MC_CUDA(cudaEventRecord(ev[1], ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (stage_ms) { cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]); cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); }
+	std::vector<int32_t> offsets(h + n_frames, h + 2 * n_frames + 1);
+	bool overflow = false;
+	for (int f = 0; f < n_frames; ++f) {
+		if (n_features) n_features[f] = h[f];
+		overflow |= h[f] > max_keypoints;
+	}
+	if (overflow) { ctx->err = "mc_process_images: more keypoints than max_keypoints in a frame (n_features[] holds the numbers found)"; return MC_ERR_CAPACITY; }
+	return process_frames_host(ctx, d_desc, d_xy, d_qimg, offsets.data(), n_frames, params, max_objects, n_objects, obj_model, obj_pose, obj_score,
+	                           frame_info, stage_ms ? stage_ms + 1 : nullptr);
+}
+
+/* With mc_set_profiling on: device time (ms, summed) of the five octave-0 Gaussian+DoG launches of the last extraction and
+ * their algorithmic bytes (per launch: one plane read, the Gaussian and the DoG plane written, for every frame of the batch). */
+extern "C" mc_status mc_sift_profile_read(mc_ctx *ctx, float *blur_ms, double *algorithmic_bytes) {
+	if (!ctx || !blur_ms) return MC_ERR_ARG;
+	SiftState *s = (SiftState *)ctx->sift_state;
+	*blur_ms = 0.f;
+	if (!s || !ctx->profile || !s->ev_valid) { ctx->err = "mc_sift_profile_read: no profiled extraction"; return MC_ERR_STATE; }
+	for (int i = 0; i < kSiftScales + 2; ++i) {
+		float ms = 0.f;
+		MC_CUDA(cudaEventSynchronize(s->ev[2 * i + 1]));
+		MC_CUDA(cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]));
+		*blur_ms += ms;
+	}
+	if (algorithmic_bytes) *algorithmic_bytes = s->ev_bytes;
+	return MC_OK;
 }
 
 mc_status mc::sift_set_two_pass(mc_ctx *ctx, int on) { state(ctx)->two_pass = on != 0; return MC_OK; }

@@ -143,3 +143,22 @@ def make_hypotheses(cl, n_hyp_per_cluster: int = 2048, n_pts_align: int = 5, see
     quat = (rng.integers(0, 256, size=(H, 4)) / 256.0).astype(np.float32)
     quat[(quat == 0).all(axis=1)] = np.array([0, 0, 0, 0.5], np.float32)
     return dict(hyp_cluster=np.concatenate(hc), sample_pos=np.ascontiguousarray(np.concatenate(sp)), init_quat=quat)
+
+
+def make_image(seed: int = 0, height: int = 480, width: int = 640, n_blobs: int = 2600) -> np.ndarray:
+    """A synthetic grey 640x480 frame for the feature-extraction workload: Gaussian blobs of random size, sign and
+    contrast over a smooth background — blob-like structure at many scales, ~2k SIFT keypoints (BASELINE: 2k feats/frame)."""
+    rng = np.random.default_rng(BASE_SEED + 7919 * seed + 13)
+    im = np.zeros((height, width), np.float32)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    im += 0.15 * np.sin(xx / 97.0 + rng.uniform(0, 6)) * np.cos(yy / 71.0 + rng.uniform(0, 6))
+    for _ in range(n_blobs):
+        cy, cx = rng.uniform(0, height), rng.uniform(0, width)
+        s = float(np.exp(rng.uniform(np.log(1.0), np.log(6.0))))
+        a = rng.uniform(0.08, 0.3) * rng.choice([-1.0, 1.0])
+        r = int(4 * s) + 1
+        y0, y1, x0, x1 = max(0, int(cy) - r), min(height, int(cy) + r + 1), max(0, int(cx) - r), min(width, int(cx) + r + 1)
+        e = rng.uniform(0.6, 1.6)
+        im[y0:y1, x0:x1] += a * np.exp(-(((yy[y0:y1, x0:x1] - cy) * e) ** 2 + ((xx[y0:y1, x0:x1] - cx) / e) ** 2) / (2 * s * s))
+    im = np.clip(0.5 + im, 0.0, 1.0)
+    return (im * 255.0 + 0.5).astype(np.uint8)

@@ -103,3 +103,34 @@ def test_cuda_path_on_real_descriptors(real, gpu_ctx, oracle_mod):
     batch = gpu_ctx.process_frames(q_all, g["q_xy"], np.zeros(len(q_all), np.int32), fo, max_objects=64)
     for b, s1 in zip(batch, singles):
         assert np.array_equal(b["model"], s1["model"]) and np.array_equal(b["pose"], s1["pose"])
+
+
+@pytest.mark.gpu
+def test_images_in_objects_out(real, gpu_ctx):
+    """mc_process_images: FEAT chained to MATCH..FILTER2 on the device, on a frame the reference ships (timing.bag frame 4
+    = frame 1 of the fixture, stored as an image in tests/golden/sift_golden.npz). Same objects as the reference's CPU
+    pipeline run on the reference's own features, poses within the reference's seed-to-seed spread; and the same objects,
+    pose for pose, as feeding the device-extracted features through the host entry points by hand."""
+    g = real
+    sg = np.load(os.path.join(ROOT, "tests", "golden", "sift_golden.npz"))
+    im = sg["bag4_full_double/image"]
+    assert g["frame_names"][1] == "bag4" and len(sg["bag4_full_double/xy"]) == len(g["f1_q_desc"])
+    n_models = len(g["n_pts"])
+    gpu_ctx.db_upload(g["db_desc"], g["db_xyz"], g["model_of_row"], n_models)
+    gpu_ctx.set_cameras(g["K"], g["cam_pose"])
+    gpu_ctx.set_tuning(8, 8, 1)
+    frames = np.stack([im, im, np.ascontiguousarray(im[:, ::-1])])        # the third frame (mirrored) shows no known object pose-consistently
+    out = gpu_ctx.process_images(frames, True, max_keypoints=2048, max_objects=64, want_times=True)
+    assert out[0]["n_features"] in (582, 583) and out[0]["stage_ms"][0] > 0
+    _same_objects(out[0]["model"], out[0]["pose"], g, 1)
+    assert np.array_equal(out[0]["model"], out[1]["model"]) and np.array_equal(out[0]["pose"], out[1]["pose"])
+    # by hand: features to the host, the MATCH stage's normalisation on the host, then the frame entry point
+    xy, so, desc = gpu_ctx.sift(im, True)
+    ss = np.zeros(len(desc), np.float32)
+    for k in range(128):
+        ss = ss + desc[:, k] * desc[:, k]                                  # sequential fp32 sum like MATCH_CUDA::normalise
+    q = desc * (1.0 / np.sqrt(ss).astype(np.float64)).astype(np.float32)[:, None]
+    hand = gpu_ctx.process_frames(q, xy, np.zeros(len(q), np.int32), np.array([0, len(q)], np.int32), max_objects=64)[0]
+    assert np.array_equal(hand["model"], out[0]["model"]) and np.array_equal(hand["pose"], out[0]["pose"])
+    with pytest.raises(Exception, match="max_keypoints"):
+        gpu_ctx.process_images(frames, True, max_keypoints=100)
