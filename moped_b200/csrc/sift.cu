@@ -13,8 +13,9 @@
 // header), everything else is compiled with -fmad=false (separate multiply and add); '/' and sqrtf are IEEE. So the
 // pyramid, the DoG extrema, the sub-pixel fit and hence the keypoint SET are bit-identical to the C restatement
 // (oracle/moped_sift_oracle.c). Only expf/atan2f/sinf/cosf/powf differ from
-// glibc's by an ulp or two. Histogram and descriptor bins are accumulated in 64-bit fixed point (2^-40 units) with
-// shared-memory atomics: order-independent, hence deterministic, and closer to the exact sum than a float chain.
+// glibc's by an ulp or two. Orientation-histogram and descriptor bins are gathered into per-thread PRIVATE accumulators
+// (no two threads ever add to the same word) and combined in a fixed order: deterministic run to run and independent
+// of the batch, within float rounding of the reference's sequential chain.
 //
 // Output order = the order FEAT_SIFT_CPU emits with one OpenMP thread: the reverse of creation order
 // (libsiftfast.cpp:941-951,1423), i.e. octave descending, then DoG index / row / column descending, then
@@ -384,25 +385,13 @@ __global__ void k_sift_detect(const float *__restrict__ dog, int32_t *__restrict
 struct SiftOctView { int rows, cols; const float *grad, *ori; const int32_t *claim; };
 struct SiftOctViews { SiftOctView o[kSiftMaxOct]; float fscale0; };
 
-__device__ __forceinline__ void smooth_histogram(float *phist) {       // SmoothHistogram (:1395-1407)
-	const int numbins = 36;
-	float ffirst = phist[0];
-	float fprev = phist[numbins - 1];
-	for (int i = 0; i < numbins - 1; ++i) {
-		float forg = phist[i];
-		phist[i] = (fprev + forg + phist[i + 1]) * 0.33333333f;
-		fprev = forg;
-	}
-	phist[numbins - 1] = (fprev + phist[numbins - 1] + ffirst) * 0.3333333f;
-}
 
+// 64-bit fixed-point accumulator (2^-40 units) in shared memory as (lo, hi) 32-bit words: a 64-bit or a float atomicAdd on
+// shared memory compiles to a compare-and-swap spin loop (ATOMS.CAST.SPIN), two native 32-bit ATOMS.ADD do not, and — unlike
+// a plain load/add/store — they carry no dependency from one sample to the next. The carry out of the low word is
+// recovered from the value the first atomic returns. Integer addition commutes: the sum does not depend on the order.
 constexpr float kFix = 1099511627776.f;        // 2^40
 constexpr float kFixInv = 1.f / 1099511627776.f;
-
-// 64-bit fixed-point accumulator in shared memory as (lo, hi) 32-bit words: a 64-bit atomicAdd on shared memory
-// compiles to a compare-and-swap spin loop (ATOMS.CAST.SPIN.64), two native 32-bit ATOMS.ADD do not. The carry out
-// of the low word is recovered from the value the first atomic returns; integer addition commutes, so the final
-// (hi, lo) pair is the exact sum whatever the order of arrival.
 struct Fix64 { unsigned int lo, hi; };
 __device__ __forceinline__ void fix_add(Fix64 *a, float v) {
 	unsigned long long q = (unsigned long long)__float2ll_rn(v * kFix);
@@ -411,15 +400,12 @@ __device__ __forceinline__ void fix_add(Fix64 *a, float v) {
 	hi += (old + lo) < old;
 	if (hi) atomicAdd(&a->hi, hi);
 }
-__device__ __forceinline__ float fix_read(const Fix64 &a) {
-	return __ll2float_rn((long long)(((unsigned long long)a.hi << 32) | a.lo)) * kFixInv;
-}
 
 __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict__ cand, const int *__restrict__ n_cand, int cap_cand,
                                                      const __grid_constant__ SiftOctViews views, SiftKp *__restrict__ kp,
                                                      int *__restrict__ kp_count, int max_kp) {
-	__shared__ Fix64 s_hist[4][36];
-	__shared__ float s_h[4][36];
+	__shared__ Fix64 s_hist[4][36][32];   // [warp][bin][lane]: one private histogram per lane (bank pair = lane): no conflicts
+	__shared__ float s_h[4][2][36];       // smoothing ping-pong
 	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int n = min(*n_cand, cap_cand);
 	for (int i = blockIdx.x * 4 + w; i < n; i += gridDim.x * 4) {
@@ -427,11 +413,9 @@ __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict_
 	const SiftOctView v = views.o[k.oct];
 	const int rows = v.rows, cols = v.cols;
 	const size_t plane = (size_t)rows * cols;
-	if (v.claim[(size_t)k.frame * plane + (size_t)k.row * cols + k.col] != k.scan_id) continue;
+	if (v.claim[(size_t)k.frame * plane + (size_t)k.row * cols + k.col] != k.scan_id) continue;     // a duplicate (warp-uniform)
 	const float *grad = v.grad + ((size_t)k.frame * kSiftScales + (k.index - 1)) * plane;
 	const float *orim = v.ori + ((size_t)k.frame * kSiftScales + (k.index - 1)) * plane;
-	float fscale = views.fscale0;
-	for (int o = 0; o < k.oct; ++o) fscale += fscale;
 	const float fSize = kSiftInitSigma * powf(2.0f, ((float)k.index + k.X[0]) / (float)kSiftScales);
 	const float frowstart = (float)k.row + k.X[1], fcolstart = (float)k.col + k.X[2];
 	const int rowstart = (int)(frowstart + 0.5f), colstart = (int)(fcolstart + 0.5f);
@@ -439,42 +423,59 @@ __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict_
 	const float fbinmult = 36.0f / (2 * SIFT_PI);
 	const float fbinadd = (float)(SIFT_PI + 0.001f) * fbinmult;
 	const int windowsize = (int)(fSize * 1.5f * 3.0f);
-	for (int b = lane; b < 36; b += 32) s_hist[w][b] = Fix64{0u, 0u};
-	__syncwarp();
-	const int side = 2 * windowsize + 1;
-	for (int t = lane; t < side * side; t += 32) {
-		int rowcur = rowstart - windowsize + t / side, colcur = colstart - windowsize + t % side;
-		if (rowcur < 0 || rowcur >= rows - 2 || colcur < 0 || colcur >= cols - 2) continue;
-		float fdx = grad[(size_t)rowcur * cols + colcur];
-		if (fdx > 0) {
-			float fdrow = (float)rowcur - frowstart, fdcol = (float)colcur - fcolstart;
-			float fradius2 = fdrow * fdrow + fdcol * fdcol;
-			if ((float)(windowsize * windowsize) + 0.5f > fradius2) {
-				float fweight = expf(fradius2 * fexpmult);
-				int binindex = (int)(orim[(size_t)rowcur * cols + colcur] * fbinmult + fbinadd);
-				if (binindex > 36) binindex = 0;
-				if (binindex == 36) binindex = 35;
-				if (binindex < 0) binindex = 0;
-				fix_add(&s_hist[w][binindex], fdx * fweight);
+#pragma unroll
+	for (int b = 0; b < 36; ++b) s_hist[w][b][lane] = Fix64{0u, 0u};
+	// the window clipped to the rows/columns the reference visits (:1294-1300): 32 consecutive pixels per step
+	const int r_lo = max(rowstart - windowsize, 0), r_hi = min(rowstart + windowsize, rows - 3);
+	const int c_lo = max(colstart - windowsize, 0), c_hi = min(colstart + windowsize, cols - 3);
+	const int bw = c_hi - c_lo + 1;
+	if (bw > 0 && r_hi >= r_lo) {
+		int rowcur = r_lo + lane / bw, colcur = c_lo + lane % bw;
+		const float wlimit = (float)(windowsize * windowsize) + 0.5f;
+		while (rowcur <= r_hi) {
+			float fdx = grad[(size_t)rowcur * cols + colcur];
+			if (fdx > 0) {
+				float fdrow = (float)rowcur - frowstart, fdcol = (float)colcur - fcolstart;
+				float fradius2 = fdrow * fdrow + fdcol * fdcol;
+				if (wlimit > fradius2) {
+					float fweight = expf(fradius2 * fexpmult);
+					int binindex = (int)(orim[(size_t)rowcur * cols + colcur] * fbinmult + fbinadd);
+					if (binindex > 36) binindex = 0;
+					if (binindex == 36) binindex = 35;
+					if (binindex < 0) binindex = 0;
+					fix_add(&s_hist[w][binindex][lane], fdx * fweight);
+				}
 			}
+			colcur += 32;
+			while (colcur > c_hi) { colcur -= bw; ++rowcur; }
 		}
 	}
 	__syncwarp();
-	for (int b = lane; b < 36; b += 32) s_h[w][b] = fix_read(s_hist[w][b]);
+	for (int b = lane; b < 36; b += 32) {          // bin = exact integer sum of the 32 private copies (rotated: conflict-free)
+		unsigned long long sum = 0ull;
+		for (int t = 0; t < 32; ++t) { const Fix64 c = s_hist[w][b][(t + lane) & 31]; sum += ((unsigned long long)c.hi << 32) | c.lo; }
+		s_h[w][0][b] = __ll2float_rn((long long)sum) * kFixInv;
+	}
+	// SmoothHistogram x6 (:1329-1330,1395-1407), all bins in parallel: its in-place loop only ever reads ORIGINAL values
+	// (fprev/forg are saved originals, phist[i+1] and ffirst are not yet overwritten), so a pass is a circular 3-tap
+	// filter new[i] = ((old[i-1] + old[i]) + old[i+1]) * c with c = 0.33333333f, and 0.3333333f for the last bin
+	int cur = 0;
+	for (int it = 0; it < 6; ++it, cur ^= 1) {
+		__syncwarp();
+		const float *h = s_h[w][cur];
+		float *hn = s_h[w][cur ^ 1];
+		hn[lane] = (h[(lane + 35) % 36] + h[lane] + h[lane + 1]) * 0.33333333f;
+		if (lane < 4) { const int b = 32 + lane; hn[b] = (h[b - 1] + h[b] + h[(b + 1) % 36]) * (b == 35 ? 0.3333333f : 0.33333333f); }
+	}
 	__syncwarp();
-	if (lane != 0) continue;
-	float hists[36];
-	for (int b = 0; b < 36; ++b) hists[b] = s_h[w][b];
-	for (int it = 0; it < 6; ++it) smooth_histogram(hists);
-	float fmaxval = 0;
-	for (int b = 0; b < 36; ++b) if (hists[b] > fmaxval) fmaxval = hists[b];
+	const float *hists = s_h[w][cur];
+	float fmaxval = fmaxf(0.f, fmaxf(hists[lane], lane < 4 ? hists[32 + lane] : 0.f));      // scalar maximum from 0 (:1352-1356)
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) fmaxval = fmaxf(fmaxval, __shfl_xor_sync(0xffffffffu, fmaxval, o));
 	fmaxval *= 0.8f;
 	const float foriadd = 0.5f * 2 * SIFT_PI / 36.0f - SIFT_PI, forimult = 2 * SIFT_PI / 36.0f;
-	int previndex = 35;
-	for (int index = 0; index < 36; ++index) {
-		if (index != 0) previndex = index - 1;
-		int nextindex = 0;
-		if (index != 35) nextindex = index + 1;
+	for (int index = lane; index < 36; index += 32) {       // every peak makes a keypoint (:1362-1379); its rank comes from the key
+		const int previndex = index == 0 ? 35 : index - 1, nextindex = index == 35 ? 0 : index + 1;
 		if (hists[index] <= hists[previndex] || hists[index] <= hists[nextindex] || hists[index] < fmaxval) continue;
 		float f0 = hists[previndex], f1 = hists[index], f2 = hists[nextindex];
 		if (f1 < 0) { f0 = -f0; f1 = -f1; f2 = -f2; }
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict_
 			kp[(size_t)k.frame * max_kp + slot] = q;
 		}
 	}
+	__syncwarp();
 	}
 }
 
@@ -514,10 +516,17 @@ __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict_
                                                        const int32_t *__restrict__ offsets, int match_normalise,
                                                        const __grid_constant__ SiftOctViews views,
                                                        float *__restrict__ out_xy, float *__restrict__ out_so, float *__restrict__ out_desc) {
-	__shared__ Fix64 s_acc[128];
+	__shared__ float s_acc[8][128];        // [orientation bin][thread]: private accumulators, bank = thread % 32
 	__shared__ float s_d[128];
 	__shared__ float s_scale;
 	__shared__ int s_clamped;
+	// Gather formulation, no atomics: the 128 threads are 16 groups of 8 lanes, group g owns descriptor cell
+	// (ci, cj) = (g / 4, g % 4) and scans the bounding box of that cell's support (the samples whose trilinear footprint
+	// touches the cell: |rx - ci| < 1, |cx - cj| < 1) in the image, 8 consecutive pixels per step. Every pixel is put
+	// through the reference's own expressions (KeySample / AddSample / PlaceInIndex), so a sample adds to this cell
+	// exactly the terms the reference adds to it; only the ORDER of the float additions differs (fixed, so results are
+	// deterministic). Same-address shared-memory atomics of the scatter formulation ran at ~1 lane per clock per SM.
+	const int g = threadIdx.x >> 3, l8 = threadIdx.x & 7, ci = g >> 2, cj = g & 3;
 	for (int item = blockIdx.x; item < n_frames * max_kp; item += gridDim.x) {
 	const int f = item / max_kp, i = item % max_kp;
 	if (i >= min(kp_count[f], max_kp)) continue;      // empty slot (block-uniform)
@@ -528,8 +537,8 @@ __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict_
 	const size_t plane = (size_t)rows * cols;
 	const float *grad = v.grad + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
 	const float *orim = v.ori + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
-	s_acc[threadIdx.x] = Fix64{0u, 0u};
-	__syncthreads();
+#pragma unroll
+	for (int b8 = 0; b8 < 8; ++b8) s_acc[b8][threadIdx.x] = 0.f;
 	const float fSize = q.fsize, frowstart = q.frow, fcolstart = q.fcol, keyori = q.ori;
 	const int rowstart = (int)(frowstart + 0.5f), colstart = (int)(fcolstart + 0.5f);
 	const float sinang = sinf(keyori), cosang = cosf(keyori);
@@ -538,45 +547,58 @@ __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict_
 	const float firealsize = 1.0f / (3.0f * fSize);
 	const int windowsize = (int)(frealsize * SIFT_SQRT2 * 5.0f * 0.5f + 0.5f);
 	const float fsr = sinang * firealsize, fcr = cosang * firealsize, fdrr = -fdrow * firealsize, fdcr = -fdcol * firealsize;
-	const int side = 2 * windowsize + 1;
-	for (int t = threadIdx.x; t < side * side; t += blockDim.x) {
-		int row = t / side - windowsize, col = t % side - windowsize;
-		float frow = (float)row, fcol = (float)col;     // the reference's running fcol takes exactly these integer values
-		float rpos = fsr * fcol + fcr * frow + fdrr;
-		float cpos = fcr * fcol - fsr * frow + fdcr;
-		float rx = rpos + (2.0f - 0.5f);
-		float cx = cpos + (2.0f - 0.5f);
-		if (!(rx > -0.9999f && rx < 3.9999f && cx > -0.9999f && cx < 3.9999f)) continue;
-		int r = rowstart + row, c = colstart + col;
-		if (r < 0 || r >= rows || c < 0 || c >= cols) continue;
-		float mag = grad[(size_t)r * cols + c] * expf(-0.125f * (rpos * rpos + cpos * cpos));
-		float fo = orim[(size_t)r * cols + c] - keyori;
-		while (fo > 2 * SIFT_PI) fo -= 2 * SIFT_PI;
-		while (fo < 0) fo += 2 * SIFT_PI;
-		// PlaceInIndex
-		float oribin = fo * (8.0f / (2 * (float)SIFT_PI));
-		int newrow = rx < 0 ? (int)(rx - 1) : (int)rx;
-		float rfrac = rx - (float)newrow;
-		int newcol = cx < 0 ? (int)(cx - 1) : (int)cx;
-		float cfrac = cx - (float)newcol;
-		int neworient = oribin < 0 ? (int)(oribin - 1) : (int)oribin;
-		float ofrac = oribin - (float)neworient;
-		for (int a = 0; a < 2; ++a) {
-			if ((unsigned)(a + newrow) >= 4) continue;
-			float frowgrad = a == 0 ? mag * (1 - rfrac) : mag * rfrac;
-			for (int b = 0; b < 2; ++b) {
-				if ((unsigned)(b + newcol) >= 4) continue;
-				float fcolgrad = b == 0 ? frowgrad * (1 - cfrac) : frowgrad * cfrac;
-				int basebin = 8 * (4 * (a + newrow) + b + newcol);
-				for (int e = 0; e < 2; ++e) {
-					float forigrad = e == 0 ? fcolgrad * (1 - ofrac) : fcolgrad * ofrac;
-					fix_add(&s_acc[basebin + ((neworient + e) & 7)], forigrad);
+	// image-space bounding box of the cell's support: (rpos, cpos) = R(row, col) / (3 fSize) + (fdrr, fdcr) inverted at the
+	// cell centre (rpos, cpos) = (ci - 1.5, cj - 1.5), half extent (|cos| + |sin|) * 3 fSize, one pixel of slack for rounding;
+	// clipped to the reference's window and to the image
+	const float rp = (float)ci - 1.5f - fdrr, cp = (float)cj - 1.5f - fdcr;
+	const float rowc = frealsize * (cosang * rp - sinang * cp), colc = frealsize * (sinang * rp + cosang * cp);
+	const float half = frealsize * (fabsf(cosang) + fabsf(sinang)) + 1.0f;
+	// NOTE (nvcc/ptxas 12.9, sm_100a): max(max(x, -w), -r) was compiled to a three-input VIMNMX3 that dropped the
+	// negation of w (lower bounds came out as +windowsize); written as max(x, -min(w, r)) the code is correct.
+	const int r_lo = max((int)floorf(rowc - half), -min(windowsize, rowstart)), r_hi = min((int)ceilf(rowc + half), min(windowsize, rows - 1 - rowstart));
+	const int c_lo = max((int)floorf(colc - half), -min(windowsize, colstart)), c_hi = min((int)ceilf(colc + half), min(windowsize, cols - 1 - colstart));
+	const int bw = c_hi - c_lo + 1;
+	if (bw > 0 && r_hi >= r_lo) {
+		int row = r_lo + l8 / bw, col = c_lo + l8 % bw;
+		for (; row <= r_hi;) {
+			float frow = (float)row, fcol = (float)col;     // the reference's running fcol takes exactly these integer values
+			float rpos = fsr * fcol + fcr * frow + fdrr;
+			float cpos = fcr * fcol - fsr * frow + fdcr;
+			float rx = rpos + (2.0f - 0.5f);
+			float cx = cpos + (2.0f - 0.5f);
+			if (rx > -0.9999f && rx < 3.9999f && cx > -0.9999f && cx < 3.9999f) {
+				// PlaceInIndex: which of the (up to) 2 x 2 cells this sample feeds, and with which weights
+				int newrow = rx < 0 ? (int)(rx - 1) : (int)rx;
+				int newcol = cx < 0 ? (int)(cx - 1) : (int)cx;
+				const int a = ci - newrow, b = cj - newcol;
+				if ((unsigned)a < 2u && (unsigned)b < 2u) {
+					const int r = rowstart + row, c = colstart + col;
+					float mag = grad[(size_t)r * cols + c] * expf(-0.125f * (rpos * rpos + cpos * cpos));
+					float fo = orim[(size_t)r * cols + c] - keyori;
+					while (fo > 2 * SIFT_PI) fo -= 2 * SIFT_PI;
+					while (fo < 0) fo += 2 * SIFT_PI;
+					float oribin = fo * (8.0f / (2 * (float)SIFT_PI));
+					float rfrac = rx - (float)newrow;
+					float cfrac = cx - (float)newcol;
+					int neworient = oribin < 0 ? (int)(oribin - 1) : (int)oribin;
+					float ofrac = oribin - (float)neworient;
+					float frowgrad = a == 0 ? mag * (1 - rfrac) : mag * rfrac;
+					float fcolgrad = b == 0 ? frowgrad * (1 - cfrac) : frowgrad * cfrac;
+					s_acc[neworient & 7][threadIdx.x] += fcolgrad * (1 - ofrac);
+					s_acc[(neworient + 1) & 7][threadIdx.x] += fcolgrad * ofrac;
 				}
 			}
+			col += 8;
+			while (col > c_hi) { col -= bw; ++row; }
 		}
 	}
 	__syncthreads();
-	s_d[threadIdx.x] = fix_read(s_acc[threadIdx.x]);
+	{   // bin (g, l8) = sum over the group's 8 lanes, in a fixed rotated order (rotation keeps the reads conflict-free)
+		float sum = 0.f;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) sum += s_acc[l8][g * 8 + ((k + l8) & 7)];
+		s_d[threadIdx.x] = sum;
+	}
 	__syncthreads();
 	// scalar normalisation branch (:1503-1516): NormalizeVec, clamp at 0.2, NormalizeVec again if anything was clamped
 	if (threadIdx.x == 0) {
