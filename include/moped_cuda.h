@@ -271,7 +271,9 @@ mc_status mc_sift_read_plane(mc_ctx *ctx, int frame, int octave, int stack, int 
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
  *                          MATCH instead of ~40 kernel launches (same kernels, same results)
  *   "sift_two_pass"        != 0: mc_sift_extract* blur with the separate row / column kernels instead of the fused
- *                          shared-memory kernel (same bits; kept for A/B measurements) */
+ *                          shared-memory kernel (same bits; kept for A/B measurements)
+ *   "sift_describe_gather" != 0: descriptors by the cell-gather kernel (one CTA per keypoint) instead of the default
+ *                          warp-per-keypoint kernel with private accumulators (same terms, other summation order) */
 mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value);
 
 /* ---- introspection for tests and bench ------------------------------------------------------ */

@@ -163,6 +163,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
 	else if (k == "sift_two_pass") return sift_set_two_pass(ctx, (int)value);
+	else if (k == "sift_describe_gather") return sift_set_gather(ctx, (int)value);
 	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }
 	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs; }
 	return MC_OK;

@@ -149,6 +149,7 @@ inline mc_status pinned(mc_ctx *ctx, size_t bytes) {
 mc_status db_build_images(mc_ctx *ctx);
 void sift_free(mc_ctx *ctx);
 mc_status sift_set_two_pass(mc_ctx *ctx, int on);
+mc_status sift_set_gather(mc_ctx *ctx, int on);
 mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, int W, int dbl, int max_kp,
                               float *d_xy, float *d_so, float *d_desc, int32_t *d_counts, int32_t *d_offsets, int match_normalise);
 mc_status process_frames_host(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, const int32_t *frame_offsets, int n_frames,

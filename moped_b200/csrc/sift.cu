@@ -48,13 +48,14 @@ struct SiftKp { int frame, oct, index; float frow, fcol, fsize, ori; unsigned lo
 struct SiftState {
 	int B = 0, H = 0, W = 0, dbl = -1, n_oct = 0, max_kp = 0, cap_cand = 0;
 	SiftOct oct[kSiftMaxOct];
-	DevBuf pyr, tmp, tmp2, gray, cand, kp, counters, lut;
+	DevBuf pyr, tmp, tmp2, gray, cand, kp, counters, lut, offs;
 	GaussK k_init, k_oct[kSiftScales + 2];
 	bool has_init = false;
 	cudaEvent_t ev[2 * (kSiftScales + 2)] = {};   // mc_set_profiling: around the five octave-0 Gaussian+DoG launches
 	bool ev_valid = false;
 	double ev_bytes = 0;
-	bool two_pass = false;        // mc_set_option("sift_two_pass"): the unfused blur kernels (A/B aid, same bits)
+	bool two_pass = false;
+	bool gather = false;          // mc_set_option("sift_describe_gather"): the cell-gather descriptor kernel (A/B aid)        // mc_set_option("sift_two_pass"): the unfused blur kernels (A/B aid, same bits)
 };
 
 // GaussianBlur's kernel (libsiftfast.cpp:470-508): ksize+1 weights enter the sum, ksize are normalised (host, glibc expf)
@@ -647,6 +648,137 @@ __global__ void __launch_bounds__(128) k_sift_describe(const SiftKp *__restrict_
 	}
 }
 
+// The same step, scatter formulation with PRIVATE accumulators (the default): one warp per keypoint, every lane owns a full
+// 128-bin copy of the descriptor in shared memory ([bin][lane], bank = lane), walks the reference's window (KeySample's
+// double loop, clipped to the image) 32 consecutive pixels per step, evaluates each sample ONCE with the reference's
+// expressions and adds its up to 8 terms to its own copy — no atomics, no two lanes ever touch the same word. The 32
+// copies are then summed in a fixed rotated order (conflict-free) and re-zeroed in the same pass. Against the gather
+// kernel above (every sample evaluated by up to four cell groups plus bounding-box waste) this executes ~6x fewer
+// instructions; the price is 16 KB of shared memory per warp.
+__global__ void __launch_bounds__(128) k_sift_describe_warp(const SiftKp *__restrict__ kp, int max_kp, int n_frames,
+                                                            const int32_t *__restrict__ offs, int compact, int match_normalise,
+                                                            const __grid_constant__ SiftOctViews views,
+                                                            float *__restrict__ out_xy, float *__restrict__ out_so, float *__restrict__ out_desc) {
+	extern __shared__ float sm_desc[];
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	float (*acc)[32] = (float (*)[32])(sm_desc + (size_t)w * 128 * 32);
+	float *sd = sm_desc + 4 * 128 * 32 + w * 128;
+#pragma unroll 8
+	for (int b = 0; b < 128; ++b) acc[b][lane] = 0.f;
+	const int total = offs[n_frames];
+	for (int idx = blockIdx.x * 4 + w; idx < total; idx += gridDim.x * 4) {
+		int f = 0, hi = n_frames;                         // frame of the idx-th keypoint of the batch: offs[f] <= idx < offs[f+1]
+		while (hi - f > 1) { const int mid = (f + hi) >> 1; if (offs[mid] <= idx) f = mid; else hi = mid; }
+		const SiftKp q = kp[(size_t)f * max_kp + (idx - offs[f])];
+		const SiftOctView v = views.o[q.oct];
+		const int rows = v.rows, cols = v.cols;
+		const size_t plane = (size_t)rows * cols;
+		const float *grad = v.grad + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
+		const float *orim = v.ori + ((size_t)f * kSiftScales + (q.index - 1)) * plane;
+		const float fSize = q.fsize, frowstart = q.frow, fcolstart = q.fcol, keyori = q.ori;
+		const int rowstart = (int)(frowstart + 0.5f), colstart = (int)(fcolstart + 0.5f);
+		const float sinang = sinf(keyori), cosang = cosf(keyori);
+		const float fdrow = frowstart - (float)rowstart, fdcol = fcolstart - (float)colstart;
+		const float frealsize = 3.0f * fSize;
+		const float firealsize = 1.0f / (3.0f * fSize);
+		const int windowsize = (int)(frealsize * SIFT_SQRT2 * 5.0f * 0.5f + 0.5f);
+		const float fsr = sinang * firealsize, fcr = cosang * firealsize, fdrr = -fdrow * firealsize, fdcr = -fdcol * firealsize;
+		// KeySample's window (:1544-1566) clipped to the image (AddSample's bounds test, :1593-1594)
+		const int r_lo = -min(windowsize, rowstart), r_hi = min(windowsize, rows - 1 - rowstart);
+		const int c_lo = -min(windowsize, colstart), c_hi = min(windowsize, cols - 1 - colstart);
+		const int bw = c_hi - c_lo + 1;
+		if (bw > 0 && r_hi >= r_lo) {
+			int row = r_lo + lane / bw, col = c_lo + lane % bw;
+			while (row <= r_hi) {
+				const float frow = (float)row, fcol = (float)col;     // the reference's running fcol takes exactly these integer values
+				const float rpos = fsr * fcol + fcr * frow + fdrr;
+				const float cpos = fcr * fcol - fsr * frow + fdcr;
+				const float rx = rpos + (2.0f - 0.5f);
+				const float cx = cpos + (2.0f - 0.5f);
+				if (rx > -0.9999f && rx < 3.9999f && cx > -0.9999f && cx < 3.9999f) {
+					const size_t px = (size_t)(rowstart + row) * cols + (colstart + col);
+					const float mag = grad[px] * expf(-0.125f * (rpos * rpos + cpos * cpos));
+					float fo = orim[px] - keyori;
+					while (fo > 2 * SIFT_PI) fo -= 2 * SIFT_PI;
+					while (fo < 0) fo += 2 * SIFT_PI;
+					// PlaceInIndex (:1609-1668)
+					const float oribin = fo * (8.0f / (2 * (float)SIFT_PI));
+					const int newrow = rx < 0 ? (int)(rx - 1) : (int)rx;
+					const float rfrac = rx - (float)newrow;
+					const int newcol = cx < 0 ? (int)(cx - 1) : (int)cx;
+					const float cfrac = cx - (float)newcol;
+					const int neworient = oribin < 0 ? (int)(oribin - 1) : (int)oribin;
+					const float ofrac = oribin - (float)neworient;
+					const int o0 = neworient & 7, o1 = (neworient + 1) & 7;
+#pragma unroll
+					for (int a = 0; a < 2; ++a) {
+						if ((unsigned)(a + newrow) >= 4) continue;
+						const float frowgrad = a == 0 ? mag * (1 - rfrac) : mag * rfrac;
+#pragma unroll
+						for (int b = 0; b < 2; ++b) {
+							if ((unsigned)(b + newcol) >= 4) continue;
+							const float fcolgrad = b == 0 ? frowgrad * (1 - cfrac) : frowgrad * cfrac;
+							const int basebin = 8 * (4 * (a + newrow) + b + newcol);
+							acc[basebin + o0][lane] += fcolgrad * (1 - ofrac);
+							acc[basebin + o1][lane] += fcolgrad * ofrac;
+						}
+					}
+				}
+				col += 32;
+				while (col > c_hi) { col -= bw; ++row; }
+			}
+		}
+		__syncwarp();
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {        // bin = sum of the 32 private copies, fixed rotated order; copies re-zeroed on the way
+			const int b = lane + 32 * j;
+			float sum = 0.f;
+#pragma unroll 8
+			for (int t = 0; t < 32; ++t) { const int c = (t + lane) & 31; sum += acc[b][c]; acc[b][c] = 0.f; }
+			sd[b] = sum;
+		}
+		__syncwarp();
+		// scalar normalisation branch (:1503-1516): NormalizeVec (sequential sum), clamp at 0.2, NormalizeVec again if clamped
+		float scale = 0.f;
+		if (lane == 0) { float faccum = 0; for (int j = 0; j < 128; ++j) faccum += sd[j] * sd[j]; scale = 1 / sqrtf(faccum); }
+		scale = __shfl_sync(0xffffffffu, scale, 0);
+		float d[4];
+		bool clamped = false;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { d[j] = sd[lane + 32 * j] * scale; if (d[j] > 0.2f) { d[j] = 0.2f; clamped = true; } }
+		if (__any_sync(0xffffffffu, clamped)) {
+#pragma unroll
+			for (int j = 0; j < 4; ++j) sd[lane + 32 * j] = d[j];
+			__syncwarp();
+			if (lane == 0) { float faccum = 0; for (int j = 0; j < 128; ++j) faccum += sd[j] * sd[j]; scale = 1 / sqrtf(faccum); }
+			scale = __shfl_sync(0xffffffffu, scale, 0);
+#pragma unroll
+			for (int j = 0; j < 4; ++j) d[j] = d[j] * scale;
+			__syncwarp();
+		}
+		if (match_normalise) {               // the MATCH stage's query normalisation (see k_sift_describe)
+#pragma unroll
+			for (int j = 0; j < 4; ++j) sd[lane + 32 * j] = d[j];
+			__syncwarp();
+			if (lane == 0) { float ss = 0; for (int j = 0; j < 128; ++j) ss += sd[j] * sd[j]; scale = (float)(1. / (double)sqrtf(ss)); }
+			scale = __shfl_sync(0xffffffffu, scale, 0);
+#pragma unroll
+			for (int j = 0; j < 4; ++j) d[j] = d[j] * scale;
+		}
+		__syncwarp();
+		const size_t o = compact ? (size_t)offs[f] + q.slot : (size_t)f * max_kp + q.slot;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) out_desc[o * 128 + lane + 32 * j] = d[j];
+		if (lane == 0) {
+			float fscale = views.fscale0;
+			for (int k = 0; k < q.oct; ++k) fscale += fscale;
+			out_xy[2 * o] = fscale * fcolstart; out_xy[2 * o + 1] = fscale * frowstart;      // coord2D = (col, row), FEAT_SIFT_CPU.hpp:102-103
+			if (out_so) { out_so[2 * o] = fscale * fSize; out_so[2 * o + 1] = keyori; }
+		}
+	}
+}
+
+
 // ---- host side -------------------------------------------------------------------------------------------------
 
 static SiftState *state(mc_ctx *ctx) {
@@ -658,7 +790,7 @@ void sift_free(mc_ctx *ctx) {
 	SiftState *s = (SiftState *)ctx->sift_state;
 	if (!s) return;
 	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
-	DevBuf *bufs[] = { &s->pyr, &s->tmp, &s->tmp2, &s->gray, &s->cand, &s->kp, &s->counters, &s->lut };
+	DevBuf *bufs[] = { &s->pyr, &s->tmp, &s->tmp2, &s->gray, &s->cand, &s->kp, &s->counters, &s->lut, &s->offs };
 	for (DevBuf *b : bufs) cudaFree(b->p);
 	delete s;
 	ctx->sift_state = nullptr;
@@ -695,6 +827,7 @@ static mc_status sift_plan(mc_ctx *ctx, SiftState *s, int B, int H, int W, int d
 	MC_TRY(reserve(ctx, s->cand, (size_t)s->cap_cand * sizeof(SiftCand)));
 	MC_TRY(reserve(ctx, s->kp, (size_t)B * max_kp * sizeof(SiftKp)));
 	MC_TRY(reserve(ctx, s->counters, (size_t)(B + 1) * sizeof(int)));
+	MC_TRY(reserve(ctx, s->offs, (size_t)(B + 1) * sizeof(int32_t)));
 	if (!s->lut.p) {
 		MC_TRY(reserve(ctx, s->lut, 256 * sizeof(float)));
 		float lut[256];
@@ -797,9 +930,18 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 	const int pgrid = ctx->num_sms * 8;
 	k_sift_orient<<<pgrid, 128, 0, st>>>((const SiftCand *)s->cand.p, n_cand, s->cap_cand, views, (SiftKp *)s->kp.p, kp_count, max_kp);
 	MC_LAUNCH_CHECK();
-	k_sift_rank<<<dim3((max_kp + 127) / 128, B), 128, 0, st>>>((SiftKp *)s->kp.p, kp_count, max_kp, d_offsets, B);
+	int32_t *offs = d_offsets ? d_offsets : (int32_t *)s->offs.p;     // keypoints of frame f = entries [offs[f], offs[f+1]) of the batch
+	k_sift_rank<<<dim3((max_kp + 127) / 128, B), 128, 0, st>>>((SiftKp *)s->kp.p, kp_count, max_kp, offs, B);
 	MC_LAUNCH_CHECK();
-	k_sift_describe<<<pgrid, 128, 0, st>>>((const SiftKp *)s->kp.p, kp_count, max_kp, B, d_offsets, match_normalise, views, d_xy, d_so, d_desc);
+	if (s->gather) {
+		k_sift_describe<<<pgrid, 128, 0, st>>>((const SiftKp *)s->kp.p, kp_count, max_kp, B, d_offsets, match_normalise, views, d_xy, d_so, d_desc);
+	} else {
+		constexpr size_t smem = (4 * 128 * 32 + 4 * 128) * sizeof(float);
+		static bool configured = false;
+		if (!configured) { MC_CUDA(cudaFuncSetAttribute(k_sift_describe_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+		k_sift_describe_warp<<<ctx->num_sms * 3, 128, smem, st>>>((const SiftKp *)s->kp.p, max_kp, B, offs, d_offsets ? 1 : 0, match_normalise, views,
+		                                                         d_xy, d_so, d_desc);
+	}
 	MC_LAUNCH_CHECK();
 	MC_CUDA(cudaMemcpyAsync(d_counts, kp_count, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
 	return MC_OK;
@@ -910,6 +1052,7 @@ extern "C" mc_status mc_sift_profile_read(mc_ctx *ctx, float *blur_ms, double *a
 }
 
 mc_status mc::sift_set_two_pass(mc_ctx *ctx, int on) { state(ctx)->two_pass = on != 0; return MC_OK; }
+mc_status mc::sift_set_gather(mc_ctx *ctx, int on) { state(ctx)->gather = on != 0; return MC_OK; }
 
 /* test/bench introspection: one plane of the scale-space of the LAST mc_sift_extract* call.
  * stack: 0 Gaussian (index 0..5), 1 DoG (0..4), 2 gradient magnitude (0..2 = Gaussian 1..3), 3 orientation (0..2) */

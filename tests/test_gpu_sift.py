@@ -112,3 +112,16 @@ def test_fused_blur_equals_two_pass_kernels(gpu_ctx, gold):
         assert np.array_equal(a, b)
     for a, b in zip(planes, planes2):
         assert np.array_equal(a, b)
+
+
+def test_descriptor_kernels_agree(gpu_ctx, gold):
+    """Warp-per-keypoint scatter (default) and cell-gather descriptor kernels add the same terms in different orders."""
+    im = gold["bag0_crop_double/image"]
+    try:
+        a = gpu_ctx.sift(im, True)
+        gpu_ctx.set_option("sift_describe_gather", 1)
+        b = gpu_ctx.sift(im, True)
+    finally:
+        gpu_ctx.set_option("sift_describe_gather", 0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.abs(a[2] - b[2]).max() < 2e-6
