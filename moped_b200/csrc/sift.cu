@@ -233,21 +233,39 @@ __global__ void __launch_bounds__(128) k_sift_gradori(const float *__restrict__ 
 	const size_t plane = (size_t)rows * cols;
 	const float *img = gauss + ((size_t)f * (kSiftScales + 3) + s + 1) * plane;
 	const int i0 = blockIdx.y * kRowsPerBlock;
+	// all loads of the thread's 8-row column strip first (rows i0-1 .. i0+8 of columns j-1, j, j+1; clamped rows are
+	// loaded but not used), then the arithmetic: the loads overlap instead of each row waiting for its own
+	const int jl = j == 0 ? 0 : j - 1, jr = j == cols - 1 ? j : j + 1;
+	float c[kRowsPerBlock + 2], l[kRowsPerBlock], r[kRowsPerBlock];
+#pragma unroll
+	for (int k = 0; k < kRowsPerBlock + 2; ++k) {
+		int i = i0 + k - 1;
+		i = i < 0 ? 0 : (i >= rows ? rows - 1 : i);
+		c[k] = __ldg(img + (size_t)i * cols + j);
+	}
+#pragma unroll
+	for (int k = 0; k < kRowsPerBlock; ++k) {
+		int i = i0 + k;
+		i = i >= rows ? rows - 1 : i;
+		l[k] = __ldg(img + (size_t)i * cols + jl);
+		r[k] = __ldg(img + (size_t)i * cols + jr);
+	}
 #pragma unroll
 	for (int k = 0; k < kRowsPerBlock; ++k) {
 		const int i = i0 + k;
-		if (i >= rows) break;
-		const float *p = img + (size_t)i * cols;
-		float fdiffc, fdiffr;
-		if (j == 0) fdiffc = 2.0f * (p[1] - p[0]);
-		else if (j == cols - 1) fdiffc = 2.0f * (p[j] - p[j - 1]);
-		else fdiffc = p[j + 1] - p[j - 1];
-		if (i == 0) fdiffr = 2.0f * (p[j] - p[cols + j]);
-		else if (i == rows - 1) fdiffr = 2.0f * (p[-cols + j] - p[j]);
-		else fdiffr = p[-cols + j] - p[cols + j];
-		size_t o = ((size_t)f * kSiftScales + s) * plane + (size_t)i * cols + j;
-		grad[o] = sqrtf(fdiffc * fdiffc + fdiffr * fdiffr);
-		ori[o] = atan2f(fdiffr, fdiffc);
+		if (i < rows) {
+			// the reference's expressions (:974-989) on p[j-1], p[j], p[j+1], p[j-cols], p[j+cols]
+			float fdiffc, fdiffr;
+			if (j == 0) fdiffc = 2.0f * (r[k] - c[k + 1]);
+			else if (j == cols - 1) fdiffc = 2.0f * (c[k + 1] - l[k]);
+			else fdiffc = r[k] - l[k];
+			if (i == 0) fdiffr = 2.0f * (c[k + 1] - c[k + 2]);
+			else if (i == rows - 1) fdiffr = 2.0f * (c[k] - c[k + 1]);
+			else fdiffr = c[k] - c[k + 2];
+			const size_t o = ((size_t)f * kSiftScales + s) * plane + (size_t)i * cols + j;
+			grad[o] = sqrtf(fdiffc * fdiffc + fdiffr * fdiffr);
+			ori[o] = atan2f(fdiffr, fdiffc);
+		}
 	}
 }
 
@@ -338,17 +356,18 @@ __global__ void k_sift_detect(const float *__restrict__ dog, int32_t *__restrict
 	// the full test (which repeats them, so the outcome is exactly LocalMaxMin x3 + NotOnEdge)
 	const int rbeg = blockIdx.y * kRowsPerBlock + 5, rend = min(rbeg + kRowsPerBlock, rows - 5);
 	const int lane = threadIdx.x & 31;
-	float up = d1[(size_t)(rbeg - 1) * cols + c0], fval = d1[(size_t)rbeg * cols + c0];
-	for (int r0 = rbeg; r0 < rend; ++r0) {
-	const float down = d1[(size_t)(r0 + 1) * cols + c0];
-	const float cur = fval;
+	// (up, centre, down) roll through registers; rows are requested two iterations before they are needed
+	float up = __ldg(d1 + (size_t)(rbeg - 1) * cols + c0), cur = __ldg(d1 + (size_t)rbeg * cols + c0);
+	float dn = __ldg(d1 + (size_t)min(rbeg + 1, rows - 1) * cols + c0), ahead = __ldg(d1 + (size_t)min(rbeg + 2, rows - 1) * cols + c0), ahead2 = 0.f;
+#pragma unroll 1
+	for (int r0 = rbeg; r0 < rend; ++r0, up = cur, cur = dn, dn = ahead, ahead = ahead2) {
+	ahead2 = __ldg(d1 + (size_t)min(r0 + 3, rows - 1) * cols + c0);
 	const float left = __shfl_up_sync(0xffffffffu, cur, 1), right = __shfl_down_sync(0xffffffffu, cur, 1);
 	bool go = valid && fabsf(cur) > peak_thresh * 0.8f;
 	if (go) {
-		if (cur > 0) go = !(up > cur || down > cur || (lane > 0 && left > cur) || (lane < 31 && c0 + 1 < cols - 5 && right > cur));
-		else go = !(cur > up || cur > down || (lane > 0 && cur > left) || (lane < 31 && c0 + 1 < cols - 5 && cur > right));
+		if (cur > 0) go = !(up > cur || dn > cur || (lane > 0 && left > cur) || (lane < 31 && c0 + 1 < cols - 5 && right > cur));
+		else go = !(cur > up || cur > dn || (lane > 0 && cur > left) || (lane < 31 && c0 + 1 < cols - 5 && cur > right));
 	}
-	up = cur; fval = down;
 	if (!go) continue;
 	{ const float fval = cur;
 	if (!(local_max_min(fval, d1, cols, r0, c0) && local_max_min(fval, d0, cols, r0, c0) && local_max_min(fval, d2, cols, r0, c0) &&
@@ -433,22 +452,34 @@ __global__ void __launch_bounds__(128) k_sift_orient(const SiftCand *__restrict_
 	if (bw > 0 && r_hi >= r_lo) {
 		int rowcur = r_lo + lane / bw, colcur = c_lo + lane % bw;
 		const float wlimit = (float)(windowsize * windowsize) + 0.5f;
+		constexpr int U = 4;                             // loads of four steps in flight (see k_sift_describe_warp)
 		while (rowcur <= r_hi) {
-			float fdx = grad[(size_t)rowcur * cols + colcur];
-			if (fdx > 0) {
-				float fdrow = (float)rowcur - frowstart, fdcol = (float)colcur - fcolstart;
-				float fradius2 = fdrow * fdrow + fdcol * fdcol;
-				if (wlimit > fradius2) {
-					float fweight = expf(fradius2 * fexpmult);
-					int binindex = (int)(orim[(size_t)rowcur * cols + colcur] * fbinmult + fbinadd);
-					if (binindex > 36) binindex = 0;
-					if (binindex == 36) binindex = 35;
-					if (binindex < 0) binindex = 0;
-					fix_add(&s_hist[w][binindex][lane], fdx * fweight);
+			int rr[U], cc[U];
+			float gg[U], oo[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				rr[u] = rowcur; cc[u] = colcur;
+				if (rowcur <= r_hi) { const size_t px = (size_t)rowcur * cols + colcur; gg[u] = __ldg(grad + px); oo[u] = __ldg(orim + px); }
+				colcur += 32;
+				while (colcur > c_hi) { colcur -= bw; ++rowcur; }
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				if (rr[u] > r_hi) continue;
+				const float fdx = gg[u];
+				if (fdx > 0) {
+					float fdrow = (float)rr[u] - frowstart, fdcol = (float)cc[u] - fcolstart;
+					float fradius2 = fdrow * fdrow + fdcol * fdcol;
+					if (wlimit > fradius2) {
+						float fweight = expf(fradius2 * fexpmult);
+						int binindex = (int)(oo[u] * fbinmult + fbinadd);
+						if (binindex > 36) binindex = 0;
+						if (binindex == 36) binindex = 35;
+						if (binindex < 0) binindex = 0;
+						fix_add(&s_hist[w][binindex][lane], fdx * fweight);
+					}
 				}
 			}
-			colcur += 32;
-			while (colcur > c_hi) { colcur -= bw; ++rowcur; }
 		}
 	}
 	__syncwarp();
@@ -688,17 +719,35 @@ __global__ void __launch_bounds__(128) k_sift_describe_warp(const SiftKp *__rest
 		const int c_lo = -min(windowsize, colstart), c_hi = min(windowsize, cols - 1 - colstart);
 		const int bw = c_hi - c_lo + 1;
 		if (bw > 0 && r_hi >= r_lo) {
+			// ncu: a third of all stall samples sat on the first use of the gradient/orientation loads (scattered windows: L1 hit
+			// 17 %, ~11 warps per SM). So the loads of EIGHT steps are issued unconditionally up front (the addresses only depend on
+			// the walk, not on the acceptance test), then the eight samples are processed: 16 loads in flight per lane.
+			constexpr int U = 8;
 			int row = r_lo + lane / bw, col = c_lo + lane % bw;
 			while (row <= r_hi) {
-				const float frow = (float)row, fcol = (float)col;     // the reference's running fcol takes exactly these integer values
-				const float rpos = fsr * fcol + fcr * frow + fdrr;
-				const float cpos = fcr * fcol - fsr * frow + fdcr;
-				const float rx = rpos + (2.0f - 0.5f);
-				const float cx = cpos + (2.0f - 0.5f);
-				if (rx > -0.9999f && rx < 3.9999f && cx > -0.9999f && cx < 3.9999f) {
-					const size_t px = (size_t)(rowstart + row) * cols + (colstart + col);
-					const float mag = grad[px] * expf(-0.125f * (rpos * rpos + cpos * cpos));
-					float fo = orim[px] - keyori;
+				int rr[U], cc[U];
+				float gg[U], oo[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					rr[u] = row; cc[u] = col;
+					if (row <= r_hi) {
+						const size_t px = (size_t)(rowstart + row) * cols + (colstart + col);
+						gg[u] = __ldg(grad + px); oo[u] = __ldg(orim + px);
+					}
+					col += 32;
+					while (col > c_hi) { col -= bw; ++row; }
+				}
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					if (rr[u] > r_hi) continue;
+					const float frow = (float)rr[u], fcol = (float)cc[u];     // the reference's running fcol takes exactly these integer values
+					const float rpos = fsr * fcol + fcr * frow + fdrr;
+					const float cpos = fcr * fcol - fsr * frow + fdcr;
+					const float rx = rpos + (2.0f - 0.5f);
+					const float cx = cpos + (2.0f - 0.5f);
+					if (!(rx > -0.9999f && rx < 3.9999f && cx > -0.9999f && cx < 3.9999f)) continue;
+					const float mag = gg[u] * expf(-0.125f * (rpos * rpos + cpos * cpos));
+					float fo = oo[u] - keyori;
 					while (fo > 2 * SIFT_PI) fo -= 2 * SIFT_PI;
 					while (fo < 0) fo += 2 * SIFT_PI;
 					// PlaceInIndex (:1609-1668)
@@ -724,8 +773,6 @@ __global__ void __launch_bounds__(128) k_sift_describe_warp(const SiftKp *__rest
 						}
 					}
 				}
-				col += 32;
-				while (col > c_hi) { col -= bw; ++row; }
 			}
 		}
 		__syncwarp();
