@@ -646,7 +646,7 @@ def run_sift_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lo, hi = rank * args.frames // world, (rank + 1) * args.frames // world      # frames are independent: partition, no collective
+    lo, hi = frame_range(args.frames, world, rank)                               # frames are independent: partition, no collective
     B = hi - lo
     pool = [sift_images(B, first=1000 * p + lo) for p in range(2)]               # two different batches, alternated
     H, W = pool[0].shape[1:]

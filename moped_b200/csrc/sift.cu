@@ -54,6 +54,7 @@ struct SiftState {
 	cudaEvent_t ev[2 * (kSiftScales + 2)] = {};   // mc_set_profiling: around the five octave-0 Gaussian+DoG launches
 	bool ev_valid = false;
 	double ev_bytes = 0;
+	unsigned smem_configured = 0;  // bit per kernel instance whose dynamic shared-memory limit was raised on this context's device
 	bool two_pass = false;
 	bool gather = false;          // mc_set_option("sift_describe_gather"): the cell-gather descriptor kernel (A/B aid)        // mc_set_option("sift_two_pass"): the unfused blur kernels (A/B aid, same bits)
 };
@@ -151,12 +152,26 @@ __global__ void __launch_bounds__(256) k_sift_blur(const float *__restrict__ src
 	float *s_in = sm, *s_mid = sm + IH * PIN;
 	const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH, f = blockIdx.z;
 	const float *p = src + (size_t)f * fstride_src;
-	for (int idx = threadIdx.x; idx < IH * IW; idx += 256) {
-		int i = idx / IW, j = idx - i * IW;
-		int y = r0 - W + i, x = c0 - W + j;
-		y = y < 0 ? 0 : (y >= rows ? rows - 1 : y);
-		x = x < 0 ? 0 : (x >= cols ? cols - 1 : x);
-		s_in[i * PIN + j] = __ldg(p + (size_t)y * cols + x);
+	{   // input tile + halo: a warp per tile row (row clamp and row pointer once per row), lanes along the row
+		const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+		const bool interior = r0 >= W && r0 + TH + W <= rows && c0 >= W && c0 + TW + W <= cols;      // block-uniform
+		for (int i = wid; i < IH; i += 8) {
+			int y = r0 - W + i;
+			y = y < 0 ? 0 : (y >= rows ? rows - 1 : y);
+			const float *prow = p + (size_t)y * cols + (c0 - W);
+			float *srow = s_in + i * PIN;
+			if (interior) {
+#pragma unroll
+				for (int j = lane; j < IW; j += 32) srow[j] = __ldg(prow + j);
+			} else {
+#pragma unroll
+				for (int j = lane; j < IW; j += 32) {
+					int x = c0 - W + j;
+					x = x < 0 ? 0 : (x >= cols ? cols - 1 : x);
+					srow[j] = __ldg(prow + (x - (c0 - W)));
+				}
+			}
+		}
 	}
 	__syncthreads();
 	for (int item = threadIdx.x; item < IH * (TW / G); item += 256) {
@@ -187,30 +202,33 @@ __global__ void __launch_bounds__(256) k_sift_blur(const float *__restrict__ src
 		for (int j = 0; j < KS; ++j)
 #pragma unroll
 			for (int k = 0; k < G; ++k) acc[k] = __fmaf_rn(v[k + j], gk.k[j], acc[k]);
-		const int x = c0 + col;
-		if (x < cols) {
+		const int x = c0 + col, nrow = rows - (r0 + h * G);        // nrow = rows of this strip inside the image
+		if (x < cols && nrow > 0) {
+			const size_t o = (size_t)(r0 + h * G) * cols + x;        // one address per strip, rows advance by `cols`
+			float *dp = dst + (size_t)f * fstride_dst + o;
+			const float *cin = s_in + (h * G + W) * PIN + col + W;
+			if (dog) {
+				float *gp = dog + (size_t)f * fstride_dog + o;
 #pragma unroll
-			for (int k = 0; k < G; ++k) {
-				int y = r0 + h * G + k;
-				if (y < rows) {
-					size_t o = (size_t)y * cols + x;
-					dst[(size_t)f * fstride_dst + o] = acc[k];
-					if (dog) dog[(size_t)f * fstride_dog + o] = s_in[(h * G + k + W) * PIN + col + W] - acc[k];
-				}
+				for (int k = 0; k < G; ++k)
+					if (k < nrow) { dp[(size_t)k * cols] = acc[k]; gp[(size_t)k * cols] = cin[k * PIN] - acc[k]; }
+			} else {
+#pragma unroll
+				for (int k = 0; k < G; ++k)
+					if (k < nrow) dp[(size_t)k * cols] = acc[k];
 			}
 		}
 	}
 }
 
 template <int KS>
-static mc_status launch_blur_t(mc_ctx *ctx, const float *src, size_t fs_src, float *dst, size_t fs_dst, float *dog, size_t fs_dog,
+static mc_status launch_blur_t(mc_ctx *ctx, unsigned &configured, const float *src, size_t fs_src, float *dst, size_t fs_dst, float *dog, size_t fs_dog,
                                int rows, int cols, int B, const GaussK &gk) {
 	constexpr int W = KS / 2, IH = 64 + 2 * W, IW = 64 + 2 * W;
 	constexpr size_t smem = ((size_t)IH * (IW + 1) + (size_t)IH * 65) * sizeof(float);
-	static bool configured = false;
-	if (!configured) {
+	if (!(configured & (1u << W))) {        // the attribute belongs to the device of this context, not to the process
 		MC_CUDA(cudaFuncSetAttribute(k_sift_blur<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		configured = true;
+		configured |= 1u << W;
 	}
 	k_sift_blur<KS><<<dim3((cols + 63) / 64, (rows + 63) / 64, B), 256, smem, ctx->stream>>>(src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, gk);
 	MC_LAUNCH_CHECK();
@@ -900,11 +918,11 @@ static mc_status blur(mc_ctx *ctx, SiftState *s, const float *src, size_t fs_src
                       int rows, int cols, size_t plane, int B, const GaussK &gk) {
 	if (!s->two_pass) {
 		switch (gk.ksize) {
-		case 11: return launch_blur_t<11>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
-		case 13: return launch_blur_t<13>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
-		case 17: return launch_blur_t<17>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
-		case 21: return launch_blur_t<21>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
-		case 25: return launch_blur_t<25>(ctx, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 11: return launch_blur_t<11>(ctx, s->smem_configured, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 13: return launch_blur_t<13>(ctx, s->smem_configured, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 17: return launch_blur_t<17>(ctx, s->smem_configured, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 21: return launch_blur_t<21>(ctx, s->smem_configured, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
+		case 25: return launch_blur_t<25>(ctx, s->smem_configured, src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, B, gk);
 		default: break;
 		}
 	}
@@ -984,8 +1002,7 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 		k_sift_describe<<<pgrid, 128, 0, st>>>((const SiftKp *)s->kp.p, kp_count, max_kp, B, d_offsets, match_normalise, views, d_xy, d_so, d_desc);
 	} else {
 		constexpr size_t smem = (4 * 128 * 32 + 4 * 128) * sizeof(float);
-		static bool configured = false;
-		if (!configured) { MC_CUDA(cudaFuncSetAttribute(k_sift_describe_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+		if (!(s->smem_configured & 1u)) { MC_CUDA(cudaFuncSetAttribute(k_sift_describe_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); s->smem_configured |= 1u; }
 		k_sift_describe_warp<<<ctx->num_sms * 3, 128, smem, st>>>((const SiftKp *)s->kp.p, max_kp, B, offs, d_offsets ? 1 : 0, match_normalise, views,
 		                                                         d_xy, d_so, d_desc);
 	}
@@ -1022,7 +1039,10 @@ extern "C" mc_status mc_sift_extract(mc_ctx *ctx, const uint8_t *gray, int n_ima
 	MC_CUDA(cudaMemcpyAsync(d_gray, gray, npx, cudaMemcpyHostToDevice, ctx->stream));
 	MC_TRY(sift_extract_device(ctx, d_gray, n_images, height, width, double_size, max_keypoints, d_xy, d_so, d_desc, d_counts, nullptr, 0));
 	MC_CUDA(cudaMemcpyAsync(counts, d_counts, (size_t)n_images * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	int n_extrema = 0;
+	MC_CUDA(cudaMemcpyAsync(&n_extrema, s->counters.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (n_extrema > s->cap_cand) { ctx->err = "mc_sift_extract: more scale-space extrema than the candidate list holds; raise max_keypoints"; return MC_ERR_CAPACITY; }
 	mc_status rc = MC_OK;
 	for (int f = 0; f < n_images; ++f) {
 		int n = counts[f];
