@@ -125,3 +125,47 @@ def test_descriptor_kernels_agree(gpu_ctx, gold):
         gpu_ctx.set_option("sift_describe_gather", 0)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert np.abs(a[2] - b[2]).max() < 2e-6
+
+
+def _texture(rng, h, w):
+    im = rng.random((h, w)).astype(np.float32)
+    for _ in range(2):
+        im = (im + np.roll(im, 1, 0) + np.roll(im, -1, 0) + np.roll(im, 1, 1) + np.roll(im, -1, 1)) / 5
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(max(4, h * w // 900)):
+        cy, cx, s = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(1.5, 7)
+        im += rng.uniform(-0.6, 0.6) * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
+    return ((im - im.min()) / (im.max() - im.min() + 1e-9) * 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape,dbl", [((13, 13), False), ((13, 200), True), ((97, 131), True), ((64, 65), False), ((240, 127), True),
+                                       ((33, 500), False), ((480, 640), False)])
+def test_random_images_of_awkward_sizes_match_oracle(gpu_ctx, oracle_mod, shape, dbl):
+    """Sizes that are not multiples of the 64-pixel blur tiles or of the 128x8 blocks, octaves that end at 13 pixels,
+    windows that hang over every image border, saturated pixels."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    im = _texture(rng, *shape)
+    im[: shape[0] // 7] = 255                                   # a saturated band: zero gradients inside, a hard edge below
+    got = gpu_ctx.sift(im, dbl)
+    want = oracle_mod.sift(im, dbl)
+    assert len(got[0]) == len(want[0])
+    if len(want[0]):
+        compare_with_oracle(got, want, min_frac=0.99)
+    n_oct = len(oracle_mod.sift_octave_dims(*shape, dbl))
+    if n_oct:
+        gauss, dog, _ = oracle_mod.sift_debug(im, dbl, n_oct - 1)
+        assert np.array_equal(gpu_ctx.sift_plane(0, n_oct - 1, 0, 5), gauss[5])
+        assert np.array_equal(gpu_ctx.sift_plane(0, n_oct - 1, 1, 4), dog[4])
+
+
+def test_mixed_batch_sizes_reuse_the_context(gpu_ctx, gold):
+    """Re-planning: different image sizes and batch sizes through one context, results independent of what ran before."""
+    a = gold["bag0_crop_double/image"]
+    b = gold["ex2_odd_double/image"]
+    ra1 = gpu_ctx.sift(a, True)
+    rb = gpu_ctx.sift(np.stack([b, b]), True)
+    ra2 = gpu_ctx.sift(a, False)
+    ra3 = gpu_ctx.sift(a, True)
+    for x, y in zip(ra1, ra3):
+        assert np.array_equal(x, y)
+    assert np.array_equal(rb[0][2], rb[1][2]) and len(ra2[0]) < len(ra1[0])
