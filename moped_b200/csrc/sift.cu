@@ -136,7 +136,7 @@ __global__ void k_sift_blur_v(const float *__restrict__ src, size_t fstride_src,
 	if (dog) dog[(size_t)f * fstride_dog + o] = prev[(size_t)f * fstride_prev + o] - acc;
 }
 
-// GaussianBlur (:470-521) as ONE kernel: a CTA loads a 64x64 output tile plus its halo (replicate-clamped at the image
+// GaussianBlur (:470-521) as ONE persistent kernel: a CTA takes 64x64 output tiles in turn; it loads a tile plus its halo (replicate-clamped at the image
 // border like ConvHorizontal/ConvVertical's padded line buffers), runs the horizontal pass into shared memory (also for
 // the halo rows the vertical pass needs), then the vertical pass, and writes the Gaussian image and — SubtractImage
 // (:460-464) fused — the DoG image = (centre of the input tile) - result. Per output pixel the taps are summed in the
@@ -144,80 +144,107 @@ __global__ void k_sift_blur_v(const float *__restrict__ src, size_t fstride_src,
 // Register blocking: a thread produces 8 consecutive outputs from one sliding window of ksize+7 shared-memory loads;
 // in the horizontal pass the lanes of a warp span ROWS (odd pitches -> conflict-free), in the vertical pass columns.
 // HBM traffic per blur: 1 plane read (+halo from L2), 2 planes written, instead of 6 plane passes unfused.
+// The tile loads are cp.async requests into a second buffer issued BEFORE the current tile is convolved (ncu on the
+// load -> barrier -> compute version: 57 % of the stall samples on the shared-memory store waiting for the global loads).
+// cp.async of one 4-byte word (global -> shared, bypassing registers): lets a CTA request its NEXT tile while it
+// convolves the current one
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 template <int KS>
 __global__ void __launch_bounds__(256) k_sift_blur(const float *__restrict__ src, size_t fstride_src, float *__restrict__ dst, size_t fstride_dst,
-                                                   float *__restrict__ dog, size_t fstride_dog, int rows, int cols, const __grid_constant__ GaussK gk) {
+                                                   float *__restrict__ dog, size_t fstride_dog, int rows, int cols, int ntx, int nty, int n_tiles,
+                                                   const __grid_constant__ GaussK gk) {
 	constexpr int W = KS / 2, TW = 64, TH = 64, IH = TH + 2 * W, IW = TW + 2 * W, PIN = IW + 1, PMID = TW + 1, G = 8;
 	extern __shared__ float sm[];
-	float *s_in = sm, *s_mid = sm + IH * PIN;
-	const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH, f = blockIdx.z;
-	const float *p = src + (size_t)f * fstride_src;
-	{   // input tile + halo: a warp per tile row (row clamp and row pointer once per row), lanes along the row
-		const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	float *s_mid = sm + 2 * IH * PIN;                  // sm[0 .. 2*IH*PIN): input tile + halo, double buffered
+	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+	// requests tile t into buffer b: a warp per tile row (row clamp and row pointer once per row), lanes along the row;
+	// replicate-clamped at the image border like ConvHorizontal/ConvVertical's padded line buffers
+	auto prefetch = [&](int t, int b) {
+		const int f = t / (ntx * nty), rem = t - f * (ntx * nty), by = rem / ntx, bx = rem - by * ntx;
+		const int c0 = bx * TW, r0 = by * TH;
+		const float *p = src + (size_t)f * fstride_src;
 		const bool interior = r0 >= W && r0 + TH + W <= rows && c0 >= W && c0 + TW + W <= cols;      // block-uniform
 		for (int i = wid; i < IH; i += 8) {
 			int y = r0 - W + i;
 			y = y < 0 ? 0 : (y >= rows ? rows - 1 : y);
 			const float *prow = p + (size_t)y * cols + (c0 - W);
-			float *srow = s_in + i * PIN;
+			float *srow = sm + b * (IH * PIN) + i * PIN;
 			if (interior) {
 #pragma unroll
-				for (int j = lane; j < IW; j += 32) srow[j] = __ldg(prow + j);
+				for (int j = lane; j < IW; j += 32) cp_async4(srow + j, prow + j);
 			} else {
 #pragma unroll
 				for (int j = lane; j < IW; j += 32) {
 					int x = c0 - W + j;
 					x = x < 0 ? 0 : (x >= cols ? cols - 1 : x);
-					srow[j] = __ldg(prow + (x - (c0 - W)));
+					cp_async4(srow + j, prow + (x - (c0 - W)));
 				}
 			}
 		}
-	}
-	__syncthreads();
-	for (int item = threadIdx.x; item < IH * (TW / G); item += 256) {
-		int row = item % IH, g = item / IH;
-		const float *in = s_in + row * PIN + g * G;
-		float v[KS + G - 1], acc[G];
+		cp_async_commit();
+	};
+
+	int t = blockIdx.x, cur = 0;
+	if (t < n_tiles) prefetch(t, 0);
+	for (; t < n_tiles; t += gridDim.x, cur ^= 1) {
+		const int tn = t + gridDim.x;
+		if (tn < n_tiles) { prefetch(tn, cur ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+		__syncthreads();                                // tile t is in s_buf[cur] for every thread
+		const float *s_in = sm + cur * (IH * PIN);
+		const int f = t / (ntx * nty), rem = t - f * (ntx * nty), by = rem / ntx, bx = rem - by * ntx;
+		const int c0 = bx * TW, r0 = by * TH;
+		for (int item = threadIdx.x; item < IH * (TW / G); item += 256) {
+			int row = item % IH, g = item / IH;
+			const float *in = s_in + row * PIN + g * G;
+			float v[KS + G - 1], acc[G];
 #pragma unroll
-		for (int t = 0; t < KS + G - 1; ++t) v[t] = in[t];
+			for (int q = 0; q < KS + G - 1; ++q) v[q] = in[q];
 #pragma unroll
-		for (int k = 0; k < G; ++k) acc[k] = 0.f;
+			for (int k = 0; k < G; ++k) acc[k] = 0.f;
 #pragma unroll
-		for (int j = 0; j < KS; ++j)
+			for (int j = 0; j < KS; ++j)
 #pragma unroll
-			for (int k = 0; k < G; ++k) acc[k] = __fmaf_rn(v[k + j], gk.k[j], acc[k]);
+				for (int k = 0; k < G; ++k) acc[k] = __fmaf_rn(v[k + j], gk.k[j], acc[k]);
 #pragma unroll
-		for (int k = 0; k < G; ++k) s_mid[row * PMID + g * G + k] = acc[k];
-	}
-	__syncthreads();
-	for (int item = threadIdx.x; item < TW * (TH / G); item += 256) {
-		int col = item % TW, h = item / TW;
-		const float *in = s_mid + (h * G) * PMID + col;
-		float v[KS + G - 1], acc[G];
+			for (int k = 0; k < G; ++k) s_mid[row * PMID + g * G + k] = acc[k];
+		}
+		__syncthreads();
+		for (int item = threadIdx.x; item < TW * (TH / G); item += 256) {
+			int col = item % TW, h = item / TW;
+			const float *in = s_mid + (h * G) * PMID + col;
+			float v[KS + G - 1], acc[G];
 #pragma unroll
-		for (int t = 0; t < KS + G - 1; ++t) v[t] = in[t * PMID];
+			for (int q = 0; q < KS + G - 1; ++q) v[q] = in[q * PMID];
 #pragma unroll
-		for (int k = 0; k < G; ++k) acc[k] = 0.f;
+			for (int k = 0; k < G; ++k) acc[k] = 0.f;
 #pragma unroll
-		for (int j = 0; j < KS; ++j)
+			for (int j = 0; j < KS; ++j)
 #pragma unroll
-			for (int k = 0; k < G; ++k) acc[k] = __fmaf_rn(v[k + j], gk.k[j], acc[k]);
-		const int x = c0 + col, nrow = rows - (r0 + h * G);        // nrow = rows of this strip inside the image
-		if (x < cols && nrow > 0) {
-			const size_t o = (size_t)(r0 + h * G) * cols + x;        // one address per strip, rows advance by `cols`
-			float *dp = dst + (size_t)f * fstride_dst + o;
-			const float *cin = s_in + (h * G + W) * PIN + col + W;
-			if (dog) {
-				float *gp = dog + (size_t)f * fstride_dog + o;
+				for (int k = 0; k < G; ++k) acc[k] = __fmaf_rn(v[k + j], gk.k[j], acc[k]);
+			const int x = c0 + col, nrow = rows - (r0 + h * G);        // nrow = rows of this strip inside the image
+			if (x < cols && nrow > 0) {
+				const size_t o = (size_t)(r0 + h * G) * cols + x;        // one address per strip, rows advance by `cols`
+				float *dp = dst + (size_t)f * fstride_dst + o;
+				const float *cin = s_in + (h * G + W) * PIN + col + W;
+				if (dog) {
+					float *gp = dog + (size_t)f * fstride_dog + o;
 #pragma unroll
-				for (int k = 0; k < G; ++k)
-					if (k < nrow) { dp[(size_t)k * cols] = acc[k]; gp[(size_t)k * cols] = cin[k * PIN] - acc[k]; }
-			} else {
+					for (int k = 0; k < G; ++k)
+						if (k < nrow) { dp[(size_t)k * cols] = acc[k]; gp[(size_t)k * cols] = cin[k * PIN] - acc[k]; }
+				} else {
 #pragma unroll
-				for (int k = 0; k < G; ++k)
-					if (k < nrow) dp[(size_t)k * cols] = acc[k];
+					for (int k = 0; k < G; ++k)
+						if (k < nrow) dp[(size_t)k * cols] = acc[k];
+				}
 			}
 		}
+		__syncthreads();                                // s_buf[cur] and s_mid are free again: the next iteration prefetches into s_buf[cur]
 	}
 }
 
@@ -225,12 +252,15 @@ template <int KS>
 static mc_status launch_blur_t(mc_ctx *ctx, unsigned &configured, const float *src, size_t fs_src, float *dst, size_t fs_dst, float *dog, size_t fs_dog,
                                int rows, int cols, int B, const GaussK &gk) {
 	constexpr int W = KS / 2, IH = 64 + 2 * W, IW = 64 + 2 * W;
-	constexpr size_t smem = ((size_t)IH * (IW + 1) + (size_t)IH * 65) * sizeof(float);
+	constexpr size_t smem = (2 * (size_t)IH * (IW + 1) + (size_t)IH * 65) * sizeof(float);
 	if (!(configured & (1u << W))) {        // the attribute belongs to the device of this context, not to the process
 		MC_CUDA(cudaFuncSetAttribute(k_sift_blur<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		configured |= 1u << W;
 	}
-	k_sift_blur<KS><<<dim3((cols + 63) / 64, (rows + 63) / 64, B), 256, smem, ctx->stream>>>(src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, gk);
+	const int ntx = (cols + 63) / 64, nty = (rows + 63) / 64, n_tiles = ntx * nty * B;
+	const int per_sm = (int)((227 * 1024) / (smem + 1024));                  // resident CTAs per SM by shared memory
+	const int grid = n_tiles < ctx->num_sms * per_sm ? n_tiles : ctx->num_sms * per_sm;
+	k_sift_blur<KS><<<grid, 256, smem, ctx->stream>>>(src, fs_src, dst, fs_dst, dog, fs_dog, rows, cols, ntx, nty, n_tiles, gk);
 	MC_LAUNCH_CHECK();
 	return MC_OK;
 }
