@@ -395,9 +395,10 @@ static int lu_solve(const float *A, const float *B, float *x, int m) {
  * libs.tgz!levmar-2.4/lm_core.c:427-836, Jacobian misc_core.c:135-168, defaults lm.h:83-85.
  * The reference build folds LM_FINITE() to true (-ffinite-math-only), so there is no stop=7.
  * Returns the iteration count, or -1 (LM_ERROR) on stop=4. info10 as levmar's info[]. */
-int mo_levmar_dif(float *p, int n_pts, int itmax, const float *xy, const float *xyz, const int *image,
-                  const mo_camera *cams, float *info) {
-	const int m = LM_M, n = 2 * n_pts;
+typedef void (*lm_fn)(const float *p7, float *res, const void *ctx);      /* residual callback: levmar's `func` + adata */
+
+static int levmar_dif_fn(float *p, int n, int itmax, lm_fn fn, const void *ctx, float *info) {
+	const int m = LM_M;
 	const float tau = 1E-03f, eps1 = 1E-17f, eps2 = 1E-17f, eps2_sq = 1E-17f * 1E-17f, eps3 = 1E-17f, delta = 1E-06f;
 	float *buf = (float *)malloc(sizeof(float) * (size_t)(5 * n + n * m));
 	float *e = buf, *hx = e + n, *wrk = hx + n, *wrk2 = wrk + n, *hxx = wrk2 + n, *jac = hxx + n;
@@ -409,7 +410,7 @@ int mo_levmar_dif(float *p, int n_pts, int itmax, const float *xy, const float *
 	unsigned csr_saved = _mm_getcsr();
 	_mm_setcsr(csr_saved | 0x8040u);
 
-	mo_lm_func(p, hx, n_pts, xy, xyz, image, cams); nfev = 1;
+	fn(p, hx, ctx); nfev = 1;
 	p_eL2 = l2_neg(e, hx, n);
 	init_eL2 = p_eL2;
 
@@ -423,7 +424,7 @@ int mo_levmar_dif(float *p, int n_pts, int itmax, const float *xy, const float *
 				if (d < delta) d = delta;
 				float save = p[j];
 				p[j] += d;
-				mo_lm_func(p, hxx, n_pts, xy, xyz, image, cams);
+				fn(p, hxx, ctx);
 				p[j] = save;
 				d = 1.0f / d;
 				for (int i = 0; i < n; i++) jac[i * m + j] = (hxx[i] - hx[i]) * d;
@@ -472,7 +473,7 @@ int mo_levmar_dif(float *p, int n_pts, int itmax, const float *xy, const float *
 			if (Dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
 			if (Dp_L2 >= (p_L2 + eps2) / (1E-12f * 1E-12f)) { stop = 4; break; }
 
-			mo_lm_func(pDp, wrk, n_pts, xy, xyz, image, cams); ++nfev;
+			fn(pDp, wrk, ctx); ++nfev;
 			pDp_eL2 = l2_neg(wrk2, wrk, n);
 			float dF = p_eL2 - pDp_eL2;
 			if (updp || dF > 0) {
@@ -512,6 +513,18 @@ int mo_levmar_dif(float *p, int n_pts, int itmax, const float *xy, const float *
 	free(buf);
 	_mm_setcsr(csr_saved);
 	return (stop != 4 && stop != 7) ? k : -1;
+}
+
+typedef struct { int n_pts; const float *xy, *xyz; const int *image; const mo_camera *cams; } reproj_ctx;
+static void reproj_fn(const float *p7, float *res, const void *c) {
+	const reproj_ctx *r = (const reproj_ctx *)c;
+	mo_lm_func(p7, res, r->n_pts, r->xy, r->xyz, r->image, r->cams);
+}
+
+int mo_levmar_dif(float *p, int n_pts, int itmax, const float *xy, const float *xyz, const int *image,
+                  const mo_camera *cams, float *info) {
+	reproj_ctx c = { n_pts, xy, xyz, image, cams };
+	return levmar_dif_fn(p, 2 * n_pts, itmax, reproj_fn, &c, info);
 }
 
 /* LM from `pose7` over the given correspondences; on success overwrites pose7 with the solution
@@ -692,4 +705,132 @@ int mo_filter(int n_models, const int *match_offsets, const int *match_image, co
 		}
 	free(keys); free(key_of); free(best_score); free(best_obj); free(in_cl); free(owned);
 	return ns;
+}
+
+/* ==== moped3d: depth-aware pose stage ====================================================
+ * Restates POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU (moped3d/libmoped/src/pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp);
+ * pinned against the class itself compiled into oracle/_ref/libmoped3d_ref.so (ref3d_harness.cpp, tests/test_oracle3d_pose.py).
+ * What differs from the moped2 stage above: every correspondence also carries world3D (the back-projected, depth-filled
+ * 3-D point of the feature) and a Cauchy weight from its fill distance (:187-190, 352-353); the two residuals per
+ * correspondence are the squared distances from the transformed model point to its projection on the feature's viewing ray
+ * and from that projection to world3D, weighted by 1-(1-Alpha)w and (1-Alpha)w (:136-173); the initial translation is the
+ * mean world3D of the samples (:262-276). randSample, testAllPoints (2-D reprojection), the RANSAC loop and levmar are the
+ * same code. The stage is compiled WITHOUT -fsingle-precision-constant (moped3d/libmoped/Makefile:44-51): literals are double. */
+
+float mo_cauchy_weight(float fill_distance) {                       /* getCauchyWeight :187-190, FillInCauchyScale = 0.100 */
+	float factor = fill_distance / (float)0.100;
+	return (float)(1.0 / (1 + factor * factor));
+}
+
+void mo_lm_func_depth(const float *p7, float *res, int n_pts, const float *xyz, const float *world, const float *cauchy,
+                      const int *image, const mo_camera *cams, float alpha) {
+	float q[4] = { p7[0], p7[1], p7[2], p7[3] };
+	quat_norm(q);
+	float T[12];
+	tm_init(T, q, p7 + 4);
+	for (int i = 0; i < n_pts; i++) {
+		const mo_camera *cam = &cams[image[i]];
+		float p3[3];
+		tm_transform(T, p3, xyz + 3 * i);
+		tm_inverse(cam->TM, p3, p3);
+		if (p3[2] < 0) {
+			res[2 * i] = -p3[2] + 10;
+			res[2 * i + 1] = -p3[2] + 10;
+		} else {
+			const float *w3 = world + 3 * i;
+			float vx = w3[0], vy = w3[1], vz = w3[2];
+			float norm = sqrtf(vx * vx + vy * vy + vz * vz);
+			float nx = vx / norm, ny = vy / norm, nz = vz / norm;
+			float dot = nx * p3[0] + ny * p3[1] + nz * p3[2];
+			float hx = nx * dot, hy = ny * dot, hz = nz * dot;                      /* pHat: projection of p3D on the viewing ray */
+			float ax = p3[0] - hx, ay = p3[1] - hy, az = p3[2] - hz;
+			float dxy = sqrtf(ax * ax + ay * ay + az * az);                        /* Pt::euclDist */
+			float bx = w3[0] - hx, by = w3[1] - hy, bz = w3[2] - hz;
+			float dz = sqrtf(bx * bx + by * by + bz * bz);
+			res[2 * i] = dxy * dxy;
+			res[2 * i + 1] = dz * dz;
+		}
+		float wi = cauchy[i];
+		float weight3D = (1 - alpha) * wi;
+		float weight2D = 1 - weight3D;
+		res[2 * i] *= weight2D;
+		res[2 * i + 1] *= weight3D;
+	}
+}
+
+typedef struct { int n_pts; const float *xyz, *world, *cauchy; const int *image; const mo_camera *cams; float alpha; } depth_ctx;
+static void depth_fn(const float *p7, float *res, const void *c) {
+	const depth_ctx *d = (const depth_ctx *)c;
+	mo_lm_func_depth(p7, res, d->n_pts, d->xyz, d->world, d->cauchy, d->image, d->cams, d->alpha);
+}
+
+float mo_optimize_camera_depth(float *pose7, int n_pts, int itmax, const float *xyz, const float *world, const float *cauchy,
+                               const int *image, const mo_camera *cams, float alpha) {
+	float p[7], info[10];
+	memcpy(p, pose7, sizeof p);
+	depth_ctx c = { n_pts, xyz, world, cauchy, image, cams, alpha };
+	int r = levmar_dif_fn(p, 2 * n_pts, itmax, depth_fn, &c, info);
+	if (r < 0) return (float)r;
+	memcpy(pose7, p, sizeof p);
+	quat_norm(pose7);
+	return info[1];
+}
+
+/* initPose :262-276: translation = mean world3D of the samples (Pt += then / n); the quaternion is the caller's */
+void mo_init_translation_depth(const float *world, const int *sample_pos, int n_samples, float *t3) {
+	float sx = 0.f, sy = 0.f, sz = 0.f;
+	for (int j = 0; j < n_samples; j++) { const float *w = world + 3 * sample_pos[j]; sx += w[0]; sy += w[1]; sz += w[2]; }
+	t3[0] = sx / n_samples; t3[1] = sy / n_samples; t3[2] = sz / n_samples;
+}
+
+/* one RANSAC iteration body (:283-312) on explicit (sample positions, initial quaternion): like mo_hypothesis */
+int mo_hypothesis_depth(int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image, const mo_camera *cams,
+                        float alpha, const int *sample_pos, int n_samples, const float *init_quat, int max_lm, float err_thr, int min_npts,
+                        float *pose_lm, float *pose_refit, float *lm_err2, unsigned char *mask) {
+	float *gxyz = (float *)malloc(sizeof(float) * 3 * (size_t)(n + 1)), *gw = (float *)malloc(sizeof(float) * 3 * (size_t)(n + 1));
+	float *gc = (float *)malloc(sizeof(float) * (size_t)(n + 1));
+	int *gim = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+	for (int j = 0; j < n_samples; j++) {
+		int s = sample_pos[j];
+		memcpy(gxyz + 3 * j, xyz + 3 * s, 12); memcpy(gw + 3 * j, world + 3 * s, 12); gc[j] = cauchy[s]; gim[j] = image[s];
+	}
+	float pose[7] = { init_quat[0], init_quat[1], init_quat[2], init_quat[3], 0, 0, 0 };
+	mo_init_translation_depth(world, sample_pos, n_samples, pose + 4);
+	memset(mask, 0, (size_t)n);
+	lm_err2[1] = -2;
+	int ret = -1;
+	float r = mo_optimize_camera_depth(pose, n_samples, max_lm, gxyz, gw, gc, gim, cams, alpha);
+	lm_err2[0] = r;
+	if ((int)r != -1) {
+		memcpy(pose_lm, pose, sizeof pose);
+		ret = mo_test_all_points(pose, n, xy, xyz, image, cams, err_thr, mask);
+		if (ret > min_npts) {
+			int k = 0;
+			for (int i = 0; i < n; i++) if (mask[i]) { memcpy(gxyz + 3 * k, xyz + 3 * i, 12); memcpy(gw + 3 * k, world + 3 * i, 12); gc[k] = cauchy[i]; gim[k] = image[i]; k++; }
+			lm_err2[1] = mo_optimize_camera_depth(pose, k, max_lm, gxyz, gw, gc, gim, cams, alpha);
+		}
+		memcpy(pose_refit, pose, sizeof pose);
+	}
+	free(gxyz); free(gw); free(gc); free(gim);
+	return ret;
+}
+
+/* RANSAC() :278-314 with the seedable stream (same draws as ref3d_ransac: randSample then four quaternion components) */
+int mo_ransac_depth(uint64_t *state, int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image,
+                    const int *tie_ids, const mo_camera *cams, float alpha, int max_ransac, int max_lm, int n_pts_align, int min_npts,
+                    float err_thr, float *pose7, int *iters) {
+	int pos[16];
+	float init[7], pose_lm[7], pose_refit[7], err2[2];
+	unsigned char *mask = (unsigned char *)malloc((size_t)n + 1);
+	int found = 0, it;
+	for (it = 0; it < max_ransac; it++) {
+		if (!mo_rand_sample(state, xy, image, tie_ids, n, n_pts_align, pos)) break;
+		mo_init_pose(state, init);                     /* the four rand() calls of initPose; its translation is replaced below */
+		int r = mo_hypothesis_depth(n, xy, xyz, world, cauchy, image, cams, alpha, pos, n_pts_align, init, max_lm, err_thr, min_npts,
+		                            pose_lm, pose_refit, err2, mask);
+		if (r > min_npts) { memcpy(pose7, pose_refit, sizeof pose_refit); found = 1; it++; break; }
+	}
+	if (iters) *iters = it;
+	free(mask);
+	return found;
 }

@@ -52,6 +52,20 @@ int mo_filter(int n_models, const int *match_offsets, const int *match_image, co
               const mo_camera *cams, int n_obj, const int *obj_model, const float *obj_pose, int min_points, float feat_dist,
               float min_score, unsigned char *keep, float *score, int *cluster_offsets, int *members);
 
+/* POSE, moped3d depth-aware variant (oracle only so far) ---------------------------------- */
+float mo_cauchy_weight(float fill_distance);
+void mo_lm_func_depth(const float *p7, float *res, int n_pts, const float *xyz, const float *world, const float *cauchy,
+                      const int *image, const mo_camera *cams, float alpha);
+float mo_optimize_camera_depth(float *pose7, int n_pts, int itmax, const float *xyz, const float *world, const float *cauchy,
+                               const int *image, const mo_camera *cams, float alpha);
+void mo_init_translation_depth(const float *world, const int *sample_pos, int n_samples, float *t3);
+int mo_hypothesis_depth(int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image, const mo_camera *cams,
+                        float alpha, const int *sample_pos, int n_samples, const float *init_quat, int max_lm, float err_thr, int min_npts,
+                        float *pose_lm, float *pose_refit, float *lm_err2, unsigned char *mask);
+int mo_ransac_depth(uint64_t *state, int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image,
+                    const int *tie_ids, const mo_camera *cams, float alpha, int max_ransac, int max_lm, int n_pts_align, int min_npts,
+                    float err_thr, float *pose7, int *iters);
+
 /* FEAT (SIFT) — moped_sift_oracle.c -------------------------------------------- */
 typedef struct { int octave, index, scan_row, scan_col, row, col; float X[3]; float fsize; int first_kp; } mo_sift_trace;
 int mo_sift_gauss_kernel(float fblur, float *kernel /* >= 64 floats */);

@@ -52,6 +52,13 @@ def _load():
                                     _f32p, _f32p, _f32p, _u8p]),
         "mo_ransac": (C.c_int, [_u64p, C.c_int, _f32p, _f32p, _i32p, C.c_void_p, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 _f32p, C.POINTER(C.c_int)]),
+        "mo_cauchy_weight": (C.c_float, [C.c_float]),
+        "mo_lm_func_depth": (None, [_f32p, _f32p, C.c_int, _f32p, _f32p, _f32p, _i32p, camp, C.c_float]),
+        "mo_init_translation_depth": (None, [_f32p, _i32p, C.c_int, _f32p]),
+        "mo_hypothesis_depth": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, camp, C.c_float, _i32p, C.c_int, _f32p, C.c_int, C.c_float,
+                                          C.c_int, _f32p, _f32p, _f32p, _u8p]),
+        "mo_ransac_depth": (C.c_int, [_u64p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_void_p, camp, C.c_float, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_float, _f32p, C.POINTER(C.c_int)]),
         "mo_sift": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]),
         "mo_sift_debug": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
         "mo_sift_gauss_kernel": (C.c_int, [C.c_float, _f32p]),
@@ -243,3 +250,38 @@ def sift_debug(gray_u8, double_size=True, octave=0, max_trace=65536):
     lib().mo_sift_debug(g, g.shape[0], g.shape[1], 1 if double_size else 0, octave, gauss.ctypes.data, dog.ctypes.data, max_trace,
                         trace.ctypes.data, C.byref(nt))
     return gauss, dog, trace[:min(nt.value, max_trace)].copy()
+
+
+# ---- moped3d depth-aware pose stage (oracle only so far) ----------------------------------------
+def cauchy_weights(fill):
+    return np.array([lib().mo_cauchy_weight(float(f)) for f in np.asarray(fill).ravel()], np.float32)
+
+
+def lm_func_depth(pose7, cl, cams, alpha):
+    n = len(cl["xy"])
+    out = np.zeros(2 * n, np.float32)
+    lib().mo_lm_func_depth(_f32(pose7), out, n, _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"]), np.zeros(n, np.int32), cams, alpha)
+    return out
+
+
+def hypothesis_depth(cl, cams, alpha, sample_pos, init_quat, max_lm, err_thr, min_npts):
+    n = len(cl["xy"])
+    lm, refit = np.zeros(7, np.float32), np.zeros(7, np.float32)
+    err = np.zeros(2, np.float32)
+    mask = np.zeros(n, np.uint8)
+    sp = _i32(sample_pos)
+    r = lib().mo_hypothesis_depth(n, _f32(cl["xy"]), _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"]), np.zeros(n, np.int32), cams,
+                                  alpha, sp, len(sp), _f32(init_quat), max_lm, err_thr, min_npts, lm, refit, err, mask)
+    return dict(n_inliers=r, pose_lm=lm, pose_refit=refit, lm_err=err, mask=mask)
+
+
+def ransac_depth(cl, cams, alpha, params, seed):
+    """params = (MaxRANSACTests, MaxLMTests, NPtsAlign, MinNPtsObject, ErrorThreshold); seed = the LCG state ref3d_srand gets"""
+    n = len(cl["xy"])
+    st = C.c_uint64(int(seed))
+    pose = np.zeros(7, np.float32)
+    it = C.c_int(0)
+    found = lib().mo_ransac_depth(C.byref(st), n, _f32(cl["xy"]), _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"]),
+                                  np.zeros(n, np.int32), None, cams, alpha, int(params[0]), int(params[1]), int(params[2]), int(params[3]),
+                                  float(params[4]), pose, C.byref(it))
+    return bool(found), pose, it.value

@@ -1,0 +1,77 @@
+"""ctypes binding of oracle/_ref/libmoped3d_ref.so — moped3d's depth-aware pose stage compiled unmodified from
+/root/reference (oracle/ref3d_harness.cpp, `make -f oracle/Makefile ref`). TEST INFRASTRUCTURE: pins the restatement
+(oracle/moped_oracle.c: mo_*_depth) for SURVEY.md §8f row 4; never imported by the product."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libmoped3d_ref.so")                  # the reference's own flags (-ffast-math)
+STRICT_PATH = os.path.join(_HERE, "_ref", "libmoped3d_ref_strict.so")        # the same sources, strict IEEE arithmetic
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_libs = {}
+_strict = False
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH) and os.path.exists(STRICT_PATH)
+
+
+def use_strict(on: bool):
+    """Select which build of the reference the calls below go to."""
+    global _strict
+    _strict = bool(on)
+
+
+def lib():
+    path = STRICT_PATH if _strict else LIB_PATH
+    if path not in _libs:
+        L = C.CDLL(path)
+        L.ref3d_cauchy_weight.restype = C.c_float
+        L.ref3d_cauchy_weight.argtypes = [C.c_float]
+        L.ref3d_lm_func.restype = None
+        L.ref3d_lm_func.argtypes = [_f32p, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p]
+        L.ref3d_hypothesis.restype = C.c_int
+        L.ref3d_hypothesis.argtypes = [C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _i32p, C.c_int, _f32p, C.c_int, C.c_float,
+                                       C.c_int, _f32p, _f32p, _f32p, _f32p, _u8p]
+        L.ref3d_ransac.restype = C.c_int
+        L.ref3d_ransac.argtypes = [C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                   C.c_uint64, _f32p]
+        _libs[path] = L
+    return _libs[path]
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def lm_func(pose7, cl, K, cam_pose, alpha):
+    n = len(cl["xy"])
+    out = np.zeros(2 * n, np.float32)
+    lib().ref3d_lm_func(_f(pose7), n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha, out)
+    return out
+
+
+def hypothesis(cl, K, cam_pose, alpha, sample_pos, init_quat, max_lm, err_thr, min_npts):
+    n = len(cl["xy"])
+    init, lm, refit = (np.zeros(7, np.float32) for _ in range(3))
+    err = np.zeros(2, np.float32)
+    mask = np.zeros(n, np.uint8)
+    sp = np.ascontiguousarray(sample_pos, dtype=np.int32)
+    r = lib().ref3d_hypothesis(n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha, sp, len(sp),
+                               _f(init_quat), max_lm, err_thr, min_npts, init, lm, refit, err, mask)
+    return dict(n_inliers=r, pose_init=init, pose_lm=lm, pose_refit=refit, lm_err=err, mask=mask)
+
+
+def ransac(cl, K, cam_pose, alpha, params, seed):
+    """params = (MaxRANSACTests, MaxLMTests, NPtsAlign, MinNPtsObject, ErrorThreshold)"""
+    n = len(cl["xy"])
+    pose = np.zeros(7, np.float32)
+    found = lib().ref3d_ransac(n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha,
+                               int(params[0]), int(params[1]), int(params[2]), int(params[3]), float(params[4]), int(seed), pose)
+    return bool(found), pose

@@ -1,0 +1,131 @@
+/*
+ * ref3d_harness.cpp — TEST INFRASTRUCTURE (never part of the product): flat-array glue around moped3d's depth-aware pose
+ * stage, POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU (moped3d/libmoped/src/pose/…:57-437), compiled UNMODIFIED from
+ * /root/reference together with the vendored levmar 2.4 into oracle/_ref/libmoped3d_ref.so by oracle/Makefile (target
+ * ref3d). It pins the C restatement of the stage (oracle/moped_oracle.c: mo_*_depth) — the checker of SURVEY.md §8f row 4's
+ * first component. A separate library because moped3d's MopedNS (FrameData::Match with depthData, typed Image) clashes with
+ * moped2's.
+ *
+ * Same shims as ref_harness.cpp: `#define class struct` (private members per hypothesis), `#define rand moped3d_ref_rand`
+ * (seedable LCG instead of libc's global rand()), FTZ|DAZ while inside reference code (the executable is -ffast-math).
+ */
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
+#include <cfloat>
+#include <stdint.h>
+#include <xmmintrin.h>
+
+#include <moped.hpp>
+#include <util.hpp>
+#include <lm.h>
+
+static __thread uint64_t g_rng_state = 0x9E3779B97F4A7C15ULL;
+extern "C" int moped3d_ref_rand(void) {
+	g_rng_state = g_rng_state * 6364136223846793005ULL + 1442695040888963407ULL;
+	return (int)((g_rng_state >> 33) & 0x7fffffffULL);
+}
+extern "C" void ref3d_srand(uint64_t seed) { g_rng_state = seed; }
+
+#ifndef MAX_THREADS
+#define MAX_THREADS 64
+#endif
+
+#define rand moped3d_ref_rand
+#define class struct
+#include <pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp>
+#undef class
+#undef rand
+
+using namespace MopedNS;
+typedef POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU POSE3D_T;
+
+struct FtzGuard {
+	unsigned saved;
+	FtzGuard() { saved = _mm_getcsr(); _mm_setcsr(saved | 0x8040u); }
+	~FtzGuard() { _mm_setcsr(saved); }
+};
+
+/* one camera (every correspondence of a call is seen by it) + the LmData records of n correspondences */
+struct Cluster3D {
+	Image image;
+	vector<POSE3D_T::LmData> data;
+	vector<POSE3D_T::LmData *> ptrs;
+	Cluster3D(POSE3D_T &alg, int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4, const float *cam_pose7)
+	: image(IMAGE_TYPE_GRAY_IMAGE) {
+		image.intrinsicLinearCalibration.init(K4[0], K4[1], K4[2], K4[3]);
+		image.cameraPose.rotation.init(cam_pose7[0], cam_pose7[1], cam_pose7[2], cam_pose7[3]);
+		image.cameraPose.translation.init(cam_pose7[4], cam_pose7[5], cam_pose7[6]);
+		image.TM.init(image.cameraPose);
+		data.resize(n);
+		for (int i = 0; i < n; i++) {                       /* preprocessAllMatches, :330-355 */
+			data[i].image = &image;
+			data[i].coord2D.init(xy[2 * i], xy[2 * i + 1]);
+			data[i].coord3D.init(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+			data[i].world3D.init(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+			data[i].cauchyWeight = alg.getCauchyWeight(fill[i]);
+			ptrs.push_back(&data[i]);
+		}
+	}
+};
+
+extern "C" {
+
+/* getCauchyWeight (:187-190) */
+float ref3d_cauchy_weight(float fill_distance) {
+	POSE3D_T alg(1, 1, 1, 5, 6, 8, 0.5);
+	return alg.getCauchyWeight(fill_distance);
+}
+
+/* lmFuncQuat (:108-183): 2 residuals per correspondence */
+void ref3d_lm_func(const float *pose7, int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4,
+                   const float *cam_pose7, float alpha, float *errors) {
+	FtzGuard g;
+	POSE3D_T alg(1, 1, 1, 5, 6, 8, alpha);
+	Cluster3D cl(alg, n, xy, xyz, world, fill, K4, cam_pose7);
+	float p[7]; memcpy(p, pose7, sizeof p);
+	POSE3D_T::lmFuncQuat(p, errors, 7, 2 * n, (void *)&cl.ptrs);
+}
+
+/* The body of one RANSAC iteration (:283-312) for an EXPLICIT (sample positions, initial quaternion) pair; the initial
+ * translation is the reference's own initPose (:262-276: mean world3D of the samples). Returns -1 when LM failed on the
+ * samples, else #inliers. Outputs like ref_hypothesis of the moped2 harness. */
+int ref3d_hypothesis(int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4, const float *cam_pose7,
+                     float alpha, const int *sample_pos, int n_samples, const float *init_quat, int maxLM, float errThr, int minNPts,
+                     float *pose_init, float *pose_lm, float *pose_refit, float *lm_err, unsigned char *inlier_mask) {
+	FtzGuard g;
+	POSE3D_T alg(1, maxLM, 1, n_samples, minNPts, errThr, alpha);
+	Cluster3D cl(alg, n, xy, xyz, world, fill, K4, cam_pose7);
+	vector<POSE3D_T::LmData *> samples;
+	for (int j = 0; j < n_samples; j++) samples.push_back(cl.ptrs[sample_pos[j]]);
+	Pose pose;
+	alg.initPose(pose, samples);
+	pose.rotation.init(init_quat[0], init_quat[1], init_quat[2], init_quat[3]);
+	for (int j = 0; j < 7; j++) pose_init[j] = pose[j];
+	Float r = alg.optimizeCamera(pose, samples, maxLM);
+	lm_err[0] = r; lm_err[1] = -2;
+	for (int i = 0; i < n; i++) inlier_mask[i] = 0;
+	if ((int)r == -1) return -1;                           /* `int LMIterations = LMInfo; if (LMIterations == -1) continue;` :292-297 */
+	for (int j = 0; j < 7; j++) pose_lm[j] = pose[j];
+	vector<POSE3D_T::LmData *> consistent;
+	alg.testAllPoints(consistent, pose, cl.ptrs, errThr);
+	for (size_t k = 0; k < consistent.size(); k++) inlier_mask[consistent[k] - &cl.data[0]] = 1;
+	if ((int)consistent.size() > minNPts) lm_err[1] = alg.optimizeCamera(pose, consistent, maxLM);
+	for (int j = 0; j < 7; j++) pose_refit[j] = pose[j];
+	return (int)consistent.size();
+}
+
+/* Whole RANSAC() (:278-314) on one cluster with the seeded RNG; returns found (0/1). */
+int ref3d_ransac(int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4, const float *cam_pose7,
+                 float alpha, int maxRansac, int maxLM, int nPtsAlign, int minNPts, float errThr, uint64_t seed, float *pose_out) {
+	FtzGuard g;
+	POSE3D_T alg(maxRansac, maxLM, 1, nPtsAlign, minNPts, errThr, alpha);
+	Cluster3D cl(alg, n, xy, xyz, world, fill, K4, cam_pose7);
+	ref3d_srand(seed);
+	Pose pose;
+	bool found = alg.RANSAC(pose, cl.ptrs);
+	for (int j = 0; j < 7; j++) pose_out[j] = pose[j];
+	return found ? 1 : 0;
+}
+
+} /* extern "C" */
