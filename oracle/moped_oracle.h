@@ -69,6 +69,7 @@ int mo_ransac_depth(uint64_t *state, int n, const float *xy, const float *xyz, c
 /* FEAT (SIFT) — moped_sift_oracle.c -------------------------------------------- */
 typedef struct { int octave, index, scan_row, scan_col, row, col; float X[3]; float fsize; int first_kp; } mo_sift_trace;
 int mo_sift_gauss_kernel(float fblur, float *kernel /* >= 64 floats */);
+void mo_sift_set_conv_fma(int on);   /* 1 (default): taps as FMA, like the CUDA kernels; 0: multiply then add, like a strict-IEEE build of the reference */
 int mo_sift(const uint8_t *gray, int height, int width, int double_size, int max_kp,
             float *xy /* (col,row) */, float *scale_ori, float *desc /* x128 */);
 int mo_sift_debug(const uint8_t *gray, int height, int width, int double_size, int dbg_octave, float *dbg_gauss /* 6 images */,

@@ -60,11 +60,18 @@ int mo_sift_gauss_kernel(float fblur, float *kernel /* >= 64 */) {
 	return ksize;
 }
 
+/* How the convolution taps accumulate: 1 (default) = fused multiply-add in tap order — the variant the CUDA kernels
+ * implement; 0 = separate multiply and add in tap order — what a strict-IEEE build of libsiftfast.cpp computes, used by
+ * tests/test_oracle_vs_strict_ref.py to compare this whole file with such a build BIT FOR BIT. */
+static int g_conv_fma = 1;
+void mo_sift_set_conv_fma(int on) { g_conv_fma = on != 0; }
+
 /* ConvBuffer (:573-581) on a replicate-padded line */
 static void conv_line(const float *buf, const float *kernel, int n, int ksize, float *out, int ostride) {
 	for (int i = 0; i < n; ++i) {
 		float faccum = 0;
-		for (int j = 0; j < ksize; ++j) faccum = fmaf(buf[i + j], kernel[j], faccum);
+		if (g_conv_fma) for (int j = 0; j < ksize; ++j) faccum = fmaf(buf[i + j], kernel[j], faccum);
+		else for (int j = 0; j < ksize; ++j) faccum += buf[i + j] * kernel[j];
 		out[(size_t)i * ostride] = faccum;
 	}
 }

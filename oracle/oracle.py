@@ -62,6 +62,7 @@ def _load():
         "mo_sift": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]),
         "mo_sift_debug": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
         "mo_sift_gauss_kernel": (C.c_int, [C.c_float, _f32p]),
+        "mo_sift_set_conv_fma": (None, [C.c_int]),
         "mo_filter": (C.c_int, [C.c_int, _i32p, _i32p, _f32p, _f32p, camp, C.c_int, _i32p, _f32p, C.c_int, C.c_float, C.c_float,
                                 _u8p, _f32p, _i32p, _i32p]),
     }

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libmoped_ref.so")
+LIB_PATH = os.path.join(_HERE, "_ref", "libmoped_ref.so")                    # the reference's own flags (-ffast-math)
+STRICT_PATH = os.path.join(_HERE, "_ref", "libmoped_ref_strict.so")          # the same sources, strict IEEE arithmetic
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -24,8 +25,12 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
-def _load():
-    lib = C.CDLL(LIB_PATH)
+def strict_available() -> bool:
+    return os.path.exists(STRICT_PATH)
+
+
+def _load(path=None):
+    lib = C.CDLL(path or LIB_PATH)
     sig = {
         "ref_create": (C.c_void_p, [C.c_int]),
         "ref_destroy": (None, [C.c_void_p]),
@@ -78,13 +83,28 @@ def _load():
 
 
 _lib = None
+_lib_fast = None
+_lib_strict = None
 
 
 def lib():
-    global _lib
+    global _lib, _lib_fast
     if _lib is None:
-        _lib = _load()
+        _lib = _lib_fast = _load()
     return _lib
+
+
+def use_strict(on: bool):
+    """Route every call of this module to the strict-IEEE build of the reference (tests only) or back to the build with the
+    reference's own flags. Contexts (Ref objects) belong to the build that created them."""
+    global _lib, _lib_fast, _lib_strict
+    lib()
+    if on:
+        if _lib_strict is None:
+            _lib_strict = _load(STRICT_PATH)
+        _lib = _lib_strict
+    else:
+        _lib = _lib_fast
 
 
 def _f32(a):
