@@ -197,3 +197,45 @@ def test_two_rank_cluster_partition_covers_every_hypothesis_once():
         s = slice(cl["offsets"][c], cl["offsets"][c + 1])
         single.append(oracle.hypothesis(cl["xy"][s], cl["xyz"][s], cl["image"][s], cams, hy["sample_pos"][h], hy["init_quat"][h], 200, 10.0, 6)[0])
     assert merged == single
+
+
+# ---- feature extraction: frames of a batch are independent -> partitioned, no data-path collective ----
+def _sift_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from moped_b200 import synth
+    from moped_b200.sharding import frame_range
+    from oracle import oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_frames = 4
+    frames = [synth.make_image(40 + i, 96, 128, n_blobs=120) for i in range(n_frames)]
+    lo, hi = frame_range(n_frames, world, rank)
+    mine = [oracle.sift(frames[f], True) for f in range(lo, hi)]               # (the oracle stands in for the GPU here)
+    counts = torch.tensor([len(m[0]) for m in mine], dtype=torch.int32)
+    digest = torch.tensor([float(np.float64(m[2]).sum()) for m in mine], dtype=torch.float64)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    all_digest = [torch.empty_like(digest) for _ in range(world)]
+    dist.all_gather(all_counts, counts)                                          # bookkeeping only: the descriptors stay where they are
+    dist.all_gather(all_digest, digest)
+    single = [oracle.sift(f, True) for f in frames]
+    ok_counts = torch.cat(all_counts).tolist() == [len(s[0]) for s in single]
+    ok_digest = np.array_equal(torch.cat(all_digest).numpy(), np.array([float(np.float64(s[2]).sum()) for s in single]))
+    q.put((rank, ok_counts, ok_digest, (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_frame_partition_of_feature_extraction():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sift_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[3] for r in res] == [(0, 2), (2, 4)]                               # contiguous blocks in frame order
+    assert all(r[1] and r[2] for r in res), res
