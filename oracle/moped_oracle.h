@@ -66,6 +66,11 @@ int mo_ransac_depth(uint64_t *state, int n, const float *xy, const float *xyz, c
                     const int *tie_ids, const mo_camera *cams, float alpha, int max_ransac, int max_lm, int n_pts_align, int min_npts,
                     float err_thr, float *pose7, int *iters);
 
+/* CLUSTER, moped3d linkage variant (oracle only so far) — moped_linkage_oracle.c ----------- */
+int mo_cluster_linkage(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,
+                       float cutoff, int min_pts, int use3DFilter, int linkage_type, float sigma2D, float sigma3D,
+                       int *cluster_offsets, int *members);
+
 /* FEAT (SIFT) — moped_sift_oracle.c -------------------------------------------- */
 typedef struct { int octave, index, scan_row, scan_col, row, col; float X[3]; float fsize; int first_kp; } mo_sift_trace;
 int mo_sift_gauss_kernel(float fblur, float *kernel /* >= 64 floats */);

@@ -59,6 +59,8 @@ def _load():
                                           C.c_int, _f32p, _f32p, _f32p, _u8p]),
         "mo_ransac_depth": (C.c_int, [_u64p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_void_p, camp, C.c_float, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_float, _f32p, C.POINTER(C.c_int)]),
+        "mo_cluster_linkage": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_float, _i32p, _i32p]),
         "mo_sift": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]),
         "mo_sift_debug": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
         "mo_sift_gauss_kernel": (C.c_int, [C.c_float, _f32p]),
@@ -286,3 +288,15 @@ def ransac_depth(cl, cams, alpha, params, seed):
                                   np.zeros(n, np.int32), None, cams, alpha, int(params[0]), int(params[1]), int(params[2]), int(params[3]),
                                   float(params[4]), pose, C.byref(it))
     return bool(found), pose, it.value
+
+
+def cluster_linkage(xy, xyz, world, depth, distance, cutoff=0.1, min_pts=7, use3d_filter=2, linkage_type=1, sigma2d=-1.0, sigma3d=-1.0):
+    """moped3d CLUSTER_LINKAGE_CPU on one model's matches -> (offsets, members). depth / distance: H x W float maps."""
+    xy, xyz, world = _f32(xy), _f32(xyz), _f32(world)
+    depth, distance = _f32(depth), _f32(distance)
+    n = len(xy)
+    off = np.zeros(n + 2, np.int32)
+    mem = np.zeros(n + 1, np.int32)
+    c = lib().mo_cluster_linkage(n, xy, xyz, world, depth.shape[1], depth.shape[0], depth, distance, cutoff, min_pts, use3d_filter, linkage_type,
+                                 sigma2d, sigma3d, off, mem)
+    return off[:c + 1].copy(), mem[:off[c]].copy()

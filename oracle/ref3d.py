@@ -42,6 +42,9 @@ def lib():
         L.ref3d_ransac.restype = C.c_int
         L.ref3d_ransac.argtypes = [C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_uint64, _f32p]
+        L.ref3d_cluster_linkage.restype = C.c_int
+        L.ref3d_cluster_linkage.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_float,
+                                            C.c_float, C.c_int, C.c_float, C.c_float, _i32p, _i32p]
         _libs[path] = L
     return _libs[path]
 
@@ -75,3 +78,15 @@ def ransac(cl, K, cam_pose, alpha, params, seed):
     found = lib().ref3d_ransac(n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha,
                                int(params[0]), int(params[1]), int(params[2]), int(params[3]), float(params[4]), int(seed), pose)
     return bool(found), pose
+
+
+def cluster_linkage(xy, xyz, world, depth, distance, cutoff=0.1, min_pts=7, use3d_filter=2, weight_gamma=1.0, alpha=0.0, linkage_type=1,
+                    sigma2d=-1.0, sigma3d=-1.0):
+    """CLUSTER_LINKAGE_CPU::process on one model's matches (constructor defaults = moped3d/libmoped/src/config.hpp:45)."""
+    xy, xyz, world, depth, distance = _f(xy), _f(xyz), _f(world), _f(depth), _f(distance)
+    n = len(xy)
+    off = np.zeros(n + 2, np.int32)
+    mem = np.zeros(n + 1, np.int32)
+    c = lib().ref3d_cluster_linkage(n, xy, xyz, world, depth.shape[1], depth.shape[0], depth, distance, cutoff, min_pts, use3d_filter, weight_gamma,
+                                    alpha, linkage_type, sigma2d, sigma3d, off, mem)
+    return off[:c + 1].copy(), mem[:off[c]].copy()

@@ -34,6 +34,7 @@ extern "C" void ref3d_srand(uint64_t seed) { g_rng_state = seed; }
 #define rand moped3d_ref_rand
 #define class struct
 #include <pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp>
+#include <cluster/CLUSTER_LINKAGE_CPU.hpp>
 #undef class
 #undef rand
 
@@ -126,6 +127,52 @@ int ref3d_ransac(int n, const float *xy, const float *xyz, const float *world, c
 	bool found = alg.RANSAC(pose, cl.ptrs);
 	for (int j = 0; j < 7; j++) pose_out[j] = pose[j];
 	return found ? 1 : 0;
+}
+
+/* CLUSTER_LINKAGE_CPU::process (moped3d/libmoped/src/cluster/CLUSTER_LINKAGE_CPU.hpp:577-704) on the matches of ONE model:
+ * coord2D, model coord3D and depthData.coord3D (world) per match, a depth map (depth per pixel; stored in slot 2 of the 4 floats
+ * per pixel the class reads, moped.hpp:281-287) and its fill-distance map. Output: clusters as CSR over match indices, in the
+ * order and with the member order the class produces. */
+int ref3d_cluster_linkage(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,
+                          float cutoff, int minPts, int use3DFilter, float weightGamma, float alpha, int linkageType, float sigma2D, float sigma3D,
+                          int *cluster_offsets, int *members) {
+	FtzGuard g;
+	omp_set_num_threads(1);
+	CLUSTER_LINKAGE_CPU alg(cutoff, minPts, use3DFilter, weightGamma, alpha, linkageType, sigma2D, sigma3D);
+	string step("CLUSTER"); alg.setStepNameAndAlg(step, 0);
+	vector<SP_Model> models(1, SP_Model(new Model));
+	models[0]->name = "m0";
+	alg.modelsUpdated(models);
+	FrameData fd;
+	SP_Image dm(new Image(IMAGE_TYPE_DEPTH_MAP));
+	dm->name = "cam/depth"; dm->width = W; dm->height = H;
+	dm->data.assign((size_t)W * H * 4 * sizeof(Float), 0);
+	for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) dm->setDepth(x, y, depth[(size_t)y * W + x]);
+	SP_Image pm(new Image(IMAGE_TYPE_PROB_MAP));
+	pm->name = dm->name + ".distance"; pm->width = W; pm->height = H;
+	pm->data.assign((size_t)W * H * sizeof(Float), 0);
+	for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) pm->setProb(x, y, distance[(size_t)y * W + x]);
+	fd.images.push_back(dm); fd.images.push_back(pm);
+	fd.matches.resize(1);
+	fd.matches[0].resize(n);
+	for (int i = 0; i < n; i++) {
+		FrameData::Match &m = fd.matches[0][i];
+		m.imageIdx = 0;
+		m.coord2D.init(xy[2 * i], xy[2 * i + 1]);
+		m.coord3D.init(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+		m.depthData.depthValid = true;
+		m.depthData.coord3D.init(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+		m.depthData.depth = world[3 * i + 2];
+		m.depthData.fillDistance = 0;
+	}
+	alg.process(fd);
+	int nc = 0, k = 0;
+	cluster_offsets[0] = 0;
+	for (size_t c = 0; c < fd.clusters[0].size(); c++) {
+		for (list<int>::iterator it = fd.clusters[0][c].begin(); it != fd.clusters[0][c].end(); ++it) members[k++] = *it;
+		cluster_offsets[++nc] = k;
+	}
+	return nc;
 }
 
 } /* extern "C" */
