@@ -878,6 +878,146 @@ def run_sift_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# --workload images: pixels in, objects out (FEAT chained to MATCH..FILTER2 on the device, mc_process_images)
+# ------------------------------------------------------------------------------------------------
+def images_setup(args):
+    """Real data only: the planar model database and a frame of the reference's shipped imagery (tests/golden/*.npz — the stand-in
+    for BASELINE configs[0]); the frame is repeated with small horizontal shifts to fill a batch."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "real_images.npz")))
+    sg = np.load(os.path.join(ROOT, "tests", "golden", "sift_golden.npz"))
+    im = sg["bag4_full_double/image"]
+    frames = np.stack([np.roll(im, (i % 8) - 4, axis=1) for i in range(args.frames)])
+    return g, frames
+
+
+def images_config(args, world):
+    return {"workload": f"images in, objects out: FEAT_SIFT + MATCH..FILTER2 on real data (a 640x480 frame of the reference's timing.bag, shifted per slot; "
+                        f"3 planar models / 1275 descriptors built from the reference's imagery); a step = a batch of {args.frames} frames",
+            "frames_per_step": args.frames, "image": "640x480 u8", "parallelism": "single-gpu" if world == 1 else f"frames partitioned x{world}"}
+
+
+def run_images_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmoped_ref.so missing and /root/reference not present to build it"}))
+        return
+    cores = os.cpu_count() or 1
+    g, frames = images_setup(args)
+    r = ref.Ref(cores)
+    r.set_models(g["n_pts"], g["db_xyz"], g["db_desc"])
+    r.set_images(g["K"], g["cam_pose"])
+    per = max(1, min(args.frames, 4))
+    tot, n_obj = 0.0, 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        k = 0
+        for f in range(per):
+            xy, desc = ref.sift(frames[f], True)
+            r.set_features(desc, xy, np.zeros(len(xy), np.int32))
+            n, _ = r.run_pipeline(seed=3 + i)
+            k += n
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            tot += dt
+            n_obj += k
+        log(f"[reference] images step {i}: {dt / per * 1e3:.1f} ms/frame, {k / per:.1f} objects/frame")
+    fps = per * args.steps / tot
+    out = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": tot / args.steps / per * args.frames * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": "real (reference's shipped imagery)", "config": images_config(args, world), "objects_per_frame": n_obj / (per * args.steps),
+           "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": f"{per} of the {args.frames} frames of a step per step: FEAT_SIFT_CPU + MATCH_ANN_CPU(eps=5) .. FILTER2 with OpenMP"},
+           "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def run_images_ours(args, rank, world, local_rank):
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    import torch
+    import torch.distributed as dist
+    from moped_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmoped_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g, frames_all = images_setup(args)
+    lo, hi = frame_range(args.frames, world, rank)
+    frames = np.ascontiguousarray(frames_all[lo:hi])
+    B = len(frames)
+    ctx = capi.Context(local_rank)
+    ctx.db_upload(g["db_desc"], g["db_xyz"], g["model_of_row"], len(g["n_pts"]))
+    ctx.set_cameras(g["K"], g["cam_pose"])
+    ctx.set_tuning(args.lanes, args.pose_warps, 1)
+    h_frames = torch.from_numpy(frames).pin_memory().numpy()
+
+    def step(i):
+        # the public call: host pixels in, objects out (H2D of the images and D2H of the objects inside)
+        return ctx.process_images(h_frames, True, max_keypoints=2048, max_objects=16, want_times=(i < 0))
+
+    for i in range(args.warmup):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    n_obj = n_feat = 0
+    for i in range(args.steps):
+        out = step(i)
+        n_obj += sum(len(o["model"]) for o in out)
+        n_feat += sum(o["n_features"] for o in out)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0              # every call synchronises: host wall clock = device time of the K steps
+    clocks = sampler.stop()
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    stage = step(-1)[0]["stage_ms"]
+    if rank == 0:
+        ms_step = float(t.item()) * 1e3 / args.steps
+        fps = args.frames * 1e3 / ms_step
+        out = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 pixels in; f16 tensor-core coarse matching)",
+               "data": "real (reference's shipped imagery)", "config": dict(images_config(args, world), l2="not flushed (scale-space of a batch >> L2)"),
+               "objects_per_frame": n_obj / (args.steps * B), "features_per_frame": n_feat / (args.steps * B),
+               "stage_ms_per_batch_rank0": {"feat": float(stage[0]), "match": float(stage[1]), "cluster_to_filter2": float(stage[2])},
+               "gpu_launches": int(ctx.launches - l0), "clocks": clocks,
+               "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": int(frames.size), "d2h_bytes_per_step": int(B * (16 + 36 * 16) + 8 * B)},
+               "note": "value == e2e here: the measured call takes host pixels and returns host objects; timed by the host clock around K synchronous calls",
+               "roofline": {"kernel": "k_sift_blur (see --workload sift for the live roofline of the dominant kernel of this chain)", "bound": "hbm",
+                            "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None}}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                from oracle import ref
+                if ref.available():
+                    cores = os.cpu_count() or 1
+                    r = ref.Ref(cores)
+                    r.set_models(g["n_pts"], g["db_xyz"], g["db_desc"])
+                    r.set_images(g["K"], g["cam_pose"])
+                    t0 = time.perf_counter()
+                    k = 0
+                    for f in range(2):
+                        xy, desc = ref.sift(frames[f], True)
+                        r.set_features(desc, xy, np.zeros(len(xy), np.int32))
+                        k += r.run_pipeline(seed=5)[0]
+                    dt = time.perf_counter() - t0
+                    out["cpu_baseline"] = {"value": 2 / dt, "unit": UNIT, "cores": cores, "kind": "reference", "objects_per_frame": k / 2,
+                                           "sample": "2 frames of the step: FEAT_SIFT_CPU + MATCH_ANN_CPU(eps=5) .. FILTER2 with OpenMP (kd-tree build included once)"}
+            except Exception as e:
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -894,9 +1034,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=0,
                     help="frames workload: 1 = MATCH of step i+1 overlaps CLUSTER..FILTER2 of step i (two contexts, two streams); 0 = one call per step")
-    ap.add_argument("--workload", default="frames", choices=["frames", "ransac", "sift"],
+    ap.add_argument("--workload", default="frames", choices=["frames", "ransac", "sift", "images"],
                     help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s; "
-                         "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1")
+                         "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1; images = pixels in, objects out on real data")
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--hyp", type=int, default=2048, help="hypotheses per cluster (ransac workload)")
     args = ap.parse_args()
@@ -909,6 +1049,12 @@ def main():
         else:
             args.warmup = max(args.warmup, 3)
             run_ransac_ours(args, rank, world, local_rank)
+    elif args.workload == "images":
+        if args.impl == "reference":
+            run_images_reference(args, rank, world)
+        else:
+            args.warmup = max(args.warmup, 3)
+            run_images_ours(args, rank, world, local_rank)
     elif args.workload == "sift":
         if args.impl == "reference":
             run_sift_reference(args, rank, world)
