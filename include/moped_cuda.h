@@ -263,6 +263,22 @@ mc_status mc_process_images(mc_ctx *ctx, const uint8_t *gray, int n_frames, int 
  * 2 gradient magnitude 0..2, 3 orientation 0..2); out may be NULL to query the octave's size. */
 mc_status mc_sift_read_plane(mc_ctx *ctx, int frame, int octave, int stack, int index, float *out, int32_t *rows, int32_t *cols);
 
+/* ---- moped3d clustering: replaces CLUSTER_LINKAGE_CPU::process for the matches of ONE model,
+ *      moped3d/libmoped/src/cluster/CLUSTER_LINKAGE_CPU.hpp:577-704 ------------------------------------------------------- */
+/* match_xy n x 2 (coord2D), match_xyz n x 3 (model coord3D), match_world n x 3 (depthData.coord3D, the back-projected point);
+ * depth / fill_distance: height x width row-major maps (Image::getDepth / the ".distance" probability map, moped.hpp:262-300).
+ * Parameters as the constructor's: cutoff (Cutoff), min_pts (MinPts, strict >), use_3d_filter (0 none, 1 sum, 2 product),
+ * linkage_type (0 minimum, 1 average, 2 maximum), sigma_2d / sigma_3d (-1 = average nearest-neighbour distance). Outputs
+ * (host): clusters in the reference's order, members in its list order; capacities n+1 / n. similarity_out (optional,
+ * n x n): the blended similarity matrix the agglomeration ran on. n_matches <= 2048. */
+mc_status mc_cluster_linkage(mc_ctx *ctx, const float *match_xy, const float *match_xyz, const float *match_world, int n_matches,
+                             const float *depth, const float *fill_distance, int width, int height,
+                             float cutoff, int min_pts, int use_3d_filter, int linkage_type, float sigma_2d, float sigma_3d,
+                             int32_t *n_clusters, int32_t *cluster_offsets, int32_t *members, float *similarity_out);
+/* hierarchicalCluster (:414-531) alone, on a caller-supplied n x n similarity matrix (host) */
+mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, float cutoff, int min_pts, int linkage_type,
+                                 int32_t *n_clusters, int32_t *cluster_offsets, int32_t *members);
+
 /* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)

@@ -76,6 +76,9 @@ SIGNATURES = {
     "mc_model_db_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]),
     "mc_model_db_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mc_model_db_load": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mc_cluster_linkage": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, C.POINTER(C.c_int32), _i32p, _i32p, C.c_void_p]),
+    "mc_linkage_agglomerate": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int32), _i32p, _i32p]),
     "mc_sift_extract": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _f32p, C.c_void_p, _f32p]),
     "mc_sift_extract_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_process_images": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PipelineParams), C.c_int, _i32p, _i32p,
@@ -297,6 +300,30 @@ class Context:
         p = PipelineParams()
         self.L.mc_pipeline_default_params(C.byref(p))
         return p
+
+    def cluster_linkage(self, xy, xyz, world, depth, distance, cutoff=0.1, min_pts=7, use3d_filter=2, linkage_type=1, sigma2d=-1.0, sigma3d=-1.0,
+                        want_similarity=False):
+        """moped3d CLUSTER_LINKAGE on one model's matches -> (offsets, members[, K])."""
+        xy, xyz, world, depth, distance = _f32(xy), _f32(xyz), _f32(world), _f32(depth), _f32(distance)
+        n = len(xy)
+        nc = C.c_int32(0)
+        off = np.zeros(n + 2, np.int32)
+        mem = np.zeros(n + 1, np.int32)
+        K = np.zeros((n, n), np.float32) if want_similarity else None
+        self._check(self.L.mc_cluster_linkage(self.h, xy.reshape(-1), xyz.reshape(-1), world.reshape(-1), n, depth.reshape(-1), distance.reshape(-1),
+                                              depth.shape[1], depth.shape[0], cutoff, min_pts, use3d_filter, linkage_type, sigma2d, sigma3d,
+                                              C.byref(nc), off, mem, K.ctypes.data if K is not None else None), "mc_cluster_linkage")
+        out = (off[:nc.value + 1].copy(), mem[:off[nc.value]].copy())
+        return out + (K,) if want_similarity else out
+
+    def linkage_agglomerate(self, K, cutoff=0.1, min_pts=7, linkage_type=1):
+        K = _f32(K)
+        n = len(K)
+        nc = C.c_int32(0)
+        off = np.zeros(n + 2, np.int32)
+        mem = np.zeros(n + 1, np.int32)
+        self._check(self.L.mc_linkage_agglomerate(self.h, K.reshape(-1), n, cutoff, min_pts, linkage_type, C.byref(nc), off, mem), "mc_linkage_agglomerate")
+        return off[:nc.value + 1].copy(), mem[:off[nc.value]].copy()
 
     def sift(self, gray, double_size=True, max_keypoints=8192):
         """FEAT step on a batch of equally sized grayscale images [B,H,W] (or one [H,W]) -> list of (xy, scale_ori, desc)."""

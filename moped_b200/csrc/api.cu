@@ -121,6 +121,7 @@ static void free_scratch(mc_ctx *ctx) {
 	for (DevBuf *b : named) cudaFree(b->p);
 	for (DevBuf &b : ctx->scratch) cudaFree(b.p);
 	cudaFree(ctx->batch_out.p);
+	cudaFree(ctx->link_buf.p);
 	cudaFree(ctx->frame_desc.p);
 	for (auto &g : ctx->fgraphs) cudaGraphExecDestroy(g.exec);
 	ctx->fgraphs.clear();

@@ -96,6 +96,7 @@ struct mc_ctx {
 	bool capturing = false;           // reserve() must not allocate while the lane's stream is being captured
 	bool frame_graphs = true;         // mc_set_option "frame_graphs"
 	int batch_stats[4] = {0, 0, 0, 0};   // {frames, accepted matches, objects, lanes used} of the last batch
+	mc::DevBuf link_buf;                 // linkage clustering (linkage.cu): inputs, similarity matrices, agglomeration state
 	void *sift_state = nullptr;          // feature extraction (sift.cu): scale-space plan and buffers, created on first use
 };
 

@@ -228,12 +228,10 @@ static int hierarchical_cluster(const float *K, int n, float cutoff, int min_pts
 	return nc;
 }
 
-/* CLUSTER_LINKAGE_CPU::process for ONE model's matches (:596-700). depth / distance: W x H row-major maps. */
-int mo_cluster_linkage(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,
-                       float cutoff, int min_pts, int use3DFilter, int linkage_type, float sigma2D, float sigma3D,
-                       int *cluster_offsets, int *members) {
-	cluster_offsets[0] = 0;
-	if (n <= 0) return 0;
+/* The similarity matrix K of CLUSTER_LINKAGE_CPU::process for ONE model's matches (:596-651); K is n x n, symmetric. */
+void mo_linkage_similarity(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,
+                           int use3DFilter, float sigma2D, float sigma3D, float *K) {
+	if (n <= 0) return;
 	float k2s, k3s;
 	if (sigma2D == -1 || sigma3D == -1) {
 		avg_nn_distances(n, xy, xyz, &k2s, &k3s);
@@ -242,7 +240,6 @@ int mo_cluster_linkage(int n, const float *xy, const float *xyz, const float *wo
 	} else { k2s = sigma2D; k3s = sigma3D; }
 	size_t nn = (size_t)n * n;
 	float *K2D = (float *)malloc(sizeof(float) * nn), *K3D = (float *)malloc(sizeof(float) * nn), *BK = (float *)malloc(sizeof(float) * nn);
-	float *K = (float *)malloc(sizeof(float) * nn);
 	gauss_k(K2D, n, xy, 2, k2s);
 	gauss_k(K3D, n, world, 3, k3s);
 	discontinuity_k(BK, n, xy, W, H, depth);
@@ -257,7 +254,25 @@ int mo_cluster_linkage(int n, const float *xy, const float *xyz, const float *wo
 		free(K3F);
 	}
 	adaptive_weight_sum(K, n, xy, W, distance, K2D, K3D, (float)0.5, 25);
+	free(K2D); free(K3D); free(BK);
+}
+
+/* hierarchicalCluster (:414-531) on a given similarity matrix */
+int mo_linkage_agglomerate(const float *K, int n, float cutoff, int min_pts, int linkage_type, int *cluster_offsets, int *members) {
+	cluster_offsets[0] = 0;
+	if (n <= 0) return 0;
+	return hierarchical_cluster(K, n, cutoff, min_pts, linkage_type, cluster_offsets, members);
+}
+
+/* CLUSTER_LINKAGE_CPU::process for ONE model's matches (:596-700). depth / distance: W x H row-major maps. */
+int mo_cluster_linkage(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,
+                       float cutoff, int min_pts, int use3DFilter, int linkage_type, float sigma2D, float sigma3D,
+                       int *cluster_offsets, int *members) {
+	cluster_offsets[0] = 0;
+	if (n <= 0) return 0;
+	float *K = (float *)malloc(sizeof(float) * (size_t)n * n);
+	mo_linkage_similarity(n, xy, xyz, world, W, H, depth, distance, use3DFilter, sigma2D, sigma3D, K);
 	int nc = hierarchical_cluster(K, n, cutoff, min_pts, linkage_type, cluster_offsets, members);
-	free(K2D); free(K3D); free(BK); free(K);
+	free(K);
 	return nc;
 }

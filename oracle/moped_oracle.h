@@ -67,6 +67,9 @@ int mo_ransac_depth(uint64_t *state, int n, const float *xy, const float *xyz, c
                     float err_thr, float *pose7, int *iters);
 
 /* CLUSTER, moped3d linkage variant (oracle only so far) — moped_linkage_oracle.c ----------- */
+void mo_linkage_similarity(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,
+                           int use3DFilter, float sigma2D, float sigma3D, float *K /* n x n */);
+int mo_linkage_agglomerate(const float *K, int n, float cutoff, int min_pts, int linkage_type, int *cluster_offsets, int *members);
 int mo_cluster_linkage(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,
                        float cutoff, int min_pts, int use3DFilter, int linkage_type, float sigma2D, float sigma3D,
                        int *cluster_offsets, int *members);

@@ -59,6 +59,8 @@ def _load():
                                           C.c_int, _f32p, _f32p, _f32p, _u8p]),
         "mo_ransac_depth": (C.c_int, [_u64p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_void_p, camp, C.c_float, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_float, _f32p, C.POINTER(C.c_int)]),
+        "mo_linkage_similarity": (None, [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_float, C.c_float, _f32p]),
+        "mo_linkage_agglomerate": (C.c_int, [_f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p]),
         "mo_cluster_linkage": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, _i32p, _i32p]),
         "mo_sift": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]),
@@ -299,4 +301,21 @@ def cluster_linkage(xy, xyz, world, depth, distance, cutoff=0.1, min_pts=7, use3
     mem = np.zeros(n + 1, np.int32)
     c = lib().mo_cluster_linkage(n, xy, xyz, world, depth.shape[1], depth.shape[0], depth, distance, cutoff, min_pts, use3d_filter, linkage_type,
                                  sigma2d, sigma3d, off, mem)
+    return off[:c + 1].copy(), mem[:off[c]].copy()
+
+
+def linkage_similarity(xy, xyz, world, depth, distance, use3d_filter=2, sigma2d=-1.0, sigma3d=-1.0):
+    xy, xyz, world, depth, distance = _f32(xy), _f32(xyz), _f32(world), _f32(depth), _f32(distance)
+    n = len(xy)
+    K = np.zeros((n, n), np.float32)
+    lib().mo_linkage_similarity(n, xy, xyz, world, depth.shape[1], depth.shape[0], depth, distance, use3d_filter, sigma2d, sigma3d, K)
+    return K
+
+
+def linkage_agglomerate(K, cutoff=0.1, min_pts=7, linkage_type=1):
+    K = _f32(K)
+    n = len(K)
+    off = np.zeros(n + 2, np.int32)
+    mem = np.zeros(n + 1, np.int32)
+    c = lib().mo_linkage_agglomerate(K, n, cutoff, min_pts, linkage_type, off, mem)
     return off[:c + 1].copy(), mem[:off[c]].copy()
