@@ -127,3 +127,29 @@ def test_dropin_feat_sift_inside_reference_api(sift_case):
     assert same >= 0.5 * cpu
     if cpu == gpu:
         assert same >= 0.99 * cpu
+
+
+# ---- moped3d CLUSTER step: CLUSTER_LINKAGE_CUDA inside moped3d's own plugin API --------------------------
+
+def test_dropin_cluster_linkage_inside_moped3d_api(tmp_path):
+    """CLUSTER_LINKAGE_CPU and CLUSTER_LINKAGE_CUDA registered in two moped3d MopedPipelines (oracle/ref3d_dropin.cpp), identical
+    FrameData: depth map, fill-distance map, the matches of three models (one of them without matches)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "moped3d_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/moped3d_dropin not built (needs /root/reference at build time)")
+    from test_oracle3d_linkage import make_scene
+    scenes = [make_scene(21), make_scene(22, n_per=(40, 0), n_out=6)]
+    depth, dist = scenes[0][3], scenes[0][4]
+    path = str(tmp_path / "linkage_case.bin")
+    with open(path, "wb") as f:
+        np.array([depth.shape[1], depth.shape[0], 3], np.int32).tofile(f)
+        np.array([len(scenes[0][0]), 0, len(scenes[1][0])], np.int32).tofile(f)
+        depth.astype(np.float32).tofile(f); dist.astype(np.float32).tofile(f)
+        for xy, xyz, world, _, _, _ in scenes:
+            np.concatenate([xy, xyz, world], axis=1).astype(np.float32).tofile(f)
+    r = subprocess.run([exe, path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "CONFIG CLUSTER:0:CLUSTER_LINKAGE_CUDA/Cutoff=0.1" in r.stdout, r.stdout
+    m = re.search(r"STEP CLUSTER same=(\d) cpu_clusters=(\d+) gpu_clusters=(\d+) old_same=(\d)", r.stdout)
+    assert m, r.stdout
+    assert m.group(1) == "1" and m.group(4) == "1" and int(m.group(2)) >= 3, r.stdout
