@@ -45,6 +45,8 @@ def lib():
         L.ref3d_cluster_linkage.restype = C.c_int
         L.ref3d_cluster_linkage.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_float,
                                             C.c_float, C.c_int, C.c_float, C.c_float, _i32p, _i32p]
+        L.ref3d_linkage_agglomerate.restype = C.c_int
+        L.ref3d_linkage_agglomerate.argtypes = [_f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p]
         _libs[path] = L
     return _libs[path]
 
@@ -89,4 +91,13 @@ def cluster_linkage(xy, xyz, world, depth, distance, cutoff=0.1, min_pts=7, use3
     mem = np.zeros(n + 1, np.int32)
     c = lib().ref3d_cluster_linkage(n, xy, xyz, world, depth.shape[1], depth.shape[0], depth, distance, cutoff, min_pts, use3d_filter, weight_gamma,
                                     alpha, linkage_type, sigma2d, sigma3d, off, mem)
+    return off[:c + 1].copy(), mem[:off[c]].copy()
+
+
+def linkage_agglomerate(K, cutoff=0.1, min_pts=7, linkage_type=1):
+    K = _f(K)
+    n = len(K)
+    off = np.zeros(n + 2, np.int32)
+    mem = np.zeros(n + 1, np.int32)
+    c = lib().ref3d_linkage_agglomerate(K, n, cutoff, min_pts, linkage_type, off, mem)
     return off[:c + 1].copy(), mem[:off[c]].copy()

@@ -175,4 +175,20 @@ int ref3d_cluster_linkage(int n, const float *xy, const float *xyz, const float 
 	return nc;
 }
 
+/* hierarchicalCluster (:414-531) alone on a caller-supplied similarity matrix (n x n, row-major) */
+int ref3d_linkage_agglomerate(const float *K, int n, float cutoff, int minPts, int linkageType, int *cluster_offsets, int *members) {
+	FtzGuard g;
+	CLUSTER_LINKAGE_CPU alg(cutoff, minPts, 0, 1, 0, linkageType, -1, -1);
+	SP_Image Ki = alg.getSimilarityMatrix(n);
+	for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) Ki->setProb(x, y, K[(size_t)y * n + x]);
+	vector<FrameData::Cluster> cl = alg.hierarchicalCluster(Ki);
+	int nc = 0, k = 0;
+	cluster_offsets[0] = 0;
+	for (size_t c = 0; c < cl.size(); c++) {
+		for (list<int>::iterator it = cl[c].begin(); it != cl[c].end(); ++it) members[k++] = *it;
+		cluster_offsets[++nc] = k;
+	}
+	return nc;
+}
+
 } /* extern "C" */

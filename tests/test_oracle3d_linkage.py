@@ -93,3 +93,27 @@ def test_explicit_sigmas_small_and_degenerate_inputs():
     # a single match, and features outside the image (coordinates are saturated for the depth path)
     oo, om = oracle.cluster_linkage(xy[:1], xyz[:1], world[:1], depth, dist, min_pts=0)
     assert len(oo) == 2 and list(om) == [0]
+
+
+@pytest.mark.parametrize("linkage", [1, 0, 2])
+def test_agglomeration_on_matrices_full_of_exact_ties(linkage):
+    """hierarchicalCluster alone, reference vs restatement, on quantised symmetric matrices: every maximum is tied many times, so
+    the scan order, the strict >, the stale entry of the merged-away cluster and the skipped list element all decide the result."""
+    rng = np.random.default_rng(100 + linkage)
+    for case in range(40):
+        n = int(rng.integers(2, 48))
+        levels = int(rng.integers(2, 6))
+        K = rng.integers(0, levels + 1, (n, n)).astype(np.float32) / levels
+        K = np.maximum(K, K.T)
+        np.fill_diagonal(K, 1.0)
+        cutoff = float(rng.choice([0.2, 0.5, 0.75, 1.0]))
+        minpts = int(rng.integers(0, 4))
+        for strict in (True, False):                     # comparisons and small-integer averages: both builds must agree exactly
+            ref3d.use_strict(strict)
+            try:
+                ro, rm = ref3d.linkage_agglomerate(K, cutoff, minpts, linkage)
+            finally:
+                ref3d.use_strict(False)
+            oo, om = oracle.linkage_agglomerate(K, cutoff, minpts, linkage)
+            if linkage != 1 or strict:
+                assert np.array_equal(ro, oo) and np.array_equal(rm, om), (case, n, cutoff, minpts, strict, as_sets(ro, rm), as_sets(oo, om))
