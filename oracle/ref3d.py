@@ -47,6 +47,9 @@ def lib():
                                             C.c_float, C.c_int, C.c_float, C.c_float, _i32p, _i32p]
         L.ref3d_linkage_agglomerate.restype = C.c_int
         L.ref3d_linkage_agglomerate.argtypes = [_f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p]
+        L.ref3d_bench_log.restype = C.c_int
+        L.ref3d_bench_log.argtypes = [C.c_char_p, C.c_int, _i32p, _f32p, _i32p, _f32p, C.c_int, _i32p, _i32p, _i32p, C.c_int, _i32p, _f32p, _f32p,
+                                      _f32p, _f32p]
         _libs[path] = L
     return _libs[path]
 
@@ -101,3 +104,21 @@ def linkage_agglomerate(K, cutoff=0.1, min_pts=7, linkage_type=1):
     mem = np.zeros(n + 1, np.int32)
     c = lib().ref3d_linkage_agglomerate(K, n, cutoff, min_pts, linkage_type, off, mem)
     return off[:c + 1].copy(), mem[:off[c]].copy()
+
+
+def bench_log(out_dir, fr):
+    """MopedBench over one frame state (the dict layout of moped_b200.bench_log.MopedBenchLog) -> text of outputMopedBench.txt."""
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    n_models = len(fr["n_matches"])
+    rec = np.zeros((len(fr["match_xy"]), 10), np.float32)
+    if len(rec):
+        rec[:, 0:2] = fr["match_xy"]; rec[:, 2:5] = fr["match_world"]; rec[:, 5] = fr["match_depth"]; rec[:, 6] = fr["match_fill"]
+        rec[:, 7] = fr["match_valid"]; rec[:, 8] = fr["match_image"]
+    xyz = np.concatenate(fr["model_xyz"]).astype(np.float32) if n_models else np.zeros((0, 3), np.float32)
+    r = lib().ref3d_bench_log(out_dir.encode(), n_models, i32([len(x) for x in fr["model_xyz"]]), _f(xyz), i32(fr["n_matches"]), _f(rec),
+                              len(fr["cluster_model"]), i32(fr["cluster_model"]), i32(fr["cluster_offsets"]), i32(fr["cluster_members"]),
+                              len(fr["obj_model"]), i32(fr["obj_model"]), _f(fr["obj_pose"]), _f(fr["obj_score"]), _f(fr["K"]), _f(fr["cam_pose"]))
+    if r != 0:
+        raise RuntimeError("ref3d_bench_log failed")
+    with open(os.path.join(out_dir, "outputMopedBench.txt")) as f:
+        return f.read()

@@ -38,6 +38,11 @@ extern "C" void ref3d_srand(uint64_t seed) { g_rng_state = seed; }
 #undef class
 #undef rand
 
+/* moped3d's benchmark log (MopedBench.cpp / Benchmark.cpp, compiled as they are): the parity-log format of SURVEY.md 8f row 4 */
+#include <unistd.h>
+#include <Benchmark.cpp>
+#include <MopedBench.cpp>
+
 using namespace MopedNS;
 typedef POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU POSE3D_T;
 
@@ -189,6 +194,79 @@ int ref3d_linkage_agglomerate(const float *K, int n, float cutoff, int minPts, i
 		cluster_offsets[++nc] = k;
 	}
 	return nc;
+}
+
+/* Runs MopedBench (MopedBench.cpp:185-227) over one frame state the way Moped::processImages drives it — init(), then
+ * beforeAlgorithm/afterAlgorithm for CLUSTER, POSE, FILTER, FILTER2, then allDone() — and leaves its text log in
+ * <out_dir>/outputMopedBench.txt. The frame state: models (n_model_pts[m] SIFT points each, xyz concatenated), matches per model
+ * (10 floats each: x y  wx wy wz  depth fillDistance depthValid  imageIdx  pad), clusters (CSR over all clusters, model id per cluster),
+ * objects (model id, pose7 = quaternion xyzw + translation, score), one grey camera image (K, pose). */
+int ref3d_bench_log(const char *out_dir, int n_models, const int *n_model_pts, const float *model_xyz, const int *n_matches, const float *match_rec,
+                    int n_clusters, const int *cluster_model, const int *cluster_offsets, const int *members,
+                    int n_obj, const int *obj_model, const float *obj_pose7, const float *obj_score, const float *K4, const float *cam_pose7) {
+	char cwd[4096];
+	if (!getcwd(cwd, sizeof cwd) || chdir(out_dir) != 0) return -1;
+	{
+		vector<SP_Model> models;
+		size_t row = 0;
+		for (int m = 0; m < n_models; m++) {
+			SP_Model mod(new Model); mod->name = "obj" + toString(m);
+			vector<Model::IP> &ips = mod->IPs["SIFT"];
+			ips.resize(n_model_pts[m]);
+			for (int i = 0; i < n_model_pts[m]; i++, row++) ips[i].coord3D.init(model_xyz[3 * row], model_xyz[3 * row + 1], model_xyz[3 * row + 2]);
+			models.push_back(mod);
+		}
+		FrameData fd;
+		list<SP_Object> objects;
+		fd.objects = &objects;
+		SP_Image im(new Image(IMAGE_TYPE_GRAY_IMAGE));
+		im->width = 640; im->height = 480;
+		im->intrinsicLinearCalibration.init(K4[0], K4[1], K4[2], K4[3]);
+		im->cameraPose.rotation.init(cam_pose7[0], cam_pose7[1], cam_pose7[2], cam_pose7[3]);
+		im->cameraPose.translation.init(cam_pose7[4], cam_pose7[5], cam_pose7[6]);
+		im->TM.init(im->cameraPose);
+		fd.images.push_back(im);
+		fd.matches.resize(n_models);
+		fd.clusters.resize(n_models);
+		size_t r = 0;
+		for (int m = 0; m < n_models; m++) {
+			fd.matches[m].resize(n_matches[m]);
+			for (int i = 0; i < n_matches[m]; i++, r++) {
+				const float *q = match_rec + 10 * r;
+				FrameData::Match &ma = fd.matches[m][i];
+				ma.coord2D.init(q[0], q[1]);
+				ma.coord3D.init(0, 0, 0);
+				ma.depthData.coord3D.init(q[2], q[3], q[4]);
+				ma.depthData.depth = q[5];
+				ma.depthData.fillDistance = q[6];
+				ma.depthData.depthValid = q[7] != 0;
+				ma.imageIdx = (int)q[8];
+			}
+		}
+		for (int c = 0; c < n_clusters; c++) {
+			FrameData::Cluster cl;
+			for (int k = cluster_offsets[c]; k < cluster_offsets[c + 1]; k++) cl.push_back(members[k]);
+			fd.clusters[cluster_model[c]].push_back(cl);
+		}
+		for (int o = 0; o < n_obj; o++) {
+			SP_Object ob(new Object);
+			ob->model = models[obj_model[o]];
+			ob->pose.rotation.init(obj_pose7[7 * o], obj_pose7[7 * o + 1], obj_pose7[7 * o + 2], obj_pose7[7 * o + 3]);
+			ob->pose.translation.init(obj_pose7[7 * o + 4], obj_pose7[7 * o + 5], obj_pose7[7 * o + 6]);
+			ob->score = obj_score[o];
+			objects.push_back(ob);
+		}
+		MopedBench mb;
+		mb.init();
+		const char *steps[4] = { "CLUSTER", "POSE", "FILTER", "FILTER2" };
+		for (int s = 0; s < 4; s++) {
+			string step(steps[s]);
+			mb.beforeAlgorithm(step, fd);
+			mb.afterAlgorithm(step, fd);
+		}
+		mb.allDone(fd);
+	}   /* ~MopedBench closes the log */
+	return chdir(cwd);
 }
 
 } /* extern "C" */
