@@ -397,6 +397,12 @@ static int lu_solve(const float *A, const float *B, float *x, int m) {
  * Returns the iteration count, or -1 (LM_ERROR) on stop=4. info10 as levmar's info[]. */
 typedef void (*lm_fn)(const float *p7, float *res, const void *ctx);      /* residual callback: levmar's `func` + adata */
 
+/* levmar's `if(!LM_FINITE(...)) stop=7` (lm_core.c:551,732). The reference is built with -ffast-math (-ffinite-math-only), which
+ * folds the test away — that is the default here (0). A strict-IEEE build of the same sources keeps it: tests that compare with
+ * such a build bit for bit switch it on (tests/test_oracle3d_pose.py). */
+static int g_lm_finite_check = 0;
+void mo_set_lm_finite_check(int on) { g_lm_finite_check = on != 0; }
+
 static int levmar_dif_fn(float *p, int n, int itmax, lm_fn fn, const void *ctx, float *info) {
 	const int m = LM_M;
 	const float tau = 1E-03f, eps1 = 1E-17f, eps2 = 1E-17f, eps2_sq = 1E-17f * 1E-17f, eps3 = 1E-17f, delta = 1E-06f;
@@ -413,6 +419,7 @@ static int levmar_dif_fn(float *p, int n, int itmax, lm_fn fn, const void *ctx, 
 	fn(p, hx, ctx); nfev = 1;
 	p_eL2 = l2_neg(e, hx, n);
 	init_eL2 = p_eL2;
+	if (g_lm_finite_check && !isfinite(p_eL2)) stop = 7;
 
 	for (k = 0; k < itmax && !stop; ++k) {
 		if (p_eL2 <= eps3) { stop = 6; break; }
@@ -475,6 +482,7 @@ static int levmar_dif_fn(float *p, int n, int itmax, lm_fn fn, const void *ctx, 
 
 			fn(pDp, wrk, ctx); ++nfev;
 			pDp_eL2 = l2_neg(wrk2, wrk, n);
+			if (g_lm_finite_check && !isfinite(pDp_eL2)) { stop = 7; break; }
 			float dF = p_eL2 - pDp_eL2;
 			if (updp || dF > 0) {
 				for (int i = 0; i < n; i++) {
@@ -828,6 +836,124 @@ int mo_ransac_depth(uint64_t *state, int n, const float *xy, const float *xyz, c
 		mo_init_pose(state, init);                     /* the four rand() calls of initPose; its translation is replaced below */
 		int r = mo_hypothesis_depth(n, xy, xyz, world, cauchy, image, cams, alpha, pos, n_pts_align, init, max_lm, err_thr, min_npts,
 		                            pose_lm, pose_refit, err2, mask);
+		if (r > min_npts) { memcpy(pose7, pose_refit, sizeof pose_refit); found = 1; it++; break; }
+	}
+	if (iters) *iters = it;
+	free(mask);
+	return found;
+}
+
+/* ---- the second depth pose variant: POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU (moped3d/libmoped/src/pose/…:57-435) --------------
+ * Three residuals per correspondence: the squared pixel differences of the moped2 stage, and 50 x the squared distance between
+ * the camera-frame point p3D and (p3D . world3D) p3D — computed and stored even when the point is behind the camera (the depth
+ * term sits outside the if/else, :188-200). Weights: (1 - w3D), (1 - w3D), w3D with w3D = (1 - Alpha) * cauchy, Cauchy scale 25
+ * (:66). initPose, randSample, testAllPoints and RANSAC are the ones of the back-projection variant. */
+float mo_cauchy_weight_v1(float fill_distance) {
+	float factor = fill_distance / (float)25.0;
+	return (float)(1.0 / (1 + factor * factor));
+}
+
+void mo_lm_func_depth_v1(const float *p7, float *res, int n_pts, const float *xy, const float *xyz, const float *world, const float *cauchy,
+                         const int *image, const mo_camera *cams, float alpha) {
+	float q[4] = { p7[0], p7[1], p7[2], p7[3] };
+	quat_norm(q);
+	float T[12];
+	tm_init(T, q, p7 + 4);
+	for (int i = 0; i < n_pts; i++) {
+		const mo_camera *cam = &cams[image[i]];
+		float p3[3];
+		tm_transform(T, p3, xyz + 3 * i);
+		tm_inverse(cam->TM, p3, p3);
+		float u = p3[0] / p3[2] * cam->K[0] + cam->K[2];
+		float v = p3[1] / p3[2] * cam->K[1] + cam->K[3];
+		if (p3[2] < 0) {
+			res[3 * i] = -p3[2] + 10;
+			res[3 * i + 1] = -p3[2] + 10;
+			res[3 * i + 2] = -p3[2] + 10;
+		} else {
+			float dx = u - xy[2 * i], dy = v - xy[2 * i + 1];
+			res[3 * i] = dx * dx;
+			res[3 * i + 1] = dy * dy;
+		}
+		const float *w3 = world + 3 * i;
+		float vecTP = p3[0] * w3[0] + p3[1] * w3[1] + p3[2] * w3[2];
+		float pw[3] = { p3[0] * vecTP, p3[1] * vecTP, p3[2] * vecTP };
+		float dx = p3[0] - pw[0], dy = p3[1] - pw[1], dz = p3[2] - pw[2];
+		float depthError = sqrtf(dx * dx + dy * dy + dz * dz);                   /* projWorld.euclDist(p3D) */
+		res[3 * i + 2] = depthError * depthError;
+		res[3 * i + 2] *= 50;
+		float wi = cauchy[i];
+		float weight3D = (1 - alpha) * wi;
+		res[3 * i] *= (1 - weight3D);
+		res[3 * i + 1] *= (1 - weight3D);
+		res[3 * i + 2] *= weight3D;
+	}
+}
+
+typedef struct { int n_pts; const float *xy, *xyz, *world, *cauchy; const int *image; const mo_camera *cams; float alpha; } depth1_ctx;
+static void depth1_fn(const float *p7, float *res, const void *c) {
+	const depth1_ctx *d = (const depth1_ctx *)c;
+	mo_lm_func_depth_v1(p7, res, d->n_pts, d->xy, d->xyz, d->world, d->cauchy, d->image, d->cams, d->alpha);
+}
+
+static float optimize_camera_depth_v1(float *pose7, int n_pts, int itmax, const float *xy, const float *xyz, const float *world, const float *cauchy,
+                                      const int *image, const mo_camera *cams, float alpha) {
+	float p[7], info[10];
+	memcpy(p, pose7, sizeof p);
+	depth1_ctx c = { n_pts, xy, xyz, world, cauchy, image, cams, alpha };
+	int r = levmar_dif_fn(p, 3 * n_pts, itmax, depth1_fn, &c, info);
+	if (r < 0) return (float)r;
+	memcpy(pose7, p, sizeof p);
+	quat_norm(pose7);
+	return info[1];
+}
+
+int mo_hypothesis_depth_v1(int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image, const mo_camera *cams,
+                           float alpha, const int *sample_pos, int n_samples, const float *init_quat, int max_lm, float err_thr, int min_npts,
+                           float *pose_lm, float *pose_refit, float *lm_err2, unsigned char *mask) {
+	size_t cap = (size_t)n + 1;
+	float *gxy = (float *)malloc(sizeof(float) * 2 * cap), *gxyz = (float *)malloc(sizeof(float) * 3 * cap), *gw = (float *)malloc(sizeof(float) * 3 * cap);
+	float *gc = (float *)malloc(sizeof(float) * cap);
+	int *gim = (int *)malloc(sizeof(int) * cap);
+	for (int j = 0; j < n_samples; j++) {
+		int s = sample_pos[j];
+		memcpy(gxy + 2 * j, xy + 2 * s, 8); memcpy(gxyz + 3 * j, xyz + 3 * s, 12); memcpy(gw + 3 * j, world + 3 * s, 12); gc[j] = cauchy[s]; gim[j] = image[s];
+	}
+	float pose[7] = { init_quat[0], init_quat[1], init_quat[2], init_quat[3], 0, 0, 0 };
+	mo_init_translation_depth(world, sample_pos, n_samples, pose + 4);
+	memset(mask, 0, (size_t)n);
+	lm_err2[1] = -2;
+	int ret = -1;
+	float r = optimize_camera_depth_v1(pose, n_samples, max_lm, gxy, gxyz, gw, gc, gim, cams, alpha);
+	lm_err2[0] = r;
+	if ((int)r != -1) {
+		memcpy(pose_lm, pose, sizeof pose);
+		ret = mo_test_all_points(pose, n, xy, xyz, image, cams, err_thr, mask);
+		if (ret > min_npts) {
+			int k = 0;
+			for (int i = 0; i < n; i++) if (mask[i]) {
+				memcpy(gxy + 2 * k, xy + 2 * i, 8); memcpy(gxyz + 3 * k, xyz + 3 * i, 12); memcpy(gw + 3 * k, world + 3 * i, 12); gc[k] = cauchy[i]; gim[k] = image[i]; k++;
+			}
+			lm_err2[1] = optimize_camera_depth_v1(pose, k, max_lm, gxy, gxyz, gw, gc, gim, cams, alpha);
+		}
+		memcpy(pose_refit, pose, sizeof pose);
+	}
+	free(gxy); free(gxyz); free(gw); free(gc); free(gim);
+	return ret;
+}
+
+int mo_ransac_depth_v1(uint64_t *state, int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image,
+                       const int *tie_ids, const mo_camera *cams, float alpha, int max_ransac, int max_lm, int n_pts_align, int min_npts,
+                       float err_thr, float *pose7, int *iters) {
+	int pos[16];
+	float init[7], pose_lm[7], pose_refit[7], err2[2];
+	unsigned char *mask = (unsigned char *)malloc((size_t)n + 1);
+	int found = 0, it;
+	for (it = 0; it < max_ransac; it++) {
+		if (!mo_rand_sample(state, xy, image, tie_ids, n, n_pts_align, pos)) break;
+		mo_init_pose(state, init);
+		int r = mo_hypothesis_depth_v1(n, xy, xyz, world, cauchy, image, cams, alpha, pos, n_pts_align, init, max_lm, err_thr, min_npts,
+		                               pose_lm, pose_refit, err2, mask);
 		if (r > min_npts) { memcpy(pose7, pose_refit, sizeof pose_refit); found = 1; it++; break; }
 	}
 	if (iters) *iters = it;

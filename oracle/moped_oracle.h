@@ -52,6 +52,8 @@ int mo_filter(int n_models, const int *match_offsets, const int *match_image, co
               const mo_camera *cams, int n_obj, const int *obj_model, const float *obj_pose, int min_points, float feat_dist,
               float min_score, unsigned char *keep, float *score, int *cluster_offsets, int *members);
 
+void mo_set_lm_finite_check(int on);   /* 0 (default): -ffinite-math-only semantics of the reference build; 1: levmar's stop=7 as in a strict build */
+
 /* POSE, moped3d depth-aware variant (oracle only so far) ---------------------------------- */
 float mo_cauchy_weight(float fill_distance);
 void mo_lm_func_depth(const float *p7, float *res, int n_pts, const float *xyz, const float *world, const float *cauchy,
@@ -65,6 +67,17 @@ int mo_hypothesis_depth(int n, const float *xy, const float *xyz, const float *w
 int mo_ransac_depth(uint64_t *state, int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image,
                     const int *tie_ids, const mo_camera *cams, float alpha, int max_ransac, int max_lm, int n_pts_align, int min_npts,
                     float err_thr, float *pose7, int *iters);
+
+/* second depth variant, POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU: three residuals per correspondence, Cauchy scale 25 */
+float mo_cauchy_weight_v1(float fill_distance);
+void mo_lm_func_depth_v1(const float *p7, float *res, int n_pts, const float *xy, const float *xyz, const float *world, const float *cauchy,
+                         const int *image, const mo_camera *cams, float alpha);
+int mo_hypothesis_depth_v1(int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image, const mo_camera *cams,
+                           float alpha, const int *sample_pos, int n_samples, const float *init_quat, int max_lm, float err_thr, int min_npts,
+                           float *pose_lm, float *pose_refit, float *lm_err2, unsigned char *mask);
+int mo_ransac_depth_v1(uint64_t *state, int n, const float *xy, const float *xyz, const float *world, const float *cauchy, const int *image,
+                       const int *tie_ids, const mo_camera *cams, float alpha, int max_ransac, int max_lm, int n_pts_align, int min_npts,
+                       float err_thr, float *pose7, int *iters);
 
 /* CLUSTER, moped3d linkage variant (oracle only so far) — moped_linkage_oracle.c ----------- */
 void mo_linkage_similarity(int n, const float *xy, const float *xyz, const float *world, int W, int H, const float *depth, const float *distance,

@@ -63,6 +63,13 @@ def _load():
         "mo_linkage_agglomerate": (C.c_int, [_f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p]),
         "mo_cluster_linkage": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_float, _i32p, _i32p]),
+        "mo_set_lm_finite_check": (None, [C.c_int]),
+        "mo_cauchy_weight_v1": (C.c_float, [C.c_float]),
+        "mo_lm_func_depth_v1": (None, [_f32p, _f32p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, camp, C.c_float]),
+        "mo_hypothesis_depth_v1": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, camp, C.c_float, _i32p, C.c_int, _f32p, C.c_int, C.c_float,
+                                             C.c_int, _f32p, _f32p, _f32p, _u8p]),
+        "mo_ransac_depth_v1": (C.c_int, [_u64p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_void_p, camp, C.c_float, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_float, _f32p, C.POINTER(C.c_int)]),
         "mo_sift": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]),
         "mo_sift_debug": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
         "mo_sift_gauss_kernel": (C.c_int, [C.c_float, _f32p]),
@@ -258,37 +265,46 @@ def sift_debug(gray_u8, double_size=True, octave=0, max_trace=65536):
 
 
 # ---- moped3d depth-aware pose stage (oracle only so far) ----------------------------------------
-def cauchy_weights(fill):
-    return np.array([lib().mo_cauchy_weight(float(f)) for f in np.asarray(fill).ravel()], np.float32)
+def cauchy_weights(fill, variant=0):
+    fn = lib().mo_cauchy_weight_v1 if variant else lib().mo_cauchy_weight
+    return np.array([fn(float(f)) for f in np.asarray(fill).ravel()], np.float32)
 
 
-def lm_func_depth(pose7, cl, cams, alpha):
+def lm_func_depth(pose7, cl, cams, alpha, variant=0):
+    """variant 0 = ..._BACKPROJECTION_DEPTH_CPU (2 residuals per correspondence), 1 = ..._REPROJECTION_DEPTH_CPU (3)."""
     n = len(cl["xy"])
-    out = np.zeros(2 * n, np.float32)
-    lib().mo_lm_func_depth(_f32(pose7), out, n, _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"]), np.zeros(n, np.int32), cams, alpha)
+    img = np.zeros(n, np.int32)
+    if variant:
+        out = np.zeros(3 * n, np.float32)
+        lib().mo_lm_func_depth_v1(_f32(pose7), out, n, _f32(cl["xy"]), _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"], 1), img, cams, alpha)
+    else:
+        out = np.zeros(2 * n, np.float32)
+        lib().mo_lm_func_depth(_f32(pose7), out, n, _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"]), img, cams, alpha)
     return out
 
 
-def hypothesis_depth(cl, cams, alpha, sample_pos, init_quat, max_lm, err_thr, min_npts):
+def hypothesis_depth(cl, cams, alpha, sample_pos, init_quat, max_lm, err_thr, min_npts, variant=0):
     n = len(cl["xy"])
     lm, refit = np.zeros(7, np.float32), np.zeros(7, np.float32)
     err = np.zeros(2, np.float32)
     mask = np.zeros(n, np.uint8)
     sp = _i32(sample_pos)
-    r = lib().mo_hypothesis_depth(n, _f32(cl["xy"]), _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"]), np.zeros(n, np.int32), cams,
-                                  alpha, sp, len(sp), _f32(init_quat), max_lm, err_thr, min_npts, lm, refit, err, mask)
+    fn = lib().mo_hypothesis_depth_v1 if variant else lib().mo_hypothesis_depth
+    r = fn(n, _f32(cl["xy"]), _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"], variant), np.zeros(n, np.int32), cams,
+           alpha, sp, len(sp), _f32(init_quat), max_lm, err_thr, min_npts, lm, refit, err, mask)
     return dict(n_inliers=r, pose_lm=lm, pose_refit=refit, lm_err=err, mask=mask)
 
 
-def ransac_depth(cl, cams, alpha, params, seed):
+def ransac_depth(cl, cams, alpha, params, seed, variant=0):
     """params = (MaxRANSACTests, MaxLMTests, NPtsAlign, MinNPtsObject, ErrorThreshold); seed = the LCG state ref3d_srand gets"""
     n = len(cl["xy"])
     st = C.c_uint64(int(seed))
     pose = np.zeros(7, np.float32)
     it = C.c_int(0)
-    found = lib().mo_ransac_depth(C.byref(st), n, _f32(cl["xy"]), _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"]),
-                                  np.zeros(n, np.int32), None, cams, alpha, int(params[0]), int(params[1]), int(params[2]), int(params[3]),
-                                  float(params[4]), pose, C.byref(it))
+    fn = lib().mo_ransac_depth_v1 if variant else lib().mo_ransac_depth
+    found = fn(C.byref(st), n, _f32(cl["xy"]), _f32(cl["xyz"]), _f32(cl["world"]), cauchy_weights(cl["fill"], variant),
+               np.zeros(n, np.int32), None, cams, alpha, int(params[0]), int(params[1]), int(params[2]), int(params[3]),
+               float(params[4]), pose, C.byref(it))
     return bool(found), pose, it.value
 
 

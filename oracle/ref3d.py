@@ -42,6 +42,15 @@ def lib():
         L.ref3d_ransac.restype = C.c_int
         L.ref3d_ransac.argtypes = [C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_uint64, _f32p]
+        for sfx in ("_v1",):
+            getattr(L, "ref3d_cauchy_weight" + sfx).restype = C.c_float
+            getattr(L, "ref3d_cauchy_weight" + sfx).argtypes = [C.c_float]
+            getattr(L, "ref3d_lm_func" + sfx).restype = None
+            getattr(L, "ref3d_lm_func" + sfx).argtypes = L.ref3d_lm_func.argtypes
+            getattr(L, "ref3d_hypothesis" + sfx).restype = C.c_int
+            getattr(L, "ref3d_hypothesis" + sfx).argtypes = L.ref3d_hypothesis.argtypes
+            getattr(L, "ref3d_ransac" + sfx).restype = C.c_int
+            getattr(L, "ref3d_ransac" + sfx).argtypes = L.ref3d_ransac.argtypes
         L.ref3d_cluster_linkage.restype = C.c_int
         L.ref3d_cluster_linkage.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_float,
                                             C.c_float, C.c_int, C.c_float, C.c_float, _i32p, _i32p]
@@ -58,29 +67,29 @@ def _f(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def lm_func(pose7, cl, K, cam_pose, alpha):
+def lm_func(pose7, cl, K, cam_pose, alpha, variant=0):
     n = len(cl["xy"])
-    out = np.zeros(2 * n, np.float32)
-    lib().ref3d_lm_func(_f(pose7), n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha, out)
+    out = np.zeros((3 if variant else 2) * n, np.float32)
+    (lib().ref3d_lm_func_v1 if variant else lib().ref3d_lm_func)(_f(pose7), n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha, out)
     return out
 
 
-def hypothesis(cl, K, cam_pose, alpha, sample_pos, init_quat, max_lm, err_thr, min_npts):
+def hypothesis(cl, K, cam_pose, alpha, sample_pos, init_quat, max_lm, err_thr, min_npts, variant=0):
     n = len(cl["xy"])
     init, lm, refit = (np.zeros(7, np.float32) for _ in range(3))
     err = np.zeros(2, np.float32)
     mask = np.zeros(n, np.uint8)
     sp = np.ascontiguousarray(sample_pos, dtype=np.int32)
-    r = lib().ref3d_hypothesis(n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha, sp, len(sp),
+    r = (lib().ref3d_hypothesis_v1 if variant else lib().ref3d_hypothesis)(n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha, sp, len(sp),
                                _f(init_quat), max_lm, err_thr, min_npts, init, lm, refit, err, mask)
     return dict(n_inliers=r, pose_init=init, pose_lm=lm, pose_refit=refit, lm_err=err, mask=mask)
 
 
-def ransac(cl, K, cam_pose, alpha, params, seed):
+def ransac(cl, K, cam_pose, alpha, params, seed, variant=0):
     """params = (MaxRANSACTests, MaxLMTests, NPtsAlign, MinNPtsObject, ErrorThreshold)"""
     n = len(cl["xy"])
     pose = np.zeros(7, np.float32)
-    found = lib().ref3d_ransac(n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha,
+    found = (lib().ref3d_ransac_v1 if variant else lib().ref3d_ransac)(n, _f(cl["xy"]), _f(cl["xyz"]), _f(cl["world"]), _f(cl["fill"]), _f(K), _f(cam_pose), alpha,
                                int(params[0]), int(params[1]), int(params[2]), int(params[3]), float(params[4]), int(seed), pose)
     return bool(found), pose
 

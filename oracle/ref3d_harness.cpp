@@ -34,6 +34,7 @@ extern "C" void ref3d_srand(uint64_t seed) { g_rng_state = seed; }
 #define rand moped3d_ref_rand
 #define class struct
 #include <pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp>
+#include <pose/POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU.hpp>
 #include <cluster/CLUSTER_LINKAGE_CPU.hpp>
 #undef class
 #undef rand
@@ -44,7 +45,8 @@ extern "C" void ref3d_srand(uint64_t seed) { g_rng_state = seed; }
 #include <MopedBench.cpp>
 
 using namespace MopedNS;
-typedef POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU POSE3D_T;
+typedef POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU POSE3D_T;      /* variant 0: the stage of moped3d's shipped pipeline (config.hpp:46,48) */
+typedef POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU POSE3R_T;        /* variant 1: three residuals per correspondence, Cauchy scale 25 */
 
 struct FtzGuard {
 	unsigned saved;
@@ -75,7 +77,87 @@ struct Cluster3D {
 	}
 };
 
+template <class ALG> struct ClusterT {
+	Image image;
+	vector<typename ALG::LmData> data;
+	vector<typename ALG::LmData *> ptrs;
+	ClusterT(ALG &alg, int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4, const float *cam_pose7)
+	: image(IMAGE_TYPE_GRAY_IMAGE) {
+		image.intrinsicLinearCalibration.init(K4[0], K4[1], K4[2], K4[3]);
+		image.cameraPose.rotation.init(cam_pose7[0], cam_pose7[1], cam_pose7[2], cam_pose7[3]);
+		image.cameraPose.translation.init(cam_pose7[4], cam_pose7[5], cam_pose7[6]);
+		image.TM.init(image.cameraPose);
+		data.resize(n);
+		for (int i = 0; i < n; i++) {
+			data[i].image = &image;
+			data[i].coord2D.init(xy[2 * i], xy[2 * i + 1]);
+			data[i].coord3D.init(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+			data[i].world3D.init(world[3 * i], world[3 * i + 1], world[3 * i + 2]);
+			data[i].cauchyWeight = alg.getCauchyWeight(fill[i]);
+			ptrs.push_back(&data[i]);
+		}
+	}
+};
+
+template <class ALG>
+static int hypothesis_t(int per_item, int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4, const float *cam_pose7,
+                        float alpha, const int *sample_pos, int n_samples, const float *init_quat, int maxLM, float errThr, int minNPts,
+                        float *pose_init, float *pose_lm, float *pose_refit, float *lm_err, unsigned char *inlier_mask) {
+	ALG alg(1, maxLM, 1, n_samples, minNPts, errThr, alpha);
+	ClusterT<ALG> cl(alg, n, xy, xyz, world, fill, K4, cam_pose7);
+	vector<typename ALG::LmData *> samples;
+	for (int j = 0; j < n_samples; j++) samples.push_back(cl.ptrs[sample_pos[j]]);
+	Pose pose;
+	alg.initPose(pose, samples);
+	pose.rotation.init(init_quat[0], init_quat[1], init_quat[2], init_quat[3]);
+	for (int j = 0; j < 7; j++) pose_init[j] = pose[j];
+	Float r = alg.optimizeCamera(pose, samples, maxLM);
+	lm_err[0] = r; lm_err[1] = -2;
+	for (int i = 0; i < n; i++) inlier_mask[i] = 0;
+	if ((int)r == -1) return -1;
+	for (int j = 0; j < 7; j++) pose_lm[j] = pose[j];
+	vector<typename ALG::LmData *> consistent;
+	alg.testAllPoints(consistent, pose, cl.ptrs, errThr);
+	for (size_t k = 0; k < consistent.size(); k++) inlier_mask[consistent[k] - &cl.data[0]] = 1;
+	if ((int)consistent.size() > minNPts) lm_err[1] = alg.optimizeCamera(pose, consistent, maxLM);
+	for (int j = 0; j < 7; j++) pose_refit[j] = pose[j];
+	return (int)consistent.size();
+}
+
 extern "C" {
+
+/* the second depth pose variant, POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU (…:57-435): lmFuncQuat (:106-213, 3 residuals per
+ * correspondence), one explicit hypothesis, whole RANSAC */
+float ref3d_cauchy_weight_v1(float fill_distance) {
+	POSE3R_T alg(1, 1, 1, 5, 6, 8, 0.5);
+	return alg.getCauchyWeight(fill_distance);
+}
+void ref3d_lm_func_v1(const float *pose7, int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4,
+                      const float *cam_pose7, float alpha, float *errors) {
+	FtzGuard g;
+	POSE3R_T alg(1, 1, 1, 5, 6, 8, alpha);
+	ClusterT<POSE3R_T> cl(alg, n, xy, xyz, world, fill, K4, cam_pose7);
+	float p[7]; memcpy(p, pose7, sizeof p);
+	POSE3R_T::lmFuncQuat(p, errors, 7, 3 * n, (void *)&cl.ptrs);
+}
+int ref3d_hypothesis_v1(int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4, const float *cam_pose7,
+                        float alpha, const int *sample_pos, int n_samples, const float *init_quat, int maxLM, float errThr, int minNPts,
+                        float *pose_init, float *pose_lm, float *pose_refit, float *lm_err, unsigned char *inlier_mask) {
+	FtzGuard g;
+	return hypothesis_t<POSE3R_T>(3, n, xy, xyz, world, fill, K4, cam_pose7, alpha, sample_pos, n_samples, init_quat, maxLM, errThr, minNPts,
+	                              pose_init, pose_lm, pose_refit, lm_err, inlier_mask);
+}
+int ref3d_ransac_v1(int n, const float *xy, const float *xyz, const float *world, const float *fill, const float *K4, const float *cam_pose7,
+                    float alpha, int maxRansac, int maxLM, int nPtsAlign, int minNPts, float errThr, uint64_t seed, float *pose_out) {
+	FtzGuard g;
+	POSE3R_T alg(maxRansac, maxLM, 1, nPtsAlign, minNPts, errThr, alpha);
+	ClusterT<POSE3R_T> cl(alg, n, xy, xyz, world, fill, K4, cam_pose7);
+	ref3d_srand(seed);
+	Pose pose;
+	bool found = alg.RANSAC(pose, cl.ptrs);
+	for (int j = 0; j < 7; j++) pose_out[j] = pose[j];
+	return found ? 1 : 0;
+}
 
 /* getCauchyWeight (:187-190) */
 float ref3d_cauchy_weight(float fill_distance) {

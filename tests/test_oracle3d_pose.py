@@ -60,7 +60,9 @@ def cams():
 @pytest.fixture
 def strict():
     ref3d.use_strict(True)
+    oracle.lib().mo_set_lm_finite_check(1)      # a strict build keeps levmar's stop=7 on a non-finite ||e||^2; -ffast-math folds it away
     yield
+    oracle.lib().mo_set_lm_finite_check(0)
     ref3d.use_strict(False)
 
 
@@ -168,3 +170,34 @@ def test_ransac_on_the_shared_stream(cams):
             for p in (pr, po):
                 assert np.abs(p[4:] - cl["gt"][4:]).max() < 0.01 and quat_angle(p[:4], cl["gt"][:4]) < 0.05
     assert found_both >= 4
+
+
+# ---- the second depth variant: POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU (three residuals per correspondence) ---------------
+
+def test_second_variant_bit_exact_against_the_strict_build(cams, strict):
+    rng = np.random.default_rng(21)
+    for f in (0.0, 0.5, 25.0, 80.0):
+        assert oracle.lib().mo_cauchy_weight_v1(f) == ref3d.lib().ref3d_cauchy_weight_v1(f)
+    n_acc = 0
+    for seed in range(5):
+        cl = make_cluster(300 + seed)
+        n = len(cl["xy"])
+        for _ in range(4):
+            pose = cl["gt"] + rng.normal(0, 0.05, 7).astype(np.float32)
+            assert np.array_equal(oracle.lm_func_depth(pose, cl, cams, ALPHA, variant=1), ref3d.lm_func(pose, cl, K, CAM, ALPHA, variant=1))
+        pose = cl["gt"].copy(); pose[6] = -2.0                 # behind the camera: the depth residual is still the 50 x distance term
+        a = oracle.lm_func_depth(pose, cl, cams, ALPHA, variant=1)
+        assert np.array_equal(a, ref3d.lm_func(pose, cl, K, CAM, ALPHA, variant=1)) and len(a) == 3 * n
+        for h in range(16):
+            pos = rng.choice(cl["good"], 5, replace=False) if h % 3 else rng.choice(n, 5, replace=False)
+            quat = (rng.integers(0, 256, 4) / 256.0).astype(np.float32)
+            r = ref3d.hypothesis(cl, K, CAM, ALPHA, pos, quat, POSE_PARAMS[1], POSE_PARAMS[4], POSE_PARAMS[3], variant=1)
+            o = oracle.hypothesis_depth(cl, cams, ALPHA, pos, quat, POSE_PARAMS[1], POSE_PARAMS[4], POSE_PARAMS[3], variant=1)
+            assert r["n_inliers"] == o["n_inliers"] and np.array_equal(r["mask"], o["mask"]) and np.array_equal(r["lm_err"], o["lm_err"])
+            if r["n_inliers"] >= 0:
+                assert np.array_equal(r["pose_lm"], o["pose_lm"]) and np.array_equal(r["pose_refit"], o["pose_refit"])
+            n_acc += r["n_inliers"] > POSE_PARAMS[3]
+        fs, ps = ref3d.ransac(cl, K, CAM, ALPHA, POSE_PARAMS, 5 + seed, variant=1)
+        fo, po, _ = oracle.ransac_depth(cl, cams, ALPHA, POSE_PARAMS, 5 + seed, variant=1)
+        assert fs == fo and (not fs or np.array_equal(ps, po))
+    assert n_acc >= 10

@@ -24,8 +24,11 @@ def strict_ref():
     if not (ref.available() and ref.strict_available()):
         pytest.skip("oracle/_ref/libmoped_ref_strict.so not built (needs /root/reference at build time)")
     os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import oracle
     ref.use_strict(True)
+    oracle.lib().mo_set_lm_finite_check(1)      # a strict build keeps levmar's stop=7 (non-finite ||e||^2); -ffast-math folds it away
     yield ref
+    oracle.lib().mo_set_lm_finite_check(0)
     ref.use_strict(False)
 
 
