@@ -135,6 +135,25 @@ mc_status mc_pose_ransac(mc_ctx *ctx, const int32_t *cluster_offsets, int n_clus
                          const float *pt_xy, const float *pt_xyz, const int32_t *pt_image,
                          const mc_pose_params *params, uint8_t *found, float *pose, int32_t *n_tests);
 
+/* ---- POSE, moped3d's depth-aware variants. variant 0 replaces
+ *      POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU::process (moped3d/libmoped/src/pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp:391-470,
+ *      the stage of moped3d's shipped pipeline, moped3d/libmoped/src/config.hpp:46); variant 1 replaces
+ *      POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU::process (…/POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU.hpp:357-435).
+ * Every correspondence additionally carries pt_world (Match::depthData.coord3D, the back-projected depth-filled point, 3 floats) and
+ * pt_cauchy (getCauchyWeight(depthData.fillDistance), computed by the caller with the stage's scale: 0.100 / 25); alpha = the stage's Alpha.
+ * The LM takes every sum in levmar's order with unfused multiply-add: results equal the strict-IEEE build of the reference bit for bit.
+ * Outputs as for mc_pose_hypotheses / mc_pose_ransac. pt_tie (nullable): each point's index in its model's match list (randSample breaks
+ * key ties by it); NULL = position in the cluster. ---- */
+mc_status mc_pose_depth_hypotheses(mc_ctx *ctx, int variant, const int32_t *cluster_offsets, int n_clusters,
+                                   const float *pt_xy, const float *pt_xyz, const float *pt_world, const float *pt_cauchy, const int32_t *pt_image,
+                                   const int32_t *hyp_cluster, const int32_t *sample_pos, const float *init_quat, int n_hyp,
+                                   const mc_pose_params *params, float alpha,
+                                   int32_t *n_inliers, float *pose_lm, float *pose_refit, float *lm_err, uint8_t *inlier_mask);
+mc_status mc_pose_depth_ransac(mc_ctx *ctx, int variant, const int32_t *cluster_offsets, int n_clusters,
+                               const float *pt_xy, const float *pt_xyz, const float *pt_world, const float *pt_cauchy, const int32_t *pt_image,
+                               const int32_t *pt_tie, const mc_pose_params *params, float alpha,
+                               uint8_t *found, float *pose, int32_t *n_tests);
+
 /* ---- FILTER: replaces FILTER_PROJECTION_CPU::process,
  *      moped2/libmoped/src/filter/FILTER_PROJECTION_CPU.hpp:80-162 ---------------------------- */
 /* matches as CSR over models (+ image, xy, xyz per match); objects in list order (obj_model, obj_pose).
@@ -282,6 +301,9 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
 /* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)
+ *   "lm_finite_check"      != 0: the depth pose stages stop an LM whose ||e||^2 became non-finite with LM_ERROR, like a strict-IEEE
+ *                          build of levmar (lm_core.c:551,732); 0 (default): the test is folded away as in the reference's
+ *                          -ffast-math build.
  *   "ransac_fused"         != 0: mc_pose_ransac / the frame pipeline use the single one-CTA-per-task RANSAC kernel
  *                          instead of the staged kernels (same results; kept for A/B measurements)
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after

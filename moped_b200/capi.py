@@ -59,6 +59,10 @@ SIGNATURES = {
                                      _i32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "mc_pose_hypotheses_dev": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.POINTER(PoseParams)] + [C.c_void_p] * 4),
     "mc_pose_ransac": (C.c_int, [C.c_void_p, _i32p, C.c_int, _f32p, _f32p, _i32p, C.POINTER(PoseParams), _u8p, _f32p, _i32p]),
+    "mc_pose_depth_hypotheses": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p, _f32p, C.c_int,
+                                           C.POINTER(PoseParams), C.c_float, _i32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "mc_pose_depth_ransac": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_void_p, C.POINTER(PoseParams),
+                                       C.c_float, _u8p, _f32p, _i32p]),
     "mc_filter_projection": (C.c_int, [C.c_void_p, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float,
                                        _u8p, _f32p, C.POINTER(C.c_int32), _i32p, _i32p]),
     "mc_model_db_create": (C.c_int, [C.POINTER(C.c_void_p)]),
@@ -272,6 +276,41 @@ class Context:
         n_tests = np.zeros(n_tasks, np.int32)
         self._check(self.L.mc_pose_ransac(self.h, co, len(co) - 1, _f32(pt_xy), _f32(pt_xyz), _i32(pt_image), C.byref(pp), found, pose, n_tests),
                     "mc_pose_ransac")
+        return found.astype(bool), pose, n_tests
+
+    # ---- POSE, moped3d depth-aware variants (0 = back-projection, 1 = reprojection + depth)
+    def pose_depth_hypotheses(self, variant, cluster_offsets, pt_xy, pt_xyz, pt_world, pt_cauchy, pt_image, hyp_cluster, sample_pos, init_quat,
+                              params, alpha, want_mask=True):
+        co = _i32(cluster_offsets)
+        hc, sp, iq = _i32(hyp_cluster), _i32(sample_pos), _f32(init_quat)
+        n_hyp = len(hc)
+        pp = params if isinstance(params, PoseParams) else PoseParams.of(params)
+        n_in = np.zeros(n_hyp, np.int32)
+        pose_lm = np.zeros((n_hyp, 7), np.float32)
+        pose_refit = np.zeros((n_hyp, 7), np.float32)
+        err = np.zeros((n_hyp, 2), np.float32)
+        sizes = (co[1:] - co[:-1])[hc]
+        mask = np.zeros(int(sizes.sum()) + 1, np.uint8) if want_mask else None
+        self._check(self.L.mc_pose_depth_hypotheses(self.h, int(variant), co, len(co) - 1, _f32(pt_xy), _f32(pt_xyz), _f32(pt_world), _f32(pt_cauchy),
+                                                    _i32(pt_image), hc, sp, iq, n_hyp, C.byref(pp), float(alpha), n_in, pose_lm, pose_refit, err,
+                                                    mask.ctypes.data if want_mask else None), "mc_pose_depth_hypotheses")
+        masks = None
+        if want_mask:
+            o = np.concatenate([[0], np.cumsum(sizes)])
+            masks = [mask[o[h]:o[h + 1]].astype(bool) for h in range(n_hyp)]
+        return n_in, pose_lm, pose_refit, err, masks
+
+    def pose_depth_ransac(self, variant, cluster_offsets, pt_xy, pt_xyz, pt_world, pt_cauchy, pt_image, params, alpha, seed=1, pt_tie=None):
+        co = _i32(cluster_offsets)
+        pp = params if isinstance(params, PoseParams) else PoseParams.of(params, seed)
+        n_tasks = (len(co) - 1) * pp.max_objects_per_cluster
+        found = np.zeros(n_tasks, np.uint8)
+        pose = np.zeros((n_tasks, 7), np.float32)
+        n_tests = np.zeros(n_tasks, np.int32)
+        tie = _i32(pt_tie) if pt_tie is not None else None
+        self._check(self.L.mc_pose_depth_ransac(self.h, int(variant), co, len(co) - 1, _f32(pt_xy), _f32(pt_xyz), _f32(pt_world), _f32(pt_cauchy),
+                                                _i32(pt_image), tie.ctypes.data if tie is not None else None, C.byref(pp), float(alpha), found, pose,
+                                                n_tests), "mc_pose_depth_ransac")
         return found.astype(bool), pose, n_tests
 
     # ---- FILTER

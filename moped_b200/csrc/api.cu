@@ -5,6 +5,7 @@
 
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 
 namespace mc {
 mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
@@ -17,6 +18,14 @@ mc_status pose_hypotheses_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, 
 mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, const int32_t *d_n_clusters, int n_clusters_cap,
                              const float *d_xy, const float *d_xyz, const int32_t *d_image, const int32_t *d_tie,
                              const mc_pose_params *pp, uint8_t *d_found, float *d_pose, int32_t *d_n_tests);
+mc_status pose_depth_hypotheses_device(mc_ctx *ctx, int variant, const int32_t *d_cluster_offsets, const float *d_xy, const float *d_xyz,
+                                       const float *d_world, const float *d_cauchy, const int32_t *d_image, const int32_t *d_hyp_cluster,
+                                       const int32_t *d_sample_pos, const float *d_init_quat, int n_hyp, int n_max, const mc_pose_params *pp,
+                                       float alpha, const int64_t *d_mask_offsets, int32_t *d_n_inliers, float *d_pose_lm, float *d_pose_refit,
+                                       float *d_lm_err, uint8_t *d_mask);
+mc_status pose_depth_ransac_device(mc_ctx *ctx, int variant, const int32_t *d_cluster_offsets, int n_clusters, int n_max, const float *d_xy,
+                                   const float *d_xyz, const float *d_world, const float *d_cauchy, const int32_t *d_image, const int32_t *d_tie,
+                                   const mc_pose_params *pp, float alpha, uint8_t *d_found, float *d_pose, int32_t *d_n_tests);
 mc_status filter_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
                         const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
                         const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score,
@@ -163,6 +172,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	if (k == "pose_fit_thread_min") ctx->fit_thread_min = value < 1 ? 1 : value;
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
+	else if (k == "lm_finite_check") ctx->lm_finite_check = value != 0;
 	else if (k == "sift_two_pass") return sift_set_two_pass(ctx, (int)value);
 	else if (k == "sift_describe_gather") return sift_set_gather(ctx, (int)value);
 	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }
@@ -397,6 +407,107 @@ mc_status mc_pose_ransac(mc_ctx *ctx, const int32_t *cluster_offsets, int n_clus
 	MC_CUDA(cudaMemsetAsync(b + o_p, 0, 28ull * n_tasks, ctx->stream));
 	MC_TRY(pose_ransac_device(ctx, (int32_t *)(b + o_co), nullptr, n_clusters, (float *)(b + o_xy), (float *)(b + o_xyz), (int32_t *)(b + o_im), nullptr,
 	                          params, (uint8_t *)(b + o_f), (float *)(b + o_p), (int32_t *)(b + o_nt)));
+	MC_TRY(d2h(ctx, found, (const uint8_t *)(b + o_f), (size_t)n_tasks));
+	MC_TRY(d2h(ctx, pose, (const float *)(b + o_p), 7 * (size_t)n_tasks));
+	MC_TRY(d2h(ctx, n_tests, (const int32_t *)(b + o_nt), (size_t)n_tasks));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+// ---- POSE, moped3d depth-aware variants (pose_depth.cu) ----------------------------------------
+static int largest_cluster(const int32_t *cluster_offsets, int n_clusters) {
+	int m = 0;
+	for (int c = 0; c < n_clusters; c++) m = std::max(m, cluster_offsets[c + 1] - cluster_offsets[c]);
+	return m;
+}
+
+mc_status mc_pose_depth_hypotheses(mc_ctx *ctx, int variant, const int32_t *cluster_offsets, int n_clusters, const float *pt_xy,
+                                   const float *pt_xyz, const float *pt_world, const float *pt_cauchy, const int32_t *pt_image,
+                                   const int32_t *hyp_cluster, const int32_t *sample_pos, const float *init_quat, int n_hyp,
+                                   const mc_pose_params *params, float alpha, int32_t *n_inliers, float *pose_lm, float *pose_refit,
+                                   float *lm_err, uint8_t *inlier_mask) {
+	if (!ctx || !cluster_offsets || !pt_xy || !pt_xyz || !pt_world || !pt_cauchy || !pt_image || !hyp_cluster || !sample_pos || !init_quat ||
+	    !params || !n_inliers || !pose_lm || !pose_refit || !lm_err || n_clusters <= 0 || n_hyp < 0) {
+		if (ctx) ctx->err = "mc_pose_depth_hypotheses: bad argument";
+		return MC_ERR_ARG;
+	}
+	if (n_hyp == 0) return MC_OK;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	const int M = cluster_offsets[n_clusters];
+	const int na = params->n_pts_align;
+	std::vector<int64_t> mask_off(n_hyp + 1, 0);
+	for (int h = 0; h < n_hyp; h++) {
+		const int c = hyp_cluster[h];
+		if (c < 0 || c >= n_clusters) { ctx->err = "mc_pose_depth_hypotheses: hyp_cluster out of range"; return MC_ERR_ARG; }
+		const int n = cluster_offsets[c + 1] - cluster_offsets[c];
+		for (int j = 0; j < na; j++) {
+			const int s = sample_pos[(size_t)h * na + j];
+			if (s < 0 || s >= n) { ctx->err = "mc_pose_depth_hypotheses: sample_pos out of range"; return MC_ERR_ARG; }
+		}
+		mask_off[h + 1] = mask_off[h] + n;
+	}
+	Arena A; A.ctx = ctx;
+	const size_t o_co = A.plan(4ull * (n_clusters + 1)), o_xy = A.plan(8ull * M), o_xyz = A.plan(12ull * M), o_w = A.plan(12ull * M),
+	             o_cw = A.plan(4ull * M), o_im = A.plan(4ull * M);
+	const size_t o_hc = A.plan(4ull * n_hyp), o_sp = A.plan(4ull * n_hyp * na), o_iq = A.plan(16ull * n_hyp), o_mo = A.plan(8ull * (n_hyp + 1));
+	const size_t o_ni = A.plan(4ull * n_hyp), o_pl = A.plan(28ull * n_hyp), o_pr = A.plan(28ull * n_hyp), o_le = A.plan(8ull * n_hyp);
+	const size_t o_mask = A.plan(inlier_mask ? (size_t)mask_off[n_hyp] + 1 : 1);
+	MC_TRY(reserve(ctx, ctx->scratch[18], A.off));
+	char *b = (char *)ctx->scratch[18].p;
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_co), cluster_offsets, (size_t)n_clusters + 1));
+	MC_TRY(h2d(ctx, (float *)(b + o_xy), pt_xy, 2 * (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_xyz), pt_xyz, 3 * (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_w), pt_world, 3 * (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_cw), pt_cauchy, (size_t)M));
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_im), pt_image, (size_t)M));
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_hc), hyp_cluster, (size_t)n_hyp));
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_sp), sample_pos, (size_t)n_hyp * na));
+	MC_TRY(h2d(ctx, (float *)(b + o_iq), init_quat, 4 * (size_t)n_hyp));
+	MC_TRY(h2d(ctx, (int64_t *)(b + o_mo), mask_off.data(), (size_t)n_hyp + 1));
+	MC_TRY(pose_depth_hypotheses_device(ctx, variant, (int32_t *)(b + o_co), (float *)(b + o_xy), (float *)(b + o_xyz), (float *)(b + o_w),
+	                                    (float *)(b + o_cw), (int32_t *)(b + o_im), (int32_t *)(b + o_hc), (int32_t *)(b + o_sp), (float *)(b + o_iq),
+	                                    n_hyp, largest_cluster(cluster_offsets, n_clusters), params, alpha, (int64_t *)(b + o_mo),
+	                                    (int32_t *)(b + o_ni), (float *)(b + o_pl), (float *)(b + o_pr), (float *)(b + o_le),
+	                                    inlier_mask ? (uint8_t *)(b + o_mask) : nullptr));
+	MC_TRY(d2h(ctx, n_inliers, (const int32_t *)(b + o_ni), (size_t)n_hyp));
+	MC_TRY(d2h(ctx, pose_lm, (const float *)(b + o_pl), 7 * (size_t)n_hyp));
+	MC_TRY(d2h(ctx, pose_refit, (const float *)(b + o_pr), 7 * (size_t)n_hyp));
+	MC_TRY(d2h(ctx, lm_err, (const float *)(b + o_le), 2 * (size_t)n_hyp));
+	if (inlier_mask) MC_TRY(d2h(ctx, inlier_mask, (const uint8_t *)(b + o_mask), (size_t)mask_off[n_hyp]));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+mc_status mc_pose_depth_ransac(mc_ctx *ctx, int variant, const int32_t *cluster_offsets, int n_clusters, const float *pt_xy, const float *pt_xyz,
+                               const float *pt_world, const float *pt_cauchy, const int32_t *pt_image, const int32_t *pt_tie,
+                               const mc_pose_params *params, float alpha, uint8_t *found, float *pose, int32_t *n_tests) {
+	if (!ctx || !cluster_offsets || !pt_xy || !pt_xyz || !pt_world || !pt_cauchy || !pt_image || !params || !found || !pose || !n_tests ||
+	    n_clusters <= 0) {
+		if (ctx) ctx->err = "mc_pose_depth_ransac: bad argument";
+		return MC_ERR_ARG;
+	}
+	MC_CUDA(cudaSetDevice(ctx->device));
+	const int M = cluster_offsets[n_clusters];
+	const int n_tasks = n_clusters * params->max_objects_per_cluster;
+	if (n_tasks <= 0) return MC_OK;
+	Arena A; A.ctx = ctx;
+	const size_t o_co = A.plan(4ull * (n_clusters + 1)), o_xy = A.plan(8ull * M), o_xyz = A.plan(12ull * M), o_w = A.plan(12ull * M),
+	             o_cw = A.plan(4ull * M), o_im = A.plan(4ull * M), o_tie = A.plan(4ull * M);
+	const size_t o_f = A.plan(n_tasks), o_p = A.plan(28ull * n_tasks), o_nt = A.plan(4ull * n_tasks);
+	MC_TRY(reserve(ctx, ctx->scratch[18], A.off));
+	char *b = (char *)ctx->scratch[18].p;
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_co), cluster_offsets, (size_t)n_clusters + 1));
+	MC_TRY(h2d(ctx, (float *)(b + o_xy), pt_xy, 2 * (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_xyz), pt_xyz, 3 * (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_w), pt_world, 3 * (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_cw), pt_cauchy, (size_t)M));
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_im), pt_image, (size_t)M));
+	if (pt_tie) MC_TRY(h2d(ctx, (int32_t *)(b + o_tie), pt_tie, (size_t)M));
+	MC_CUDA(cudaMemsetAsync(b + o_p, 0, 28ull * n_tasks, ctx->stream));
+	MC_TRY(pose_depth_ransac_device(ctx, variant, (int32_t *)(b + o_co), n_clusters, largest_cluster(cluster_offsets, n_clusters), (float *)(b + o_xy),
+	                                (float *)(b + o_xyz), (float *)(b + o_w), (float *)(b + o_cw), (int32_t *)(b + o_im),
+	                                pt_tie ? (int32_t *)(b + o_tie) : nullptr, params, alpha, (uint8_t *)(b + o_f), (float *)(b + o_p),
+	                                (int32_t *)(b + o_nt)));
 	MC_TRY(d2h(ctx, found, (const uint8_t *)(b + o_f), (size_t)n_tasks));
 	MC_TRY(d2h(ctx, pose, (const float *)(b + o_p), 7 * (size_t)n_tasks));
 	MC_TRY(d2h(ctx, n_tests, (const int32_t *)(b + o_nt), (size_t)n_tasks));

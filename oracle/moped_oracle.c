@@ -361,6 +361,10 @@ static int lu_solve(const float *A, const float *B, float *x, int m) {
 			float t = work[i] * fabsf(sum);
 			if (t >= mx) { mx = t; maxi = i; }
 		}
+		/* levmar initialises maxi = -1 and a first column of NaNs (0 * inf after an overflowed J^T J) never sets it: the reference
+		 * then swaps with the row BEFORE its matrix — undefined behaviour, whatever happens to lie on its stack decides. No
+		 * reference result exists for that input; the restatement (and the CUDA LM) call the system singular instead. */
+		if (maxi < 0) return 0;
 		if (j != maxi) {
 			for (int k = 0; k < m; k++) { float t = a[maxi * m + k]; a[maxi * m + k] = a[j * m + k]; a[j * m + k] = t; }
 			work[maxi] = work[j];
