@@ -83,6 +83,7 @@ k_depth_ransac(const int32_t *__restrict__ cluster_offsets, int n_clusters, cons
                uint8_t *__restrict__ found, float *__restrict__ pose_out, int32_t *__restrict__ n_tests) {
 	constexpr int R = lmx::DepthResiduals<V>::R;
 	__shared__ int s_first, s_fail;
+	__shared__ float s_pose[kDepthWarps][7];           // refitted pose of each warp's successful test of the current round
 	const int task = blockIdx.x;
 	const int cidx = task / max_obj;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -108,9 +109,8 @@ k_depth_ransac(const int32_t *__restrict__ cluster_offsets, int n_clusters, cons
 				const int cnt = lmx::hypothesis<V, 32>(team, c, pos, n_align, quat, max_lm, thr, min_npts, my, my_mask, finite_check != 0, pose_lm,
 				                                       pose_refit, err2);
 				if (cnt > min_npts) {
-					const int before = atomicMin(&s_first, h);       // every lane of the warp; idempotent
-					(void)before;
-					if (lane == 0) for (int j = 0; j < 7; j++) my[j] = pose_refit[j];   // the slice's head is free again after hypothesis()
+					atomicMin(&s_first, h);                          // every lane of the warp; idempotent
+					if (lane == 0) for (int j = 0; j < 7; j++) s_pose[w][j] = pose_refit[j];
 				}
 			} else if (lane == 0) s_fail = 1;                        // randSample fails for every test of the task alike -> RANSAC returns false
 		}
@@ -123,7 +123,7 @@ k_depth_ransac(const int32_t *__restrict__ cluster_offsets, int n_clusters, cons
 	const int first = s_first;
 	const bool ok = first != kNoSuccess;
 	if (ok && w == first % kDepthWarps && lane == 0)
-		for (int j = 0; j < 7; j++) pose_out[7 * task + j] = my[j];
+		for (int j = 0; j < 7; j++) pose_out[7 * task + j] = s_pose[w][j];
 	if (threadIdx.x == 0) { found[task] = ok ? 1 : 0; n_tests[task] = tests; }
 }
 
