@@ -301,6 +301,10 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
 /* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)
+ *   "pose_exact_order"     != 0: mc_pose_hypotheses / mc_pose_ransac (host entries) run the order-preserving LM of the depth stages
+ *                          (pose_depth.cu, lm_exact.cuh) with the moped2 residual: every sum in levmar's order, unfused multiply-add —
+ *                          poses, inlier masks and ||e||^2 equal the strict-IEEE build of POSE_RANSAC_LM_DIFF_REPROJECTION_CPU bit for
+ *                          bit (slower than the default kernels, which re-associate; the frame pipeline keeps the default).
  *   "lm_finite_check"      != 0: the depth pose stages stop an LM whose ||e||^2 became non-finite with LM_ERROR, like a strict-IEEE
  *                          build of levmar (lm_core.c:551,732); 0 (default): the test is folded away as in the reference's
  *                          -ffast-math build.

@@ -173,6 +173,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
 	else if (k == "lm_finite_check") ctx->lm_finite_check = value != 0;
+	else if (k == "pose_exact_order") ctx->pose_exact_order = value != 0;
 	else if (k == "sift_two_pass") return sift_set_two_pass(ctx, (int)value);
 	else if (k == "sift_describe_gather") return sift_set_gather(ctx, (int)value);
 	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }
@@ -359,6 +360,19 @@ mc_status mc_pose_hypotheses(mc_ctx *ctx, const int32_t *cluster_offsets, int n_
 	MC_TRY(h2d(ctx, (int32_t *)(b + o_sp), sample_pos, (size_t)n_hyp * na));
 	MC_TRY(h2d(ctx, (float *)(b + o_iq), init_quat, 4 * (size_t)n_hyp));
 	MC_TRY(h2d(ctx, (int64_t *)(b + o_mo), mask_off.data(), (size_t)n_hyp + 1));
+	if (ctx->pose_exact_order) {
+		int n_max = 0;
+		for (int c = 0; c < n_clusters; c++) n_max = std::max(n_max, cluster_offsets[c + 1] - cluster_offsets[c]);
+		for (int h = 0; h < n_hyp; h++)
+			for (int j = 0; j < na; j++) {
+				const int sp = sample_pos[(size_t)h * na + j], c = hyp_cluster[h];
+				if (sp < 0 || sp >= cluster_offsets[c + 1] - cluster_offsets[c]) { ctx->err = "mc_pose_hypotheses: sample_pos out of range"; return MC_ERR_ARG; }
+			}
+		MC_TRY(pose_depth_hypotheses_device(ctx, 2, (int32_t *)(b + o_co), (float *)(b + o_xy), (float *)(b + o_xyz), nullptr, nullptr,
+		                                    (int32_t *)(b + o_im), (int32_t *)(b + o_hc), (int32_t *)(b + o_sp), (float *)(b + o_iq), n_hyp, n_max, params,
+		                                    0.f, (int64_t *)(b + o_mo), (int32_t *)(b + o_ni), (float *)(b + o_pl), (float *)(b + o_pr),
+		                                    (float *)(b + o_le), inlier_mask ? (uint8_t *)(b + o_mask) : nullptr));
+	} else
 	MC_TRY(pose_hypotheses_device(ctx, (int32_t *)(b + o_co), (float *)(b + o_xy), (float *)(b + o_xyz), (int32_t *)(b + o_im), (int32_t *)(b + o_hc),
 	                              (int32_t *)(b + o_sp), (float *)(b + o_iq), n_hyp, params, (int64_t *)(b + o_mo), (int32_t *)(b + o_ni),
 	                              (float *)(b + o_pl), (float *)(b + o_pr), (float *)(b + o_le), inlier_mask ? (uint8_t *)(b + o_mask) : nullptr));
@@ -405,6 +419,12 @@ mc_status mc_pose_ransac(mc_ctx *ctx, const int32_t *cluster_offsets, int n_clus
 	MC_TRY(h2d(ctx, (float *)(b + o_xyz), pt_xyz, 3 * (size_t)M));
 	MC_TRY(h2d(ctx, (int32_t *)(b + o_im), pt_image, (size_t)M));
 	MC_CUDA(cudaMemsetAsync(b + o_p, 0, 28ull * n_tasks, ctx->stream));
+	if (ctx->pose_exact_order) {
+		int n_max = 0;
+		for (int c = 0; c < n_clusters; c++) n_max = std::max(n_max, cluster_offsets[c + 1] - cluster_offsets[c]);
+		MC_TRY(pose_depth_ransac_device(ctx, 2, (int32_t *)(b + o_co), n_clusters, n_max, (float *)(b + o_xy), (float *)(b + o_xyz), nullptr, nullptr,
+		                                (int32_t *)(b + o_im), nullptr, params, 0.f, (uint8_t *)(b + o_f), (float *)(b + o_p), (int32_t *)(b + o_nt)));
+	} else
 	MC_TRY(pose_ransac_device(ctx, (int32_t *)(b + o_co), nullptr, n_clusters, (float *)(b + o_xy), (float *)(b + o_xyz), (int32_t *)(b + o_im), nullptr,
 	                          params, (uint8_t *)(b + o_f), (float *)(b + o_p), (int32_t *)(b + o_nt)));
 	MC_TRY(d2h(ctx, found, (const uint8_t *)(b + o_f), (size_t)n_tasks));

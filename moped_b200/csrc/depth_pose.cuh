@@ -108,6 +108,32 @@ template <> struct DepthResiduals<1> {
 	}
 };
 
+// variant 2: lmFuncQuat of the moped2 stage POSE_RANSAC_LM_DIFF_REPROJECTION_CPU (moped2/libmoped/src/pose/
+// POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:100-138): squared pixel differences, (-z + 10) twice behind the camera. No depth
+// inputs (Cluster::world / cauchy unused). With it the same order-preserving LM serves the moped2 POSE / POSE2 steps
+// ("pose_exact_order"): results equal the strict-IEEE build of that stage bit for bit.
+template <> struct DepthResiduals<2> {
+	static constexpr int R = 2;
+	Cluster c;
+	const int32_t *sel;
+	LMX_MEM void point(const float *T, int k, float *res) const {
+		const int i = sel[k];
+		const Cam &cam = c.cams[c.image[i]];
+		float p3[3];
+		to_camera(T, cam.TM, c.xyz + 3 * i, p3);
+		const float u = p3[0] / p3[2] * cam.K[0] + cam.K[2];
+		const float v = p3[1] / p3[2] * cam.K[1] + cam.K[3];
+		if (p3[2] < 0) {
+			res[0] = -p3[2] + 10;
+			res[1] = -p3[2] + 10;
+		} else {
+			const float a = u - c.xy[2 * i], b = v - c.xy[2 * i + 1];
+			res[0] = a * a;
+			res[1] = b * b;
+		}
+	}
+};
+
 // optimizeCamera (:222-250): LM from `pose` on the selected correspondences; on success the pose is replaced (quaternion
 // re-normalised) and ||e||^2 returned, on LM_ERROR the pose is untouched and -1 returned.
 template <int V, int W>
@@ -169,7 +195,9 @@ LMX_FN int hypothesis(const Team<W> &team, const Cluster &c, const int32_t *samp
 	int32_t *sel = (int32_t *)(scratch + work_floats(R * c.n));
 	int32_t *count_slot = sel + c.n;
 	float pose[M] = { init_quat[0], init_quat[1], init_quat[2], init_quat[3], 0, 0, 0 };
-	{   // initPose (:262-276): Pt += over the samples, then / n
+	if (V == 2) {   // moped2's initPose (POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:182-186)
+		pose[6] = 0.5f;
+	} else {        // initPose (:262-276): Pt += over the samples, then / n
 		float sx = 0.f, sy = 0.f, sz = 0.f;
 		for (int j = 0; j < n_samples; j++) { const float *w = c.world + 3 * sample_pos[j]; sx += w[0]; sy += w[1]; sz += w[2]; }
 		pose[4] = sx / n_samples; pose[5] = sy / n_samples; pose[6] = sz / n_samples;

@@ -1,6 +1,8 @@
 // pose_depth.cu — moped3d's depth-aware POSE stages:
 //   variant 0  POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU (moped3d/libmoped/src/pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp:57-470)
 //   variant 1  POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU   (moped3d/libmoped/src/pose/POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU.hpp:57-435)
+// and, with the same machinery, the moped2 stage in "exact order" mode (mc_set_option "pose_exact_order"):
+//   variant 2  POSE_RANSAC_LM_DIFF_REPROJECTION_CPU         (moped2/libmoped/src/pose/POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:57-307)
 //
 // One WARP owns one RANSAC test (sample fit -> inlier test -> refit on the inliers) through depth_pose.cuh /
 // lm_exact.cuh: an LM whose every sum runs in levmar's order, so the poses are those of the strict-IEEE build of the
@@ -33,7 +35,7 @@ __device__ __forceinline__ lmx::Cluster cluster_view(const int32_t *cluster_offs
 	const int lo = cluster_offsets[c];
 	lmx::Cluster v;
 	v.n = cluster_offsets[c + 1] - lo;
-	v.xy = xy + 2 * (size_t)lo; v.xyz = xyz + 3 * (size_t)lo; v.world = world + 3 * (size_t)lo; v.cauchy = cauchy + lo; v.image = image + lo;
+	v.xy = xy + 2 * (size_t)lo; v.xyz = xyz + 3 * (size_t)lo; v.world = world ? world + 3 * (size_t)lo : nullptr; v.cauchy = cauchy ? cauchy + lo : nullptr; v.image = image + lo;
 	v.cams = reinterpret_cast<const lmx::Cam *>(cams); v.alpha = alpha;
 	return v;
 }
@@ -142,10 +144,11 @@ mc_status pose_depth_hypotheses_device(mc_ctx *ctx, int variant, const int32_t *
                                        float alpha, const int64_t *d_mask_offsets, int32_t *d_n_inliers, float *d_pose_lm, float *d_pose_refit,
                                        float *d_lm_err, uint8_t *d_mask) {
 	if (!ctx->d_cams) { ctx->err = "pose (depth): cameras not set (mc_set_cameras)"; return MC_ERR_STATE; }
-	if (variant != 0 && variant != 1) { ctx->err = "pose (depth): variant must be 0 (back-projection) or 1 (reprojection + depth)"; return MC_ERR_ARG; }
+	if (variant < 0 || variant > 2) { ctx->err = "pose (exact order): variant must be 0 (back-projection + depth), 1 (reprojection + depth) or 2 (moped2 reprojection)"; return MC_ERR_ARG; }
+	if (variant != 2 && (!d_world || !d_cauchy)) { ctx->err = "pose (depth): world3D and Cauchy weights are required"; return MC_ERR_ARG; }
 	if (pp->n_pts_align < 1 || pp->n_pts_align > kMaxAlign) { ctx->err = "pose (depth): n_pts_align must be in 1..8"; return MC_ERR_ARG; }
 	if (n_hyp <= 0) return MC_OK;
-	const int R = variant == 0 ? 2 : 3;
+	const int R = variant == 1 ? 3 : 2;
 	const size_t slice = depth_slice_floats(n_max, R);
 	int grid = (n_hyp + kDepthWarps - 1) / kDepthWarps;
 	const int cap = ctx->num_sms * 4;                              // persistent: 16 warps per SM
@@ -159,7 +162,7 @@ mc_status pose_depth_hypotheses_device(mc_ctx *ctx, int variant, const int32_t *
 	                                                                 pp->max_lm_tests, pp->error_threshold, pp->min_npts_object,               \
 	                                                                 ctx->lm_finite_check ? 1 : 0, scratch, slice, n_max, d_mask_offsets,      \
 	                                                                 d_n_inliers, d_pose_lm, d_pose_refit, d_lm_err, d_mask)
-	if (variant == 0) MC_DEPTH_HYP(0); else MC_DEPTH_HYP(1);
+	if (variant == 0) MC_DEPTH_HYP(0); else if (variant == 1) MC_DEPTH_HYP(1); else MC_DEPTH_HYP(2);
 #undef MC_DEPTH_HYP
 	MC_LAUNCH_CHECK();
 	return MC_OK;
@@ -169,11 +172,12 @@ mc_status pose_depth_ransac_device(mc_ctx *ctx, int variant, const int32_t *d_cl
                                    const float *d_xyz, const float *d_world, const float *d_cauchy, const int32_t *d_image, const int32_t *d_tie,
                                    const mc_pose_params *pp, float alpha, uint8_t *d_found, float *d_pose, int32_t *d_n_tests) {
 	if (!ctx->d_cams) { ctx->err = "pose (depth): cameras not set (mc_set_cameras)"; return MC_ERR_STATE; }
-	if (variant != 0 && variant != 1) { ctx->err = "pose (depth): variant must be 0 (back-projection) or 1 (reprojection + depth)"; return MC_ERR_ARG; }
+	if (variant < 0 || variant > 2) { ctx->err = "pose (exact order): variant must be 0 (back-projection + depth), 1 (reprojection + depth) or 2 (moped2 reprojection)"; return MC_ERR_ARG; }
+	if (variant != 2 && (!d_world || !d_cauchy)) { ctx->err = "pose (depth): world3D and Cauchy weights are required"; return MC_ERR_ARG; }
 	if (pp->n_pts_align < 1 || pp->n_pts_align > kMaxAlign) { ctx->err = "pose (depth): n_pts_align must be in 1..8"; return MC_ERR_ARG; }
 	const int n_tasks = n_clusters * pp->max_objects_per_cluster;
 	if (n_tasks <= 0) return MC_OK;
-	const int R = variant == 0 ? 2 : 3;
+	const int R = variant == 1 ? 3 : 2;
 	const size_t slice = depth_slice_floats(n_max, R);
 	float *scratch = nullptr;
 	MC_TRY(depth_scratch(ctx, (size_t)n_tasks * kDepthWarps, slice, &scratch));
@@ -183,7 +187,7 @@ mc_status pose_depth_ransac_device(mc_ctx *ctx, int variant, const int32_t *d_cl
 	                                                                pp->max_lm_tests, pp->n_pts_align, pp->min_npts_object, pp->error_threshold, \
 	                                                                pp->seed, ctx->lm_finite_check ? 1 : 0, scratch, slice, n_max, d_found,    \
 	                                                                d_pose, d_n_tests)
-	if (variant == 0) MC_DEPTH_RANSAC(0); else MC_DEPTH_RANSAC(1);
+	if (variant == 0) MC_DEPTH_RANSAC(0); else if (variant == 1) MC_DEPTH_RANSAC(1); else MC_DEPTH_RANSAC(2);
 #undef MC_DEPTH_RANSAC
 	MC_LAUNCH_CHECK();
 	return MC_OK;

@@ -37,6 +37,8 @@ extern "C" int dh_hypothesis(int variant, int width, int lane_order, int n, cons
 	else if (variant == 0 && width == 32) DH_RUN(0, 32);
 	else if (variant == 1 && width == 1) DH_RUN(1, 1);
 	else if (variant == 1 && width == 32) DH_RUN(1, 32);
+	else if (variant == 2 && width == 1) DH_RUN(2, 1);
+	else if (variant == 2 && width == 32) DH_RUN(2, 32);
 #undef DH_RUN
 	_mm_setcsr(csr);
 	return r;

@@ -115,3 +115,38 @@ def test_degenerate_inputs(host_lib, cams):
                 assert np.array_equal(d["lm_err"], o["lm_err"], equal_nan=True)
                 if o["n_inliers"] >= 0:
                     assert np.array_equal(d["pose_lm"], o["pose_lm"], equal_nan=True) and np.array_equal(d["pose_refit"], o["pose_refit"], equal_nan=True)
+
+
+@pytest.mark.parametrize("finite_check", [0, 1])
+def test_moped2_reprojection_variant_equals_oracle_bit_for_bit(host_lib, finite_check):
+    """variant 2 = the moped2 stage's residual (POSE_RANSAC_LM_DIFF_REPROJECTION_CPU) under the same order-preserving LM — the
+    "pose_exact_order" mode of mc_pose_hypotheses / mc_pose_ransac — against mo_hypothesis, which tests/test_oracle_vs_strict_ref.py
+    pins bit for bit to the strict build of that stage (with levmar's non-finite stop on, hence both settings here)."""
+    from moped_b200 import synth
+    cams2 = oracle.cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    rng = np.random.default_rng(77)
+    oracle.lib().mo_set_lm_finite_check(finite_check)
+    try:
+        accepted = 0
+        for pts, frac, n_align, (max_lm, thr, min_npts) in ((80, 0.5, 5, (200, 10.0, 6)), (40, 0.1, 6, (500, 5.0, 8)), (150, 0.3, 5, (200, 10.0, 6))):
+            cl = synth.make_ransac_clusters(3, pts, frac, seed=900 + pts)
+            for k in range(3):
+                s = slice(cl["offsets"][k], cl["offsets"][k + 1])
+                xy, xyz, img = cl["xy"][s], cl["xyz"][s], cl["image"][s]
+                n = len(xy)
+                zeros3, zeros1 = np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+                for h in range(10):
+                    pos = rng.choice(n, n_align, replace=False).astype(np.int32)
+                    quat = (rng.integers(0, 256, 4) / 256.0).astype(np.float32)
+                    on, olm, orefit, oerr, omask = oracle.hypothesis(xy, xyz, img, cams2, pos, quat, max_lm, thr, min_npts)
+                    for width, order in ((1, 0), (32, 0), (32, 1)):
+                        lm, rf, er, mk = np.zeros(7, np.float32), np.zeros(7, np.float32), np.zeros(2, np.float32), np.zeros(n, np.uint8)
+                        r = host_lib.dh_hypothesis(2, width, order, n, xy, xyz, zeros3, zeros1, img, C.addressof(cams2), 0.0, pos, n_align, quat,
+                                                   max_lm, thr, min_npts, finite_check, lm, rf, er, mk)
+                        assert r == on and np.array_equal(mk, omask) and np.array_equal(er, oerr), (pts, k, h, width, order, r, on, er, oerr)
+                        if on >= 0:
+                            assert np.array_equal(lm, olm) and np.array_equal(rf, orefit), (pts, k, h, width, order)
+                    accepted += on > min_npts
+        assert accepted >= 15
+    finally:
+        oracle.lib().mo_set_lm_finite_check(0)

@@ -172,3 +172,40 @@ def test_stage_class_inside_moped3ds_own_pipeline(tmp_path, cams, variant):
         for gt in gt_list:
             assert min(max(np.abs(p[4:] - gt[4:]).max() / tol_t, quat_angle(p[:4], gt[:4]) / tol_r) for p in poses) < 1.0, name
     assert "old_cpu=%d" % len(objs["cpu"]) in r.stdout and "old_cuda=%d" % len(objs["cuda"]) in r.stdout
+
+
+def test_moped2_pose_in_exact_order_mode_is_bit_exact(gpu_ctx):
+    """mc_set_option("pose_exact_order", 1): mc_pose_hypotheses / mc_pose_ransac run the order-preserving LM with the moped2 residual.
+    Where the default kernels meet the oracle statistically (they re-associate), this mode meets it bit for bit — hypotheses,
+    inlier masks, ||e||^2, the RANSAC winner and its refitted pose (north_star's RANSAC/LM parity, without a tolerance)."""
+    from moped_b200 import synth
+    cams2 = oracle.cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    gpu_ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    cl = synth.make_ransac_clusters(6, 80, 0.25, seed=321)        # the oracle accepts 18 of these 96 hypotheses and finds all 12 tasks at tests 1-9
+    hyp = synth.make_hypotheses(cl, 16, 5, seed=322)
+    P = (40, 200, 2, 5, 6, 10.0)
+    gpu_ctx.set_option("pose_exact_order", 1)
+    try:
+        n_in, pose_lm, pose_refit, err, masks = gpu_ctx.pose_hypotheses(cl["offsets"], cl["xy"], cl["xyz"], cl["image"], hyp["hyp_cluster"],
+                                                                        hyp["sample_pos"], hyp["init_quat"], P, want_mask=True)
+        accepted = 0
+        for h in range(len(n_in)):
+            k = hyp["hyp_cluster"][h]; s = slice(cl["offsets"][k], cl["offsets"][k + 1])
+            on, olm, orefit, oerr, omask = oracle.hypothesis(cl["xy"][s], cl["xyz"][s], cl["image"][s], cams2, hyp["sample_pos"][h], hyp["init_quat"][h],
+                                                             P[1], P[5], P[4])
+            assert n_in[h] == on and np.array_equal(masks[h], omask.astype(bool)) and np.array_equal(err[h], oerr), h
+            if on >= 0:
+                assert np.array_equal(pose_lm[h], olm) and np.array_equal(pose_refit[h], orefit), h
+            accepted += on > P[4]
+        assert accepted >= 10
+        found, pose, nt = gpu_ctx.pose_ransac(cl["offsets"], cl["xy"], cl["xyz"], cl["image"], P, seed=5)
+        for task in range(len(found)):
+            k = task // P[2]; s = slice(cl["offsets"][k], cl["offsets"][k + 1])
+            seed = (5 + 0x9E3779B97F4A7C15 * (task + 1)) & 0xFFFFFFFFFFFFFFFF
+            f, p, it = oracle.ransac(cl["xy"][s], cl["xyz"][s], cl["image"][s], None, cams2, P, seed)
+            assert bool(found[task]) == bool(f) and nt[task] == it, (task, found[task], f, nt[task], it)
+            if f:
+                assert np.array_equal(pose[task], p), task
+        assert found.all()
+    finally:
+        gpu_ctx.set_option("pose_exact_order", 0)
