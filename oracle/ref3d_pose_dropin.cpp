@@ -7,7 +7,9 @@
  * by the same line with ..._CUDA. Runs both stages in two reference MopedPipelines on identical FrameData (matches with depthData,
  * clusters, one camera) and prints the objects each produced; the two draw different random samples (libc rand() vs the seedable
  * stream), so the caller compares object counts per model and poses within the stage's own spread.
- * argv: case file, variant (0 back-projection / 1 reprojection + depth).
+ * argv: case file, variant (0 back-projection / 1 reprojection + depth / 2 = the steps after CLUSTER of moped3d's shipped pipeline,
+ * POSE -> FILTER -> POSE2 -> FILTER2 with the parameters of moped3d/libmoped/src/config.hpp:46-49, FILTER_PROJECTION_CUDA being the
+ * moped2 class unchanged: moped3d's FILTER_PROJECTION_CPU is the same code).
  * Case file: int32 n_models; float K[4]; per model int32 {n_matches, n_clusters}, float {x, y, X, Y, Z, wx, wy, wz, fill} per match,
  * then per cluster int32 size followed by that many match indices.
  */
@@ -27,7 +29,9 @@
 #include <lm.h>
 #include <pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp>
 #include <pose/POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU.hpp>
+#include <filter/FILTER_PROJECTION_CPU.hpp>
 #include <POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA.hpp>
+#include <FILTER_PROJECTION_CUDA.hpp>
 #include <POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CUDA.hpp>
 
 using namespace MopedNS;
@@ -96,9 +100,18 @@ int main(int argc, char **argv) {
 	if (variant == 0) {
 		cpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU( 192, 100, 4, 5, 6, 8, 0.5) );
 		gpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA( 192, 100, 4, 5, 6, 8, 0.5) );
-	} else {
+	} else if (variant == 1) {
 		cpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU( 192, 100, 4, 5, 6, 8, 0.5) );
 		gpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CUDA( 192, 100, 4, 5, 6, 8, 0.5) );
+	} else {
+		cpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU( 192, 100, 4, 5, 6, 8, 0.5) );
+		cpu.addAlg( "FILTER", new FILTER_PROJECTION_CPU( 6, 4096., 2) );
+		cpu.addAlg( "POSE2", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU( 64, 250, 4, 6, 8, 5, 0.5) );
+		cpu.addAlg( "FILTER2", new FILTER_PROJECTION_CPU( 8, 8192., 1e-4) );
+		gpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA( 192, 100, 4, 5, 6, 8, 0.5) );
+		gpu.addAlg( "FILTER", new FILTER_PROJECTION_CUDA( 6, 4096., 2) );
+		gpu.addAlg( "POSE2", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA( 64, 250, 4, 6, 8, 5, 0.5) );
+		gpu.addAlg( "FILTER2", new FILTER_PROJECTION_CUDA( 8, 8192., 1e-4) );
 	}
 	map<string,string> cfg;
 	list<MopedAlg *> ca = cpu.getAlgs(true), ga = gpu.getAlgs(true);

@@ -209,3 +209,30 @@ def test_moped2_pose_in_exact_order_mode_is_bit_exact(gpu_ctx):
         assert found.all()
     finally:
         gpu_ctx.set_option("pose_exact_order", 0)
+
+
+def test_moped3d_chain_after_cluster_inside_its_own_pipeline(tmp_path):
+    """The steps after CLUSTER of moped3d's shipped pipeline (POSE -> FILTER -> POSE2 -> FILTER2, moped3d/libmoped/src/config.hpp:46-49)
+    with every stage replaced by its CUDA class, next to the CPU classes, in the reference's own MopedPipeline: the same final
+    objects (one per planted instance, none for the junk cluster), each within 1 cm / 60 mrad of the planted pose on both sides."""
+    import os
+    import subprocess
+    from conftest import quat_angle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "moped3d_pose_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/moped3d_pose_dropin not built (needs /root/reference at build time)")
+    models = [[make_cluster(600, n=40, outliers=0.2)], [make_cluster(601, n=60, outliers=0.3), make_cluster(602, n=30, outliers=0.1)],
+              [make_cluster(603, n=30, outliers=1.0)]]
+    case = str(tmp_path / "pose_case.bin")
+    write_pose_case(case, models)
+    r = subprocess.run([exe, case, "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    objs = parse_objects(r.stdout)
+    gts = {"obj0": [models[0][0]["gt"]], "obj1": [models[1][0]["gt"], models[1][1]["gt"]]}
+    for side in ("cpu", "cuda"):
+        assert sorted(n for n, _ in objs[side]) == ["obj0", "obj1", "obj1"], (side, objs[side])
+        for name, gt_list in gts.items():
+            poses = [p for n, p in objs[side] if n == name]
+            for gt in gt_list:
+                assert min(max(np.abs(p[4:] - gt[4:]).max() / 0.01, quat_angle(p[:4], gt[:4]) / 0.06) for p in poses) < 1.0, (side, name)
