@@ -301,6 +301,9 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
 /* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)
+ *   "linkage_cached"       != 0: mc_cluster_linkage / mc_linkage_agglomerate with average linkage keep a cached maximum per row
+ *                          (same merge sequence and clusters; O(n) per merge instead of an O(n^2) scan). Default 0 until it has
+ *                          run on a GPU.
  *   "pose_exact_order"     != 0: mc_pose_hypotheses / mc_pose_ransac (host entries) run the order-preserving LM of the depth stages
  *                          (pose_depth.cu, lm_exact.cuh) with the moped2 residual: every sum in levmar's order, unfused multiply-add —
  *                          poses, inlier masks and ||e||^2 equal the strict-IEEE build of POSE_RANSAC_LM_DIFF_REPROJECTION_CPU bit for

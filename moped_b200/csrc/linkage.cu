@@ -18,6 +18,7 @@
 // compared with strict >, so the FIRST maximum in (list position, list position) order wins; adaptiveWeightSum runs with
 // alpha = 0.5, gamma = 25 whatever the constructor got.
 #include "common.cuh"
+#include "linkage_cached.cuh"
 
 #include <float.h>
 #include <math.h>
@@ -280,14 +281,33 @@ __global__ void __launch_bounds__(kLinkThreads) k_link_agglomerate(int n, const 
 	}
 }
 
+// The same agglomeration with a cached maximum per row (linkage_cached.cuh; average linkage only): O(n) per merge plus repairs
+// instead of an O(n^2) scan. mc_set_option("linkage_cached", 1).
+__global__ void __launch_bounds__(kLinkThreads) k_link_agglomerate_cached(int n, const float *__restrict__ K, float *__restrict__ D, float cutoff, int min_pts,
+                                                                         int *__restrict__ L, int *__restrict__ lists, int *__restrict__ sz,
+                                                                         float *__restrict__ tmp3, int *__restrict__ ints3,
+                                                                         int *__restrict__ out_count, int *__restrict__ out_offsets,
+                                                                         int *__restrict__ out_members) {
+	__shared__ float s_val[kLinkThreads];
+	__shared__ int s_idx[kLinkThreads], s_ctl[16];
+	lkx::State s;
+	s.n = n; s.D = D; s.L = L; s.lists = lists; s.sz = sz;
+	s.tmp = tmp3; s.oldcol = tmp3 + n; s.best = tmp3 + 2 * (size_t)n;
+	s.posOf = ints3; s.arg = ints3 + n; s.tmpi = ints3 + 2 * (size_t)n;
+	s.s_val = s_val; s.s_idx = s_idx; s.ctl = s_ctl;
+	lkx::Block<kLinkThreads> blk;
+	blk.tid = threadIdx.x;
+	lkx::agglomerate_average(blk, s, K, cutoff, min_pts, out_count, out_offsets, out_members);
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------------
 
-struct LinkBufs { float *xy, *xyz, *world, *depth, *distance, *K2D, *K3D, *K3F, *K, *D, *tmp, *scal; int *valid, *lists, *sz, *out; };
+struct LinkBufs { float *xy, *xyz, *world, *depth, *distance, *K2D, *K3D, *K3F, *K, *D, *tmp, *scal; int *valid, *lists, *sz, *ints3, *out; };
 
 static mc_status link_alloc(mc_ctx *ctx, int n, size_t px, LinkBufs &B) {
 	const size_t nn = (size_t)n * n;
 	size_t floats = (size_t)n * 8 + 2 * px + 5 * nn + (size_t)n * 3 + 16;
-	size_t ints = (size_t)n + nn + (size_t)n + (size_t)2 * n + 8;
+	size_t ints = (size_t)n + nn + (size_t)n + (size_t)3 * n + (size_t)2 * n + 8;
 	MC_TRY(reserve(ctx, ctx->link_buf, floats * sizeof(float) + ints * sizeof(int) + 1024));
 	float *f = (float *)ctx->link_buf.p;
 	B.xy = f; f += 2 * (size_t)n; B.xyz = f; f += 3 * (size_t)n; B.world = f; f += 3 * (size_t)n;
@@ -295,7 +315,7 @@ static mc_status link_alloc(mc_ctx *ctx, int n, size_t px, LinkBufs &B) {
 	B.K2D = f; f += nn; B.K3D = f; f += nn; B.K3F = f; f += nn; B.K = f; f += nn; B.D = f; f += nn;
 	B.tmp = f; f += 3 * (size_t)n; B.scal = f; f += 16;
 	int *i = (int *)f;
-	B.valid = i; i += n; B.lists = i; i += nn; B.sz = i; i += n; B.out = i;
+	B.valid = i; i += n; B.lists = i; i += nn; B.sz = i; i += n; B.ints3 = i; i += 3 * (size_t)n; B.out = i;
 	return MC_OK;
 }
 
@@ -328,6 +348,9 @@ static mc_status link_agglomerate_device(mc_ctx *ctx, const LinkBufs &B, int n, 
                                          int32_t *n_clusters, int32_t *cluster_offsets, int32_t *members) {
 	cudaStream_t st = ctx->stream;
 	int *d_count = B.out, *d_off = B.out + 1, *d_mem = B.out + 2 + n;
+	if (ctx->linkage_cached && linkage == 1)
+		k_link_agglomerate_cached<<<1, kLinkThreads, 0, st>>>(n, B.K, B.D, cutoff, min_pts, B.valid, B.lists, B.sz, B.tmp, B.ints3, d_count, d_off, d_mem);
+	else
 	k_link_agglomerate<<<1, kLinkThreads, 0, st>>>(n, B.K, B.D, cutoff, min_pts, linkage, B.valid, B.lists, B.sz, B.tmp, d_count, d_off, d_mem);
 	MC_LAUNCH_CHECK();
 	MC_TRY(pinned(ctx, (size_t)(2 * n + 4) * sizeof(int)));

@@ -23,5 +23,14 @@ for n_per, n_out in (((30, 22), 10), ((120, 80), 40), ((300, 200), 100)):
         t0 = time.perf_counter()
         r = ref3d.cluster_linkage(xy, xyz, world, depth, dist)
         cpu_ms = (time.perf_counter() - t0) * 1e3
-    print(json.dumps(dict(n_matches=n, gpu_ms_per_call=gpu_ms, reference_cpu_ms_per_call=cpu_ms, clusters=len(out[0]) - 1,
+    ctx.set_option("linkage_cached", 1)
+    for _ in range(3):
+        out_c = ctx.cluster_linkage(xy, xyz, world, depth, dist)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out_c = ctx.cluster_linkage(xy, xyz, world, depth, dist)
+    cached_ms = (time.perf_counter() - t0) / reps * 1e3
+    ctx.set_option("linkage_cached", 0)
+    assert np.array_equal(out[0], out_c[0]) and np.array_equal(out[1], out_c[1]), "cached agglomeration changed the clusters"
+    print(json.dumps(dict(n_matches=n, gpu_ms_per_call=gpu_ms, gpu_ms_per_call_cached_maxima=cached_ms, reference_cpu_ms_per_call=cpu_ms, clusters=len(out[0]) - 1,
                           note="mc_cluster_linkage with host buffers (two 320x240 maps + matches up, clusters down) vs CLUSTER_LINKAGE_CPU, one model")))

@@ -236,3 +236,37 @@ def test_moped3d_chain_after_cluster_inside_its_own_pipeline(tmp_path):
             poses = [p for n, p in objs[side] if n == name]
             for gt in gt_list:
                 assert min(max(np.abs(p[4:] - gt[4:]).max() / 0.01, quat_angle(p[:4], gt[:4]) / 0.06) for p in poses) < 1.0, (side, name)
+
+
+def test_cached_agglomeration_equals_default_kernel(gpu_ctx):
+    """mc_set_option("linkage_cached", 1): the cached-row-maximum agglomeration (linkage_cached.cuh) gives the oracle's clusters —
+    and therefore the default kernel's — on the oracle's own similarity matrices, on tie-heavy quantised ones and on a 600-match
+    block-structured one (the host-emulated source already does: tests/test_linkage_cached_host.py)."""
+    from test_oracle3d_linkage import make_scene
+    from test_linkage_cached_host import random_similarity
+    rng = np.random.default_rng(2)
+    mats = []
+    for seed in range(3):
+        xy, xyz, world, depth, dist, _ = make_scene(seed)
+        mats.append((oracle.linkage_similarity(xy, xyz, world, depth, dist), 0.1, 7))
+    for case in range(12):
+        mats.append((random_similarity(rng, int(rng.integers(2, 300)), case % 2 == 1), float(rng.choice([0.2, 0.5, 0.75])), int(rng.integers(0, 4))))
+    n, groups = 600, 4
+    g = rng.integers(0, groups + 1, n)
+    K = np.where((g[:, None] == g[None, :]) & (g[:, None] < groups), 0.6 + 0.4 * rng.random((n, n)), 0.05 * rng.random((n, n))).astype(np.float32)
+    K = np.maximum(K, K.T); np.fill_diagonal(K, 1.0)
+    mats.append((K, 0.1, 7))
+    gpu_ctx.set_option("linkage_cached", 1)
+    try:
+        for K, cutoff, min_pts in mats:
+            oo, om = oracle.linkage_agglomerate(K, cutoff, min_pts, 1)
+            go, gm = gpu_ctx.linkage_agglomerate(K, cutoff, min_pts, 1)
+            assert np.array_equal(oo, go) and np.array_equal(om, gm), (len(K), cutoff, min_pts)
+        # other linkage types keep the default kernel
+        K = mats[3][0]
+        for linkage in (0, 2):
+            oo, om = oracle.linkage_agglomerate(K, 0.5, 1, linkage)
+            go, gm = gpu_ctx.linkage_agglomerate(K, 0.5, 1, linkage)
+            assert np.array_equal(oo, go) and np.array_equal(om, gm), linkage
+    finally:
+        gpu_ctx.set_option("linkage_cached", 0)
