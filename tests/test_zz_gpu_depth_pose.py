@@ -270,3 +270,16 @@ def test_cached_agglomeration_equals_default_kernel(gpu_ctx):
             assert np.array_equal(oo, go) and np.array_equal(om, gm), linkage
     finally:
         gpu_ctx.set_option("linkage_cached", 0)
+
+
+def test_match_adaptive_stage_class_inside_moped3ds_own_pipeline():
+    """MATCH_ADAPTIVE_CUDA as shipped (mc_match on the device) next to MATCH_ADAPTIVE_FLANN_CPU over an exhaustive stand-in index
+    (oracle/_ref/moped3d_match_dropin): identical FrameData::matches, identical in-place normalisation of features and models."""
+    from test_match_adaptive_host import EXE, run_dropin
+    import os
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/moped3d_match_dropin not built (needs /root/reference at build time)")
+    for seed in (1, 2):
+        info, _ = run_dropin(seed)
+        assert info["same"] == "1" and info["normalised_features_same"] == "1" and info["normalised_models_same"] == "1", (seed, info)
+        assert int(info["matches"]) > 200
