@@ -63,3 +63,21 @@ def cluster_partition(hyp_cluster: np.ndarray, world: int, rank: int) -> np.ndar
     rank owns every hypothesis of its clusters and no data-path collective is needed. Returns the indices (ascending)
     of the hypotheses rank `rank` evaluates; the union over ranks is a partition of range(len(hyp_cluster))."""
     return np.nonzero(np.asarray(hyp_cluster) % world == rank)[0]
+
+
+RANSAC_STREAM_STRIDE = 0x9E3779B97F4A7C15      # task t of a call draws from seed + stride * (t + 1)  (pose.cu / pose_depth.cu)
+
+
+def ransac_cluster_range(n_clusters: int, world: int, rank: int):
+    """Full RANSAC (mc_pose_ransac / mc_pose_depth_ransac) distributed by cluster: rank r runs the contiguous cluster block
+    [lo, hi) — contiguous, so that one seed offset (ransac_shard_seed) keeps every task on the random stream it has in a
+    single-GPU call and the result does not depend on the number of ranks."""
+    per, extra = divmod(n_clusters, world)
+    lo = rank * per + min(rank, extra)
+    return lo, lo + per + (1 if rank < extra else 0)
+
+
+def ransac_shard_seed(seed: int, first_cluster: int, max_objects_per_cluster: int) -> int:
+    """The `seed` a shard passes so that its LOCAL task t (cluster first_cluster + t // MaxObjectsPerCluster) draws from the
+    stream of GLOBAL task first_cluster * MaxObjectsPerCluster + t: seed + stride * first_task, modulo 2^64."""
+    return (seed + RANSAC_STREAM_STRIDE * first_cluster * max_objects_per_cluster) & 0xFFFFFFFFFFFFFFFF

@@ -239,3 +239,61 @@ def test_two_rank_frame_partition_of_feature_extraction():
         p.join(timeout=60)
     assert [r[3] for r in res] == [(0, 2), (2, 4)]                               # contiguous blocks in frame order
     assert all(r[1] and r[2] for r in res), res
+
+
+# ---- full RANSAC by cluster (moped3d's depth-aware POSE stage): contiguous cluster blocks + one seed offset ----
+def _depth_ransac_rank(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from moped_b200.sharding import RANSAC_STREAM_STRIDE, ransac_cluster_range, ransac_shard_seed
+    from oracle import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle3d_pose import ALPHA, CAM, K, make_cluster
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    clusters = [make_cluster(700 + i, n=30, outliers=0.3) for i in range(5)]
+    max_obj, seed, params = 2, 17, (12, 100, 5, 6, 8.0)
+    cams = oracle.cameras(K[None], CAM[None])
+    lo, hi = ransac_cluster_range(len(clusters), world, rank)
+    shard_seed = ransac_shard_seed(seed, lo, max_obj)
+    out = np.zeros((len(clusters) * max_obj, 9), np.float32)           # found, tests, pose: zero outside this rank's block
+    for t in range((hi - lo) * max_obj):                               # what mc_pose_depth_ransac does with the shard's clusters and seed
+        task_seed = (shard_seed + RANSAC_STREAM_STRIDE * (t + 1)) & 0xFFFFFFFFFFFFFFFF
+        f, p, it = oracle.ransac_depth(clusters[lo + t // max_obj], cams, ALPHA, params, task_seed)
+        out[lo * max_obj + t] = [f, it, *p]
+    g = torch.from_numpy(out.view(np.int32).copy())
+    dist.all_reduce(g, op=dist.ReduceOp.SUM)                            # disjoint blocks: the sum of bit patterns is the gather
+    if rank == 0:
+        q.put(((lo, hi), g.numpy().view(np.float32).tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_depth_ransac_by_cluster_is_independent_of_the_number_of_ranks():
+    import torch.multiprocessing as mp
+    from moped_b200.sharding import RANSAC_STREAM_STRIDE, ransac_cluster_range
+    from oracle import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle3d_pose import ALPHA, CAM, K, make_cluster
+    assert [ransac_cluster_range(5, 2, r) for r in range(2)] == [(0, 3), (3, 5)]
+    assert [ransac_cluster_range(7, 4, r) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 7)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29870 + os.getpid() % 100
+    procs = [ctx.Process(target=_depth_ransac_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    (lo, hi), merged = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (lo, hi) == (0, 3)
+    clusters = [make_cluster(700 + i, n=30, outliers=0.3) for i in range(5)]
+    cams = oracle.cameras(K[None], CAM[None])
+    found = 0
+    for t in range(10):                                                 # the single-rank call: seed 17, global task index
+        f, p, it = oracle.ransac_depth(clusters[t // 2], cams, ALPHA, (12, 100, 5, 6, 8.0), (17 + RANSAC_STREAM_STRIDE * (t + 1)) & 0xFFFFFFFFFFFFFFFF)
+        assert merged[t][0] == float(f) and merged[t][1] == float(it), t
+        if f:
+            assert np.array_equal(np.array(merged[t][2:], np.float32), p), t
+        found += f
+    assert found >= 5
