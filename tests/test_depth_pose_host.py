@@ -150,3 +150,18 @@ def test_moped2_reprojection_variant_equals_oracle_bit_for_bit(host_lib, finite_
         assert accepted >= 15
     finally:
         oracle.lib().mo_set_lm_finite_check(0)
+
+
+def test_large_cluster_refit_and_eight_samples(host_lib, cams):
+    """700 correspondences, ~630 inliers: the refit runs on 1256 (variant 0) / 1902 (variant 1) residual rows — no cap on the
+    consistent set (the reference has none); NPtsAlign = 8 is the kernels' upper limit."""
+    rng = np.random.default_rng(0)
+    for variant in (0, 1):
+        cl = make_cluster(900 + variant, n=700, outliers=0.1)
+        for n_align in (5, 8):
+            pos = rng.choice(cl["good"], n_align, replace=False)
+            quat = np.array([0.5, 0.25, 0.75, 0.5], np.float32)
+            o = oracle.hypothesis_depth(cl, cams, ALPHA, pos, quat, PARAMS[0], PARAMS[1], PARAMS[2], variant=variant)
+            d = run_host(host_lib, variant, 32, 1, cl, cams, pos, quat)
+            assert same(d, o), (variant, n_align)
+        assert o["n_inliers"] >= 0
