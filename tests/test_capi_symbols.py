@@ -59,3 +59,14 @@ def test_sass_has_blackwell_tensor_and_tma_instructions():
     sass = subprocess.run([cuobjdump, "-sass", build.build()], capture_output=True, text=True).stdout
     for mnem in ("UTCHMMA", "LDTM", "UBLKCP"):
         assert mnem in sass, mnem
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """mc_set_option keys accepted by api.cu == keys described in include/moped_cuda.h."""
+    api = open(os.path.join(ROOT, "moped_b200", "csrc", "api.cu")).read()
+    body = api[api.index("mc_status mc_set_option("):]
+    body = body[:body.index("return MC_OK;")]
+    accepted = set(re.findall(r'k == "([a-z0-9_]+)"', body))
+    header = open(os.path.join(ROOT, "include", "moped_cuda.h")).read()
+    documented = set(re.findall(r'^\s*\*\s+"([a-z0-9_]+)"\s', header, flags=re.M))
+    assert accepted and accepted <= documented, sorted(accepted - documented)
