@@ -634,8 +634,15 @@ def run_ransac_ours(args, rank, world, local_rank):
              torch.zeros((H, 7), dtype=torch.float32, device=dev), torch.zeros((H, 2), dtype=torch.float32, device=dev)]
     h_out = [torch.zeros(H, dtype=torch.int32).pin_memory(), torch.zeros((H, 7), dtype=torch.float32).pin_memory()]
 
+    max_cluster = int(np.diff(cl["offsets"]).max())
+
     def launch(bufs):
-        ctx.pose_hypotheses_dev(*[t.data_ptr() for t in bufs], H, pp, *[t.data_ptr() for t in d_out])
+        if args.pose_mode == "exact":      # the order-preserving LM (pose_depth.cu, variant 2 = this stage's residual): the oracle's bits
+            p = [t.data_ptr() for t in bufs]
+            ctx.pose_depth_hypotheses_dev(2, p[0], max_cluster, p[1], p[2], None, None, p[3], p[4], p[5], p[6], H, pp, 0.0,
+                                          *[t.data_ptr() for t in d_out])
+        else:
+            ctx.pose_hypotheses_dev(*[t.data_ptr() for t in bufs], H, pp, *[t.data_ptr() for t in d_out])
 
     def step_dev(i):
         launch(d_in)
@@ -679,13 +686,14 @@ def run_ransac_ours(args, rank, world, local_rank):
         ms_step = total_ms / args.steps
         out = {"metric": "hypotheses_per_s", "value": Htot * 1e3 / ms_step, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": dict(ransac_config(args, world), l2="working set (a few hundred KB) is cache resident by nature; not flushed"),
+               "config": dict(ransac_config(args, world), l2="working set (a few hundred KB) is cache resident by nature; not flushed",
+                              pose_mode=args.pose_mode),
                "accepted_fraction_rank0": float((n_in > RANSAC_PARAMS[4]).mean()), "lm_failed_fraction_rank0": float((n_in < 0).mean()),
                "gpu_launches": int(launches), "clocks": clocks,
                "e2e": {"value": Htot * 1e3 / (e2e_ms / args.steps), "unit": "hypotheses/s",
                        "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_in)),
                        "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_out))},
-               "roofline": {"kernel": "k_pose_fit", "bound": "fp32-issue/divergence (latency-shaped; see profiles/ for the ncu issue-slot figures)",
+               "roofline": {"kernel": "k_pose_fit" if args.pose_mode == "default" else "k_depth_hypotheses<2>", "bound": "fp32-issue/divergence (latency-shaped; see profiles/ for the ncu issue-slot figures)",
                             "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None}}
         if not args.no_cpu_baseline and world == 1:
             try:
@@ -1037,6 +1045,8 @@ def main():
     ap.add_argument("--workload", default="frames", choices=["frames", "ransac", "sift", "images"],
                     help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s; "
                          "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1; images = pixels in, objects out on real data")
+    ap.add_argument("--pose-mode", default="default", choices=["default", "exact"],
+                    help="ransac workload: default kernels (re-associating) or the order-preserving LM (bit-exact with the oracle)")
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--hyp", type=int, default=2048, help="hypotheses per cluster (ransac workload)")
     args = ap.parse_args()

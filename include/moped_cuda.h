@@ -149,6 +149,14 @@ mc_status mc_pose_depth_hypotheses(mc_ctx *ctx, int variant, const int32_t *clus
                                    const int32_t *hyp_cluster, const int32_t *sample_pos, const float *init_quat, int n_hyp,
                                    const mc_pose_params *params, float alpha,
                                    int32_t *n_inliers, float *pose_lm, float *pose_refit, float *lm_err, uint8_t *inlier_mask);
+/* The explicit-hypothesis entry with every array resident on the device (no inlier masks); asynchronous on the context's stream.
+ * max_cluster_size = the largest cluster (sizes the per-warp LM scratch). variant 2 = the moped2 residual in exact-order mode
+ * (pt_world_dev / pt_cauchy_dev may be NULL): the configs[3] workload of bench.py --pose-mode exact. */
+mc_status mc_pose_depth_hypotheses_dev(mc_ctx *ctx, int variant, const int32_t *cluster_offsets_dev, int max_cluster_size,
+                                       const float *pt_xy_dev, const float *pt_xyz_dev, const float *pt_world_dev, const float *pt_cauchy_dev,
+                                       const int32_t *pt_image_dev, const int32_t *hyp_cluster_dev, const int32_t *sample_pos_dev,
+                                       const float *init_quat_dev, int n_hyp, const mc_pose_params *params, float alpha,
+                                       int32_t *n_inliers_dev, float *pose_lm_dev, float *pose_refit_dev, float *lm_err_dev);
 mc_status mc_pose_depth_ransac(mc_ctx *ctx, int variant, const int32_t *cluster_offsets, int n_clusters,
                                const float *pt_xy, const float *pt_xyz, const float *pt_world, const float *pt_cauchy, const int32_t *pt_image,
                                const int32_t *pt_tie, const mc_pose_params *params, float alpha,

@@ -61,6 +61,8 @@ SIGNATURES = {
     "mc_pose_ransac": (C.c_int, [C.c_void_p, _i32p, C.c_int, _f32p, _f32p, _i32p, C.POINTER(PoseParams), _u8p, _f32p, _i32p]),
     "mc_pose_depth_hypotheses": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p, _f32p, C.c_int,
                                            C.POINTER(PoseParams), C.c_float, _i32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "mc_pose_depth_hypotheses_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.POINTER(PoseParams), C.c_float]
+                                     + [C.c_void_p] * 4),
     "mc_pose_depth_ransac": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_void_p, C.POINTER(PoseParams),
                                        C.c_float, _u8p, _f32p, _i32p]),
     "mc_filter_projection": (C.c_int, [C.c_void_p, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float,
@@ -299,6 +301,14 @@ class Context:
             o = np.concatenate([[0], np.cumsum(sizes)])
             masks = [mask[o[h]:o[h + 1]].astype(bool) for h in range(n_hyp)]
         return n_in, pose_lm, pose_refit, err, masks
+
+    def pose_depth_hypotheses_dev(self, variant, co_ptr, max_cluster_size, xy_ptr, xyz_ptr, world_ptr, cauchy_ptr, img_ptr, hc_ptr, sp_ptr, iq_ptr,
+                                  n_hyp, params, alpha, n_in_ptr, pose_lm_ptr, pose_refit_ptr, err_ptr):
+        """Device-pointer variant (asynchronous on the context's stream); world_ptr / cauchy_ptr may be None for variant 2."""
+        pp = params if isinstance(params, PoseParams) else PoseParams.of(params)
+        self._check(self.L.mc_pose_depth_hypotheses_dev(self.h, int(variant), co_ptr, int(max_cluster_size), xy_ptr, xyz_ptr, world_ptr, cauchy_ptr,
+                                                        img_ptr, hc_ptr, sp_ptr, iq_ptr, n_hyp, C.byref(pp), float(alpha), n_in_ptr, pose_lm_ptr,
+                                                        pose_refit_ptr, err_ptr), "mc_pose_depth_hypotheses_dev")
 
     def pose_depth_ransac(self, variant, cluster_offsets, pt_xy, pt_xyz, pt_world, pt_cauchy, pt_image, params, alpha, seed=1, pt_tie=None):
         co = _i32(cluster_offsets)

@@ -499,6 +499,23 @@ mc_status mc_pose_depth_hypotheses(mc_ctx *ctx, int variant, const int32_t *clus
 	return MC_OK;
 }
 
+mc_status mc_pose_depth_hypotheses_dev(mc_ctx *ctx, int variant, const int32_t *cluster_offsets_dev, int max_cluster_size, const float *pt_xy_dev,
+                                       const float *pt_xyz_dev, const float *pt_world_dev, const float *pt_cauchy_dev, const int32_t *pt_image_dev,
+                                       const int32_t *hyp_cluster_dev, const int32_t *sample_pos_dev, const float *init_quat_dev, int n_hyp,
+                                       const mc_pose_params *params, float alpha, int32_t *n_inliers_dev, float *pose_lm_dev,
+                                       float *pose_refit_dev, float *lm_err_dev) {
+	if (!ctx || !cluster_offsets_dev || !pt_xy_dev || !pt_xyz_dev || !pt_image_dev || !hyp_cluster_dev || !sample_pos_dev || !init_quat_dev ||
+	    !params || !n_inliers_dev || !pose_lm_dev || !pose_refit_dev || !lm_err_dev || n_hyp < 0 || max_cluster_size < 1) {
+		if (ctx) ctx->err = "mc_pose_depth_hypotheses_dev: bad argument";
+		return MC_ERR_ARG;
+	}
+	if (n_hyp == 0) return MC_OK;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	return pose_depth_hypotheses_device(ctx, variant, cluster_offsets_dev, pt_xy_dev, pt_xyz_dev, pt_world_dev, pt_cauchy_dev, pt_image_dev,
+	                                    hyp_cluster_dev, sample_pos_dev, init_quat_dev, n_hyp, max_cluster_size, params, alpha, nullptr,
+	                                    n_inliers_dev, pose_lm_dev, pose_refit_dev, lm_err_dev, nullptr);
+}
+
 mc_status mc_pose_depth_ransac(mc_ctx *ctx, int variant, const int32_t *cluster_offsets, int n_clusters, const float *pt_xy, const float *pt_xyz,
                                const float *pt_world, const float *pt_cauchy, const int32_t *pt_image, const int32_t *pt_tie,
                                const mc_pose_params *params, float alpha, uint8_t *found, float *pose, int32_t *n_tests) {

@@ -287,3 +287,33 @@ def test_match_adaptive_stage_class_inside_moped3ds_own_pipeline():
         info, _ = run_dropin(seed)
         assert info["same"] == "1" and info["normalised_features_same"] == "1" and info["normalised_models_same"] == "1", (seed, info)
         assert int(info["matches"]) > 200
+
+
+def test_device_resident_entry_equals_host_entry(gpu_ctx):
+    """mc_pose_depth_hypotheses_dev (the entry bench.py --workload ransac --pose-mode exact is measured through) == the host entry,
+    for the moped2 residual (variant 2, no depth arrays) and for variant 0."""
+    import torch
+    from moped_b200 import synth
+    dev = torch.device("cuda", 0)
+    cl = synth.make_ransac_clusters(4, 80, 0.3, seed=41)
+    hy = synth.make_hypotheses(cl, 32, 5, seed=42)
+    P = (600, 200, 1, 5, 6, 10.0)
+    gpu_ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    rng = np.random.default_rng(1)
+    world = (cl["xyz"] + rng.normal(0, 0.01, cl["xyz"].shape)).astype(np.float32) + np.array([0, 0, 0.9], np.float32)
+    cw = rng.random(len(cl["xyz"])).astype(np.float32)
+    H = len(hy["hyp_cluster"])
+    for variant in (2, 0):
+        n_in, plm, prf, err, _ = gpu_ctx.pose_depth_hypotheses(variant, cl["offsets"], cl["xy"], cl["xyz"], world, cw, cl["image"], hy["hyp_cluster"],
+                                                               hy["sample_pos"], hy["init_quat"], P, 0.5, want_mask=False)
+        d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in
+             (cl["offsets"], cl["xy"], cl["xyz"], world, cw, cl["image"], hy["hyp_cluster"], hy["sample_pos"], hy["init_quat"])]
+        out = [torch.zeros(H, dtype=torch.int32, device=dev), torch.zeros((H, 7), device=dev), torch.zeros((H, 7), device=dev), torch.zeros((H, 2), device=dev)]
+        torch.cuda.synchronize()
+        gpu_ctx.pose_depth_hypotheses_dev(variant, d[0].data_ptr(), 80, d[1].data_ptr(), d[2].data_ptr(), None if variant == 2 else d[3].data_ptr(),
+                                          None if variant == 2 else d[4].data_ptr(), d[5].data_ptr(), d[6].data_ptr(), d[7].data_ptr(), d[8].data_ptr(),
+                                          H, P, 0.5, *[t.data_ptr() for t in out])
+        gpu_ctx.synchronize()
+        assert np.array_equal(out[0].cpu().numpy(), n_in) and np.array_equal(out[3].cpu().numpy(), err), variant
+        assert np.array_equal(out[1].cpu().numpy(), plm) and np.array_equal(out[2].cpu().numpy(), prf), variant
+    assert (n_in >= 0).any()

@@ -24,6 +24,7 @@ NODES = [
     "test_moped3d_chain_after_cluster_inside_its_own_pipeline",
     "test_cached_agglomeration_equals_default_kernel",
     "test_match_adaptive_stage_class_inside_moped3ds_own_pipeline",
+    "test_device_resident_entry_equals_host_entry",
 ]
 
 UNVERIFIED = [pytest.mark.gpu,
