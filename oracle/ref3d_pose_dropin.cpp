@@ -32,6 +32,7 @@
 #include <filter/FILTER_PROJECTION_CPU.hpp>
 #include <POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA.hpp>
 #include <FILTER_PROJECTION_CUDA.hpp>
+#include <pipeline3d_cuda.hpp>
 #include <POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CUDA.hpp>
 
 using namespace MopedNS;
@@ -97,6 +98,16 @@ int main(int argc, char **argv) {
 	fdCpu.objects = &objCpu; fdGpu.objects = &objGpu;
 
 	MopedPipeline cpu, gpu;
+	if (variant == 3) {                 // registration check of pipeline3d_cuda.hpp: every step of config.hpp:41-49 has its CUDA class
+		MopedPipeline all;
+		addCudaMatch3d(all); addCudaRecognition3d(all);
+		list<MopedAlg *> algs = all.getAlgs(true);
+		map<string,string> c;
+		foreach( alg, algs ) alg->getConfig(c);
+		foreach( kv, c ) printf("CONFIG %s=%s\n", kv.first.c_str(), kv.second.c_str());
+		printf("STEP REGISTER algs=%d\n", (int)algs.size());
+		return 0;
+	}
 	if (variant == 0) {
 		cpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU( 192, 100, 4, 5, 6, 8, 0.5) );
 		gpu.addAlg( "POSE", new POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA( 192, 100, 4, 5, 6, 8, 0.5) );

@@ -34,3 +34,27 @@ def test_adaptive_ratio_logic_equals_the_reference_class():
     for key in ("MinRatioMin", "MinRatioMax", "MaxRatioMin", "MaxRatioMax", "DimensionPeak", "DimensionFade", "NumTrees", "DescriptorType",
                 "DescriptorSize"):
         assert "CONFIG MATCH_SIFT:0:MATCH_ADAPTIVE_CUDA/%s=" % key in out, key
+
+
+def test_moped3d_cuda_pipeline_registers_with_the_reference_config_keys(tmp_path):
+    """moped_b200/stages/pipeline3d_cuda.hpp inside moped3d's own MopedPipeline (no device needed to register and read the
+    configuration): six algorithms for the six recognition steps of config.hpp:41-49, each exposing the config keys of the CPU
+    class it replaces (9 / 6 / 5 / 3 / 5 / 3)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "moped3d_pose_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/moped3d_pose_dropin not built (needs /root/reference at build time)")
+    case = tmp_path / "empty.bin"
+    import numpy as np
+    with open(case, "wb") as f:
+        np.array([0], np.int32).tofile(f); np.zeros(4, np.float32).tofile(f)
+    out = subprocess.run([exe, str(case), "3"], capture_output=True, text=True, timeout=60).stdout
+    assert "STEP REGISTER algs=6" in out
+    keys = {}
+    for line in out.splitlines():
+        if line.startswith("CONFIG "):
+            step, _, rest = line[7:].split(":", 2)
+            keys.setdefault((step, rest.split("/")[0]), []).append(rest.split("/")[1].split("=")[0])
+    assert {k: len(v) for k, v in keys.items()} == {
+        ("MATCH_SIFT", "MATCH_ADAPTIVE_CUDA"): 9, ("CLUSTER", "CLUSTER_LINKAGE_CUDA"): 6,
+        ("POSE", "POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA"): 5, ("FILTER", "FILTER_PROJECTION_CUDA"): 3,
+        ("POSE2", "POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CUDA"): 5, ("FILTER2", "FILTER_PROJECTION_CUDA"): 3}
