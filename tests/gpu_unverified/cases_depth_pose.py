@@ -94,7 +94,7 @@ def test_depth_pose_argument_errors(gpu_ctx):
     off, xy, xyz, world, cw, img = pack([cl], 0)
     gpu_ctx.set_cameras(K[None], CAM[None])
     with pytest.raises(capi.MopedCudaError):          # variant out of range
-        gpu_ctx.pose_depth_ransac(2, off, xy, xyz, world, cw, img, (8, LM, 1, 5, MIN_NPTS, THR), ALPHA)
+        gpu_ctx.pose_depth_ransac(3, off, xy, xyz, world, cw, img, (8, LM, 1, 5, MIN_NPTS, THR), ALPHA)
     with pytest.raises(capi.MopedCudaError):          # sample position outside its cluster
         gpu_ctx.pose_depth_hypotheses(0, off, xy, xyz, world, cw, img, np.zeros(1, np.int32), np.array([[0, 1, 2, 3, 400]], np.int32),
                                       np.full((1, 4), 0.5, np.float32), (8, LM, 1, 5, MIN_NPTS, THR), ALPHA)
