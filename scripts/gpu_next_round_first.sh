@@ -13,3 +13,9 @@ timeout 300 python bench.py --workload ransac --hyp 256 --steps 5 --no-cpu-basel
 timeout 200 python scripts/gpu_linkage_bench.py > gpurun_out/linkage_bench_$TAG.jsonl 2>&1; cat gpurun_out/linkage_bench_$TAG.jsonl
 DEPTH_BENCH_HYP=32 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${TAG}_depth_pose.csv python scripts/gpu_depth_pose_bench.py > /dev/null 2>&1
 timeout 400 python bench.py > gpurun_out/bench_${TAG}_1gpu.json 2> gpurun_out/bench_${TAG}_1gpu.err; cut -c1-600 gpurun_out/bench_${TAG}_1gpu.json
+# one full ncu capture of the depth pose kernels (explicit hypotheses + RANSAC) and of the cached agglomeration, for profiles/
+DEPTH_BENCH_HYP=64 timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_depth_hypotheses|k_depth_ransac' -s 2 -c 2 -f \
+    -o gpurun_out/prof_depth_pose_$TAG python scripts/gpu_depth_pose_bench.py > gpurun_out/prof_depth_pose_$TAG.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_link_agglomerate' -s 6 -c 2 -f \
+    -o gpurun_out/prof_linkage_$TAG python scripts/gpu_linkage_bench.py > gpurun_out/prof_linkage_$TAG.log 2>&1
+ls -la gpurun_out | tail -15
