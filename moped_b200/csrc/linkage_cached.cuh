@@ -16,34 +16,14 @@
 #include <stdint.h>
 #include <stddef.h>
 
-#if defined(__CUDACC__)
-#define LKX_FN __device__ __forceinline__
-#define LKX_MEM __device__ __forceinline__
-#else
-#define LKX_FN static inline
-#define LKX_MEM inline
-#endif
+#include "simt_phases.cuh"
+
+#define LKX_FN PHX_FN
+#define LKX_MEM PHX_MEM
 
 namespace lkx {
 
-#if !defined(__CUDA_ARCH__)
-static int g_host_thread_order = 0;        // host emulation only: 0 ascending, 1 descending
-#endif
-
-template <int W>
-struct Block {
-	int tid;
-	template <class F> LKX_MEM void each(F f) const {
-#if defined(__CUDA_ARCH__)
-		__syncthreads();
-		f(tid);
-		__syncthreads();
-#else
-		if (g_host_thread_order == 0) for (int t = 0; t < W; t++) f(t);
-		else for (int t = W - 1; t >= 0; t--) f(t);
-#endif
-	}
-};
+template <int W> using Block = phx::BlockTeam<W>;    // the CTA as a team (simt_phases.cuh)
 
 struct State {
 	int n;

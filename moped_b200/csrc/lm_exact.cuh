@@ -15,11 +15,10 @@
 //   * ||e||^2 is levmar's four interleaved accumulators -> one accumulator per lane (4 lanes), summed s0+s1+s2+s3;
 //   * the 7x7 Crout LU, the damping logic and the stop tests are scalar -> every lane runs them redundantly on the
 //     same values (no communication).
-// State that crosses lanes lives in a scratch block (`Work`, shared or global memory); a phase is `team.each(f)`,
-// which on the device is  __syncwarp(); f(lane); __syncwarp();  and on the HOST is a loop over the lanes. The second form
-// is what tests/cpp/depth_host.cpp compiles with g++: the very same source is checked against the oracle (and through it
-// against the compiled reference) on the CPU, with the lanes of a phase visited in ascending and in descending order.
-// Nothing here is a CPU path of the product: the library only instantiates these templates inside kernels.
+// State that crosses lanes lives in a scratch block (`Work`, shared or global memory); the code is a sequence of phases
+// (simt_phases.cuh: `team.each(f)` = __syncwarp(); f(lane); __syncwarp(); on the device, a loop over the lanes on the host),
+// which is what lets tests/cpp/depth_host.cpp compile this very source with g++ and check it against the oracle (and through it
+// against the compiled reference) on the CPU. Nothing here is a CPU path of the product.
 #pragma once
 
 #include <float.h>
@@ -27,43 +26,16 @@
 #include <stdint.h>
 #include <stddef.h>
 
-#if defined(__CUDACC__)
-#define LMX_FN __device__ __forceinline__
-#define LMX_MEM __device__ __forceinline__
-#else
-#define LMX_FN static inline
-#define LMX_MEM inline
-#endif
+#include "simt_phases.cuh"
+
+#define LMX_FN PHX_FN
+#define LMX_MEM PHX_MEM
 
 namespace lmx {
 
 constexpr int M = 7;                 // parameters: raw quaternion (x,y,z,w) + translation
 
-#if !defined(__CUDA_ARCH__)
-// host emulation only: order in which team.each visits the lanes (0 ascending, 1 descending)
-static int g_host_lane_order = 0;
-#endif
-
-template <int W>
-struct Team {
-	int lane;                        // 0..W-1 on the device; unused on the host
-	LMX_MEM void sync() const {
-#if defined(__CUDA_ARCH__)
-		if (W > 1) __syncwarp();
-#endif
-	}
-	// one phase: f(l) for every lane l, all of them finished (and visible) before anything that follows
-	template <class F> LMX_MEM void each(F f) const {
-#if defined(__CUDA_ARCH__)
-		sync();
-		f(lane);
-		sync();
-#else
-		if (g_host_lane_order == 0) for (int l = 0; l < W; l++) f(l);
-		else for (int l = W - 1; l >= 0; l--) f(l);
-#endif
-	}
-};
+template <int W> using Team = phx::WarpTeam<W>;      // W lanes working on one LM problem (simt_phases.cuh)
 
 // scratch of one team for a problem with up to n residuals
 struct Work {

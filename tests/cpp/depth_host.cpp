@@ -27,7 +27,7 @@ extern "C" int dh_hypothesis(int variant, int width, int lane_order, int n, cons
 	lmx::Cluster c;
 	c.n = n; c.xy = xy; c.xyz = xyz; c.world = world; c.cauchy = cauchy; c.image = image;
 	c.cams = reinterpret_cast<const lmx::Cam *>(cams16); c.alpha = alpha;
-	lmx::g_host_lane_order = lane_order;
+	phx::g_host_order = lane_order;
 	const unsigned csr = _mm_getcsr();
 	_mm_setcsr(csr | 0x8040u);                       // FTZ | DAZ: the .cu is built with -ftz=true, the reference process runs that way
 	int r = -2;

@@ -17,7 +17,7 @@ extern "C" void lh_agglomerate(int thread_order, int n, const float *K, float cu
 	s.tmp = f3.data(); s.oldcol = f3.data() + n; s.best = f3.data() + 2 * (size_t)n;
 	s.posOf = i3.data(); s.arg = i3.data() + n; s.tmpi = i3.data() + 2 * (size_t)n;
 	s.s_val = s_val.data(); s.s_idx = s_idx.data(); s.ctl = ctl.data();
-	lkx::g_host_thread_order = thread_order;
+	phx::g_host_order = thread_order;
 	lkx::Block<W> blk;
 	blk.tid = 0;
 	lkx::agglomerate_average(blk, s, K, cutoff, min_pts, out_count, out_offsets, out_members);

@@ -28,7 +28,7 @@ def host_lib():
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "libdepth_host.so")
     src = os.path.join(ROOT, "tests", "cpp", "depth_host.cpp")
-    deps = [src] + [os.path.join(ROOT, "moped_b200", "csrc", f) for f in ("lm_exact.cuh", "depth_pose.cuh")]
+    deps = [src] + [os.path.join(ROOT, "moped_b200", "csrc", f) for f in ("lm_exact.cuh", "depth_pose.cuh", "simt_phases.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         # -ffp-contract=off = the .cu's -fmad=false; x86-64-v3 like the oracle (FMA available, so a contraction would show)
         subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-Wall",

@@ -24,7 +24,7 @@ def host_lib():
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "liblinkage_host.so")
     src = os.path.join(ROOT, "tests", "cpp", "linkage_host.cpp")
-    deps = [src, os.path.join(ROOT, "moped_b200", "csrc", "linkage_cached.cuh")]
+    deps = [src] + [os.path.join(ROOT, "moped_b200", "csrc", f) for f in ("linkage_cached.cuh", "simt_phases.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-Wall",
                                "-o", out, src])
