@@ -151,7 +151,11 @@ mc_status pose_depth_hypotheses_device(mc_ctx *ctx, int variant, const int32_t *
 	const int R = variant == 1 ? 3 : 2;
 	const size_t slice = depth_slice_floats(n_max, R);
 	int grid = (n_hyp + kDepthWarps - 1) / kDepthWarps;
-	const int cap = ctx->num_sms * 4;                              // persistent: 16 warps per SM
+	// persistent grid: exactly the CTAs that are resident at once (a CTA that had to wait for a slot would start its strided share late)
+	int per_sm = 0;
+	const void *fn = variant == 0 ? (const void *)k_depth_hypotheses<0> : variant == 1 ? (const void *)k_depth_hypotheses<1> : (const void *)k_depth_hypotheses<2>;
+	MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * kDepthWarps, 0));
+	const int cap = ctx->num_sms * (per_sm > 0 ? per_sm : 1);
 	if (grid > cap) grid = cap;
 	while (grid > 1 && (size_t)grid * kDepthWarps * slice * sizeof(float) > ((size_t)1 << 30)) grid = (grid + 1) / 2;
 	float *scratch = nullptr;
