@@ -55,7 +55,7 @@ k_depth_hypotheses(const int32_t *__restrict__ cluster_offsets, const float *__r
 	float *my = scratch + (size_t)warp * slice;
 	uint8_t *my_mask = reinterpret_cast<uint8_t *>(my + lmx::hypothesis_scratch_floats(n_max, R));
 	lmx::Team<32> team;
-	team.lane = lane;
+	team.init(lane);
 	for (int h = warp; h < n_hyp; h += n_warps) {
 		const lmx::Cluster c = cluster_view(cluster_offsets, hyp_cluster[h], xy, xyz, world, cauchy, image, cams, alpha);
 		uint8_t *mask = mask_out ? mask_out + mask_offsets[h] : my_mask;
@@ -96,7 +96,7 @@ k_depth_ransac(const int32_t *__restrict__ cluster_offsets, int n_clusters, cons
 	uint8_t *my_mask = reinterpret_cast<uint8_t *>(my + lmx::hypothesis_scratch_floats(n_max, R));
 	const uint64_t task_seed = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(task + 1);
 	lmx::Team<32> team;
-	team.lane = lane;
+	team.init(lane);
 	if (threadIdx.x == 0) { s_first = kNoSuccess; s_fail = 0; }
 	__syncthreads();
 	int tests = 0;

@@ -25,11 +25,16 @@ static int g_host_order = 0;             // host emulation only: 0 = members asc
 #endif
 
 template <int W>
-struct WarpTeam {                        // W lanes of one warp (1 or 32)
-	int lane;
+struct WarpTeam {                        // W consecutive lanes of one warp: 1, 8 (four teams per warp) or 32
+	int lane;                            // index inside the team, 0..W-1
+	unsigned mask;                       // the team's lanes inside its warp (device only)
+	PHX_MEM void init(int lane_in_warp) {
+		lane = lane_in_warp % W;
+		mask = W >= 32 ? 0xffffffffu : ((1u << W) - 1u) << (lane_in_warp - lane);
+	}
 	PHX_MEM void sync() const {
 #if defined(__CUDA_ARCH__)
-		if (W > 1) __syncwarp();
+		if (W > 1) __syncwarp(mask);
 #endif
 	}
 	template <class F> PHX_MEM void each(F f) const {

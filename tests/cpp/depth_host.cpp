@@ -14,7 +14,7 @@ int run(const lmx::Cluster &c, const int32_t *sample_pos, int n_samples, const f
         bool finite_check, float *pose_lm, float *pose_refit, float *lm_err2, uint8_t *mask) {
 	std::vector<float> scratch(lmx::hypothesis_scratch_floats(c.n, lmx::DepthResiduals<V>::R));
 	lmx::Team<W> team;
-	team.lane = 0;
+	team.init(0);
 	return lmx::hypothesis<V, W>(team, c, sample_pos, n_samples, init_quat, max_lm, err_thr, min_npts, scratch.data(), mask, finite_check, pose_lm,
 	                             pose_refit, lm_err2);
 }
@@ -39,6 +39,9 @@ extern "C" int dh_hypothesis(int variant, int width, int lane_order, int n, cons
 	else if (variant == 1 && width == 32) DH_RUN(1, 32);
 	else if (variant == 2 && width == 1) DH_RUN(2, 1);
 	else if (variant == 2 && width == 32) DH_RUN(2, 32);
+	else if (variant == 0 && width == 8) DH_RUN(0, 8);
+	else if (variant == 1 && width == 8) DH_RUN(1, 8);
+	else if (variant == 2 && width == 8) DH_RUN(2, 8);
 #undef DH_RUN
 	_mm_setcsr(csr);
 	return r;

@@ -71,7 +71,7 @@ def test_device_source_equals_oracle_bit_for_bit(host_lib, cams, variant):
             pos = rng.choice(cl["good"], n_align, replace=False) if h % 3 else rng.choice(n, n_align, replace=False)
             quat = (rng.integers(0, 256, 4) / 256.0).astype(np.float32)
             o = oracle.hypothesis_depth(cl, cams, ALPHA, pos, quat, PARAMS[0], PARAMS[1], PARAMS[2], variant=variant)
-            for width, order in ((1, 0), (32, 0), (32, 1)):
+            for width, order in ((1, 0), (32, 0), (32, 1), (8, 1)):          # 8 = four teams per warp (not used by the kernels yet)
                 d = run_host(host_lib, variant, width, order, cl, cams, pos, quat)
                 assert same(d, o), (variant, seed, h, width, order, d, o)
             accepted += o["n_inliers"] > PARAMS[2]
