@@ -309,6 +309,8 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
 /* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)
+ *   "depth_team_lanes"     32 (default) or 8: lanes that share one explicit hypothesis in mc_pose_depth_hypotheses* (8 = four hypotheses
+ *                          per warp). Results do not depend on it (the LM keeps levmar's summation order for any team width).
  *   "linkage_cached"       != 0: mc_cluster_linkage / mc_linkage_agglomerate with average linkage keep a cached maximum per row
  *                          (same merge sequence and clusters; O(n) per merge instead of an O(n^2) scan). Default 0 until it has
  *                          run on a GPU.

@@ -175,6 +175,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "lm_finite_check") ctx->lm_finite_check = value != 0;
 	else if (k == "pose_exact_order") ctx->pose_exact_order = value != 0;
 	else if (k == "linkage_cached") ctx->linkage_cached = value != 0;
+	else if (k == "depth_team_lanes") { if (value != 8 && value != 32) { ctx->err = "mc_set_option: depth_team_lanes must be 8 or 32"; return MC_ERR_ARG; } ctx->depth_team_lanes = (int)value; }
 	else if (k == "sift_two_pass") return sift_set_two_pass(ctx, (int)value);
 	else if (k == "sift_describe_gather") return sift_set_gather(ctx, (int)value);
 	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }

@@ -85,6 +85,7 @@ struct mc_ctx {
 	int pose_warps = 8;               // warps per RANSAC task CTA (mc_set_tuning); results do not depend on it
 	int64_t fit_thread_min = 16384;   // mc_set_option: explicit-hypothesis calls with at least this many use one thread per hypothesis
 	bool ransac_fused = false;        // mc_set_option: the one-CTA-per-task RANSAC kernel instead of the staged kernels (A/B aid)
+	int depth_team_lanes = 32;        // mc_set_option: lanes per explicit hypothesis in k_depth_hypotheses (32 or 8)
 	bool linkage_cached = false;      // mc_set_option: cached-row-maximum agglomeration (linkage_cached.cuh) for average linkage
 	bool pose_exact_order = false;    // mc_set_option: mc_pose_hypotheses / mc_pose_ransac run the order-preserving LM (pose_depth.cu, variant 2)
 	bool lm_finite_check = false;     // mc_set_option: depth pose stages keep levmar's stop on a non-finite ||e||^2 (a strict-IEEE build of the reference)

@@ -40,8 +40,10 @@ __device__ __forceinline__ lmx::Cluster cluster_view(const int32_t *cluster_offs
 	return v;
 }
 
-// ---- explicit hypotheses: persistent grid, one warp per (sample set, initial quaternion) ----
-template <int V>
+// ---- explicit hypotheses: persistent grid, one TEAM of W lanes per (sample set, initial quaternion) ----
+// W = 32: a warp per hypothesis (default). W = 8: four hypotheses per warp (mc_set_option "depth_team_lanes", 8) — a 10-row sample fit
+// leaves most of a warp idle, but teams of one warp that take different LM paths serialise; which wins is a measurement.
+template <int V, int W>
 __global__ void __launch_bounds__(32 * kDepthWarps)
 k_depth_hypotheses(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
                    const float *__restrict__ world, const float *__restrict__ cauchy, const int32_t *__restrict__ image,
@@ -50,21 +52,22 @@ k_depth_hypotheses(const int32_t *__restrict__ cluster_offsets, const float *__r
                    float *__restrict__ scratch, size_t slice, int n_max, const int64_t *__restrict__ mask_offsets, int32_t *__restrict__ n_inliers,
                    float *__restrict__ pose_lm_out, float *__restrict__ pose_refit_out, float *__restrict__ lm_err_out, uint8_t *__restrict__ mask_out) {
 	constexpr int R = lmx::DepthResiduals<V>::R;
+	constexpr int kTeams = 32 / W;                                  // teams per warp
 	const int lane = threadIdx.x & 31;
-	const int warp = blockIdx.x * kDepthWarps + (threadIdx.x >> 5), n_warps = gridDim.x * kDepthWarps;
-	float *my = scratch + (size_t)warp * slice;
+	const int team_id = (blockIdx.x * kDepthWarps + (threadIdx.x >> 5)) * kTeams + lane / W, n_teams = gridDim.x * kDepthWarps * kTeams;
+	float *my = scratch + (size_t)team_id * slice;
 	uint8_t *my_mask = reinterpret_cast<uint8_t *>(my + lmx::hypothesis_scratch_floats(n_max, R));
-	lmx::Team<32> team;
+	lmx::Team<W> team;
 	team.init(lane);
-	for (int h = warp; h < n_hyp; h += n_warps) {
+	for (int h = team_id; h < n_hyp; h += n_teams) {
 		const lmx::Cluster c = cluster_view(cluster_offsets, hyp_cluster[h], xy, xyz, world, cauchy, image, cams, alpha);
 		uint8_t *mask = mask_out ? mask_out + mask_offsets[h] : my_mask;
 		const float quat[4] = { init_quat[4 * h], init_quat[4 * h + 1], init_quat[4 * h + 2], init_quat[4 * h + 3] };
 		float pose_lm[7] = { 0, 0, 0, 0, 0, 0, 0 }, pose_refit[7] = { 0, 0, 0, 0, 0, 0, 0 }, err2[2];
 		// the LM work area is laid out for THIS cluster's size (hypothesis() carves it with c.n), inside the slice sized for n_max
-		const int cnt = lmx::hypothesis<V, 32>(team, c, sample_pos + (size_t)h * n_align, n_align, quat, max_lm, thr, min_npts, my, mask,
-		                                       finite_check != 0, pose_lm, pose_refit, err2);
-		if (lane == 0) {
+		const int cnt = lmx::hypothesis<V, W>(team, c, sample_pos + (size_t)h * n_align, n_align, quat, max_lm, thr, min_npts, my, mask,
+		                                      finite_check != 0, pose_lm, pose_refit, err2);
+		if (team.lane == 0) {
 			n_inliers[h] = cnt;
 			lm_err_out[2 * h] = err2[0]; lm_err_out[2 * h + 1] = err2[1];
 			for (int j = 0; j < 7; j++) { pose_lm_out[7 * h + j] = pose_lm[j]; pose_refit_out[7 * h + j] = pose_refit[j]; }
@@ -152,21 +155,25 @@ mc_status pose_depth_hypotheses_device(mc_ctx *ctx, int variant, const int32_t *
 	const size_t slice = depth_slice_floats(n_max, R);
 	int grid = (n_hyp + kDepthWarps - 1) / kDepthWarps;
 	// persistent grid: exactly the CTAs that are resident at once (a CTA that had to wait for a slot would start its strided share late)
+	const int W = ctx->depth_team_lanes == 8 ? 8 : 32, teams_per_cta = kDepthWarps * (32 / W);
+	grid = (n_hyp + teams_per_cta - 1) / teams_per_cta;
 	int per_sm = 0;
-	const void *fn = variant == 0 ? (const void *)k_depth_hypotheses<0> : variant == 1 ? (const void *)k_depth_hypotheses<1> : (const void *)k_depth_hypotheses<2>;
+	const void *fn = W == 32 ? (variant == 0 ? (const void *)k_depth_hypotheses<0, 32> : variant == 1 ? (const void *)k_depth_hypotheses<1, 32> : (const void *)k_depth_hypotheses<2, 32>)
+	                         : (variant == 0 ? (const void *)k_depth_hypotheses<0, 8> : variant == 1 ? (const void *)k_depth_hypotheses<1, 8> : (const void *)k_depth_hypotheses<2, 8>);
 	MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * kDepthWarps, 0));
 	const int cap = ctx->num_sms * (per_sm > 0 ? per_sm : 1);
 	if (grid > cap) grid = cap;
-	while (grid > 1 && (size_t)grid * kDepthWarps * slice * sizeof(float) > ((size_t)1 << 30)) grid = (grid + 1) / 2;
+	while (grid > 1 && (size_t)grid * teams_per_cta * slice * sizeof(float) > ((size_t)1 << 30)) grid = (grid + 1) / 2;
 	float *scratch = nullptr;
-	MC_TRY(depth_scratch(ctx, (size_t)grid * kDepthWarps, slice, &scratch));
-#define MC_DEPTH_HYP(V)                                                                                                                         \
-	k_depth_hypotheses<V><<<grid, 32 * kDepthWarps, 0, ctx->stream>>>(d_cluster_offsets, d_xy, d_xyz, d_world, d_cauchy, d_image, ctx->d_cams, alpha, \
+	MC_TRY(depth_scratch(ctx, (size_t)grid * teams_per_cta, slice, &scratch));
+#define MC_DEPTH_HYP(V, TW)                                                                                                                     \
+	k_depth_hypotheses<V, TW><<<grid, 32 * kDepthWarps, 0, ctx->stream>>>(d_cluster_offsets, d_xy, d_xyz, d_world, d_cauchy, d_image, ctx->d_cams, alpha, \
 	                                                                 d_hyp_cluster, d_sample_pos, d_init_quat, n_hyp, pp->n_pts_align,         \
 	                                                                 pp->max_lm_tests, pp->error_threshold, pp->min_npts_object,               \
 	                                                                 ctx->lm_finite_check ? 1 : 0, scratch, slice, n_max, d_mask_offsets,      \
 	                                                                 d_n_inliers, d_pose_lm, d_pose_refit, d_lm_err, d_mask)
-	if (variant == 0) MC_DEPTH_HYP(0); else if (variant == 1) MC_DEPTH_HYP(1); else MC_DEPTH_HYP(2);
+	if (W == 32) { if (variant == 0) MC_DEPTH_HYP(0, 32); else if (variant == 1) MC_DEPTH_HYP(1, 32); else MC_DEPTH_HYP(2, 32); }
+	else { if (variant == 0) MC_DEPTH_HYP(0, 8); else if (variant == 1) MC_DEPTH_HYP(1, 8); else MC_DEPTH_HYP(2, 8); }
 #undef MC_DEPTH_HYP
 	MC_LAUNCH_CHECK();
 	return MC_OK;

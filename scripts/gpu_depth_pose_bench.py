@@ -53,6 +53,14 @@ def main():
                                                           want_mask=False))
         print(json.dumps(dict(what="explicit hypotheses, order-preserving LM", variant=variant, hypotheses=len(hyp_cluster), s_per_call=dt,
                               hypotheses_per_s=len(hyp_cluster) / dt, accepted=int((out[0] > MIN_NPTS).sum()), lm_failed=int((out[0] < 0).sum()))))
+    ctx.set_option("depth_team_lanes", 8)
+    for variant in (0, 2):
+        cw = np.concatenate([oracle.cauchy_weights(c["fill"], min(variant, 1)) for c in clusters])
+        dt, out = timed(lambda: ctx.pose_depth_hypotheses(variant, off, xy, xyz, world, cw, img, hyp_cluster, sample_pos, init_quat, P, ALPHA,
+                                                          want_mask=False))
+        print(json.dumps(dict(what="explicit hypotheses, order-preserving LM, teams of 8 lanes (four hypotheses per warp)", variant=variant,
+                              hypotheses=len(hyp_cluster), s_per_call=dt, hypotheses_per_s=len(hyp_cluster) / dt)))
+    ctx.set_option("depth_team_lanes", 32)
     dt, out = timed(lambda: ctx.pose_hypotheses(off, xy, xyz, img, hyp_cluster, sample_pos, init_quat, P, want_mask=False))
     print(json.dumps(dict(what="explicit hypotheses, default moped2 kernels (re-associating), same clusters", hypotheses=len(hyp_cluster),
                           s_per_call=dt, hypotheses_per_s=len(hyp_cluster) / dt, accepted=int((out[0] > MIN_NPTS).sum()))))

@@ -317,3 +317,30 @@ def test_device_resident_entry_equals_host_entry(gpu_ctx):
         assert np.array_equal(out[0].cpu().numpy(), n_in) and np.array_equal(out[3].cpu().numpy(), err), variant
         assert np.array_equal(out[1].cpu().numpy(), plm) and np.array_equal(out[2].cpu().numpy(), prf), variant
     assert (n_in >= 0).any()
+
+
+def test_team_width_8_gives_the_same_bits(gpu_ctx, cams):
+    """mc_set_option("depth_team_lanes", 8): four explicit hypotheses per warp instead of one — identical outputs (the LM keeps
+    levmar's summation order for any team width; host emulation already shows it for widths 1, 8 and 32)."""
+    gpu_ctx.set_cameras(K[None], CAM[None])
+    rng = np.random.default_rng(5)
+    clusters = [make_cluster(800 + i, n=n, outliers=0.3) for i, n in enumerate((40, 64, 33, 9))]
+    hyp_cluster, sample_pos, init_quat = [], [], []
+    for ci, cl in enumerate(clusters):
+        for h in range(13):                                             # 52 hypotheses: not a multiple of the teams per CTA
+            hyp_cluster.append(ci); sample_pos.append(rng.choice(cl["good"], 5, replace=False)); init_quat.append(rng.integers(0, 256, 4) / 256.0)
+    hyp_cluster = np.array(hyp_cluster, np.int32); sample_pos = np.array(sample_pos, np.int32); init_quat = np.array(init_quat, np.float32)
+    P = (192, LM, 1, 5, MIN_NPTS, THR)
+    for variant in (0, 1):
+        off, xy, xyz, world, cw, img = pack(clusters, variant)
+        ref_out = gpu_ctx.pose_depth_hypotheses(variant, off, xy, xyz, world, cw, img, hyp_cluster, sample_pos, init_quat, P, ALPHA, want_mask=True)
+        gpu_ctx.set_option("depth_team_lanes", 8)
+        try:
+            out8 = gpu_ctx.pose_depth_hypotheses(variant, off, xy, xyz, world, cw, img, hyp_cluster, sample_pos, init_quat, P, ALPHA, want_mask=True)
+        finally:
+            gpu_ctx.set_option("depth_team_lanes", 32)
+        for a, b in zip(ref_out[:4], out8[:4]):
+            assert np.array_equal(a, b), variant
+        assert all(np.array_equal(a, b) for a, b in zip(ref_out[4], out8[4]))
+        o = oracle.hypothesis_depth(clusters[0], cams, ALPHA, sample_pos[0], init_quat[0], LM, THR, MIN_NPTS, variant=variant)
+        assert out8[0][0] == o["n_inliers"] and np.array_equal(out8[3][0], o["lm_err"])
