@@ -18,7 +18,7 @@ import pytest
 from oracle import oracle
 from test_oracle3d_pose import ALPHA, CAM, K, make_cluster
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(200, method="thread")]
 
 LM, THR, MIN_NPTS = 100, 8.0, 6                  # MaxLMTests, ErrorThreshold, MinNPtsObject (moped3d/libmoped/src/config.hpp:46)
 
