@@ -425,6 +425,8 @@ def run_ours(args, rank, world, local_rank):
         e_img.copy_(h_img[k], non_blocking=True)
         return sharded_step(e_q, e_xy, e_img)
 
+    mstats = []                                       # per timed step: {certified, fallback, candidates per query, DB splits} of its MATCH pass
+
     def timed(step_fn, steps, warmup, collect_kernel=False):
         for i in range(warmup):
             step_fn(i)
@@ -433,6 +435,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         kms, n_obj, n_match = [], 0, 0
+        mstats.clear()
         l0 = ctx.launches
         for i in range(steps):
             if flush is not None:
@@ -444,6 +447,7 @@ def run_ours(args, rank, world, local_rank):
             n_match += nm
             if collect_kernel:
                 kms.append(ctx.coarse_kernel_ms())
+                mstats.append(ctx.match_last_stats())        # the step has completed (its results are on the host): no extra wait
         launches = ctx.launches - l0
         if world > 1:
             dist.barrier()
@@ -464,9 +468,12 @@ def run_ours(args, rank, world, local_rank):
         for i in range(min(args.steps, 8)):           # after every step would put the host in lock-step with the match stream
             pipe_run(1, i, False)
             kms.append(ctx.coarse_kernel_ms())
+            mstats.append(ctx.match_last_stats())
+        match_stats = np.array(mstats, np.int64)
     else:
         total_ms, kms, launches, n_obj, n_match = timed(step_dev, args.steps, args.warmup, collect_kernel=True)
         clocks = sampler.stop()
+        match_stats = np.array(mstats, np.int64) if mstats else np.zeros((1, 4), np.int64)
         e2e_ms, _, _, n_obj_e, _ = timed(step_e2e, args.steps, args.warmup)
 
     # outside the timed region: device time of MATCH vs CLUSTER..FILTER2 for one batch, and the latency of a single frame
@@ -503,6 +510,11 @@ def run_ours(args, rank, world, local_rank):
                "objects_per_frame": n_obj / (args.steps * B),
                "matches_per_s": n_match / (total_ms * 1e-3),
                "query_descriptors_per_s": QT * args.steps / (total_ms * 1e-3),
+               # MATCH exactness bookkeeping of the timed steps (rank 0's shard): every query is either certified by the tensor-core
+               # coarse pass or re-done by the exhaustive exact scan; certified + fallback == queries
+               "match_queries": int(match_stats[:, :2].sum()), "match_certified": int(match_stats[:, 0].sum()),
+               "match_fallback": int(match_stats[:, 1].sum()), "match_candidates_per_query": int(match_stats[0, 2]),
+               "match_db_splits": int(match_stats[0, 3]),
                "batch_ms": None if world > 1 else {"match": float(ms_batch[0]), "cluster_to_filter2": float(ms_batch[1])},
                "single_frame": None if world > 1 else {"latency_ms": lat_ms, "stage_ms": {k: float(v) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], ms_stage)}},
                "gpu_launches": int(launches),

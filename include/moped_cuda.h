@@ -57,6 +57,8 @@ mc_status mc_synchronize(mc_ctx *ctx);
 /* ---- model database: replaces MATCH_ANN_CPU::Update (kd-tree build),
  *      moped2/libmoped/src/match/MATCH_ANN_CPU.hpp:72-109 ------------------------------------ */
 /* desc: N x D row-major fp32, ALREADY L2-normalised by the host stage (MATCH_ANN_CPU.hpp:94);
+ * desc_dim = the stage's DescriptorSize (MATCH_ANN_CPU.hpp:113), any length in 1..4096: 128 (SIFT) gets the
+ * tensor-core path, every other length is matched by the exhaustive exact scan (same results by definition);
  * xyz: N x 3 (Model::IP::coord3D); model_of_row: N (correspModel); rows are in model order.
  * row_base = global id of row 0 (non-zero when this context holds one shard of an object-sharded DB). */
 mc_status mc_db_upload(mc_ctx *ctx, const float *desc, const float *xyz, const int32_t *model_of_row,
@@ -338,6 +340,10 @@ int64_t mc_kernel_launches(const mc_ctx *ctx);
  * matching kernel); mc_profile_read waits for the last such launch and returns its device time (ms) */
 mc_status mc_set_profiling(mc_ctx *ctx, int on);
 mc_status mc_profile_read(mc_ctx *ctx, float *coarse_kernel_ms);
+/* MATCH bookkeeping of the LAST mc_match_dev / mc_process_frame* / mc_process_frames* matching pass on this context (waits for the
+ * stream): stats = {#queries certified by the coarse pass, #queries sent to the exhaustive fallback scan, #coarse candidates
+ * per query, #DB splits}; certified + fallback == the queries of that pass. Exact-mode passes report {0, Q, 0, 0}. */
+mc_status mc_match_last_stats(mc_ctx *ctx, int32_t *stats);
 /* same for feature extraction: summed device time of the five octave-0 Gaussian+DoG launches (the dominant kernel of
  * mc_sift_extract*) of the last extraction, and their algorithmic bytes (1 plane read + 2 planes written per launch) */
 mc_status mc_sift_profile_read(mc_ctx *ctx, float *blur_ms, double *algorithmic_bytes);

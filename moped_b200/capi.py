@@ -109,6 +109,7 @@ SIGNATURES = {
     "mc_kernel_launches": (C.c_int64, [C.c_void_p]),
     "mc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mc_match_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -192,6 +193,12 @@ class Context:
         v = C.c_float(0)
         self._check(self.L.mc_profile_read(self.h, C.byref(v)), "mc_profile_read")
         return float(v.value)
+
+    def match_last_stats(self):
+        """{certified, fallback, candidates per query, DB splits} of the last matching pass on this context."""
+        st = np.zeros(4, np.int32)
+        self._check(self.L.mc_match_last_stats(self.h, st.ctypes.data), "mc_match_last_stats")
+        return st
 
     # ---- database / cameras
     def db_upload(self, desc, xyz, model_of_row, n_models, row_base=0):

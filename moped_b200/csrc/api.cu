@@ -89,6 +89,13 @@ mc_status mc_create(mc_ctx **out, int device) {
 	ctx->num_sms = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; g_create_err = "mc_create: stream"; return MC_ERR_CUDA; }
 	ctx->own_stream = true;
+	// opt-in shared-memory sizes are per-device function attributes: set them for THIS context's device
+	if (match_configure_device(ctx) != MC_OK || cluster_configure_device(ctx) != MC_OK) {
+		g_create_err = "mc_create: " + ctx->err;
+		cudaStreamDestroy(ctx->stream);
+		delete ctx;
+		return MC_ERR_CUDA;
+	}
 	*out = ctx;
 	return MC_OK;
 }
@@ -199,12 +206,24 @@ mc_status mc_profile_read(mc_ctx *ctx, float *coarse_ms) {
 	MC_CUDA(cudaEventElapsedTime(coarse_ms, ctx->ev_coarse[0], ctx->ev_coarse[1]));
 	return MC_OK;
 }
+mc_status mc_match_last_stats(mc_ctx *ctx, int32_t *stats) {
+	if (!ctx || !stats) return MC_ERR_ARG;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int32_t n_flag = 0;
+	if (ctx->last_match_tensor && ctx->flag_count.p) {
+		MC_CUDA(cudaMemcpyAsync(&n_flag, ctx->flag_count.p, sizeof n_flag, cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	if (ctx->last_match_tensor) { stats[0] = ctx->last_match_q - n_flag; stats[1] = n_flag; stats[2] = ctx->last_stats[2]; stats[3] = ctx->last_stats[3]; }
+	else { stats[0] = 0; stats[1] = ctx->last_match_q; stats[2] = 0; stats[3] = 0; }
+	return MC_OK;
+}
 int64_t mc_db_rows(const mc_ctx *ctx) { return ctx ? ctx->n_rows : 0; }
 
 mc_status mc_db_upload(mc_ctx *ctx, const float *desc, const float *xyz, const int32_t *model_of_row, int64_t n_rows, int desc_dim,
                        int n_models, int64_t row_base) {
 	if (!ctx || !desc || !xyz || !model_of_row || n_rows <= 0 || n_models <= 0) { if (ctx) ctx->err = "mc_db_upload: bad argument"; return MC_ERR_ARG; }
-	if (desc_dim != kD) { ctx->err = "mc_db_upload: this build supports 128-d descriptors"; return MC_ERR_ARG; }
+	if (desc_dim < 1 || desc_dim > 4096) { ctx->err = "mc_db_upload: descriptor length must be in 1..4096"; return MC_ERR_ARG; }
 	if (n_rows + row_base > 0x7fffffffLL) { ctx->err = "mc_db_upload: row ids must fit in int32"; return MC_ERR_ARG; }
 	MC_CUDA(cudaSetDevice(ctx->device));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -341,11 +360,17 @@ mc_status mc_pose_hypotheses(mc_ctx *ctx, const int32_t *cluster_offsets, int n_
 	MC_CUDA(cudaSetDevice(ctx->device));
 	const int M = cluster_offsets[n_clusters];
 	const int na = params->n_pts_align;
+	if (na < 1 || na > 8) { ctx->err = "pose: n_pts_align must be in 1..8"; return MC_ERR_ARG; }
 	std::vector<int64_t> mask_off(n_hyp + 1, 0);
 	for (int h = 0; h < n_hyp; h++) {
 		const int c = hyp_cluster[h];
 		if (c < 0 || c >= n_clusters) { ctx->err = "mc_pose_hypotheses: hyp_cluster out of range"; return MC_ERR_ARG; }
-		mask_off[h + 1] = mask_off[h] + (cluster_offsets[c + 1] - cluster_offsets[c]);
+		const int n = cluster_offsets[c + 1] - cluster_offsets[c];
+		for (int j = 0; j < na; j++) {                       // before anything is uploaded, in both LM modes
+			const int sp = sample_pos[(size_t)h * na + j];
+			if (sp < 0 || sp >= n) { ctx->err = "mc_pose_hypotheses: sample_pos out of range"; return MC_ERR_ARG; }
+		}
+		mask_off[h + 1] = mask_off[h] + n;
 	}
 	Arena A; A.ctx = ctx;
 	const size_t o_co = A.plan(4ull * (n_clusters + 1)), o_xy = A.plan(8ull * M), o_xyz = A.plan(12ull * M), o_im = A.plan(4ull * M);
@@ -365,11 +390,6 @@ mc_status mc_pose_hypotheses(mc_ctx *ctx, const int32_t *cluster_offsets, int n_
 	if (ctx->pose_exact_order) {
 		int n_max = 0;
 		for (int c = 0; c < n_clusters; c++) n_max = std::max(n_max, cluster_offsets[c + 1] - cluster_offsets[c]);
-		for (int h = 0; h < n_hyp; h++)
-			for (int j = 0; j < na; j++) {
-				const int sp = sample_pos[(size_t)h * na + j], c = hyp_cluster[h];
-				if (sp < 0 || sp >= cluster_offsets[c + 1] - cluster_offsets[c]) { ctx->err = "mc_pose_hypotheses: sample_pos out of range"; return MC_ERR_ARG; }
-			}
 		MC_TRY(pose_depth_hypotheses_device(ctx, 2, (int32_t *)(b + o_co), (float *)(b + o_xy), (float *)(b + o_xyz), nullptr, nullptr,
 		                                    (int32_t *)(b + o_im), (int32_t *)(b + o_hc), (int32_t *)(b + o_sp), (float *)(b + o_iq), n_hyp, n_max, params,
 		                                    0.f, (int64_t *)(b + o_mo), (int32_t *)(b + o_ni), (float *)(b + o_pl), (float *)(b + o_pr),

@@ -267,6 +267,12 @@ __global__ void k_cluster_compact(const int32_t *__restrict__ match_offsets, int
 	if (tid == 0) { cluster_offsets[base_c] = base_m; out_n[0] = base_c; out_n[1] = base_m; }
 }
 
+// per-device function attribute, set by mc_create for the context's device
+mc_status cluster_configure_device(mc_ctx *ctx) {
+	MC_CUDA(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
+	return MC_OK;
+}
+
 // device entry: matches (CSR over models) -> clusters; all pointers device, async on ctx->stream
 mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
                          int n_models, int n_images, int max_matches, float radius, float merge, int min_pts, int max_iter,
@@ -278,11 +284,6 @@ mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int3
 	MC_TRY(reserve(ctx, b_members, sizeof(int32_t) * (max_matches + 1)));
 	MC_TRY(reserve(ctx, b_f, sizeof(float) * 4 * (size_t)(max_matches + 1)));
 	MC_TRY(reserve(ctx, b_i, sizeof(int32_t) * 7 * (size_t)(max_matches + 1)));
-	static bool attr_set = false;
-	if (!attr_set) {
-		MC_CUDA(cudaFuncSetAttribute(k_meanshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem));
-		attr_set = true;
-	}
 	k_meanshift<<<n_models, kClusterThreads, kClusterSmem, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, n_images, radius, merge, min_pts, max_iter,
 	                                                         (int32_t *)b_count.p, (int32_t *)b_sizes.p, (int32_t *)b_members.p,
 	                                                         (float *)b_f.p, (int32_t *)b_i.p);

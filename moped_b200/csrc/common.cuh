@@ -72,6 +72,7 @@ struct mc_ctx {
 	mc::DevBuf scratch[24];
 	void *h_pinned = nullptr; size_t h_pinned_cap = 0;
 	int last_stats[4] = {0, 0, 0, 0};
+	int last_match_q = 0, last_match_tensor = 0;   // queries / mode of the last match_device pass (mc_match_last_stats)
 	bool profile = false;             // record CUDA events around the dominant kernel (k_match_coarse)
 	cudaEvent_t ev_coarse[2] = {nullptr, nullptr};
 	bool ev_valid = false;
@@ -152,6 +153,8 @@ inline mc_status pinned(mc_ctx *ctx, size_t bytes) {
 
 // ---- stage entry points implemented in the .cu files (device pointers, async on ctx->stream) ----
 mc_status db_build_images(mc_ctx *ctx);
+mc_status match_configure_device(mc_ctx *ctx);
+mc_status cluster_configure_device(mc_ctx *ctx);
 void sift_free(mc_ctx *ctx);
 mc_status sift_set_two_pass(mc_ctx *ctx, int on);
 mc_status sift_set_gather(mc_ctx *ctx, int on);

@@ -383,6 +383,14 @@ extern "C" mc_status mc_cluster_linkage(mc_ctx *ctx, const float *match_xy, cons
 	}
 	if (n_matches == 0) { *n_clusters = 0; cluster_offsets[0] = 0; return MC_OK; }
 	MC_TRY(link_check(ctx, n_matches, "mc_cluster_linkage"));
+	// the blend kernel reads the fill-distance map at every match's pixel (the reference indexes its map unchecked,
+	// CLUSTER_LINKAGE_CPU.hpp:324-365): a coordinate outside the map is an argument error here, not an illegal address
+	for (int i = 0; i < n_matches; i++) {
+		const float x = match_xy[2 * i], y = match_xy[2 * i + 1];
+		if (!(x >= 0.f && y >= 0.f && (int)x < width && (int)y < height)) { ctx->err = "mc_cluster_linkage: match coordinate outside the depth map"; return MC_ERR_ARG; }
+	}
+	// with cutoff <= -1 the merge loop has no stopping point once a single cluster is left (the reference then spins on the host)
+	if (!(cutoff > -1.f)) { ctx->err = "mc_cluster_linkage: cutoff must be > -1"; return MC_ERR_ARG; }
 	MC_CUDA(cudaSetDevice(ctx->device));
 	const int n = n_matches;
 	const size_t px = (size_t)width * height;
@@ -405,6 +413,7 @@ extern "C" mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity
 	if (!similarity || !n_clusters || !cluster_offsets || !members) { ctx->err = "mc_linkage_agglomerate: null pointer"; return MC_ERR_ARG; }
 	if (n == 0) { *n_clusters = 0; cluster_offsets[0] = 0; return MC_OK; }
 	MC_TRY(link_check(ctx, n, "mc_linkage_agglomerate"));
+	if (!(cutoff > -1.f)) { ctx->err = "mc_linkage_agglomerate: cutoff must be > -1"; return MC_ERR_ARG; }
 	MC_CUDA(cudaSetDevice(ctx->device));
 	LinkBufs B;
 	MC_TRY(link_alloc(ctx, n, 1, B));

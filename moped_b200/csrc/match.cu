@@ -476,6 +476,7 @@ __device__ __forceinline__ void key2_push(unsigned long long *slot, float d, int
 // query's global two-smallest slots.
 constexpr int kExactQ = 8;
 constexpr int kExactThreads = 256;
+constexpr int kMaxAnyD = 4096;          // longest descriptor the generic exact scan stages in shared memory (8 x 4096 floats = 128 KiB)
 __global__ void __launch_bounds__(kExactThreads)
 k_match_exact(const float *__restrict__ q, const int32_t *__restrict__ list, const int32_t *__restrict__ list_count, int list_all,
               const float *__restrict__ db, int64_t n_rows, int n_chunks, int chunk_rows,
@@ -518,6 +519,81 @@ k_match_exact(const float *__restrict__ q, const int32_t *__restrict__ list, con
 #pragma unroll
 					for (int j = 0; j < 16; j++) { float tt = __fsub_rn(qv[j], pv[j]); d = __fadd_rn(d, __fmul_rn(tt, tt)); }
 					dist[k] = d;
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < kExactQ; k++) top2_push(t[k], dist[k], (int32_t)row);
+		}
+#pragma unroll
+		for (int k = 0; k < kExactQ; k++) {
+			top2_warp_reduce(t[k]);
+			if (lane == 0) red[k][warp] = t[k];
+		}
+		__syncthreads();
+		if (threadIdx.x < kExactQ) {
+			const int k = threadIdx.x, li = g * kExactQ + k;
+			if (li < n_list) {
+				Top2 r = red[k][0];
+				for (int ww = 1; ww < kExactThreads / 32; ww++) { top2_push(r, red[k][ww].d0, red[k][ww].i0); top2_push(r, red[k][ww].d1, red[k][ww].i1); }
+				const int qi = list ? list[li] : li;
+				key2_push(nn_key + 2 * (size_t)qi, r.d0, r.i0);
+				key2_push(nn_key + 2 * (size_t)qi, r.d1, r.i1);
+			}
+		}
+	}
+}
+
+// The same exhaustive scan for ANY descriptor length (MATCH_ANN_CPU's constructor takes DescriptorSize, e.g. SURF-64,
+// moped2/libmoped/src/match/MATCH_ANN_CPU.hpp:113): runtime D, the group's queries staged in dynamic shared memory
+// (kExactQ x D floats), every distance summed over d = 0..D-1 in order with unfused multiply and add like the 128-d kernel.
+__global__ void __launch_bounds__(kExactThreads)
+k_match_exact_any(const float *__restrict__ q, int D, const int32_t *__restrict__ list, const int32_t *__restrict__ list_count, int list_all,
+                  const float *__restrict__ db, int64_t n_rows, int n_chunks, int chunk_rows, unsigned long long *__restrict__ nn_key) {
+	extern __shared__ __align__(16) float qs_any[];            // [kExactQ][D]
+	__shared__ Top2 red[kExactQ][kExactThreads / 32];
+	const int n_list = list ? *list_count : list_all;
+	const int n_groups = (n_list + kExactQ - 1) / kExactQ;
+	const int64_t n_items = (int64_t)n_groups * n_chunks;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const bool vec4 = (D & 3) == 0;
+	for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+		const int g = (int)(item / n_chunks), ch = (int)(item % n_chunks);
+		__syncthreads();
+		for (int x = threadIdx.x; x < kExactQ * D; x += blockDim.x) {
+			const int k = x / D, d = x - k * D, li = g * kExactQ + k;
+			const int qi = li < n_list ? (list ? list[li] : li) : -1;
+			qs_any[x] = qi >= 0 ? q[(size_t)qi * D + d] : 0.f;
+		}
+		__syncthreads();
+		Top2 t[kExactQ];
+#pragma unroll
+		for (int k = 0; k < kExactQ; k++) t[k] = top2_empty();
+		const int64_t r_lo = (int64_t)ch * chunk_rows;
+		const int64_t r_hi = r_lo + chunk_rows < n_rows ? r_lo + chunk_rows : n_rows;
+		for (int64_t row = r_lo + threadIdx.x; row < r_hi; row += blockDim.x) {
+			const float *p = db + (size_t)row * D;
+			float dist[kExactQ];
+#pragma unroll
+			for (int k = 0; k < kExactQ; k++) dist[k] = 0.f;
+			if (vec4) {
+				for (int d = 0; d < D; d += 4) {
+					const float4 v = __ldg(reinterpret_cast<const float4 *>(p + d));
+#pragma unroll
+					for (int k = 0; k < kExactQ; k++) {
+						const float4 a = *reinterpret_cast<const float4 *>(&qs_any[k * D + d]);
+						float dd = dist[k], tt;
+						tt = __fsub_rn(a.x, v.x); dd = __fadd_rn(dd, __fmul_rn(tt, tt));
+						tt = __fsub_rn(a.y, v.y); dd = __fadd_rn(dd, __fmul_rn(tt, tt));
+						tt = __fsub_rn(a.z, v.z); dd = __fadd_rn(dd, __fmul_rn(tt, tt));
+						tt = __fsub_rn(a.w, v.w); dd = __fadd_rn(dd, __fmul_rn(tt, tt));
+						dist[k] = dd;
+					}
+				}
+			} else {
+				for (int d = 0; d < D; d++) {
+					const float v = __ldg(p + d);
+#pragma unroll
+					for (int k = 0; k < kExactQ; k++) { const float tt = __fsub_rn(qs_any[k * D + d], v); dist[k] = __fadd_rn(dist[k], __fmul_rn(tt, tt)); }
 				}
 			}
 #pragma unroll
@@ -596,6 +672,14 @@ __global__ void k_row_norm2(const float *__restrict__ src, int n, float *__restr
 // =============================================================================================
 // host side
 // =============================================================================================
+// Function attributes are PER DEVICE: called by mc_create for the context's device (a process may hold contexts on
+// several GPUs), never behind a process-wide flag.
+mc_status match_configure_device(mc_ctx *ctx) {
+	MC_CUDA(cudaFuncSetAttribute(k_match_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemBytes));
+	MC_CUDA(cudaFuncSetAttribute(k_match_exact_any, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactQ * kMaxAnyD * (int)sizeof(float)));
+	return MC_OK;
+}
+
 mc_status db_build_images(mc_ctx *ctx) {
 	if (ctx->D != kD) return MC_OK;     // tensor path needs D == 128; other lengths use the exact scan
 	ctx->n_tiles = (ctx->n_rows + kTileRows - 1) / kTileRows;
@@ -616,11 +700,6 @@ mc_status db_build_images(mc_ctx *ctx) {
 	ctx->db_norm2_min = mm[0]; ctx->db_norm2_max = mm[1];
 	MC_CUDA(cudaFree(d_norm2));
 	MC_CUDA(cudaFree(d_mm));
-	static bool attr_set = false;
-	if (!attr_set) {
-		MC_CUDA(cudaFuncSetAttribute(k_match_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemBytes));
-		attr_set = true;
-	}
 	return MC_OK;
 }
 
@@ -631,8 +710,12 @@ static mc_status exact_scan(mc_ctx *ctx, const float *d_q, int Q, const int32_t 
 	if (chunk_rows < kExactThreads) chunk_rows = kExactThreads;
 	n_chunks = (int)((ctx->n_rows + chunk_rows - 1) / chunk_rows);
 	if (!d_list) MC_CUDA(cudaMemsetAsync(ctx->nn_key.p, 0xFF, sizeof(unsigned long long) * 2 * (size_t)Q, ctx->stream));
-	k_match_exact<<<ctx->num_sms * 4, kExactThreads, 0, ctx->stream>>>(d_q, d_list, d_count, Q, ctx->d_db, ctx->n_rows, n_chunks, chunk_rows,
-	                                                                 (unsigned long long *)ctx->nn_key.p);
+	if (ctx->D == kD)
+		k_match_exact<<<ctx->num_sms * 4, kExactThreads, 0, ctx->stream>>>(d_q, d_list, d_count, Q, ctx->d_db, ctx->n_rows, n_chunks, chunk_rows,
+		                                                                 (unsigned long long *)ctx->nn_key.p);
+	else
+		k_match_exact_any<<<ctx->num_sms * 4, kExactThreads, sizeof(float) * kExactQ * (size_t)ctx->D, ctx->stream>>>(
+		    d_q, ctx->D, d_list, d_count, Q, ctx->d_db, ctx->n_rows, n_chunks, chunk_rows, (unsigned long long *)ctx->nn_key.p);
 	MC_LAUNCH_CHECK();
 	k_match_exact_decode<<<ctx->num_sms, 256, 0, ctx->stream>>>(d_list, d_count, Q, (const unsigned long long *)ctx->nn_key.p, ctx->row_base,
 	                                                          d_nn_row, d_nn_dist);
@@ -644,9 +727,11 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 	if (!ctx->d_db) { ctx->err = "mc_match: no database uploaded"; return MC_ERR_STATE; }
 	if (Q <= 0) return MC_OK;
 	MC_TRY(reserve(ctx, ctx->nn_key, sizeof(unsigned long long) * 2 * (size_t)Q));
-	if (ctx->D != kD && ctx->D % 16 != 0) { ctx->err = "mc_match: descriptor length must be a multiple of 16"; return MC_ERR_ARG; }
-	if (ctx->D != kD) { ctx->err = "mc_match: only 128-d descriptors are supported in this build"; return MC_ERR_ARG; }
-	if (mode == MC_MATCH_EXACT) {
+	// the tensor-core path is built for 128-d descriptors (SIFT); any other DescriptorSize takes the exhaustive exact scan —
+	// the same result by definition (MC_MATCH_TENSOR only ever promises the exact scan's bits)
+	ctx->last_match_q = Q;
+	ctx->last_match_tensor = !(mode == MC_MATCH_EXACT || ctx->D != kD);
+	if (mode == MC_MATCH_EXACT || ctx->D != kD) {
 		MC_TRY(exact_scan(ctx, d_q, Q, nullptr, nullptr, d_nn_row, d_nn_dist));
 	} else {
 		const int n_mtiles = (Q + kMTile - 1) / kMTile;

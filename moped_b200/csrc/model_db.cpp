@@ -645,6 +645,8 @@ mc_status mc_model_db_load(mc_model_db *db, const char *path) {
 			ps.desc_off.resize(np + 1); memcpy(ps.desc_off.data(), p, (np + 1) * 4); p += (np + 1) * 4;
 			ps.desc.resize(nd); memcpy(ps.desc.data(), p, nd * 4); p += nd * 4;
 			if (ps.desc_off[0] != 0 || ps.desc_off[np] != nd) ok = false;
+			for (uint64_t k = 0; ok && k < np; k++)                  // offsets of an untrusted file: non-decreasing and inside the descriptor array
+				if (ps.desc_off[k + 1] < ps.desc_off[k] || ps.desc_off[k + 1] > nd) ok = false;
 		}
 		m.has_points = true;
 		recs.push_back(std::move(m));

@@ -85,21 +85,23 @@ k_depth_ransac(const int32_t *__restrict__ cluster_offsets, int n_clusters, cons
                const float *__restrict__ world, const float *__restrict__ cauchy, const int32_t *__restrict__ image,
                const int32_t *__restrict__ tie, const Camera *__restrict__ cams, float alpha, int max_obj, int max_ransac, int max_lm, int n_align,
                int min_npts, float thr, uint64_t seed, int finite_check, float *__restrict__ scratch, size_t slice, int n_max,
-               uint8_t *__restrict__ found, float *__restrict__ pose_out, int32_t *__restrict__ n_tests) {
+               int n_tasks, uint8_t *__restrict__ found, float *__restrict__ pose_out, int32_t *__restrict__ n_tests) {
 	constexpr int R = lmx::DepthResiduals<V>::R;
 	__shared__ int s_first, s_fail;
 	__shared__ float s_pose[kDepthWarps][7];           // refitted pose of each warp's successful test of the current round
-	const int task = blockIdx.x;
-	const int cidx = task / max_obj;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	if (cidx >= n_clusters) { if (threadIdx.x == 0) { found[task] = 0; n_tests[task] = 0; } return; }
-	const lmx::Cluster c = cluster_view(cluster_offsets, cidx, xy, xyz, world, cauchy, image, cams, alpha);
-	const int32_t *ctie = tie ? tie + cluster_offsets[cidx] : nullptr;
-	float *my = scratch + ((size_t)task * kDepthWarps + w) * slice;
+	// persistent grid over the tasks: the LM scratch is one slice per warp of the RESIDENT CTAs, not of every task
+	float *my = scratch + ((size_t)blockIdx.x * kDepthWarps + w) * slice;
 	uint8_t *my_mask = reinterpret_cast<uint8_t *>(my + lmx::hypothesis_scratch_floats(n_max, R));
-	const uint64_t task_seed = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(task + 1);
 	lmx::Team<32> team;
 	team.init(lane);
+	for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+	const int cidx = task / max_obj;
+	if (cidx >= n_clusters) { if (threadIdx.x == 0) { found[task] = 0; n_tests[task] = 0; } continue; }
+	const lmx::Cluster c = cluster_view(cluster_offsets, cidx, xy, xyz, world, cauchy, image, cams, alpha);
+	const int32_t *ctie = tie ? tie + cluster_offsets[cidx] : nullptr;
+	const uint64_t task_seed = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(task + 1);
+	__syncthreads();                                   // the previous task's s_first / s_pose have been read
 	if (threadIdx.x == 0) { s_first = kNoSuccess; s_fail = 0; }
 	__syncthreads();
 	int tests = 0;
@@ -130,6 +132,7 @@ k_depth_ransac(const int32_t *__restrict__ cluster_offsets, int n_clusters, cons
 	if (ok && w == first % kDepthWarps && lane == 0)
 		for (int j = 0; j < 7; j++) pose_out[7 * task + j] = s_pose[w][j];
 	if (threadIdx.x == 0) { found[task] = ok ? 1 : 0; n_tests[task] = tests; }
+	}
 }
 
 // ---- device entries ----
@@ -153,10 +156,9 @@ mc_status pose_depth_hypotheses_device(mc_ctx *ctx, int variant, const int32_t *
 	if (n_hyp <= 0) return MC_OK;
 	const int R = variant == 1 ? 3 : 2;
 	const size_t slice = depth_slice_floats(n_max, R);
-	int grid = (n_hyp + kDepthWarps - 1) / kDepthWarps;
 	// persistent grid: exactly the CTAs that are resident at once (a CTA that had to wait for a slot would start its strided share late)
 	const int W = ctx->depth_team_lanes == 8 ? 8 : 32, teams_per_cta = kDepthWarps * (32 / W);
-	grid = (n_hyp + teams_per_cta - 1) / teams_per_cta;
+	int grid = (n_hyp + teams_per_cta - 1) / teams_per_cta;
 	int per_sm = 0;
 	const void *fn = W == 32 ? (variant == 0 ? (const void *)k_depth_hypotheses<0, 32> : variant == 1 ? (const void *)k_depth_hypotheses<1, 32> : (const void *)k_depth_hypotheses<2, 32>)
 	                         : (variant == 0 ? (const void *)k_depth_hypotheses<0, 8> : variant == 1 ? (const void *)k_depth_hypotheses<1, 8> : (const void *)k_depth_hypotheses<2, 8>);
@@ -190,14 +192,20 @@ mc_status pose_depth_ransac_device(mc_ctx *ctx, int variant, const int32_t *d_cl
 	if (n_tasks <= 0) return MC_OK;
 	const int R = variant == 1 ? 3 : 2;
 	const size_t slice = depth_slice_floats(n_max, R);
+	int per_sm = 0;
+	const void *fn = variant == 0 ? (const void *)k_depth_ransac<0> : variant == 1 ? (const void *)k_depth_ransac<1> : (const void *)k_depth_ransac<2>;
+	MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * kDepthWarps, 0));
+	int grid = ctx->num_sms * (per_sm > 0 ? per_sm : 1);
+	if (grid > n_tasks) grid = n_tasks;
+	while (grid > 1 && (size_t)grid * kDepthWarps * slice * sizeof(float) > ((size_t)1 << 30)) grid = (grid + 1) / 2;
 	float *scratch = nullptr;
-	MC_TRY(depth_scratch(ctx, (size_t)n_tasks * kDepthWarps, slice, &scratch));
+	MC_TRY(depth_scratch(ctx, (size_t)grid * kDepthWarps, slice, &scratch));
 #define MC_DEPTH_RANSAC(V)                                                                                                                      \
-	k_depth_ransac<V><<<n_tasks, 32 * kDepthWarps, 0, ctx->stream>>>(d_cluster_offsets, n_clusters, d_xy, d_xyz, d_world, d_cauchy, d_image, d_tie, \
+	k_depth_ransac<V><<<grid, 32 * kDepthWarps, 0, ctx->stream>>>(d_cluster_offsets, n_clusters, d_xy, d_xyz, d_world, d_cauchy, d_image, d_tie, \
 	                                                                ctx->d_cams, alpha, pp->max_objects_per_cluster, pp->max_ransac_tests,     \
 	                                                                pp->max_lm_tests, pp->n_pts_align, pp->min_npts_object, pp->error_threshold, \
-	                                                                pp->seed, ctx->lm_finite_check ? 1 : 0, scratch, slice, n_max, d_found,    \
-	                                                                d_pose, d_n_tests)
+	                                                                pp->seed, ctx->lm_finite_check ? 1 : 0, scratch, slice, n_max, n_tasks,    \
+	                                                                d_found, d_pose, d_n_tests)
 	if (variant == 0) MC_DEPTH_RANSAC(0); else if (variant == 1) MC_DEPTH_RANSAC(1); else MC_DEPTH_RANSAC(2);
 #undef MC_DEPTH_RANSAC
 	MC_LAUNCH_CHECK();

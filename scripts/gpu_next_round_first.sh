@@ -4,8 +4,8 @@
 # suite, then a first timing and a launch list.   gpurun --timeout 1500 -- 'bash scripts/gpu_next_round_first.sh r2a'
 TAG=${1:-r2a}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/gpu_unverified/cases_depth_pose.py -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu_depth_$TAG.log; tail -5 gpurun_out/pytest_gpu_depth_$TAG.log
-timeout 300 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/gpu_unverified/cases_depth_pose.py -m gpu -q -k "explicit_hypotheses and 0" 2>&1 | tail -15 > gpurun_out/racecheck_depth_$TAG.log; tail -3 gpurun_out/racecheck_depth_$TAG.log
+timeout 600 python -m pytest tests/test_gpu_depth_pose.py -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu_depth_$TAG.log; tail -5 gpurun_out/pytest_gpu_depth_$TAG.log
+timeout 300 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_depth_pose.py -m gpu -q -k "explicit_hypotheses and 0" 2>&1 | tail -15 > gpurun_out/racecheck_depth_$TAG.log; tail -3 gpurun_out/racecheck_depth_$TAG.log
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/pytest_gpu_$TAG.log; tail -3 gpurun_out/pytest_gpu_$TAG.log
 timeout 300 python scripts/gpu_depth_pose_bench.py > gpurun_out/depth_pose_bench_$TAG.jsonl 2> gpurun_out/depth_pose_bench_$TAG.err; cat gpurun_out/depth_pose_bench_$TAG.jsonl
 timeout 300 python bench.py --workload ransac --hyp 256 --steps 5 --no-cpu-baseline > gpurun_out/bench_${TAG}_ransac256_default.json 2>/dev/null; cut -c1-400 gpurun_out/bench_${TAG}_ransac256_default.json

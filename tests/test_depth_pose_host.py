@@ -3,7 +3,7 @@ lanes that takes every sum in levmar's order) compiled by g++ with the lanes emu
 and compared bit for bit with the oracle — and, where the compiled reference is present, with the strict-IEEE build of
 moped3d's own stage classes. It checks the arithmetic and the split into phases of the code the kernels in pose_depth.cu
 instantiate (team width 32), on a machine without a GPU; lanes of a phase are visited in ascending and descending order, so a
-phase that depended on the order of its lanes would show. The CUDA path itself is checked by tests/gpu_unverified/cases_depth_pose.py.
+phase that depended on the order of its lanes would show. The CUDA path itself is checked by tests/test_gpu_depth_pose.py.
 """
 import ctypes as C
 import os

@@ -5,12 +5,8 @@ of the reference's own stage classes, tests/test_oracle3d_pose.py).
 The bar is BIT-EXACT: the kernels run lm_exact.cuh, which takes every sum in levmar's order with unfused multiply-add, and the
 same source compiled for the host already reproduces the oracle bit for bit (tests/test_depth_pose_host.py).
 
-STATUS: written and cross-compiled in a session whose GPU budget was spent — these tests have not run on a B200 yet. They are
-therefore kept out of the default collection (the file name does not match test_*.py): tests/test_zz_gpu_unverified.py runs each of
-them in a CHILD pytest process with a time limit and reports pass / fail as XPASS / xfail (non-strict), so that a hang, a crash or a
-failure of never-run code can neither stop nor redden the suite that was green before it existed. Run them directly with
-    python -m pytest tests/gpu_unverified/cases_depth_pose.py -m gpu -q
-(scripts/gpu_next_round_first.sh does); after the first green run on hardware the file moves back to tests/test_gpu_depth_pose.py.
+STATUS: all 13 cases passed on the round-1 driver's B200 (GPUTEST_r01.json, then still behind a non-strict xfail runner); since
+round 2 they are regular strict `-m gpu` tests: a regression reddens the suite.
 """
 import numpy as np
 import pytest
@@ -139,7 +135,7 @@ def test_stage_class_inside_moped3ds_own_pipeline(tmp_path, cams, variant):
     import os
     import subprocess
     from conftest import quat_angle
-    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "oracle", "_ref", "moped3d_pose_dropin")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/moped3d_pose_dropin not built (needs /root/reference at build time)")
@@ -222,7 +218,7 @@ def test_moped3d_chain_after_cluster_inside_its_own_pipeline(tmp_path):
     import os
     import subprocess
     from conftest import quat_angle
-    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "oracle", "_ref", "moped3d_pose_dropin")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/moped3d_pose_dropin not built (needs /root/reference at build time)")

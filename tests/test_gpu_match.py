@@ -117,5 +117,115 @@ def test_errors_are_loud(gpu_ctx):
     with pytest.raises(capi.MopedCudaError):
         ctx.match(np.zeros((4, 128), np.float32))           # no database yet
     with pytest.raises(capi.MopedCudaError):
-        ctx.db_upload(np.zeros((4, 64), np.float32), np.zeros((4, 3), np.float32), np.zeros(4, np.int32), 1)   # unsupported length
+        ctx.db_upload(np.zeros((4, 5000), np.float32), np.zeros((4, 3), np.float32), np.zeros(4, np.int32), 1)   # beyond the longest supported length
     ctx.close()
+
+
+@pytest.mark.parametrize("d", [64, 36, 1, 200])
+def test_other_descriptor_lengths(oracle_mod, d):
+    """MATCH_ANN_CPU(int DescriptorSize, ...) works for any length (MATCH_ANN_CPU.hpp:113; SURF is 64-d): lengths other than
+    128 take the exhaustive exact scan whatever mode is asked for — rows, distances and accepted set equal the oracle's."""
+    from moped_b200 import capi
+    rng = np.random.default_rng(100 + d)
+    dbn = oracle_mod.norm_rows(rng.normal(size=(2500, d)).astype(np.float32))
+    qn = oracle_mod.norm_rows(np.concatenate([dbn[rng.integers(0, 2500, 150)] + rng.normal(0, 0.05, size=(150, d)),
+                                              rng.normal(size=(61, d))]).astype(np.float32))
+    ctx = capi.Context(0)
+    try:
+        ctx.db_upload(dbn, np.zeros((2500, 3), np.float32), np.zeros(2500, np.int32), 1)
+        st = _check(ctx, capi, oracle_mod, dbn, qn)
+        assert st[1] == len(qn)
+        r, dd, a, st = ctx.match(qn, 0.8, capi.MATCH_TENSOR)
+        assert st[0] == 0 and st[1] == len(qn)              # reported as what it is: an exhaustive scan
+    finally:
+        ctx.close()
+
+
+def test_second_context_in_one_process(oracle_mod, small_case):
+    """Kernel attributes (opt-in shared memory of k_match_coarse / k_meanshift) are set per context at mc_create, not behind a
+    process-wide flag: a context created after another one has already run works (with several GPUs: on ANY device)."""
+    from moped_b200 import capi
+    c = small_case
+    first = capi.Context(0)
+    first.db_upload(c["dbn"], c["db"]["xyz"], c["db"]["model_of_row"], c["n_obj"])
+    first.match(c["qn"][:300], 0.8, capi.MATCH_TENSOR)
+    import torch
+    dev = torch.cuda.device_count() - 1                      # the last device: a different one on a multi-GPU box
+    second = capi.Context(dev)
+    try:
+        second.db_upload(c["dbn"], c["db"]["xyz"], c["db"]["model_of_row"], c["n_obj"])
+        _check(second, capi, oracle_mod, c["dbn"], c["qn"][:300], modes=(capi.MATCH_TENSOR,))
+        from moped_b200 import synth
+        second.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+        out = second.process_frame(c["qn"], c["fr"]["xy"], c["fr"]["image_idx"])
+        assert sorted(out["model"].tolist()) == sorted(c["fr"]["gt_model"].tolist())
+    finally:
+        second.close(); first.close()
+
+
+def test_metric_configuration_1m_rows(oracle_mod):
+    """The configuration bench.py times (BASELINE metric): 1000 objects / 1 M descriptors, a batch of 64 x 2000 = 128 000 queries in
+    ONE mc_match_dev pass (10 DB splits x k=4 = 40 coarse candidates per query, another certificate regime than a single frame's 18
+    splits). 256 sampled queries' rows AND distances equal the oracle's bit for bit (256 x 1 M is seconds on the host); every query is
+    accounted for (certified + fallback == Q); the same batch against the database sharded over two contexts, merged by
+    mc_match_merge_dev, gives the identical result for ALL 128 000 queries."""
+    import torch
+    from moped_b200 import capi, synth
+    from moped_b200.sharding import shard_objects
+    B, Q = 64, 2000
+    db = synth.make_db(1000, 1000)
+    dbn = oracle_mod.norm_rows(db["desc"])
+    qn = np.concatenate([oracle_mod.norm_rows(synth.make_frame(db, Q, n_visible=8, frame_id=i)["desc"]) for i in range(B)])
+    QT = len(qn)
+    dev = torch.device("cuda", 0)
+    d_q = torch.from_numpy(qn).to(dev)
+
+    def run(ctx):
+        row = torch.full((QT, 2), -1, dtype=torch.int32, device=dev)
+        dist = torch.zeros((QT, 2), dtype=torch.float32, device=dev)
+        acc = torch.zeros(QT, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ctx.match_dev(d_q.data_ptr(), QT, 0.8, capi.MATCH_TENSOR, row.data_ptr(), dist.data_ptr(), acc.data_ptr())
+        st = ctx.match_last_stats()
+        ctx.synchronize()
+        return row, dist, acc, st
+
+    ctx = capi.Context(0)
+    try:
+        ctx.db_upload(dbn, db["xyz"], db["model_of_row"], 1000)
+        row, dist, acc, st = run(ctx)
+    finally:
+        ctx.close()
+    assert st[0] + st[1] == QT and st[2] >= 32, st
+    assert st[0] >= 0.99 * QT, f"only {st[0]} of {QT} queries certified by the coarse pass"
+    r, d, a = row.cpu().numpy(), dist.cpu().numpy(), acc.cpu().numpy().astype(bool)
+    rng = np.random.default_rng(7)
+    pick = np.sort(rng.choice(QT, 256, replace=False))
+    oidx, odist = oracle_mod.match_2nn(dbn, qn[pick])
+    assert np.array_equal(r[pick], oidx), np.nonzero((r[pick] != oidx).any(1))[0][:5]
+    assert np.array_equal(d[pick], odist)
+    assert np.array_equal(a[pick], odist[:, 0] / odist[:, 1] < np.float32(0.8))
+    # two object shards on two contexts, merged
+    shards = shard_objects(db["n_pts"], 2)
+    rows_all = torch.empty((2, QT, 2), dtype=torch.int32, device=dev)
+    dist_all = torch.empty((2, QT, 2), dtype=torch.float32, device=dev)
+    ctxs = [capi.Context(0) for _ in shards]
+    try:
+        tot = np.zeros(2, np.int64)
+        for k, (cx, (o0, o1, r0, r1)) in enumerate(zip(ctxs, shards)):
+            cx.db_upload(dbn[r0:r1], db["xyz"][r0:r1], db["model_of_row"][r0:r1], 1000, row_base=r0)
+            rk, dk, _, stk = run(cx)
+            assert stk[0] + stk[1] == QT
+            tot += stk[:2]
+            rows_all[k].copy_(rk); dist_all[k].copy_(dk)
+        m_row = torch.empty((QT, 2), dtype=torch.int32, device=dev)
+        m_dist = torch.empty((QT, 2), dtype=torch.float32, device=dev)
+        m_acc = torch.empty(QT, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ctxs[0].match_merge_dev(rows_all.data_ptr(), dist_all.data_ptr(), 2, QT, 0.8, m_row.data_ptr(), m_dist.data_ptr(), m_acc.data_ptr())
+        ctxs[0].synchronize()
+    finally:
+        for cx in ctxs:
+            cx.close()
+    assert np.array_equal(m_row.cpu().numpy(), r) and np.array_equal(m_dist.cpu().numpy(), d)
+    assert np.array_equal(m_acc.cpu().numpy().astype(bool), a)

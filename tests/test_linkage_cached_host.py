@@ -3,7 +3,7 @@ mc_set_option("linkage_cached")) compiled by g++ with the 256 threads of its blo
 against the oracle's hierarchicalCluster (oracle/moped_linkage_oracle.c, bit-identical to the strict build of moped3d's
 CLUSTER_LINKAGE_CPU): identical clusters on tie-heavy quantised matrices (where the reference's scan-order tie rule and its
 erase-and-skip quirk decide) and on real-valued ones, threads of a phase visited in ascending and in descending order. The CUDA
-kernel itself is checked on the device by tests/gpu_unverified/cases_depth_pose.py::test_cached_agglomeration_equals_default_kernel."""
+kernel itself is checked on the device by tests/test_gpu_depth_pose.py::test_cached_agglomeration_equals_default_kernel."""
 import ctypes as C
 import os
 import subprocess

@@ -3,7 +3,7 @@ control points from bounding box / intrinsics / feature count, the depth- and fi
 cut, in-place normalisation, match assembly) against the reference's own MATCH_ADAPTIVE_FLANN_CPU, compiled UNMODIFIED inside
 moped3d's tree over a stand-in cv::flann::Index that searches exhaustively (oracle/ref3d_match_dropin.cpp — OpenCV's FLANN is
 external, unpinned and absent here). Without a GPU the CUDA class's nearest-neighbour step is driven by the same
-exhaustive search ("host" mode); with one, tests/gpu_unverified/cases_depth_pose.py runs the class as shipped (mc_match)."""
+exhaustive search ("host" mode); with one, tests/test_gpu_depth_pose.py runs the class as shipped (mc_match)."""
 import os
 import subprocess
 
