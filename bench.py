@@ -176,6 +176,12 @@ def reference_sample_step(r, frame, frac_inv, seed):
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own unmodified CPU stage classes (oracle/_ref) on the configuration of our arm. A timed step
+    is ONE FULL frame of the step's batch — all its features through MATCH_ANN_CPU (eps = 5, the shipped default) and the complete
+    match set through CLUSTER..FILTER2, per-stage wall clock like moped.cpp:183-191 — i.e. a bounded sample (1 of the --frames
+    frames) of the workload, nothing extrapolated inside a frame. Warm-up steps use a quarter of a frame's features (they only
+    page the kd-tree in). frames/s = 1 / seconds per frame: the reference processes the frames of a batch one after the other
+    (Moped::processImages, moped.cpp:166-194), its stages use every host core through OpenMP."""
     if rank != 0:
         return
     from oracle import ref
@@ -186,26 +192,32 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     db = synth.make_db(args.objects, args.pts)
-    frames = [synth.make_frame(db, args.features, n_visible=8, frame_id=i) for i in range(4)]   # frames of our arm's first batch
+    n_fr = min(args.frames, max(1, args.steps))
+    frames = [synth.make_frame(db, args.features, n_visible=8, frame_id=i) for i in range(n_fr)]   # frames of our arm's first batch
     r = reference_setup(db, cores)
-    # size the sample from a probe so that warmup + steps stay near two minutes of CPU work
-    s_probe, _, _ = reference_sample_step(r, frames[0], 32, seed=3)
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    frac_inv = int(min(32, max(4, np.ceil(s_probe / budget))))
+    for i in range(args.warmup):
+        s, _, n = reference_sample_step(r, frames[i % n_fr], 4, seed=3 + i)
+        log(f"[reference] warm-up {i}: {s:.2f}s/frame (quarter sample, scaled) objects={n}")
     tot = 0.0
     stages = np.zeros(6)
-    for i in range(args.warmup + args.steps):
-        s, st, n = reference_sample_step(r, frames[i % len(frames)], frac_inv, seed=11 + i)
-        if i >= args.warmup:
-            tot += s
-            stages += st
+    n_obj = 0
+    for i in range(args.steps):
+        fr = frames[i % n_fr]
+        r.clear_frame()
+        r.set_features(fr["desc"], fr["xy"], fr["image_idx"])
+        t0 = time.perf_counter()
+        n, st = r.run_pipeline(seed=11 + i)
+        s = time.perf_counter() - t0
+        tot += s
+        stages += np.array(st)
+        n_obj += n
         log(f"[reference] step {i}: {s:.2f}s/frame objects={n}")
     sec = tot / args.steps
-    sample = (f"per step: MATCH_ANN_CPU(eps=5) on a uniform 1/{frac_inv} of the {args.features} features, time x{frac_inv}; "
-              "CLUSTER..FILTER2 on the planted features' matches; kd-tree build excluded")
+    sample = (f"per timed step: 1 full frame of the {args.frames}-frame batch ({args.features} features) through MATCH_ANN_CPU(eps=5)..FILTER2, "
+              f"OpenMP on {cores} cores; kd-tree build excluded (as the GPU database upload is)")
     out = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(args, world),
+           "config": workload_config(args, world), "objects_per_frame": n_obj / args.steps,
            "stage_ms": {k: float(v / args.steps * 1e3) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], stages)},
            "cpu_baseline": {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -213,12 +225,18 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world):
+    """The SAME dict on both arms (the driver compares them): the workload, and how our arm schedules it."""
+    img_bytes = ((args.objects * args.pts // world + 127) // 128) * 32768
     return {"workload": f"synthetic {args.objects}-object DB ({args.objects * args.pts} x 128-d SIFT-like descriptors), "
                         f"{args.features} features/frame 640x480, MATCH..FILTER2 with config.hpp defaults; "
                         f"a step = a batch of {args.frames} independent frames",
             "db_objects": args.objects, "db_descriptors": args.objects * args.pts, "features_per_frame": args.features,
             "frames_per_step": args.frames,
-            "parallelism": f"db-sharded-by-object x{world}, frames after MATCH partitioned x{world}" if world > 1 else "single-gpu"}
+            "parallelism": f"db-sharded-by-object x{world}, frames after MATCH partitioned x{world}" if world > 1 else "single-gpu",
+            "l2": "db tile image > 2x L2, not flushed" if img_bytes >= 2 * L2_BYTES else "L2 flushed between steps (256 MiB write)",
+            "batches_pool": 2, "frame_lanes": args.lanes, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
+            "pipeline": ("MATCH of step i+1 (mc_match_dev) overlaps CLUSTER..FILTER2 of step i (mc_process_frames_matched_dev) on a second "
+                         "context/stream; every step completes inside the timed region" if args.pipeline else "one mc_process_frames* call per step")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -503,10 +521,7 @@ def run_ours(args, rank, world, local_rank):
         out = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f16 tensor-core coarse pass + f32 exact re-rank/LM", "data": "synthetic",
-               "config": dict(workload_config(args, world), l2="db tile image > 2x L2, not flushed" if not need_flush else "L2 flushed between steps (256 MiB write)",
-                              batches_pool=n_pool, frame_lanes=args.lanes, pose_warps_per_task=args.pose_warps, match_chunks=args.chunks,
-                              pipeline=("MATCH of step i+1 (mc_match_dev) overlaps CLUSTER..FILTER2 of step i (mc_process_frames_matched_dev) on a second "
-                                        "context/stream; every step completes inside the timed region" if args.pipeline else "one mc_process_frames* call per step")),
+               "config": workload_config(args, world),
                "objects_per_frame": n_obj / (args.steps * B),
                "matches_per_s": n_match / (total_ms * 1e-3),
                "query_descriptors_per_s": QT * args.steps / (total_ms * 1e-3),
@@ -638,6 +653,7 @@ def run_ransac_ours(args, rank, world, local_rank):
     ctx.set_stream(stream.cuda_stream)
     ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
     pp = capi.PoseParams.of(RANSAC_PARAMS)
+    ctx.set_option("depth_team_lanes", args.depth_team)
     h_in = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
             (cl["offsets"], cl["xy"], cl["xyz"], cl["image"], hy["hyp_cluster"][mine], hy["sample_pos"][mine], hy["init_quat"][mine])]
     d_in = [t.to(dev) for t in h_in]
@@ -699,7 +715,7 @@ def run_ransac_ours(args, rank, world, local_rank):
         out = {"metric": "hypotheses_per_s", "value": Htot * 1e3 / ms_step, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": dict(ransac_config(args, world), l2="working set (a few hundred KB) is cache resident by nature; not flushed",
-                              pose_mode=args.pose_mode),
+                              pose_mode=args.pose_mode, depth_team_lanes=args.depth_team),
                "accepted_fraction_rank0": float((n_in > RANSAC_PARAMS[4]).mean()), "lm_failed_fraction_rank0": float((n_in < 0).mean()),
                "gpu_launches": int(launches), "clocks": clocks,
                "e2e": {"value": Htot * 1e3 / (e2e_ms / args.steps), "unit": "hypotheses/s",
@@ -1059,6 +1075,7 @@ def main():
                          "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1; images = pixels in, objects out on real data")
     ap.add_argument("--pose-mode", default="default", choices=["default", "exact"],
                     help="ransac workload: default kernels (re-associating) or the order-preserving LM (bit-exact with the oracle)")
+    ap.add_argument("--depth-team", type=int, default=32, choices=[8, 32], help="ransac workload, --pose-mode exact: lanes per hypothesis (same bits)")
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--hyp", type=int, default=2048, help="hypotheses per cluster (ransac workload)")
     args = ap.parse_args()

@@ -88,6 +88,31 @@ mc_status mc_match_dev(mc_ctx *ctx, const float *q_desc_dev, int n_queries, floa
 mc_status mc_match_merge_dev(mc_ctx *ctx, const int32_t *nn_row_all_dev, const float *nn_dist_all_dev, int n_shards,
                              int n_queries, float ratio, int32_t *nn_row_dev, float *nn_dist_dev, uint8_t *accepted_dev);
 
+/* ---- MATCH, moped3d's depth-adaptive variant: replaces MATCH_ADAPTIVE_FLANN_CPU::Update / process,
+ *      moped3d/libmoped/src/match/MATCH_ADAPTIVE_FLANN_CPU.hpp:101-174,419-490 ---------------------------------------- */
+/* Ratio curve of one model over depth: the acceptance threshold rises linearly from ratio_low (depth 0) to ratio_high
+ * (depth_peak), stays there up to depth_fade and falls linearly to zero at 2 * depth_fade. */
+typedef struct {
+	float depth_peak, depth_fade;    /* metres */
+	float ratio_low, ratio_high;
+} mc_adaptive_model;
+/* Host helper, once per model change (what Update() derives per model, :146-169): depth_peak / depth_fade = the depths at which
+ * the largest face of the bounding box projects to dimension_peak / dimension_fade pixels under intrinsics K = (fx, fy, cx, cy);
+ * ratio_low / ratio_high = points inside [min_ratio_min, min_ratio_max] / [max_ratio_min, max_ratio_max] chosen by the model's
+ * feature count (sparse models get the permissive end). The six trailing arguments are the stage's constructor parameters. */
+void mc_adaptive_model_init(mc_adaptive_model *out, const float *bbox_min, const float *bbox_max, const float *K, int n_features,
+                            float min_ratio_min, float min_ratio_max, float max_ratio_min, float max_ratio_max, float dimension_peak,
+                            float dimension_fade);
+/* q_desc Q x D normalised queries, q_xy Q x 2 their coord2D (host); depth / fill_distance: height x width planes (host) — the depth
+ * component of the IMAGE_TYPE_DEPTH_MAP image and its "<name>.distance" probability map (moped3d/libmoped/include/moped.hpp:261-284);
+ * models: one curve per database model. maximum_depth / default_depth / cauchy_scale: 4.0 / 1.0 / 0.1 in the reference (:106-108).
+ * Outputs (host, query order): the two nearest rows and squared distances as mc_match returns them, and accepted[i] = the feature lies
+ * within maximum_depth and nn_dist[0]/nn_dist[1] is below the blend of its model's curve at the feature's depth and at default_depth
+ * (Cauchy weight of the fill distance). The threshold is evaluated on the device, one thread per feature. */
+mc_status mc_match_adaptive(mc_ctx *ctx, const float *q_desc, const float *q_xy, int n_queries, const float *depth, const float *fill_distance,
+                            int width, int height, const mc_adaptive_model *models, int n_models, float maximum_depth, float default_depth,
+                            float cauchy_scale, int32_t *nn_row, float *nn_dist, uint8_t *accepted);
+
 /* ---- CLUSTER: replaces CLUSTER_MEAN_SHIFT_CPU::process,
  *      moped2/libmoped/src/cluster/CLUSTER_MEAN_SHIFT_CPU.hpp:182-199 ------------------------- */
 /* matches as CSR over models (match_offsets[n_models+1]); match_image / match_xy per match (host).

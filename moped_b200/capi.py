@@ -110,6 +110,9 @@ SIGNATURES = {
     "mc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mc_match_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mc_adaptive_model_init": (None, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "mc_match_adaptive": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                    C.c_float, _i32p, _f32p, _u8p]),
 }
 
 _lib = None

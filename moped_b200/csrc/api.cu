@@ -299,10 +299,11 @@ mc_status mc_match(mc_ctx *ctx, const float *q_desc, int Q, float ratio, int mod
 	MC_TRY(d2h(ctx, nn_dist, (const float *)ctx->nn_dist.p, 2 * (size_t)Q));
 	MC_TRY(d2h(ctx, accepted, (const uint8_t *)ctx->accepted.p, (size_t)Q));
 	int32_t n_flag = 0;
-	if (stats && mode == MC_MATCH_TENSOR) MC_TRY(d2h(ctx, &n_flag, (const int32_t *)ctx->flag_count.p, 1));
+	const bool tensor = ctx->last_match_tensor != 0;         // descriptor lengths other than 128 take the exact scan whatever `mode` says
+	if (stats && tensor) MC_TRY(d2h(ctx, &n_flag, (const int32_t *)ctx->flag_count.p, 1));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	if (stats) {
-		if (mode == MC_MATCH_TENSOR) { stats[0] = Q - n_flag; stats[1] = n_flag; stats[2] = ctx->last_stats[2]; stats[3] = ctx->last_stats[3]; }
+		if (tensor) { stats[0] = Q - n_flag; stats[1] = n_flag; stats[2] = ctx->last_stats[2]; stats[3] = ctx->last_stats[3]; }
 		else { stats[0] = 0; stats[1] = Q; stats[2] = 0; stats[3] = 0; }
 	}
 	return MC_OK;

@@ -6,9 +6,10 @@
  * (sequential fp32 sum of squared differences; ties to the lower row), so that everything else the class does — normalisation,
  * the per-model control points from bounding box / intrinsics / feature count, the depth- and fill-distance-dependent ratio
  * threshold, the depth cut, match assembly — runs UNMODIFIED and pins the CUDA class's host logic.
- * Both stages run on identical FrameData generated from argv[1] (seed); with a GPU the CUDA class runs as shipped (mc_match),
- * without one its host logic is driven by the same exhaustive search (argv[2] = "host"). Built with strict IEEE flags so that the
- * two sides' float expressions round alike.
+ * Both stages run on identical FrameData generated from argv[1] (seed); with a GPU the CUDA class runs as shipped
+ * (mc_match_adaptive: search and threshold on the device), without one (argv[2] = "host") its host side runs as shipped and the
+ * device's two jobs are stood in for by the same exhaustive search and by the kernel's decision header compiled for the host
+ * (moped_b200/csrc/adaptive_threshold.cuh). Built with strict IEEE flags so that the two sides' float expressions round alike.
  */
 #include <cstdlib>
 #include <cstdio>
@@ -59,6 +60,8 @@ namespace cv {
 
 #include <match/MATCH_ADAPTIVE_FLANN_CPU.hpp>
 #include <MATCH_ADAPTIVE_CUDA.hpp>
+// "host" mode only: the device kernel's per-feature decision, compiled for the host from the kernel's own header
+#include "../moped_b200/csrc/adaptive_threshold.cuh"
 
 using namespace MopedNS;
 
@@ -151,15 +154,25 @@ int main(int argc, char **argv) {
 		foreach( alg, ca ) alg->process(fdCpu);
 		if (!hostOnly) { foreach( alg, ga ) alg->process(fdGpu); }
 		else if (cu->prepare(fdGpu, false)) {
-			vector<float> queries, dataset;
-			cu->packQueries(fdGpu, queries);
+			// no device: the class's host side (Update -> rows and ratio curves, gather, emit) runs as shipped; the two things the device does
+			// are stood in for by the exhaustive search above and by adaptive_threshold.cuh compiled for the host
+			MATCH_ADAPTIVE_CUDA::FrameInputs in;
+			cu->gather(fdGpu, in);
+			vector<float> dataset;
 			for (size_t m = 0; m < modelsGpu.size(); m++) {
 				vector<Model::IP> &ips = modelsGpu[m]->IPs["SIFT"];
 				for (size_t f = 0; f < ips.size(); f++) dataset.insert(dataset.end(), ips[f].descriptor.begin(), ips[f].descriptor.end());
 			}
-			vector<int32_t> nnRow(2 * (size_t)Q); vector<float> nnDist(2 * (size_t)Q);
-			for (int i = 0; i < Q; i++) { int nx[2]; cv::flann::exhaustive2nn(dataset, D, &queries[(size_t)i * D], nx, &nnDist[2 * i]); nnRow[2 * i] = nx[0]; nnRow[2 * i + 1] = nx[1]; }
-			cu->acceptMatches(fdGpu, nnRow, nnDist);
+			vector<int32_t> nnRow(2 * (size_t)Q); vector<float> nnDist(2 * (size_t)Q); vector<uint8_t> accepted(Q);
+			mc::AdaptiveParams P; P.maximum_depth = 4.0f; P.default_depth = 1.0f; P.cauchy_scale = 0.1f;
+			for (int i = 0; i < Q; i++) {
+				int nx[2];
+				cv::flann::exhaustive2nn(dataset, D, &in.desc[(size_t)i * D], nx, &nnDist[2 * i]);
+				nnRow[2 * i] = nx[0]; nnRow[2 * i + 1] = nx[1];
+				const int px = mc::adaptive_pixel(in.xy[2 * i], in.xy[2 * i + 1], in.width, in.height);
+				accepted[i] = mc::adaptive_accept(cu->modelCurves()[cu->modelOfRow(nx[0])], in.depth[px], in.fill[px], nnDist[2 * i], nnDist[2 * i + 1], P) ? 1 : 0;
+			}
+			cu->emit(fdGpu, nnRow, accepted);
 		}
 	} catch (string &e) { fprintf(stderr, "ERROR %s\n", e.c_str()); return 1; }
 	dump("cpu", fdCpu.matches);
