@@ -234,7 +234,7 @@ def workload_config(args, world):
             "frames_per_step": args.frames,
             "parallelism": f"db-sharded-by-object x{world}, frames after MATCH partitioned x{world}" if world > 1 else "single-gpu",
             "l2": "db tile image > 2x L2, not flushed" if img_bytes >= 2 * L2_BYTES else "L2 flushed between steps (256 MiB write)",
-            "batches_pool": 2, "frame_lanes": args.lanes, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
+            "pose_mode": args.pose_mode, "batches_pool": 2, "frame_lanes": args.lanes, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
             "pipeline": ("MATCH of step i+1 (mc_match_dev) overlaps CLUSTER..FILTER2 of step i (mc_process_frames_matched_dev) on a second "
                          "context/stream; every step completes inside the timed region" if args.pipeline else "one mc_process_frames* call per step")}
 
@@ -277,6 +277,8 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
     ctx.set_profiling(True)
     ctx.set_tuning(args.lanes, args.pose_warps, args.chunks)
+    if args.pose_mode == "exact":          # POSE / POSE2 with the order-preserving LM: every frame equals the oracle chain bit for bit
+        ctx.set_option("pose_exact_order", 1)
     params = ctx.default_params()
     MO = 64                                            # object slots per frame in the result arrays
 
@@ -337,6 +339,8 @@ def run_ours(args, rank, world, local_rank):
         ctx_s.db_set_global_tables(db["xyz"], db["model_of_row"], args.objects)
         ctx_s.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
         ctx_s.set_tuning(args.lanes, args.pose_warps, 1)
+        if args.pose_mode == "exact":
+            ctx_s.set_option("pose_exact_order", 1)
         pg_res = dist.new_group(backend="nccl") if world > 1 else None
         pf_lo, pf_hi = frame_range(B, world, rank)
         pBl = pf_hi - pf_lo
@@ -1074,7 +1078,8 @@ def main():
                     help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s; "
                          "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1; images = pixels in, objects out on real data")
     ap.add_argument("--pose-mode", default="default", choices=["default", "exact"],
-                    help="ransac workload: default kernels (re-associating) or the order-preserving LM (bit-exact with the oracle)")
+                    help="POSE / POSE2 arithmetic: default kernels (re-associating, fused multiply-add) or the order-preserving LM (bit-exact with "
+                         "the oracle and the strict-IEEE build of the reference)")
     ap.add_argument("--depth-team", type=int, default=32, choices=[8, 32], help="ransac workload, --pose-mode exact: lanes per hypothesis (same bits)")
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--hyp", type=int, default=2048, help="hypotheses per cluster (ransac workload)")

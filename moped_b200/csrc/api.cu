@@ -15,7 +15,7 @@ mc_status pose_hypotheses_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, 
                                  const int32_t *d_hyp_cluster, const int32_t *d_sample_pos, const float *d_init_quat, int n_hyp,
                                  const mc_pose_params *pp, const int64_t *d_mask_offsets, int32_t *d_n_inliers, float *d_pose_lm,
                                  float *d_pose_refit, float *d_lm_err, uint8_t *d_mask);
-mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, const int32_t *d_n_clusters, int n_clusters_cap,
+mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, const int32_t *d_n_clusters, int n_clusters_cap, int n_points_cap,
                              const float *d_xy, const float *d_xyz, const int32_t *d_image, const int32_t *d_tie,
                              const mc_pose_params *pp, uint8_t *d_found, float *d_pose, int32_t *d_n_tests);
 mc_status pose_depth_hypotheses_device(mc_ctx *ctx, int variant, const int32_t *d_cluster_offsets, const float *d_xy, const float *d_xyz,
@@ -442,13 +442,8 @@ mc_status mc_pose_ransac(mc_ctx *ctx, const int32_t *cluster_offsets, int n_clus
 	MC_TRY(h2d(ctx, (float *)(b + o_xyz), pt_xyz, 3 * (size_t)M));
 	MC_TRY(h2d(ctx, (int32_t *)(b + o_im), pt_image, (size_t)M));
 	MC_CUDA(cudaMemsetAsync(b + o_p, 0, 28ull * n_tasks, ctx->stream));
-	if (ctx->pose_exact_order) {
-		int n_max = 0;
-		for (int c = 0; c < n_clusters; c++) n_max = std::max(n_max, cluster_offsets[c + 1] - cluster_offsets[c]);
-		MC_TRY(pose_depth_ransac_device(ctx, 2, (int32_t *)(b + o_co), n_clusters, n_max, (float *)(b + o_xy), (float *)(b + o_xyz), nullptr, nullptr,
-		                                (int32_t *)(b + o_im), nullptr, params, 0.f, (uint8_t *)(b + o_f), (float *)(b + o_p), (int32_t *)(b + o_nt)));
-	} else
-	MC_TRY(pose_ransac_device(ctx, (int32_t *)(b + o_co), nullptr, n_clusters, (float *)(b + o_xy), (float *)(b + o_xyz), (int32_t *)(b + o_im), nullptr,
+	// exact-order mode (mc_set_option "pose_exact_order") is handled inside: the same staged driver with the order-preserving LM
+	MC_TRY(pose_ransac_device(ctx, (int32_t *)(b + o_co), nullptr, n_clusters, M, (float *)(b + o_xy), (float *)(b + o_xyz), (int32_t *)(b + o_im), nullptr,
 	                          params, (uint8_t *)(b + o_f), (float *)(b + o_p), (int32_t *)(b + o_nt)));
 	MC_TRY(d2h(ctx, found, (const uint8_t *)(b + o_f), (size_t)n_tasks));
 	MC_TRY(d2h(ctx, pose, (const float *)(b + o_p), 7 * (size_t)n_tasks));

@@ -138,13 +138,13 @@ template <> struct DepthResiduals<2> {
 // re-normalised) and ||e||^2 returned, on LM_ERROR the pose is untouched and -1 returned.
 template <int V, int W>
 LMX_FN float optimize_camera(const Team<W> &team, const Cluster &c, const int32_t *sel, int n_sel, float *pose, int itmax, float *scratch,
-                             bool finite_check) {
+                             bool finite_check, const volatile int *stop_flag = nullptr, int my_index = 0) {
 	DepthResiduals<V> fn;
 	fn.c = c; fn.sel = sel;
 	const Work w = work_carve(scratch, DepthResiduals<V>::R * n_sel);
 	float p[M], err;
 	for (int i = 0; i < M; i++) p[i] = pose[i];
-	const int r = levmar_dif(team, fn, p, n_sel, itmax, w, finite_check, &err);
+	const int r = levmar_dif(team, fn, p, n_sel, itmax, w, finite_check, &err, stop_flag, my_index);
 	if (r < 0) return (float)r;
 	for (int i = 0; i < M; i++) pose[i] = p[i];
 	quat_norm(pose);

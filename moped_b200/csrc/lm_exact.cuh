@@ -74,59 +74,96 @@ LMX_FN void pose_matrix(const float *p7, float *T) {
 // sAx_eq_b_LU_noLapack (Axb_core.c:888-1035) for the damped normal equations (JtJ + mu I) x = Jte; JtJ's lower triangle
 // is read from L (row-major M x M). Crout LU, implicit row scaling, partial pivoting; forward substitution with the
 // permutation vector and levmar's skip of leading zeros. Returns false if singular.
+// Every array index is a compile-time constant (loops fully unrolled, the data-dependent pivot row handled by selects), so the
+// 7 x 7 matrix lives in registers: a dynamically indexed row would put the whole matrix into local memory. The arithmetic — which
+// products, in which order, rounded where — is levmar's, including what it does on a column of NaNs (`maxi` keeps the previous
+// column's row, which may lie ABOVE the diagonal; a first column of NaNs counts as singular, see below).
 LMX_FN bool lu_solve(const float *L, float mu, const float *B, float *x) {
-	float a[M * M], work[M];
+	float a[M][M], work[M];
 	int idx[M], maxi = -1;
+#pragma unroll
 	for (int i = 0; i < M; i++)
-		for (int j = 0; j < M; j++) a[i * M + j] = i >= j ? L[i * M + j] : L[j * M + i];
-	for (int i = 0; i < M; i++) { a[i * M + i] += mu; x[i] = B[i]; }
+#pragma unroll
+		for (int j = 0; j < M; j++) a[i][j] = i >= j ? L[i * M + j] : L[j * M + i];
+#pragma unroll
+	for (int i = 0; i < M; i++) { a[i][i] += mu; x[i] = B[i]; }
+	bool singular = false;
+#pragma unroll
 	for (int i = 0; i < M; i++) {
 		float mx = 0.f;
-		for (int j = 0; j < M; j++) { float t = fabsf(a[i * M + j]); if (t > mx) mx = t; }
-		if (mx == 0.f) return false;
+#pragma unroll
+		for (int j = 0; j < M; j++) { const float t = fabsf(a[i][j]); if (t > mx) mx = t; }
+		if (mx == 0.f) singular = true;
 		work[i] = 1.0f / mx;
 	}
+	if (singular) return false;
+#pragma unroll
 	for (int j = 0; j < M; j++) {
+#pragma unroll
 		for (int i = 0; i < j; i++) {
-			float sum = a[i * M + j];
-			for (int k = 0; k < i; k++) sum -= a[i * M + k] * a[k * M + j];
-			a[i * M + j] = sum;
+			float sum = a[i][j];
+#pragma unroll
+			for (int k = 0; k < i; k++) sum -= a[i][k] * a[k][j];
+			a[i][j] = sum;
 		}
 		float mx = 0.f;
+#pragma unroll
 		for (int i = j; i < M; i++) {
-			float sum = a[i * M + j];
-			for (int k = 0; k < j; k++) sum -= a[i * M + k] * a[k * M + j];
-			a[i * M + j] = sum;
-			float t = work[i] * fabsf(sum);
+			float sum = a[i][j];
+#pragma unroll
+			for (int k = 0; k < j; k++) sum -= a[i][k] * a[k][j];
+			a[i][j] = sum;
+			const float t = work[i] * fabsf(sum);
 			if (t >= mx) { mx = t; maxi = i; }
 		}
 		// levmar starts with maxi = -1 and a column of NaNs never sets it (t >= mx is false): the reference then swaps with the
 		// row BEFORE its matrix (undefined behaviour). No such access here: the system counts as singular.
 		if (maxi < 0) return false;
 		if (j != maxi) {
-			for (int k = 0; k < M; k++) { float t = a[maxi * M + k]; a[maxi * M + k] = a[j * M + k]; a[j * M + k] = t; }
-			work[maxi] = work[j];
+			// rows j and maxi trade places (maxi is any row: below the diagonal normally, possibly above after a NaN column)
+#pragma unroll
+			for (int i = 0; i < M; i++) {
+				if (i == j) continue;
+				const bool sw = maxi == i;
+#pragma unroll
+				for (int k = 0; k < M; k++) {
+					const float u = a[i][k], v = a[j][k];
+					a[i][k] = sw ? v : u; a[j][k] = sw ? u : v;
+				}
+				work[i] = sw ? work[j] : work[i];
+			}
 		}
 		idx[j] = maxi;
-		if (a[j * M + j] == 0.f) a[j * M + j] = FLT_EPSILON;
+		if (a[j][j] == 0.f) a[j][j] = FLT_EPSILON;
 		if (j != M - 1) {
-			float t = 1.0f / a[j * M + j];
-			for (int i = j + 1; i < M; i++) a[i * M + j] *= t;
+			const float t = 1.0f / a[j][j];
+#pragma unroll
+			for (int i = j + 1; i < M; i++) a[i][j] *= t;
 		}
 	}
 	int k = 0;
+#pragma unroll
 	for (int i = 0; i < M; i++) {
-		int j = idx[i];
-		float sum = x[j];
-		x[j] = x[i];
-		if (k != 0) { for (j = k - 1; j < i; j++) sum -= a[i * M + j] * x[j]; }
-		else if (sum != 0.f) k = i + 1;
+		// sum = x[idx[i]]; x[idx[i]] = x[i];  with the data-dependent index resolved by selects
+		const int pj = idx[i];
+		float sum = x[0];
+#pragma unroll
+		for (int r = 1; r < M; r++) sum = pj == r ? x[r] : sum;
+		const float xi = x[i];
+#pragma unroll
+		for (int r = 0; r < M; r++) x[r] = pj == r ? xi : x[r];
+		if (k != 0) {
+#pragma unroll
+			for (int j = 0; j < i; j++) if (j >= k - 1) sum -= a[i][j] * x[j];
+		} else if (sum != 0.f) k = i + 1;
 		x[i] = sum;
 	}
+#pragma unroll
 	for (int i = M - 1; i >= 0; i--) {
 		float sum = x[i];
-		for (int j = i + 1; j < M; j++) sum -= a[i * M + j] * x[j];
-		x[i] = sum / a[i * M + i];
+#pragma unroll
+		for (int j = i + 1; j < M; j++) sum -= a[i][j] * x[j];
+		x[i] = sum / a[i][i];
 	}
 	return true;
 }
@@ -167,8 +204,11 @@ LMX_FN void eval(const Team<W> &team, const Fn &fn, const float *p, int n_pts, f
 // slevmar_dif(func, p, x = 0, m = 7, n = R * n_pts, itmax, opts = NULL, ...) — lm_core.c:427-836 with the defaults of
 // lm.h:83-85. `finite_check` keeps levmar's stop = 7 on a non-finite ||e||^2 (the reference's -ffast-math build folds it
 // away; a strict build keeps it). Returns the iteration count or -1 (stop 4 / 7); *err_out = ||e||^2 at the solution.
+// `stop_flag` (nullable): a word that may drop below `my_index` while the LM runs — a RANSAC test with a lower index has succeeded,
+// so this one cannot be chosen any more and gives up (returns -1; its result is never used). Read by member 0 and broadcast.
 template <int W, class Fn>
-LMX_FN int levmar_dif(const Team<W> &team, const Fn &fn, float *p, int n_pts, int itmax, const Work &w, bool finite_check, float *err_out) {
+LMX_FN int levmar_dif(const Team<W> &team, const Fn &fn, float *p, int n_pts, int itmax, const Work &w, bool finite_check, float *err_out,
+                      const volatile int *stop_flag = nullptr, int my_index = 0) {
 	const int n = Fn::R * n_pts;
 	const float tau = 1E-03f, eps1 = 1E-17f, eps2 = 1E-17f, eps2_sq = 1E-17f * 1E-17f, eps3 = 1E-17f, delta = 1E-06f;
 	float Dp[M], diag[M], pDp[M];
@@ -180,6 +220,7 @@ LMX_FN int levmar_dif(const Team<W> &team, const Fn &fn, float *p, int n_pts, in
 	if (finite_check && !isfinite(p_eL2)) stop = 7;
 
 	for (k = 0; k < itmax && !stop; ++k) {
+		if (stop_flag && team.from_first(*stop_flag) < my_index) { stop = 4; break; }
 		if (p_eL2 <= eps3) { stop = 6; break; }
 
 		if ((updp && nu > 16) || updjac == K) {

@@ -13,7 +13,7 @@ namespace mc {
 mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
                          int n_models, int n_images, int max_matches, float radius, float merge, int min_pts, int max_iter,
                          int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets, int32_t *d_members);
-mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, const int32_t *d_n_clusters, int n_clusters_cap,
+mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, const int32_t *d_n_clusters, int n_clusters_cap, int n_points_cap,
                              const float *d_xy, const float *d_xyz, const int32_t *d_image, const int32_t *d_tie,
                              const mc_pose_params *pp, uint8_t *d_found, float *d_pose, int32_t *d_n_tests);
 mc_status pose_append_device(mc_ctx *ctx, const int32_t *d_cluster_model, const int32_t *d_n_clusters, int n_clusters_cap, int max_obj,
@@ -225,7 +225,7 @@ static mc_status frame_enqueue(mc_ctx *ctx, const float *d_q, int Q, const mc_pi
 	k_gather_points<<<ctx->num_sms, 128, 0, ctx->stream>>>(B.cl_n, B.cl_model, B.cl_offsets, B.cl_members, B.match_offsets, B.match_image, B.match_xy,
 	                                                     B.match_xyz, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie);
 	MC_LAUNCH_CHECK();
-	MC_TRY(pose_ransac_device(ctx, B.cl_offsets, B.cl_n, cl_cap, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie, &P->pose, B.found, B.task_pose, B.n_tests));
+	MC_TRY(pose_ransac_device(ctx, B.cl_offsets, B.cl_n, cl_cap, Q, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie, &P->pose, B.found, B.task_pose, B.n_tests));
 	MC_TRY(pose_append_device(ctx, B.cl_model, B.cl_n, cl_cap, P->pose.max_objects_per_cluster, B.found, B.task_pose, B.n_obj, obj_cap, B.obj_model, B.obj_pose));
 	mark(3);
 	// FILTER
@@ -240,7 +240,7 @@ static mc_status frame_enqueue(mc_ctx *ctx, const float *d_q, int Q, const mc_pi
 	                                                     B.match_xyz, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie);
 	MC_LAUNCH_CHECK();
 	const int cl2_cap = obj_cap / 2;
-	MC_TRY(pose_ransac_device(ctx, B.f_offsets, B.f_n, cl2_cap, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie, &P->pose2, B.found, B.task_pose, B.n_tests));
+	MC_TRY(pose_ransac_device(ctx, B.f_offsets, B.f_n, cl2_cap, Q, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie, &P->pose2, B.found, B.task_pose, B.n_tests));
 	MC_TRY(pose_append_device(ctx, B.f_model, B.f_n, cl2_cap, P->pose2.max_objects_per_cluster, B.found, B.task_pose, B.n_obj, obj_cap, B.obj_model, B.obj_pose));
 	mark(5);
 	// FILTER2
@@ -286,7 +286,7 @@ static mc_status frame_chain(mc_ctx *lane, int Q, const mc_pipeline_params *P, c
 	}
 	uint64_t cfg = fnv(1469598103934665603ULL, &q_cap, sizeof q_cap);
 	cfg = fnv(cfg, P, sizeof *P);
-	const int64_t ints[] = { lane->n_models, lane->n_images, lane->table_base, lane->pose_warps, lane->ransac_fused, (int64_t)lane->num_sms };
+	const int64_t ints[] = { lane->n_models, lane->n_images, lane->table_base, lane->pose_warps, lane->ransac_fused, (int64_t)lane->num_sms, lane->pose_exact_order };
 	cfg = fnv(cfg, ints, sizeof ints);
 	const void *ptrs[] = { lane->d_cams, lane->d_xyz, lane->d_model_of_row };
 	cfg = fnv(cfg, ptrs, sizeof ptrs);
@@ -405,6 +405,7 @@ static void lane_borrow(mc_ctx *ctx, mc_ctx *lane) {
 	lane->d_cams = ctx->d_cams; lane->n_images = ctx->n_images;
 	lane->pose_warps = ctx->pose_warps;
 	lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs;
+	lane->pose_exact_order = ctx->pose_exact_order;
 }
 
 static mc_status ensure_lanes(mc_ctx *ctx, int n) {
@@ -412,7 +413,11 @@ static mc_status ensure_lanes(mc_ctx *ctx, int n) {
 	while ((int)ctx->lanes.size() < n) {
 		mc_ctx *lane = new mc_ctx;
 		lane->parent = ctx;
-		if (cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking) != cudaSuccess ||
+		// highest priority: when MATCH of a later chunk (or of the next step) is queued on the context's stream, the small
+		// latency-bound stage kernels of the lanes get the SM slots that free up first
+		int prio_least = 0, prio_greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+		if (cudaStreamCreateWithPriority(&lane->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&lane->ev_done, cudaEventDisableTiming) != cudaSuccess) {
 			delete lane;
 			ctx->err = "process_frames: cannot create a lane stream";

@@ -27,10 +27,20 @@ static int g_host_order = 0;             // host emulation only: 0 = members asc
 template <int W>
 struct WarpTeam {                        // W consecutive lanes of one warp: 1, 8 (four teams per warp) or 32
 	int lane;                            // index inside the team, 0..W-1
+	int base;                            // the team's first lane inside its warp
 	unsigned mask;                       // the team's lanes inside its warp (device only)
 	PHX_MEM void init(int lane_in_warp) {
 		lane = lane_in_warp % W;
-		mask = W >= 32 ? 0xffffffffu : ((1u << W) - 1u) << (lane_in_warp - lane);
+		base = lane_in_warp - lane;
+		mask = W >= 32 ? 0xffffffffu : ((1u << W) - 1u) << base;
+	}
+	// the value member 0 holds, on every member (keeps data-dependent control flow uniform inside the team)
+	PHX_MEM int from_first(int v) const {
+#if defined(__CUDA_ARCH__)
+		return W > 1 ? __shfl_sync(mask, v, base) : v;
+#else
+		return v;
+#endif
 	}
 	PHX_MEM void sync() const {
 #if defined(__CUDA_ARCH__)
