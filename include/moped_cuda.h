@@ -113,6 +113,12 @@ mc_status mc_match_adaptive(mc_ctx *ctx, const float *q_desc, const float *q_xy,
                             int width, int height, const mc_adaptive_model *models, int n_models, float maximum_depth, float default_depth,
                             float cauchy_scale, int32_t *nn_row, float *nn_dist, uint8_t *accepted);
 
+/* The same for shards gathered as ONE packed block each — [nn_row Q x 2 int32 | nn_dist Q x 2 fp32], 16 Q bytes per shard, n_shards
+ * blocks back to back: mc_match_dev can write both halves of a rank's block directly (nn_row_dev = block, nn_dist_dev = block + 8 Q
+ * bytes), so one all-gather moves everything the merge needs. */
+mc_status mc_match_merge_packed_dev(mc_ctx *ctx, const void *packed_all_dev, int n_shards, int n_queries, float ratio,
+                                    int32_t *nn_row_dev, float *nn_dist_dev, uint8_t *accepted_dev);
+
 /* ---- CLUSTER: replaces CLUSTER_MEAN_SHIFT_CPU::process,
  *      moped2/libmoped/src/cluster/CLUSTER_MEAN_SHIFT_CPU.hpp:182-199 ------------------------- */
 /* matches as CSR over models (match_offsets[n_models+1]); match_image / match_xy per match (host).
@@ -251,6 +257,10 @@ mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, 
                                         const int32_t *q_image_dev, const int32_t *frame_offsets, int n_frames, int frame_begin, int frame_end,
                                         const mc_pipeline_params *params, int max_objects, int32_t *frame_info_dev, int32_t *obj_model_dev,
                                         float *obj_pose_dev, float *obj_score_dev);
+/* With mc_set_option("defer_lane_join", 1) mc_process_frames_matched_dev returns WITHOUT ordering the context's stream after the frame
+ * lanes, so that work enqueued next on that stream (MATCH and the exchange of the batch's next chunk) overlaps the stages just started;
+ * mc_join_lanes orders the context's stream after everything the lanes were given since the last join. */
+mc_status mc_join_lanes(mc_ctx *ctx);
 /* Scheduling knobs that never change results: frame_lanes = concurrent frames after MATCH in a batch (1..64,
  * default 8); pose_warps_per_task = hypotheses of EVERY RANSAC task tested by the first RANSAC kernel (1..8, default
  * 8: lowest single-frame latency when a task's first hypotheses fail; 1 packs the first hypothesis of four tasks into
@@ -350,6 +360,7 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
  *                          -ffast-math build.
  *   "ransac_fused"         != 0: mc_pose_ransac / the frame pipeline use the single one-CTA-per-task RANSAC kernel
  *                          instead of the staged kernels (same results; kept for A/B measurements)
+ *   "defer_lane_join"      != 0: see mc_join_lanes (default 0)
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
  *                          MATCH instead of ~40 kernel launches (same kernels, same results)
  *   "sift_two_pass"        != 0: mc_sift_extract* blur with the separate row / column kernels instead of the fused

@@ -110,6 +110,8 @@ SIGNATURES = {
     "mc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mc_match_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mc_match_merge_packed_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_join_lanes": (C.c_int, [C.c_void_p]),
     "mc_adaptive_model_init": (None, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
     "mc_match_adaptive": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float,
                                     C.c_float, _i32p, _f32p, _u8p]),
@@ -237,6 +239,13 @@ class Context:
     def match_merge_dev(self, rows_all_ptr, dist_all_ptr, n_shards, Q, ratio, nn_row_ptr, nn_dist_ptr, acc_ptr):
         self._check(self.L.mc_match_merge_dev(self.h, rows_all_ptr, dist_all_ptr, n_shards, Q, ratio, nn_row_ptr, nn_dist_ptr, acc_ptr),
                     "mc_match_merge_dev")
+
+    def match_merge_packed_dev(self, packed_all_ptr, n_shards, Q, ratio, nn_row_ptr, nn_dist_ptr, acc_ptr):
+        self._check(self.L.mc_match_merge_packed_dev(self.h, packed_all_ptr, n_shards, Q, ratio, nn_row_ptr, nn_dist_ptr, acc_ptr),
+                    "mc_match_merge_packed_dev")
+
+    def join_lanes(self):
+        self._check(self.L.mc_join_lanes(self.h), "mc_join_lanes")
 
     # ---- CLUSTER
     def cluster(self, matches, n_images=1, radius=200.0, merge=20.0, minpts=7, maxiter=100):

@@ -38,6 +38,7 @@ mc_status process_frames_device(mc_ctx *ctx, const float *d_q, const float *d_qx
                                 int f_begin, int f_end, const mc_pipeline_params *P, int max_objects, const int32_t *d_nn_row_in,
                                 const uint8_t *d_accepted_in, int32_t *d_out_info, int32_t *d_out_model, float *d_out_pose, float *d_out_score,
                                 cudaEvent_t *ev3);
+mc_status join_lanes(mc_ctx *ctx);
 mc_status process_frames_host(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, const int32_t *frame_offsets, int n_frames,
                               const mc_pipeline_params *P, int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score,
                               int32_t *frame_info, float *stage_ms);
@@ -179,6 +180,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	if (k == "pose_fit_thread_min") ctx->fit_thread_min = value < 1 ? 1 : value;
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
+	else if (k == "defer_lane_join") ctx->defer_lane_join = value != 0;
 	else if (k == "lm_finite_check") ctx->lm_finite_check = value != 0;
 	else if (k == "pose_exact_order") ctx->pose_exact_order = value != 0;
 	else if (k == "linkage_cached") ctx->linkage_cached = value != 0;
@@ -313,7 +315,15 @@ mc_status mc_match_merge_dev(mc_ctx *ctx, const int32_t *rows_all, const float *
                              int32_t *nn_row_dev, float *nn_dist_dev, uint8_t *accepted_dev) {
 	if (!ctx || !rows_all || !dist_all || n_shards <= 0 || Q < 0) { if (ctx) ctx->err = "mc_match_merge_dev: bad argument"; return MC_ERR_ARG; }
 	MC_CUDA(cudaSetDevice(ctx->device));
-	return match_merge_device(ctx, rows_all, dist_all, n_shards, Q, ratio, nn_row_dev, nn_dist_dev, accepted_dev);
+	return match_merge_device(ctx, rows_all, dist_all, 2 * (size_t)Q, n_shards, Q, ratio, nn_row_dev, nn_dist_dev, accepted_dev);
+}
+
+mc_status mc_match_merge_packed_dev(mc_ctx *ctx, const void *packed_all, int n_shards, int Q, float ratio, int32_t *nn_row_dev, float *nn_dist_dev,
+                                    uint8_t *accepted_dev) {
+	if (!ctx || !packed_all || n_shards <= 0 || Q < 0) { if (ctx) ctx->err = "mc_match_merge_packed_dev: bad argument"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	const int32_t *rows = (const int32_t *)packed_all;
+	return match_merge_device(ctx, rows, (const float *)(rows + 2 * (size_t)Q), 4 * (size_t)Q, n_shards, Q, ratio, nn_row_dev, nn_dist_dev, accepted_dev);
 }
 
 // ---- CLUSTER ---------------------------------------------------------------------------------
@@ -714,6 +724,12 @@ mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, 
 	MC_CUDA(cudaSetDevice(ctx->device));
 	return process_frames_device(ctx, nullptr, q_xy_dev, q_image_dev, frame_offsets, frame_begin, frame_end, params, max_objects, nn_row_dev, accepted_dev,
 	                             frame_info_dev, obj_model_dev, obj_pose_dev, obj_score_dev, nullptr);
+}
+
+mc_status mc_join_lanes(mc_ctx *ctx) {
+	if (!ctx) return MC_ERR_ARG;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	return join_lanes(ctx);
 }
 
 } // extern "C"

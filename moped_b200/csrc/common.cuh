@@ -100,6 +100,9 @@ struct mc_ctx {
 	std::vector<FrameGraph> fgraphs;  // one per configuration seen on this lane (sizes, parameters), most recent last
 	bool capturing = false;           // reserve() must not allocate while the lane's stream is being captured
 	bool frame_graphs = true;         // mc_set_option "frame_graphs"
+	bool defer_lane_join = false;     // mc_set_option "defer_lane_join": mc_process_frames_matched_dev returns without ordering the context's
+	                                  // stream after the lanes; mc_join_lanes does that later (MATCH of the next chunk overlaps this chunk's stages)
+	int lanes_pending = 0;            // lanes used since the last join
 	int batch_stats[4] = {0, 0, 0, 0};   // {frames, accepted matches, objects, lanes used} of the last batch
 	mc::DevBuf link_buf;                 // linkage clustering (linkage.cu): inputs, similarity matrices, agglomeration state
 	void *sift_state = nullptr;          // feature extraction (sift.cu): scale-space plan and buffers, created on first use
@@ -165,7 +168,7 @@ mc_status process_frames_host(mc_ctx *ctx, const float *d_q, const float *d_qxy,
                               int32_t *frame_info, float *stage_ms);
 mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mode,
                        int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted);
-mc_status match_merge_device(mc_ctx *ctx, const int32_t *rows_all, const float *dist_all, int n_shards, int Q, float ratio,
+mc_status match_merge_device(mc_ctx *ctx, const int32_t *rows_all, const float *dist_all, size_t stride, int n_shards, int Q, float ratio,
                              int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted);
 
 } // namespace mc

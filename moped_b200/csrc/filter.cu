@@ -14,28 +14,41 @@
 
 namespace mc {
 
+// TransformMatrix::init (moped.hpp:175-182), each term rounded on its own in source order
+__device__ __forceinline__ float tm_diag(float a, float b) {      // 1 - 2 a a - 2 b b
+	return __fsub_rn(__fsub_rn(1.f, __fmul_rn(__fmul_rn(2.f, a), a)), __fmul_rn(__fmul_rn(2.f, b), b));
+}
+__device__ __forceinline__ float tm_off(float a, float b, float c, float d, float sign) {      // 2 a b +- 2 c d
+	const float l = __fmul_rn(__fmul_rn(2.f, a), b), r = __fmul_rn(__fmul_rn(2.f, c), d);
+	return sign > 0.f ? __fadd_rn(l, r) : __fsub_rn(l, r);
+}
 __device__ __forceinline__ void pose_matrix(const float *q, const float *t, float *T) {
-	T[0] = 1 - 2 * q[1] * q[1] - 2 * q[2] * q[2]; T[1] = 2 * q[0] * q[1] - 2 * q[3] * q[2]; T[2] = 2 * q[0] * q[2] + 2 * q[3] * q[1]; T[3] = t[0];
-	T[4] = 2 * q[0] * q[1] + 2 * q[3] * q[2]; T[5] = 1 - 2 * q[0] * q[0] - 2 * q[2] * q[2]; T[6] = 2 * q[1] * q[2] - 2 * q[3] * q[0]; T[7] = t[1];
-	T[8] = 2 * q[0] * q[2] - 2 * q[3] * q[1]; T[9] = 2 * q[1] * q[2] + 2 * q[3] * q[0]; T[10] = 1 - 2 * q[0] * q[0] - 2 * q[1] * q[1]; T[11] = t[2];
+	T[0] = tm_diag(q[1], q[2]); T[1] = tm_off(q[0], q[1], q[3], q[2], -1.f); T[2] = tm_off(q[0], q[2], q[3], q[1], 1.f); T[3] = t[0];
+	T[4] = tm_off(q[0], q[1], q[3], q[2], 1.f); T[5] = tm_diag(q[0], q[2]); T[6] = tm_off(q[1], q[2], q[3], q[0], -1.f); T[7] = t[1];
+	T[8] = tm_off(q[0], q[2], q[3], q[1], -1.f); T[9] = tm_off(q[1], q[2], q[3], q[0], 1.f); T[10] = tm_diag(q[0], q[1]); T[11] = t[2];
 }
 
-// squared reprojection error of model point X under pose matrix T into camera cam vs observed (u0, v0)
+// squared reprojection error of model point X under pose matrix T into camera cam vs observed (u0, v0). Every product and sum is
+// rounded on its own, left to right (explicit _rn intrinsics: no fused multiply-add whatever the compiler flags), the order of
+// TransformMatrix::transform / inverseTransform and project() (moped.hpp:183-200,330-354) as the oracle restates them.
+__device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2) {
+	return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+}
 __device__ __forceinline__ float reproj_err(const float *T, const Camera &cam, const float *X, float u0, float v0) {
-	const float x = X[0] * T[0] + X[1] * T[1] + X[2] * T[2] + T[3];
-	const float y = X[0] * T[4] + X[1] * T[5] + X[2] * T[6] + T[7];
-	const float z = X[0] * T[8] + X[1] * T[9] + X[2] * T[10] + T[11];
-	const float a = x - cam.TM[3], b = y - cam.TM[7], c = z - cam.TM[11];
-	const float cx = a * cam.TM[0] + b * cam.TM[4] + c * cam.TM[8];
-	const float cy = a * cam.TM[1] + b * cam.TM[5] + c * cam.TM[9];
-	const float cz = a * cam.TM[2] + b * cam.TM[6] + c * cam.TM[10];
+	const float x = __fadd_rn(dot3_rn(X[0], T[0], X[1], T[1], X[2], T[2]), T[3]);
+	const float y = __fadd_rn(dot3_rn(X[0], T[4], X[1], T[5], X[2], T[6]), T[7]);
+	const float z = __fadd_rn(dot3_rn(X[0], T[8], X[1], T[9], X[2], T[10]), T[11]);
+	const float a = __fsub_rn(x, cam.TM[3]), b = __fsub_rn(y, cam.TM[7]), c = __fsub_rn(z, cam.TM[11]);
+	const float cx = dot3_rn(a, cam.TM[0], b, cam.TM[4], c, cam.TM[8]);
+	const float cy = dot3_rn(a, cam.TM[1], b, cam.TM[5], c, cam.TM[9]);
+	const float cz = dot3_rn(a, cam.TM[2], b, cam.TM[6], c, cam.TM[10]);
 	float u = FLT_MAX, v = FLT_MAX;
 	if (!((double)cz < 0.001)) {
-		u = cx / cz * cam.K[0] + cam.K[2];
-		v = cy / cz * cam.K[1] + cam.K[3];
+		u = __fadd_rn(__fmul_rn(__fdiv_rn(cx, cz), cam.K[0]), cam.K[2]);
+		v = __fadd_rn(__fmul_rn(__fdiv_rn(cy, cz), cam.K[1]), cam.K[3]);
 	}
-	const float du = u - u0, dv = v - v0;
-	return du * du + dv * dv;
+	const float du = __fsub_rn(u, u0), dv = __fsub_rn(v, v0);
+	return __fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv));
 }
 
 // in_cluster: n_objects x max_per_model bytes, row o covers the matches of model(o) (index j - lo).
@@ -64,7 +77,7 @@ __global__ void k_filter_score(const int32_t *__restrict__ match_offsets, const 
 			const int l = __ffs(msk) - 1;
 			msk &= msk - 1;
 			const float e = __shfl_sync(0xffffffffu, err, l);
-			s = (float)((double)s + 1. / ((double)e + 1.));
+			s = __double2float_rn(__dadd_rn((double)s, __ddiv_rn(1., __dadd_rn((double)e, 1.))));
 		}
 	}
 	if (lane == 0) score[o] = s;

@@ -645,13 +645,14 @@ __global__ void k_match_finalize(const int32_t *__restrict__ nn_row, const float
 }
 
 // global top-2 over object shards: (smaller distance, then smaller global row id)
-__global__ void k_match_merge(const int32_t *__restrict__ rows_all, const float *__restrict__ dist_all, int n_shards, int Q, float ratio,
+// shard s's rows / distances start `stride` elements after shard s-1's (2 Q for two separate arrays, 4 Q for packed blocks)
+__global__ void k_match_merge(const int32_t *__restrict__ rows_all, const float *__restrict__ dist_all, size_t stride, int n_shards, int Q, float ratio,
                               int32_t *__restrict__ nn_row, float *__restrict__ nn_dist, uint8_t *__restrict__ accepted) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= Q) return;
 	Top2 t = top2_empty();
 	for (int s = 0; s < n_shards; s++) {
-		size_t o = ((size_t)s * Q + i) * 2;
+		size_t o = (size_t)s * stride + (size_t)i * 2;
 		top2_push(t, dist_all[o], rows_all[o]);
 		top2_push(t, dist_all[o + 1], rows_all[o + 1]);
 	}
@@ -789,10 +790,10 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 	return MC_OK;
 }
 
-mc_status match_merge_device(mc_ctx *ctx, const int32_t *rows_all, const float *dist_all, int n_shards, int Q, float ratio,
+mc_status match_merge_device(mc_ctx *ctx, const int32_t *rows_all, const float *dist_all, size_t stride, int n_shards, int Q, float ratio,
                              int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted) {
 	if (Q <= 0) return MC_OK;
-	k_match_merge<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(rows_all, dist_all, n_shards, Q, ratio, d_nn_row, d_nn_dist, d_accepted);
+	k_match_merge<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(rows_all, dist_all, stride, n_shards, Q, ratio, d_nn_row, d_nn_dist, d_accepted);
 	MC_LAUNCH_CHECK();
 	return MC_OK;
 }

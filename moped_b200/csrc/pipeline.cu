@@ -430,6 +430,18 @@ static mc_status ensure_lanes(mc_ctx *ctx, int n) {
 	return MC_OK;
 }
 
+// order ctx->stream after everything the lanes have been given since the last join
+mc_status join_lanes(mc_ctx *ctx) {
+	for (int l = 0; l < ctx->lanes_pending && l < (int)ctx->lanes.size(); l++) {
+		mc_ctx *lane = ctx->lanes[l];
+		MC_CUDA(cudaEventRecord(lane->ev_done, lane->stream));
+		MC_CUDA(cudaStreamWaitEvent(ctx->stream, lane->ev_done, 0));
+		ctx->launches += lane->launches; lane->launches = 0;
+	}
+	ctx->lanes_pending = 0;
+	return MC_OK;
+}
+
 // Frames [f_begin, f_end) of a batch whose queries (all frames, concatenated) are resident on the device.
 // d_nn_row_in / d_accepted_in (nullable, all frames): merged nearest neighbours of an object-sharded database;
 // otherwise MATCH runs here for the queries of frames [f_begin, f_end). Outputs are DEVICE arrays with one slot
@@ -510,12 +522,8 @@ mc_status process_frames_device(mc_ctx *ctx, const float *d_q, const float *d_qx
 			if (st != MC_OK) { ctx->err = lane->err; return st; }
 		}
 	}
-	for (int l = 0; l < n_lanes; l++) {
-		mc_ctx *lane = ctx->lanes[l];
-		MC_CUDA(cudaEventRecord(lane->ev_done, lane->stream));
-		MC_CUDA(cudaStreamWaitEvent(ctx->stream, lane->ev_done, 0));
-		ctx->launches += lane->launches; lane->launches = 0;
-	}
+	if (n_lanes > ctx->lanes_pending) ctx->lanes_pending = n_lanes;
+	if (!ctx->defer_lane_join) MC_TRY(join_lanes(ctx));
 	if (ev3) MC_CUDA(cudaEventRecord(ev3[2], ctx->stream));
 	if (trace) {
 		cudaStreamSynchronize(ctx->stream);

@@ -22,7 +22,7 @@ def exact_ctx(gpu_ctx):
 def _same_objects(out, want):
     assert np.array_equal(out["model"], want["model"]), (out["model"], want["model"])
     assert np.array_equal(out["pose"], want["pose"]), np.abs(out["pose"] - want["pose"]).max()
-    assert np.allclose(out["score"], want["score"], rtol=0, atol=1e-4)
+    assert np.array_equal(out["score"], want["score"]), np.abs(out["score"] - want["score"]).max()
 
 
 def test_staged_exact_ransac_equals_the_oracle_on_golden_clusters(exact_ctx, golden, oracle_mod):
