@@ -234,7 +234,7 @@ def workload_config(args, world):
             "frames_per_step": args.frames,
             "parallelism": f"db-sharded-by-object x{world}, frames after MATCH partitioned x{world}" if world > 1 else "single-gpu",
             "l2": "db tile image > 2x L2, not flushed" if img_bytes >= 2 * L2_BYTES else "L2 flushed between steps (256 MiB write)",
-            "pose_mode": args.pose_mode, "batches_pool": 2, "frame_lanes": args.lanes, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
+            "pose_mode": args.pose_mode, "match_coarse_kind": args.coarse_kind, "match_reserve_sms": args.reserve_sms, "batches_pool": 2, "frame_lanes": args.lanes, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
             "pipeline": ("MATCH of step i+1 (mc_match_dev) overlaps CLUSTER..FILTER2 of step i (mc_process_frames_matched_dev) on a second "
                          "context/stream; every step completes inside the timed region" if args.pipeline else "one mc_process_frames* call per step")}
 
@@ -277,6 +277,8 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
     ctx.set_profiling(True)
     ctx.set_tuning(args.lanes, args.pose_warps, args.chunks)
+    ctx.set_option("match_coarse_kind", args.coarse_kind)
+    ctx.set_option("match_reserve_sms", args.reserve_sms)
     if args.pose_mode == "exact":          # POSE / POSE2 with the order-preserving LM: every frame equals the oracle chain bit for bit
         ctx.set_option("pose_exact_order", 1)
     params = ctx.default_params()
@@ -293,11 +295,14 @@ def run_ours(args, rank, world, local_rank):
         e_q = torch.empty((QT, 128), dtype=torch.float32, device=dev)
         e_xy = torch.empty((QT, 2), dtype=torch.float32, device=dev)
         e_img = torch.empty((QT,), dtype=torch.int32, device=dev)
+        # this rank's (row, distance) pairs as ONE block [rows QT x 2 int32 | distances QT x 2 fp32]: mc_match_dev writes both halves in
+        # place, one all-gather moves them, mc_match_merge_packed_dev reads the gathered blocks
+        nn_blk = torch.empty((4 * QT,), dtype=torch.int32, device=dev)
+        nn_all = torch.empty((world, 4 * QT), dtype=torch.int32, device=dev)
         nn_row = torch.empty((QT, 2), dtype=torch.int32, device=dev)
         nn_dist = torch.empty((QT, 2), dtype=torch.float32, device=dev)
         acc = torch.empty((QT,), dtype=torch.uint8, device=dev)
-        all_row = torch.empty((world, QT, 2), dtype=torch.int32, device=dev)
-        all_dist = torch.empty((world, QT, 2), dtype=torch.float32, device=dev)
+        q_lo, q_hi = rank * (QT // world), (rank + 1) * (QT // world)     # the slice of the batch's queries this rank uploads (e2e leg)
         f_lo, f_hi = frame_range(B, world, rank)       # frames of this rank after MATCH
         Bl = f_hi - f_lo
         blk = ResultBlock(Bl, MO)                      # written in place by mc_process_frames_matched_dev, all-gathered as one tensor
@@ -312,10 +317,9 @@ def run_ours(args, rank, world, local_rank):
     def sharded_step(q, xy, img):
         """N > 1: shard-local MATCH of all B*Q queries, all-gather of the (row, distance) pairs, merge, this rank's
         B/N frames through CLUSTER..FILTER2, all-gather of the per-frame results, read-back."""
-        ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
-        dist.all_gather_into_tensor(all_row, nn_row)
-        dist.all_gather_into_tensor(all_dist, nn_dist)
-        ctx.match_merge_dev(all_row.data_ptr(), all_dist.data_ptr(), world, QT, params.match_ratio, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+        ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, nn_blk.data_ptr(), nn_blk.data_ptr() + 8 * QT, acc.data_ptr())
+        dist.all_gather_into_tensor(nn_all, nn_blk)
+        ctx.match_merge_packed_dev(nn_all.data_ptr(), world, QT, params.match_ratio, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
         ctx.process_frames_matched_dev(nn_row.data_ptr(), acc.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, f_lo, f_hi, params, MO,
                                        res_local.data_ptr() + 4 * blk.o_info, res_local.data_ptr() + 4 * blk.o_model,
                                        res_local.data_ptr() + 4 * blk.o_pose, res_local.data_ptr() + 4 * blk.o_score)
@@ -352,8 +356,8 @@ def run_ours(args, rank, world, local_rank):
         p_row = [torch.empty((QT, 2), dtype=torch.int32, device=dev) for _ in range(P)]
         p_dist = [torch.empty((QT, 2), dtype=torch.float32, device=dev) for _ in range(P)]
         p_acc = [torch.empty((QT,), dtype=torch.uint8, device=dev) for _ in range(P)]
-        p_allrow = [torch.empty((world, QT, 2), dtype=torch.int32, device=dev) for _ in range(P)] if world > 1 else None
-        p_alldist = [torch.empty((world, QT, 2), dtype=torch.float32, device=dev) for _ in range(P)] if world > 1 else None
+        p_blk = [torch.empty((4 * QT,), dtype=torch.int32, device=dev) for _ in range(P)] if world > 1 else None
+        p_all = [torch.empty((world, 4 * QT), dtype=torch.int32, device=dev) for _ in range(P)] if world > 1 else None
         p_res = [torch.zeros((pblk.words,), dtype=torch.int32, device=dev) for _ in range(P)]
         p_resall = [torch.zeros((world, pblk.words), dtype=torch.int32, device=dev) for _ in range(P)]
         p_reshost = [torch.zeros((world, pblk.words), dtype=torch.int32).pin_memory() for _ in range(P)]
@@ -365,19 +369,26 @@ def run_ours(args, rank, world, local_rank):
             with torch.cuda.stream(stream):
                 if flush is not None:
                     flush.zero_()
-                if e2e:                                   # host buffers in: the step's features go up inside the timed region
+                if e2e and world == 1:                    # host buffers in: the step's features go up inside the timed region
                     p_q[b].copy_(h_q[k], non_blocking=True)
                     p_xy[b].copy_(h_xy[k], non_blocking=True)
                     p_img[b].copy_(h_img[k], non_blocking=True)
                     q, xy, img = p_q[b], p_xy[b], p_img[b]
+                elif e2e:                                 # N > 1: 1/N of the descriptors per rank + NVLink all-gather; coordinates of its own frames
+                    ql, qh = rank * (QT // world), (rank + 1) * (QT // world)
+                    p_q[b][ql:qh].copy_(h_q[k][ql:qh], non_blocking=True)
+                    dist.all_gather_into_tensor(p_q[b], p_q[b][ql:qh])
+                    p_xy[b][fo[pf_lo]:fo[pf_hi]].copy_(h_xy[k][fo[pf_lo]:fo[pf_hi]], non_blocking=True)
+                    p_img[b][fo[pf_lo]:fo[pf_hi]].copy_(h_img[k][fo[pf_lo]:fo[pf_hi]], non_blocking=True)
+                    q, xy, img = p_q[b], p_xy[b], p_img[b]
                 else:
                     q, xy, img = d_q[k], d_xy[k], d_img[k]
-                ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
                 if world > 1:
-                    dist.all_gather_into_tensor(p_allrow[b], p_row[b])
-                    dist.all_gather_into_tensor(p_alldist[b], p_dist[b])
-                    ctx.match_merge_dev(p_allrow[b].data_ptr(), p_alldist[b].data_ptr(), world, QT, params.match_ratio,
-                                        p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
+                    ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, p_blk[b].data_ptr(), p_blk[b].data_ptr() + 8 * QT, p_acc[b].data_ptr())
+                    dist.all_gather_into_tensor(p_all[b], p_blk[b])
+                    ctx.match_merge_packed_dev(p_all[b].data_ptr(), world, QT, params.match_ratio, p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
+                else:
+                    ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
                 ev_match[b].record(stream)
             with torch.cuda.stream(stream2):
                 stream2.wait_event(ev_match[b])
@@ -442,11 +453,15 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             out = ctx.process_frames(h_q[k].numpy(), h_xy[k].numpy(), h_img[k].numpy(), fo, params, MO)
             return sum(len(o["model"]) for o in out), sum(int(o["info"][2]) for o in out)
-        e_q.copy_(h_q[k], non_blocking=True)
-        e_xy.copy_(h_xy[k], non_blocking=True)
-        e_img.copy_(h_img[k], non_blocking=True)
+        # host buffers in: every rank uploads 1/N of the batch's descriptors and they are all-gathered over NVLink (N replicated PCIe
+        # copies of the whole batch were 29 % of the 8-GPU step); coordinates / image indices only of the frames this rank runs after MATCH
+        e_q[q_lo:q_hi].copy_(h_q[k][q_lo:q_hi], non_blocking=True)
+        dist.all_gather_into_tensor(e_q, e_q[q_lo:q_hi])
+        e_xy[fo[f_lo]:fo[f_hi]].copy_(h_xy[k][fo[f_lo]:fo[f_hi]], non_blocking=True)
+        e_img[fo[f_lo]:fo[f_hi]].copy_(h_img[k][fo[f_lo]:fo[f_hi]], non_blocking=True)
         return sharded_step(e_q, e_xy, e_img)
 
+    mtiers = []                                       # per timed step: {queries, certified by the 8-bit pass, by the fp16 pass, exact scan}
     mstats = []                                       # per timed step: {certified, fallback, candidates per query, DB splits} of its MATCH pass
 
     def timed(step_fn, steps, warmup, collect_kernel=False):
@@ -458,6 +473,7 @@ def run_ours(args, rank, world, local_rank):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         kms, n_obj, n_match = [], 0, 0
         mstats.clear()
+        mtiers.clear()
         l0 = ctx.launches
         for i in range(steps):
             if flush is not None:
@@ -470,6 +486,7 @@ def run_ours(args, rank, world, local_rank):
             if collect_kernel:
                 kms.append(ctx.coarse_kernel_ms())
                 mstats.append(ctx.match_last_stats())        # the step has completed (its results are on the host): no extra wait
+                mtiers.append(ctx.match_tier_stats())
         launches = ctx.launches - l0
         if world > 1:
             dist.barrier()
@@ -491,12 +508,15 @@ def run_ours(args, rank, world, local_rank):
             pipe_run(1, i, False)
             kms.append(ctx.coarse_kernel_ms())
             mstats.append(ctx.match_last_stats())
+            mtiers.append(ctx.match_tier_stats())
         match_stats = np.array(mstats, np.int64)
     else:
         total_ms, kms, launches, n_obj, n_match = timed(step_dev, args.steps, args.warmup, collect_kernel=True)
         clocks = sampler.stop()
         match_stats = np.array(mstats, np.int64) if mstats else np.zeros((1, 4), np.int64)
+        tier_rows = list(mtiers)                      # (the e2e leg below reuses the lists)
         e2e_ms, _, _, n_obj_e, _ = timed(step_e2e, args.steps, args.warmup)
+        mtiers[:] = tier_rows
 
     # outside the timed region: device time of MATCH vs CLUSTER..FILTER2 for one batch, and the latency of a single frame
     ms_batch = np.zeros(2, np.float32)
@@ -515,7 +535,13 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peak_tf, peak_gbs, peak_src = measured_peaks()
         peak_sus = measured_sustained_tflops()
-        traffic = measured_traffic("k_match_coarse", db_descriptors=args.objects * args.pts, features_per_frame=Q, frames_per_step=B, n_gpus=world)
+        i8 = args.coarse_kind == 1
+        kname = "k_match_coarse<1> (tcgen05 kind::i8)" if i8 else "k_match_coarse<0> (tcgen05 kind::f16)"
+        traffic = measured_traffic("k_match_coarse_i8" if i8 else "k_match_coarse_f16", db_descriptors=args.objects * args.pts, features_per_frame=Q,
+                                   frames_per_step=B, n_gpus=world)
+        if i8:      # no measured 8-bit figure in MEASURED_PEAKS.json: the 8-bit kinds run at twice the 16-bit MMA rate (4.5 vs 2.25 PF nominal)
+            peak_16, peak_tf, peak_sus = peak_tf, 2.0 * peak_tf, (2.0 * peak_sus if peak_sus else None)
+        tiers = np.array(mtiers, np.int64) if mtiers else np.zeros((1, 4), np.int64)
         ms_step = total_ms / args.steps
         fps = B * 1e3 / ms_step
         k_ms = float(np.mean(kms)) if kms else None
@@ -524,7 +550,8 @@ def run_ours(args, rank, world, local_rank):
         achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
         out = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f16 tensor-core coarse pass + f32 exact re-rank/LM", "data": "synthetic",
+               "dtype": ("u8/s8 tensor-core coarse pass (exact int32 accumulation), f16 second-chance pass, f32 exact re-rank/LM" if i8 else
+                         "f16 tensor-core coarse pass + f32 exact re-rank/LM"), "data": "synthetic",
                "config": workload_config(args, world),
                "objects_per_frame": n_obj / (args.steps * B),
                "matches_per_s": n_match / (total_ms * 1e-3),
@@ -534,19 +561,24 @@ def run_ours(args, rank, world, local_rank):
                "match_queries": int(match_stats[:, :2].sum()), "match_certified": int(match_stats[:, 0].sum()),
                "match_fallback": int(match_stats[:, 1].sum()), "match_candidates_per_query": int(match_stats[0, 2]),
                "match_db_splits": int(match_stats[0, 3]),
+               # the cascade by tier (timed steps): certified by the 8-bit pass / by the fp16 pass / sent to the exhaustive scan
+               "match_tiers": {"queries": int(tiers[:, 0].sum()), "certified_8bit": int(tiers[:, 1].sum()), "certified_fp16": int(tiers[:, 2].sum()),
+                               "exact_scan": int(tiers[:, 3].sum())},
                "batch_ms": None if world > 1 else {"match": float(ms_batch[0]), "cluster_to_filter2": float(ms_batch[1])},
                "single_frame": None if world > 1 else {"latency_ms": lat_ms, "stage_ms": {k: float(v) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], ms_stage)}},
                "gpu_launches": int(launches),
                "clocks": clocks,
-               "e2e": {"value": B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(QT * (128 + 2 + 1) * 4),
+               "e2e": {"value": B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(QT * (128 + 2 + 1) * 4),   # summed over the ranks
                        "d2h_bytes_per_step": int(B * (16 + 36 * MO))},
-               "roofline": {"kernel": "k_match_coarse", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+               "roofline": {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                             "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic["bytes"] if traffic else None,
                             "traffic_source": traffic["source"] if traffic else None,
-                            "peak_source": f"{peak_src} (MEASURED_PEAKS.json bf16_tflops, burst)", "kernel_ms": k_ms,
+                            "peak_source": (f"2 x {peak_src} MEASURED_PEAKS.json bf16_tflops (burst): 8-bit operand kinds issue at twice the 16-bit MMA rate; "
+                                            "integer multiply-adds counted as 2 ops like flops") if i8 else f"{peak_src} (MEASURED_PEAKS.json bf16_tflops, burst)",
+                            "kernel_ms": k_ms, "frac_of_bf16_peak": (achieved / peak_16) if (i8 and achieved) else None,
                             "peak_sustained": peak_sus, "frac_of_sustained": (achieved / peak_sus) if achieved and peak_sus else None,
                             "algorithmic_flops_per_launch": flops,
-                            "algorithmic_bytes_per_launch": int((r1 - r0 + 127) // 128 * 32768 + QT * 256)}}
+                            "algorithmic_bytes_per_launch": int((r1 - r0 + 127) // 128 * (16384 if i8 else 32768) + QT * (128 if i8 else 256))}}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref
@@ -1071,6 +1103,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=32, help="concurrent frames after MATCH (mc_set_tuning)")
     ap.add_argument("--pose-warps", type=int, default=4, help="first-round hypotheses per RANSAC task (mc_set_tuning)")
     ap.add_argument("--chunks", type=int, default=1, help="MATCH launches per batch (mc_set_tuning)")
+    ap.add_argument("--coarse-kind", type=int, default=1, choices=[0, 1], help="1 = 8-bit integer coarse pass first (default), 0 = fp16 coarse pass only; same results")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent matching kernel leaves free for concurrent stage kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=0,
                     help="frames workload: 1 = MATCH of step i+1 overlaps CLUSTER..FILTER2 of step i (two contexts, two streams); 0 = one call per step")

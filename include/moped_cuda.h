@@ -361,6 +361,14 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
  *   "ransac_fused"         != 0: mc_pose_ransac / the frame pipeline use the single one-CTA-per-task RANSAC kernel
  *                          instead of the staged kernels (same results; kept for A/B measurements)
  *   "defer_lane_join"      != 0: see mc_join_lanes (default 0)
+ *   "match_coarse_kind"    1 (default): MC_MATCH_TENSOR runs the 8-bit integer coarse pass (tcgen05 kind::i8, twice the fp16 MMA
+ *                          rate) first and the fp16 pass only for the queries whose certificate it fails; 0: fp16 pass for all
+ *                          queries. Same results bit for bit (both end in the exact re-rank and, failing the certificate, in the
+ *                          exhaustive scan).
+ *   "match_stagger"        != 0 (default): the CTAs that scan the same database split at the same time start at different tiles
+ *                          (kept as a switch for A/B measurements; results do not depend on it)
+ *   "match_reserve_sms"    0..64 (default 0): the persistent coarse matching kernel runs on (SMs - this many) CTAs, so that
+ *                          concurrent work (the frame lanes' stage kernels of an earlier chunk or step) finds free SMs
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
  *                          MATCH instead of ~40 kernel launches (same kernels, same results)
  *   "sift_two_pass"        != 0: mc_sift_extract* blur with the separate row / column kernels instead of the fused
@@ -380,6 +388,10 @@ mc_status mc_profile_read(mc_ctx *ctx, float *coarse_kernel_ms);
  * stream): stats = {#queries certified by the coarse pass, #queries sent to the exhaustive fallback scan, #coarse candidates
  * per query, #DB splits}; certified + fallback == the queries of that pass. Exact-mode passes report {0, Q, 0, 0}. */
 mc_status mc_match_last_stats(mc_ctx *ctx, int32_t *stats);
+/* The same pass by tier of the matching cascade: tiers = {#queries, #certified by the 8-bit integer coarse pass, #certified by
+ * the fp16 coarse pass, #sent to the exhaustive exact scan}; the last three add up to the first. Every tier returns the exact
+ * scan's bits. */
+mc_status mc_match_tier_stats(mc_ctx *ctx, int32_t *tiers);
 /* same for feature extraction: summed device time of the five octave-0 Gaussian+DoG launches (the dominant kernel of
  * mc_sift_extract*) of the last extraction, and their algorithmic bytes (1 plane read + 2 planes written per launch) */
 mc_status mc_sift_profile_read(mc_ctx *ctx, float *blur_ms, double *algorithmic_bytes);

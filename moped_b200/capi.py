@@ -110,6 +110,7 @@ SIGNATURES = {
     "mc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mc_match_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mc_match_tier_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mc_match_merge_packed_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_join_lanes": (C.c_int, [C.c_void_p]),
     "mc_adaptive_model_init": (None, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
@@ -203,6 +204,12 @@ class Context:
         """{certified, fallback, candidates per query, DB splits} of the last matching pass on this context."""
         st = np.zeros(4, np.int32)
         self._check(self.L.mc_match_last_stats(self.h, st.ctypes.data), "mc_match_last_stats")
+        return st
+
+    def match_tier_stats(self):
+        """{queries, certified by the 8-bit pass, certified by the fp16 pass, exhaustive exact scan} of the last matching pass."""
+        st = np.zeros(4, np.int32)
+        self._check(self.L.mc_match_tier_stats(self.h, st.ctypes.data), "mc_match_tier_stats")
         return st
 
     # ---- database / cameras

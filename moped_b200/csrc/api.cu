@@ -102,8 +102,8 @@ mc_status mc_create(mc_ctx **out, int device) {
 }
 
 static void free_db(mc_ctx *ctx) {
-	cudaFree(ctx->d_db); cudaFree(ctx->d_db_img); cudaFree(ctx->d_xyz); cudaFree(ctx->d_model_of_row);
-	ctx->d_db = nullptr; ctx->d_db_img = nullptr; ctx->d_xyz = nullptr; ctx->d_model_of_row = nullptr;
+	cudaFree(ctx->d_db); cudaFree(ctx->d_db_img); cudaFree(ctx->d_db_img8); cudaFree(ctx->d_xyz); cudaFree(ctx->d_model_of_row);
+	ctx->d_db = nullptr; ctx->d_db_img = nullptr; ctx->d_db_img8 = nullptr; ctx->d_xyz = nullptr; ctx->d_model_of_row = nullptr;
 	ctx->n_rows = 0; ctx->n_tiles = 0;
 }
 
@@ -134,7 +134,8 @@ void mc_destroy(mc_ctx *ctx) {
 
 static void free_scratch(mc_ctx *ctx) {
 	DevBuf *named[] = { &ctx->q_desc, &ctx->q_img, &ctx->q_norm2, &ctx->tau, &ctx->cand_score, &ctx->cand_row, &ctx->flag_list, &ctx->flag_count,
-	                    &ctx->nn_key, &ctx->nn_row, &ctx->nn_dist, &ctx->accepted, &ctx->q_xy, &ctx->q_image };
+	                    &ctx->nn_key, &ctx->nn_row, &ctx->nn_dist, &ctx->accepted, &ctx->q_xy, &ctx->q_image,
+	                    &ctx->q_img8, &ctx->q_signed, &ctx->q_scale, &ctx->q_err, &ctx->flag_list2, &ctx->tau2, &ctx->cand_score2, &ctx->cand_row2 };
 	for (DevBuf *b : named) cudaFree(b->p);
 	for (DevBuf &b : ctx->scratch) cudaFree(b.p);
 	cudaFree(ctx->batch_out.p);
@@ -181,6 +182,9 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
 	else if (k == "defer_lane_join") ctx->defer_lane_join = value != 0;
+	else if (k == "match_coarse_kind") { if (value != 0 && value != 1) { ctx->err = "mc_set_option: match_coarse_kind must be 0 (fp16) or 1 (8-bit first)"; return MC_ERR_ARG; } ctx->coarse_kind = (int)value; }
+	else if (k == "match_stagger") ctx->match_stagger = value != 0;
+	else if (k == "match_reserve_sms") { if (value < 0 || value > 64) { ctx->err = "mc_set_option: match_reserve_sms must be in 0..64"; return MC_ERR_ARG; } ctx->match_reserve_sms = (int)value; }
 	else if (k == "lm_finite_check") ctx->lm_finite_check = value != 0;
 	else if (k == "pose_exact_order") ctx->pose_exact_order = value != 0;
 	else if (k == "linkage_cached") ctx->linkage_cached = value != 0;
@@ -213,11 +217,27 @@ mc_status mc_match_last_stats(mc_ctx *ctx, int32_t *stats) {
 	MC_CUDA(cudaSetDevice(ctx->device));
 	int32_t n_flag = 0;
 	if (ctx->last_match_tensor && ctx->flag_count.p) {
-		MC_CUDA(cudaMemcpyAsync(&n_flag, ctx->flag_count.p, sizeof n_flag, cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaMemcpyAsync(&n_flag, (const int32_t *)ctx->flag_count.p + 1, sizeof n_flag, cudaMemcpyDeviceToHost, ctx->stream));
 		MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	}
 	if (ctx->last_match_tensor) { stats[0] = ctx->last_match_q - n_flag; stats[1] = n_flag; stats[2] = ctx->last_stats[2]; stats[3] = ctx->last_stats[3]; }
 	else { stats[0] = 0; stats[1] = ctx->last_match_q; stats[2] = 0; stats[3] = 0; }
+	return MC_OK;
+}
+mc_status mc_match_tier_stats(mc_ctx *ctx, int32_t *tiers) {
+	if (!ctx || !tiers) return MC_ERR_ARG;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int32_t n[2] = { 0, 0 };
+	if (ctx->last_match_tensor && ctx->flag_count.p) {
+		MC_CUDA(cudaMemcpyAsync(n, ctx->flag_count.p, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	const bool i8 = ctx->last_match_tensor && ctx->coarse_kind == 1 && ctx->db_scale > 0.f;
+	tiers[0] = ctx->last_match_q;
+	tiers[1] = !ctx->last_match_tensor ? 0 : i8 ? ctx->last_match_q - n[0] : 0;         // certified by the 8-bit pass
+	tiers[3] = ctx->last_match_tensor ? n[1] : ctx->last_match_q;                          // exhaustive exact scan
+	tiers[2] = ctx->last_match_q - tiers[1] - tiers[3];                                    // certified by the fp16 pass
+	if (i8 && tiers[1] < 0) tiers[1] = 0;
 	return MC_OK;
 }
 int64_t mc_db_rows(const mc_ctx *ctx) { return ctx ? ctx->n_rows : 0; }
@@ -302,7 +322,7 @@ mc_status mc_match(mc_ctx *ctx, const float *q_desc, int Q, float ratio, int mod
 	MC_TRY(d2h(ctx, accepted, (const uint8_t *)ctx->accepted.p, (size_t)Q));
 	int32_t n_flag = 0;
 	const bool tensor = ctx->last_match_tensor != 0;         // descriptor lengths other than 128 take the exact scan whatever `mode` says
-	if (stats && tensor) MC_TRY(d2h(ctx, &n_flag, (const int32_t *)ctx->flag_count.p, 1));
+	if (stats && tensor) MC_TRY(d2h(ctx, &n_flag, (const int32_t *)ctx->flag_count.p + 1, 1));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	if (stats) {
 		if (tensor) { stats[0] = Q - n_flag; stats[1] = n_flag; stats[2] = ctx->last_stats[2]; stats[3] = ctx->last_stats[3]; }

@@ -19,7 +19,8 @@ constexpr int kMTile = 256;             // queries per CTA (two 128-row halves)
 #ifndef MC_TOPK
 #define MC_TOPK 4
 #endif
-constexpr int kTopK = MC_TOPK;          // coarse candidates kept per (query, DB split)
+constexpr int kTopK = MC_TOPK;          // coarse candidates kept per (query, DB split) by the fp16 pass
+constexpr int kTopK8 = 8;               // ... by the 8-bit pass (its certificate charges a ~12x larger score error)
 constexpr int kMaxSplits = 64;
 
 struct Camera {            // FrameData::images[i]: K=(fx,fy,cx,cy), TM = 3x4 of cameraPose (moped.hpp:226-241)
@@ -57,6 +58,10 @@ struct mc_ctx {
 	int D = 0, n_models = 0;
 	float *d_db = nullptr;            // n_rows x D fp32, row-major (exact re-rank / exact scan)
 	__half *d_db_img = nullptr;       // n_tiles x 32 KiB pre-swizzled fp16 operand tiles (tcgen05 B operand)
+	uint8_t *d_db_img8 = nullptr;     // n_tiles x 16 KiB pre-swizzled u8 / s8 operand tiles, one scale for all rows
+	float db_scale = 0.f;             // 8-bit image: q8 = round(db_scale * x); 0 = no usable image (empty / non-finite database)
+	bool db_signed = false;           // 8-bit image holds s8 (some element is negative) instead of u8
+	float db_err_max = 0.f;           // max over rows of |x - q8 / db_scale|_2
 	float *d_xyz = nullptr;           // table_rows x 3 (coord3D of rows table_base .. table_base+table_rows)
 	int32_t *d_model_of_row = nullptr;
 	int64_t table_base = 0, table_rows = 0;   // = this shard's rows unless mc_db_set_global_tables was called
@@ -68,6 +73,10 @@ struct mc_ctx {
 
 	// scratch
 	mc::DevBuf q_desc, q_img, q_norm2, tau, cand_score, cand_row, flag_list, flag_count, nn_key;
+	mc::DevBuf q_img8, q_signed, q_scale, q_err, flag_list2, tau2, cand_score2, cand_row2;   // 8-bit pass + fp16 second-chance pass
+	int coarse_kind = 1;              // mc_set_option "match_coarse_kind": 1 = 8-bit pass first (default), 0 = fp16 pass only
+	int match_stagger = 1;            // mc_set_option "match_stagger": CTAs of one DB split start at different tiles
+	int match_reserve_sms = 0;        // mc_set_option "match_reserve_sms": SMs the persistent matching kernel leaves to concurrent work
 	mc::DevBuf nn_row, nn_dist, accepted, q_xy, q_image;
 	mc::DevBuf scratch[24];
 	void *h_pinned = nullptr; size_t h_pinned_cap = 0;

@@ -7,13 +7,24 @@ pytestmark = pytest.mark.gpu
 
 
 def _check(ctx, capi, oracle, dbn, qn, ratio=0.8, modes=None):
+    """every mode — the cascade that starts with the 8-bit integer coarse pass (the default), the fp16 coarse pass alone, the
+    exhaustive scan — returns the oracle's rows, distances and accepted set bit for bit"""
     oidx, odist = oracle.match_2nn(dbn, qn)
     acc_o = (odist[:, 0] / odist[:, 1] < np.float32(ratio)) & (oidx[:, 1] >= 0)
     for mode in modes or (capi.MATCH_TENSOR, capi.MATCH_EXACT):
-        r, d, a, st = ctx.match(qn, ratio, mode)
-        assert np.array_equal(r, oidx), f"mode {mode}: rows differ at {np.nonzero((r != oidx).any(1))[0][:5]}"
-        assert np.array_equal(d, odist), f"mode {mode}: distances differ"
-        assert np.array_equal(a, acc_o)
+        for kind in ((1, 0) if mode == capi.MATCH_TENSOR else (1,)):
+            ctx.set_option("match_coarse_kind", kind)
+            try:
+                r, d, a, st = ctx.match(qn, ratio, mode)
+                tiers = ctx.match_tier_stats()
+            finally:
+                ctx.set_option("match_coarse_kind", 1)
+            assert np.array_equal(r, oidx), f"mode {mode} kind {kind}: rows differ at {np.nonzero((r != oidx).any(1))[0][:5]}"
+            assert np.array_equal(d, odist), f"mode {mode} kind {kind}: distances differ"
+            assert np.array_equal(a, acc_o)
+            assert tiers[0] == len(qn) and tiers[1] + tiers[2] + tiers[3] == len(qn), tiers
+            if mode == capi.MATCH_TENSOR and ctx.D == 128:
+                assert st[1] == tiers[3] and (kind == 1 or tiers[1] == 0), (st, tiers)
     return st
 
 
@@ -72,6 +83,35 @@ def test_signed_descriptors(gpu_ctx, oracle_mod):
     qn = oracle_mod.norm_rows((dbn[rng.integers(0, 3000, 200)] + rng.normal(0, 0.02, size=(200, 128))).astype(np.float32))
     gpu_ctx.db_upload(dbn, np.zeros((3000, 3), np.float32), np.zeros(3000, np.int32), 1)
     _check(gpu_ctx, capi, oracle_mod, dbn, qn)
+
+
+def test_awkward_value_ranges_for_the_8_bit_pass(gpu_ctx, oracle_mod):
+    """What the 8-bit quantisation has to get right or hand to the next tier: query tiles of mixed signedness (128 non-negative
+    queries next to 128 signed ones: u8 and s8 A operands in one launch), an all-zero query, queries of very different norms
+    (the scale is per query), a database row with one huge element (it sets the database-wide scale, everything else quantises
+    coarsely and the certificate has to refuse), un-normalised rows."""
+    from moped_b200 import capi, synth
+    rng = np.random.default_rng(31)
+    db = synth.sift_like(rng, 5000)
+    db[17] *= 3.0
+    qpos = synth.sift_like(rng, 128)
+    qneg = oracle_mod.norm_rows(rng.normal(size=(128, 128)).astype(np.float32))
+    qmix = np.concatenate([qpos, qneg, 40.0 * synth.sift_like(rng, 60), 1e-3 * synth.sift_like(rng, 60), np.zeros((1, 128), np.float32),
+                           db[rng.integers(0, 5000, 100)] + rng.normal(0, 0.01, size=(100, 128)).astype(np.float32)]).astype(np.float32)
+    gpu_ctx.db_upload(db, np.zeros((5000, 3), np.float32), np.zeros(5000, np.int32), 1)
+    _check(gpu_ctx, capi, oracle_mod, db, qmix)
+    spiky = db.copy()
+    spiky[100, 5] = 50.0                               # one outlier element: database-wide scale 255 / 50
+    gpu_ctx.db_upload(spiky, np.zeros((5000, 3), np.float32), np.zeros(5000, np.int32), 1)
+    _check(gpu_ctx, capi, oracle_mod, spiky, qmix[:300])
+    tiers = gpu_ctx.match_tier_stats()                 # (exact mode ran last)
+    gpu_ctx.set_option("match_coarse_kind", 1)
+    gpu_ctx.match(qmix[:300], 0.8, capi.MATCH_TENSOR)
+    tiers = gpu_ctx.match_tier_stats()
+    assert tiers[1] < 300                              # the 8-bit pass could not certify everything here; the fp16 pass picked it up
+    signed_db = oracle_mod.norm_rows(rng.normal(size=(3000, 128)).astype(np.float32))
+    gpu_ctx.db_upload(signed_db, np.zeros((3000, 3), np.float32), np.zeros(3000, np.int32), 1)
+    _check(gpu_ctx, capi, oracle_mod, signed_db, qmix)
 
 
 def test_row_base_offsets_global_ids(gpu_ctx, oracle_mod):
@@ -187,6 +227,8 @@ def test_metric_configuration_1m_rows(oracle_mod):
         torch.cuda.synchronize()
         ctx.match_dev(d_q.data_ptr(), QT, 0.8, capi.MATCH_TENSOR, row.data_ptr(), dist.data_ptr(), acc.data_ptr())
         st = ctx.match_last_stats()
+        tiers = ctx.match_tier_stats()
+        assert tiers[0] == QT and tiers[1] + tiers[2] + tiers[3] == QT and tiers[3] == st[1], (tiers, st)
         ctx.synchronize()
         return row, dist, acc, st
 
@@ -194,6 +236,11 @@ def test_metric_configuration_1m_rows(oracle_mod):
     try:
         ctx.db_upload(dbn, db["xyz"], db["model_of_row"], 1000)
         row, dist, acc, st = run(ctx)
+        tiers = ctx.match_tier_stats()
+        assert tiers[1] >= 0.98 * QT, f"the 8-bit pass certified only {tiers[1]} of {QT} queries"
+        ctx.set_option("match_coarse_kind", 0)         # the fp16 pass alone: the same bits for all 128 000 queries
+        row0, dist0, acc0, st0 = run(ctx)
+        assert torch.equal(row0, row) and torch.equal(dist0, dist) and torch.equal(acc0, acc)
     finally:
         ctx.close()
     assert st[0] + st[1] == QT and st[2] >= 32, st
