@@ -235,8 +235,23 @@ def workload_config(args, world):
             "parallelism": f"db-sharded-by-object x{world}, frames after MATCH partitioned x{world}" if world > 1 else "single-gpu",
             "l2": "db tile image > 2x L2, not flushed" if img_bytes >= 2 * L2_BYTES else "L2 flushed between steps (256 MiB write)",
             "pose_mode": args.pose_mode, "match_coarse_kind": args.coarse_kind, "match_reserve_sms": args.reserve_sms, "batches_pool": 2, "frame_lanes": args.lanes, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
-            "pipeline": ("MATCH of step i+1 (mc_match_dev) overlaps CLUSTER..FILTER2 of step i (mc_process_frames_matched_dev) on a second "
-                         "context/stream; every step completes inside the timed region" if args.pipeline else "one mc_process_frames* call per step")}
+            "pipeline": (f"software-pipelined on one context: MATCH of step i+1 (mc_match_dev, coarse kernel on the MATCH partition) runs beside "
+                         f"CLUSTER..FILTER2 of step i (mc_process_frames_matched_dev with deferred lane join, lanes on a {args.stage_sms}-SM stage "
+                         "partition, CUDA green contexts); every step completes inside the timed region" if args.pipeline else "one mc_process_frames* call per step")}
+
+
+def resolve_auto(args, world):
+    """--pipeline / --stage-sms -1 = by frames per GPU: with few frames per GPU the stage chain is a ~2 ms latency chain that hides
+    completely beside the next step's MATCH on a 16-SM partition; with many (64 on one GPU) it is throughput-bound on so few SMs
+    and the partition costs MATCH more than it hides (measured: scripts/gpu_overlap_probe.py, profiles/overlap_r2.md)."""
+    per_gpu = args.frames // max(1, world)
+    if args.pipeline < 0:
+        args.pipeline = 1 if per_gpu <= 16 else 0
+    if args.stage_sms < 0:
+        args.stage_sms = 16 if args.pipeline else 0
+    if args.pipeline and args.stage_sms and args.lanes > 16:
+        args.lanes = 16            # lane streams + the MATCH streams must stay below the 32 hardware connections (no false dependencies)
+    return args
 
 
 # ------------------------------------------------------------------------------------------------
@@ -255,6 +270,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    log(f"[bench] rank {rank}/{world} on cuda:{local_rank}: pipeline={args.pipeline} stage_sms={args.stage_sms} lanes={args.lanes}")
     B, Q = args.frames, args.features
     if B % world:
         raise SystemExit(f"bench.py: --frames {B} must be a multiple of the number of GPUs ({world})")
@@ -330,26 +346,21 @@ def run_ours(args, rank, world, local_rank):
         return int(info[:, 0].sum()), int(info[:, 2].sum())
 
     # ---- pipelined stream of batches (--pipeline 1) --------------------------------------------------------------------
-    # A second context (own stream, own scratch and lanes; it holds the coord3D / model tables of the whole database but
-    # never matches) runs CLUSTER..FILTER2 of step i while the first context already matches step i+1. Same C-ABI calls and
-    # the same results as the one-call-per-step path; buffers that cross the two streams are double buffered and the host
-    # stays one step behind the device. With N > 1 the result all-gather has its own communicator so that it does not queue
-    # behind the next step's (row, distance) all-gathers.
+    # ONE context, software-pipelined: MATCH of step i+1 (the context's stream; its coarse kernel on the MATCH partition of the
+    # GPU) runs beside CLUSTER..FILTER2 of step i (the frame lanes, on the stage partition: mc_set_option "stage_sm_partition").
+    # mc_process_frames_matched_dev returns without joining the lanes ("defer_lane_join"); the join, the all-gather of the
+    # results and their read-back are enqueued AFTER the next step's MATCH. Same C-ABI calls and the same results as the
+    # one-call-per-step path; buffers are triple-buffered and the host stays two steps behind the device. Every step completes
+    # inside the timed region.
     if args.pipeline:
-        ctx_s = capi.Context(local_rank)
-        stream2 = torch.cuda.Stream()
-        ctx_s.set_stream(stream2.cuda_stream)
-        ctx_s.db_upload(dbn[:256], db["xyz"][:256], db["model_of_row"][:256], args.objects, row_base=0)      # placeholder rows: this context never matches
-        ctx_s.db_set_global_tables(db["xyz"], db["model_of_row"], args.objects)
-        ctx_s.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
-        ctx_s.set_tuning(args.lanes, args.pose_warps, 1)
-        if args.pose_mode == "exact":
-            ctx_s.set_option("pose_exact_order", 1)
-        pg_res = dist.new_group(backend="nccl") if world > 1 else None
+        if args.stage_sms:
+            ctx.set_option("stage_sm_partition", args.stage_sms)
+        ctx.set_option("defer_lane_join", 1)
+        sms_match, sms_stage = ctx.sm_partition()
         pf_lo, pf_hi = frame_range(B, world, rank)
         pBl = pf_hi - pf_lo
         pblk = ResultBlock(pBl, MO)
-        P = 2
+        P = 3
         p_q = [torch.empty((QT, 128), dtype=torch.float32, device=dev) for _ in range(P)]
         p_xy = [torch.empty((QT, 2), dtype=torch.float32, device=dev) for _ in range(P)]
         p_img = [torch.empty((QT,), dtype=torch.int32, device=dev) for _ in range(P)]
@@ -361,47 +372,50 @@ def run_ours(args, rank, world, local_rank):
         p_res = [torch.zeros((pblk.words,), dtype=torch.int32, device=dev) for _ in range(P)]
         p_resall = [torch.zeros((world, pblk.words), dtype=torch.int32, device=dev) for _ in range(P)]
         p_reshost = [torch.zeros((world, pblk.words), dtype=torch.int32).pin_memory() for _ in range(P)]
-        ev_match = [torch.cuda.Event() for _ in range(P)]
         ev_done = [torch.cuda.Event() for _ in range(P)]
 
-        def pipe_enqueue(i, e2e):
+        def pipe_match(i, e2e):
             k, b = i % n_pool, i % P
-            with torch.cuda.stream(stream):
-                if flush is not None:
-                    flush.zero_()
-                if e2e and world == 1:                    # host buffers in: the step's features go up inside the timed region
-                    p_q[b].copy_(h_q[k], non_blocking=True)
-                    p_xy[b].copy_(h_xy[k], non_blocking=True)
-                    p_img[b].copy_(h_img[k], non_blocking=True)
-                    q, xy, img = p_q[b], p_xy[b], p_img[b]
-                elif e2e:                                 # N > 1: 1/N of the descriptors per rank + NVLink all-gather; coordinates of its own frames
-                    ql, qh = rank * (QT // world), (rank + 1) * (QT // world)
-                    p_q[b][ql:qh].copy_(h_q[k][ql:qh], non_blocking=True)
-                    dist.all_gather_into_tensor(p_q[b], p_q[b][ql:qh])
-                    p_xy[b][fo[pf_lo]:fo[pf_hi]].copy_(h_xy[k][fo[pf_lo]:fo[pf_hi]], non_blocking=True)
-                    p_img[b][fo[pf_lo]:fo[pf_hi]].copy_(h_img[k][fo[pf_lo]:fo[pf_hi]], non_blocking=True)
-                    q, xy, img = p_q[b], p_xy[b], p_img[b]
-                else:
-                    q, xy, img = d_q[k], d_xy[k], d_img[k]
-                if world > 1:
-                    ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, p_blk[b].data_ptr(), p_blk[b].data_ptr() + 8 * QT, p_acc[b].data_ptr())
-                    dist.all_gather_into_tensor(p_all[b], p_blk[b])
-                    ctx.match_merge_packed_dev(p_all[b].data_ptr(), world, QT, params.match_ratio, p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
-                else:
-                    ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
-                ev_match[b].record(stream)
-            with torch.cuda.stream(stream2):
-                stream2.wait_event(ev_match[b])
-                r = p_res[b]
-                ctx_s.process_frames_matched_dev(p_row[b].data_ptr(), p_acc[b].data_ptr(), xy.data_ptr(), img.data_ptr(), fo, pf_lo, pf_hi, params, MO,
-                                                 r.data_ptr() + 4 * pblk.o_info, r.data_ptr() + 4 * pblk.o_model,
-                                                 r.data_ptr() + 4 * pblk.o_pose, r.data_ptr() + 4 * pblk.o_score)
-                if world > 1:
-                    dist.all_gather_into_tensor(p_resall[b], r, group=pg_res)
-                    p_reshost[b].copy_(p_resall[b], non_blocking=True)
-                else:
-                    p_reshost[b][0].copy_(r, non_blocking=True)
-                ev_done[b].record(stream2)
+            if flush is not None:
+                flush.zero_()
+            if e2e and world == 1:                    # host buffers in: the step's features go up inside the timed region
+                p_q[b].copy_(h_q[k], non_blocking=True)
+                p_xy[b].copy_(h_xy[k], non_blocking=True)
+                p_img[b].copy_(h_img[k], non_blocking=True)
+                q = p_q[b]
+            elif e2e:                                 # N > 1: 1/N of the descriptors per rank + NVLink all-gather; coordinates of its own frames
+                ql, qh = rank * (QT // world), (rank + 1) * (QT // world)
+                p_q[b][ql:qh].copy_(h_q[k][ql:qh], non_blocking=True)
+                dist.all_gather_into_tensor(p_q[b], p_q[b][ql:qh])
+                p_xy[b][fo[pf_lo]:fo[pf_hi]].copy_(h_xy[k][fo[pf_lo]:fo[pf_hi]], non_blocking=True)
+                p_img[b][fo[pf_lo]:fo[pf_hi]].copy_(h_img[k][fo[pf_lo]:fo[pf_hi]], non_blocking=True)
+                q = p_q[b]
+            else:
+                q = d_q[k]
+            if world > 1:
+                ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, p_blk[b].data_ptr(), p_blk[b].data_ptr() + 8 * QT, p_acc[b].data_ptr())
+                dist.all_gather_into_tensor(p_all[b], p_blk[b])
+                ctx.match_merge_packed_dev(p_all[b].data_ptr(), world, QT, params.match_ratio, p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
+            else:
+                ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, p_row[b].data_ptr(), p_dist[b].data_ptr(), p_acc[b].data_ptr())
+
+        def pipe_stages(i, e2e):
+            k, b = i % n_pool, i % P
+            xy, img = (p_xy[b], p_img[b]) if e2e else (d_xy[k], d_img[k])
+            r = p_res[b]
+            ctx.process_frames_matched_dev(p_row[b].data_ptr(), p_acc[b].data_ptr(), xy.data_ptr(), img.data_ptr(), fo, pf_lo, pf_hi, params, MO,
+                                           r.data_ptr() + 4 * pblk.o_info, r.data_ptr() + 4 * pblk.o_model,
+                                           r.data_ptr() + 4 * pblk.o_pose, r.data_ptr() + 4 * pblk.o_score)
+
+        def pipe_finish(i):
+            b = i % P
+            ctx.join_lanes()                              # the stream now waits for the lanes of step i
+            if world > 1:
+                dist.all_gather_into_tensor(p_resall[b], p_res[b])
+                p_reshost[b].copy_(p_resall[b], non_blocking=True)
+            else:
+                p_reshost[b][0].copy_(p_res[b], non_blocking=True)
+            ev_done[b].record(stream)
 
         def pipe_collect(i):
             b = i % P
@@ -410,14 +424,19 @@ def run_ours(args, rank, world, local_rank):
             return int(info[:, 0].sum()), int(info[:, 2].sum())
 
         def pipe_run(n, first, e2e):
+            """steps first .. first+n-1, all complete (results on the host) on return"""
             n_obj = n_match = 0
             for j in range(n):
-                if j >= P:
-                    no, nm = pipe_collect(first + j - P)
+                pipe_match(first + j, e2e)
+                if j >= 1:
+                    pipe_finish(first + j - 1)            # behind MATCH of step j on the stream: the lanes of step j-1 ran beside it
+                pipe_stages(first + j, e2e)
+                if j >= 2:
+                    no, nm = pipe_collect(first + j - 2)
                     n_obj += no
                     n_match += nm
-                pipe_enqueue(first + j, e2e)
-            for j in range(max(0, n - P), n):
+            pipe_finish(first + n - 1)
+            for j in range(max(0, n - 2), n):
                 no, nm = pipe_collect(first + j)
                 n_obj += no
                 n_match += nm
@@ -429,17 +448,17 @@ def run_ours(args, rank, world, local_rank):
                 dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            l0 = ctx.launches + ctx_s.launches
+            l0 = ctx.launches
             e0.record(stream)
             n_obj, n_match = pipe_run(steps, warmup, e2e)
-            e1.record(stream2)                            # the last step's read-back is the last thing enqueued on stream2
+            e1.record(stream)                             # the last step's read-back is the last thing on the stream
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item()), ctx.launches + ctx_s.launches - l0, n_obj, n_match
+            return float(t.item()), ctx.launches - l0, n_obj, n_match
 
     def step_dev(i):
         k = i % n_pool
@@ -497,6 +516,8 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), kms, launches, n_obj, n_match
 
+    if rank == 0:
+        log("[bench] setup done, timing")
     sampler = ClockSampler(local_rank)
     sampler.start()
     if args.pipeline:
@@ -510,6 +531,7 @@ def run_ours(args, rank, world, local_rank):
             mstats.append(ctx.match_last_stats())
             mtiers.append(ctx.match_tier_stats())
         match_stats = np.array(mstats, np.int64)
+        ctx.set_option("defer_lane_join", 0)
     else:
         total_ms, kms, launches, n_obj, n_match = timed(step_dev, args.steps, args.warmup, collect_kernel=True)
         clocks = sampler.stop()
@@ -533,6 +555,7 @@ def run_ours(args, rank, world, local_rank):
         ctx.set_tuning(0, args.pose_warps, 0)
 
     if rank == 0:
+        log(f"[bench] timed: {total_ms / args.steps:.3f} ms/step")
         peak_tf, peak_gbs, peak_src = measured_peaks()
         peak_sus = measured_sustained_tflops()
         i8 = args.coarse_kind == 1
@@ -567,6 +590,7 @@ def run_ours(args, rank, world, local_rank):
                "batch_ms": None if world > 1 else {"match": float(ms_batch[0]), "cluster_to_filter2": float(ms_batch[1])},
                "single_frame": None if world > 1 else {"latency_ms": lat_ms, "stage_ms": {k: float(v) for k, v in zip(["match", "cluster", "pose", "filter", "pose2", "filter2"], ms_stage)}},
                "gpu_launches": int(launches),
+               "sm_partition": {"match_sms": sms_match, "stage_sms": sms_stage} if args.pipeline else None,
                "clocks": clocks,
                "e2e": {"value": B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(QT * (128 + 2 + 1) * 4),   # summed over the ranks
                        "d2h_bytes_per_step": int(B * (16 + 36 * MO))},
@@ -1106,8 +1130,11 @@ def main():
     ap.add_argument("--coarse-kind", type=int, default=1, choices=[0, 1], help="1 = 8-bit integer coarse pass first (default), 0 = fp16 coarse pass only; same results")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent matching kernel leaves free for concurrent stage kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=0,
-                    help="frames workload: 1 = MATCH of step i+1 overlaps CLUSTER..FILTER2 of step i (two contexts, two streams); 0 = one call per step")
+    ap.add_argument("--stage-sms", type=int, default=-1,
+                    help="--pipeline: SMs of the stage partition (CUDA green contexts; multiple of 8, 0 = no partition, -1 = pick by frames per GPU)")
+    ap.add_argument("--pipeline", type=int, default=-1,
+                    help="frames workload: 1 = MATCH of step i+1 runs beside CLUSTER..FILTER2 of step i (one context, SM partition); 0 = one call per step; "
+                         "-1 = by frames per GPU")
     ap.add_argument("--workload", default="frames", choices=["frames", "ransac", "sift", "images"],
                     help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s; "
                          "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1; images = pixels in, objects out on real data")
@@ -1121,6 +1148,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    resolve_auto(args, world)
     if args.workload == "ransac":
         if args.impl == "reference":
             run_ransac_reference(args, rank, world)

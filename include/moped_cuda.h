@@ -367,6 +367,11 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
  *                          exhaustive scan).
  *   "match_stagger"        != 0 (default): the CTAs that scan the same database split at the same time start at different tiles
  *                          (kept as a switch for A/B measurements; results do not depend on it)
+ *   "stage_sm_partition"   0 (default) or a multiple of 8 up to 96: partition the GPU with CUDA green contexts — this many SMs for the
+ *                          streams of the frame lanes (the stages after MATCH), the rest for the stream the persistent coarse matching
+ *                          kernel runs on — so that MATCH of one batch or chunk really runs beside the stages of the previous one
+ *                          (without it a stage CTA on an SM keeps a whole matching CTA out). Existing lanes are recreated.
+ *                          mc_sm_partition reports the SM counts the driver granted.
  *   "match_reserve_sms"    0..64 (default 0): the persistent coarse matching kernel runs on (SMs - this many) CTAs, so that
  *                          concurrent work (the frame lanes' stage kernels of an earlier chunk or step) finds free SMs
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
@@ -392,6 +397,8 @@ mc_status mc_match_last_stats(mc_ctx *ctx, int32_t *stats);
  * the fp16 coarse pass, #sent to the exhaustive exact scan}; the last three add up to the first. Every tier returns the exact
  * scan's bits. */
 mc_status mc_match_tier_stats(mc_ctx *ctx, int32_t *tiers);
+/* sms = {SMs (persistent CTAs) of the coarse matching kernel, SMs of the stage partition (0 = the GPU is not partitioned)} */
+mc_status mc_sm_partition(mc_ctx *ctx, int32_t *sms);
 /* same for feature extraction: summed device time of the five octave-0 Gaussian+DoG launches (the dominant kernel of
  * mc_sift_extract*) of the last extraction, and their algorithmic bytes (1 plane read + 2 planes written per launch) */
 mc_status mc_sift_profile_read(mc_ctx *ctx, float *blur_ms, double *algorithmic_bytes);

@@ -111,6 +111,7 @@ SIGNATURES = {
     "mc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mc_match_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mc_match_tier_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mc_sm_partition": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mc_match_merge_packed_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_join_lanes": (C.c_int, [C.c_void_p]),
     "mc_adaptive_model_init": (None, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
@@ -211,6 +212,12 @@ class Context:
         st = np.zeros(4, np.int32)
         self._check(self.L.mc_match_tier_stats(self.h, st.ctypes.data), "mc_match_tier_stats")
         return st
+
+    def sm_partition(self):
+        """(SMs of the coarse matching kernel, SMs of the stage partition or 0)"""
+        st = np.zeros(2, np.int32)
+        self._check(self.L.mc_sm_partition(self.h, st.ctypes.data), "mc_sm_partition")
+        return int(st[0]), int(st[1])
 
     # ---- database / cameras
     def db_upload(self, desc, xyz, model_of_row, n_models, row_base=0):

@@ -109,10 +109,7 @@ static void free_db(mc_ctx *ctx) {
 
 static void free_scratch(mc_ctx *ctx);
 
-void mc_destroy(mc_ctx *ctx) {
-	if (!ctx) return;
-	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
+static void destroy_lanes(mc_ctx *ctx) {
 	for (mc_ctx *lane : ctx->lanes) {          // lanes borrow the database and cameras: free only what they own
 		cudaStreamSynchronize(lane->stream);
 		free_scratch(lane);
@@ -121,6 +118,15 @@ void mc_destroy(mc_ctx *ctx) {
 		delete lane;
 	}
 	ctx->lanes.clear();
+	ctx->lanes_pending = 0;
+}
+
+void mc_destroy(mc_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	destroy_lanes(ctx);
+	sm_partition_destroy(ctx);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
 	for (cudaEvent_t e : ctx->ev_chunk) cudaEventDestroy(e);
 	if (ctx->ev_coarse[0]) { cudaEventDestroy(ctx->ev_coarse[0]); cudaEventDestroy(ctx->ev_coarse[1]); }
@@ -184,6 +190,13 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "defer_lane_join") ctx->defer_lane_join = value != 0;
 	else if (k == "match_coarse_kind") { if (value != 0 && value != 1) { ctx->err = "mc_set_option: match_coarse_kind must be 0 (fp16) or 1 (8-bit first)"; return MC_ERR_ARG; } ctx->coarse_kind = (int)value; }
 	else if (k == "match_stagger") ctx->match_stagger = value != 0;
+	else if (k == "stage_sm_partition") {
+		if (value < 0 || value > 96 || value % 8) { ctx->err = "mc_set_option: stage_sm_partition must be 0 or a multiple of 8 up to 96"; return MC_ERR_ARG; }
+		MC_CUDA(cudaSetDevice(ctx->device));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+		destroy_lanes(ctx);                        // their streams belong to the old partition
+		return sm_partition_create(ctx, (int)value);
+	}
 	else if (k == "match_reserve_sms") { if (value < 0 || value > 64) { ctx->err = "mc_set_option: match_reserve_sms must be in 0..64"; return MC_ERR_ARG; } ctx->match_reserve_sms = (int)value; }
 	else if (k == "lm_finite_check") ctx->lm_finite_check = value != 0;
 	else if (k == "pose_exact_order") ctx->pose_exact_order = value != 0;
@@ -238,6 +251,12 @@ mc_status mc_match_tier_stats(mc_ctx *ctx, int32_t *tiers) {
 	tiers[3] = ctx->last_match_tensor ? n[1] : ctx->last_match_q;                          // exhaustive exact scan
 	tiers[2] = ctx->last_match_q - tiers[1] - tiers[3];                                    // certified by the fp16 pass
 	if (i8 && tiers[1] < 0) tiers[1] = 0;
+	return MC_OK;
+}
+mc_status mc_sm_partition(mc_ctx *ctx, int32_t *sms) {
+	if (!ctx || !sms) return MC_ERR_ARG;
+	sms[0] = ctx->match_sms ? ctx->match_sms : ctx->num_sms - ctx->match_reserve_sms;
+	sms[1] = ctx->stage_sms;
 	return MC_OK;
 }
 int64_t mc_db_rows(const mc_ctx *ctx) { return ctx ? ctx->n_rows : 0; }

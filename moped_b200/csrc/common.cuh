@@ -75,6 +75,11 @@ struct mc_ctx {
 	mc::DevBuf q_desc, q_img, q_norm2, tau, cand_score, cand_row, flag_list, flag_count, nn_key;
 	mc::DevBuf q_img8, q_signed, q_scale, q_err, flag_list2, tau2, cand_score2, cand_row2;   // 8-bit pass + fp16 second-chance pass
 	int coarse_kind = 1;              // mc_set_option "match_coarse_kind": 1 = 8-bit pass first (default), 0 = fp16 pass only
+	// spatial partition (sm_partition.cu, mc_set_option "stage_sm_partition"): green contexts, the stream the coarse kernel runs on
+	void *green_match = nullptr, *green_stage = nullptr;
+	cudaStream_t match_green_stream = nullptr;
+	cudaEvent_t ev_green[2] = {nullptr, nullptr};
+	int match_sms = 0, stage_sms = 0; // SMs of the two partitions (0 = no partition)
 	int match_stagger = 1;            // mc_set_option "match_stagger": CTAs of one DB split start at different tiles
 	int match_reserve_sms = 0;        // mc_set_option "match_reserve_sms": SMs the persistent matching kernel leaves to concurrent work
 	mc::DevBuf nn_row, nn_dist, accepted, q_xy, q_image;
@@ -167,6 +172,9 @@ inline mc_status pinned(mc_ctx *ctx, size_t bytes) {
 mc_status db_build_images(mc_ctx *ctx);
 mc_status match_configure_device(mc_ctx *ctx);
 mc_status cluster_configure_device(mc_ctx *ctx);
+mc_status sm_partition_create(mc_ctx *ctx, int stage_sms);
+void sm_partition_destroy(mc_ctx *ctx);
+mc_status sm_partition_stage_stream(mc_ctx *ctx, cudaStream_t *out, int priority);
 void sift_free(mc_ctx *ctx);
 mc_status sift_set_two_pass(mc_ctx *ctx, int on);
 mc_status sift_set_gather(mc_ctx *ctx, int on);

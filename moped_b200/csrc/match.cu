@@ -366,13 +366,16 @@ struct CoarseArgs {
 	const uint8_t *a_signed;       // KIND 1: signedness of every 128-query half tile (k_pack_tiles_q8)
 	uint32_t b_signed;             // KIND 1: signedness of the database image
 	int stagger;                   // CTAs of one split start at different tiles (see k_match_coarse)
+	uint32_t *item_counter;        // zeroed before the launch: next work item (dynamic assignment)
 	uint32_t *g_tau;               // per query: best published k-th score over all work items (encoded, 0 = none)
 	uint32_t *cand_score;          // [query][split][column group][k] raw accumulator bits (float / int32)
 	int32_t *cand_row;             // [query][split][column group][k] shard-local row, -1 = empty
 };
 
-// A CTA is persistent: it walks the work items blockIdx.x, blockIdx.x + gridDim.x, ... (item = query tile + live tiles x DB
-// split, so that the CTAs running at the same time stream the same DB split out of L2). Per item it keeps the 256 queries'
+// A CTA is persistent: its TMA thread takes the next work item from a global counter and hands the number to the other warps
+// through a two-slot ring in shared memory (item = query tile + live tiles x DB split, handed out in order, so that the CTAs
+// running at the same time stream the same DB split out of L2). Dynamic, because the kernel shares the GPU: a CTA that gets its
+// SM late — stage kernels of an earlier batch still hold it — simply takes fewer items instead of delaying the whole launch. Per item it keeps the 256 queries'
 // image resident in shared memory (A, double-buffered for the 8-bit kind) and streams the split's DB tile images through a
 // ring (B) with one elected TMA thread; one elected MMA thread issues the MMAs of a DB tile, 128 queries (a "half") at a
 // time, into one of two TMEM accumulator stages; the 8 epilogue warps (4 per half, warp%4 = TMEM lane quarter) read their
@@ -400,7 +403,7 @@ k_match_coarse(const CoarseArgs a) {
 	int n_mt = a.n_mtiles;
 	if (a.q_count) { const int live = (*a.q_count + kMTile - 1) / kMTile; n_mt = live < n_mt ? live : n_mt; }
 	const int n_items = n_mt * a.n_splits;
-	if ((int)blockIdx.x >= n_items) return;
+	if (n_items <= 0) return;
 
 	// barrier block (8 B each): full[8], empty[8], a_full[2], a_empty[2], tfull[2] (+2 unused), tempty[2][2], then the TMEM base slot
 	const uint32_t bar0 = smem_base + kSmemBar;
@@ -411,10 +414,14 @@ k_match_coarse(const CoarseArgs a) {
 	auto bar_tfull = [&](int s) { return bar0 + 8u * (20 + s); };
 	auto bar_tempty = [&](int s, int h) { return bar0 + 8u * (24 + 2 * s + h); };
 	volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_gen + kSmemBar + 8 * 28);
+	auto bar_ifull = [&](int s) { return bar0 + 8u * (22 + s); };
+	auto bar_iempty = [&](int s) { return bar0 + 8u * (29 + s); };
+	volatile int32_t *item_ring = reinterpret_cast<volatile int32_t *>(smem_gen + kSmemBar + 8 * 31);   // two slots
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < C::kStages; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
 		for (int s = 0; s < 2; s++) { mbar_init(bar_afull(s), 1); mbar_init(bar_aempty(s), MC_MMA_THREADS); }
+		for (int s = 0; s < 2; s++) { mbar_init(bar_ifull(s), 1); mbar_init(bar_iempty(s), MC_MMA_THREADS + 8 * kCG); }
 		for (int s = 0; s < 2; s++) {
 			mbar_init(bar_tfull(s), 1);
 			for (int h = 0; h < 2; h++) mbar_init(bar_tempty(s, h), 4 * kCG);
@@ -435,12 +442,28 @@ k_match_coarse(const CoarseArgs a) {
 		first = a.stagger ? (int)((int64_t)ntiles * blockIdx.x / gridDim.x) : 0;
 	};
 	auto tile_at = [](int i, int first, int ntiles) { const int t = i + first; return t >= ntiles ? t - ntiles : t; };
+	// consumers of the item ring: the it-th item of this CTA, or -1 when the counter has run out
+	auto next_item = [&](uint32_t it, bool whole_warp) {      // whole_warp: called by all 32 lanes (epilogue) / by one thread (MMA issuer)
+		const uint32_t sl = it & 1;
+		mbar_wait(bar_ifull(sl), (it >> 1) & 1);
+		const int item = item_ring[sl];
+		if (whole_warp) __syncwarp();
+		if (lane == 0) mbar_arrive(bar_iempty(sl));
+		return item;
+	};
 
 	if (warp == 0) {
 		// ===== TMA producer =====
 		if (lane == 0) {
-			uint32_t it = 0, tc = 0;
-			for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+			uint32_t tc = 0;
+			for (uint32_t it = 0;; it++) {
+				const uint32_t sl = it & 1;
+				mbar_wait(bar_iempty(sl), ((it >> 1) & 1) ^ 1);
+				int item = (int)atomicAdd(a.item_counter, 1u);
+				if (item >= n_items) item = -1;
+				item_ring[sl] = item;
+				mbar_arrive(bar_ifull(sl));            // release: the consumers' wait acquires the slot
+				if (item < 0) break;
 				int mtile, split, ntiles, first; int64_t t0;
 				item_range(item, mtile, split, t0, ntiles, first);
 				const uint32_t ab = it % C::kABuf;
@@ -467,8 +490,10 @@ k_match_coarse(const CoarseArgs a) {
 		// an epilogue thread once it has seen this commit, and a second issuer fills the gap of the first.
 		const int p = warp == 3 ? 1 : 0;
 		if (lane == 0) {
-			uint32_t it = 0, tc = 0;
-			for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+			uint32_t tc = 0;
+			for (uint32_t it = 0;; it++) {
+				const int item = next_item(it, false);
+				if (item < 0) break;
 				int mtile, split, ntiles, first; int64_t t0;
 				item_range(item, mtile, split, t0, ntiles, first);
 				const uint32_t ab = it % C::kABuf;
@@ -519,7 +544,9 @@ k_match_coarse(const CoarseArgs a) {
 		uint32_t (&ua)[32] = reinterpret_cast<uint32_t (&)[32]>(ra);
 		uint32_t (&ub)[32] = reinterpret_cast<uint32_t (&)[32]>(rb);
 		constexpr int kCols = 128 / kCG;                   // accumulator columns (DB rows of a tile) per thread
-		for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+		for (uint32_t it = 0;; it++) {
+			const int item = next_item(it, true);
+			if (item < 0) break;
 			int mtile, split, ntiles, first; int64_t t0;
 			item_range(item, mtile, split, t0, ntiles, first);
 			const int qid = mtile * kMTile + half * 128 + quarter * 32 + lane;
@@ -1074,8 +1101,21 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 		const bool i8 = ctx->coarse_kind == 1 && ctx->db_scale > 0.f;
 		const int n_mtiles = (Q + kMTile - 1) / kMTile;
 		const int q_pad = n_mtiles * kMTile;
-		int ctas = ctx->num_sms - ctx->match_reserve_sms;
+		// persistent CTAs: the SMs of the MATCH partition when the GPU is partitioned (the coarse kernel is then launched on that
+		// partition's stream), otherwise all SMs minus match_reserve_sms
+		int ctas = ctx->match_green_stream ? ctx->match_sms : ctx->num_sms - ctx->match_reserve_sms;
 		if (ctas < 8) ctas = 8;
+		cudaStream_t cs = ctx->match_green_stream ? ctx->match_green_stream : ctx->stream;
+		auto fork = [&]() -> cudaError_t {
+			if (!ctx->match_green_stream) return cudaSuccess;
+			cudaError_t e = cudaEventRecord(ctx->ev_green[0], ctx->stream);
+			return e != cudaSuccess ? e : cudaStreamWaitEvent(cs, ctx->ev_green[0], 0);
+		};
+		auto join = [&]() -> cudaError_t {
+			if (!ctx->match_green_stream) return cudaSuccess;
+			cudaError_t e = cudaEventRecord(ctx->ev_green[1], cs);
+			return e != cudaSuccess ? e : cudaStreamWaitEvent(ctx->stream, ctx->ev_green[1], 0);
+		};
 		int n_splits, tiles_per_split;
 		choose_splits(ctx, n_mtiles, ctas, n_splits, tiles_per_split);
 		const int k1 = (i8 ? CoarseKind<1>::kK : CoarseKind<0>::kK) * kCG;     // candidates per (query, split)
@@ -1087,7 +1127,7 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 		MC_TRY(reserve(ctx, ctx->flag_list, sizeof(int32_t) * q_pad));          // exact-scan list
 		MC_TRY(reserve(ctx, ctx->flag_count, 256));                             // [0] uncertified by the 8-bit pass, [1] exact-scan list length
 		MC_CUDA(cudaMemsetAsync(ctx->tau.p, 0, sizeof(uint32_t) * q_pad, ctx->stream));
-		MC_CUDA(cudaMemsetAsync(ctx->flag_count.p, 0, 2 * sizeof(int32_t), ctx->stream));
+		MC_CUDA(cudaMemsetAsync(ctx->flag_count.p, 0, 4 * sizeof(int32_t), ctx->stream));   // + [2], [3]: work-item counters of the two coarse launches
 		int32_t *d_counts = (int32_t *)ctx->flag_count.p;
 		RerankArgs r;
 		r.q = d_q; r.Q = Q; r.list = nullptr; r.list_count = nullptr; r.list_cap = 0;
@@ -1110,13 +1150,15 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 			MC_LAUNCH_CHECK();
 			c.q_img = (const uint8_t *)ctx->q_img8.p; c.db_img = ctx->d_db_img8;
 			c.tiles_per_split = tiles_per_split; c.n_splits = n_splits; c.n_mtiles = n_mtiles; c.q_count = nullptr;
-			c.a_signed = (const uint8_t *)ctx->q_signed.p; c.stagger = ctx->match_stagger;
+			c.a_signed = (const uint8_t *)ctx->q_signed.p; c.stagger = ctx->match_stagger; c.item_counter = (uint32_t *)d_counts + 2;
 			c.g_tau = (uint32_t *)ctx->tau.p; c.cand_score = (uint32_t *)ctx->cand_score.p; c.cand_row = (int32_t *)ctx->cand_row.p;
 			const int grid = (int64_t)n_mtiles * n_splits < ctas ? n_mtiles * n_splits : ctas;
-			if (ctx->profile) MC_CUDA(cudaEventRecord(ctx->ev_coarse[0], ctx->stream));
-			k_match_coarse<1><<<grid, kCoarseThreads, kCoarseSmemBytes, ctx->stream>>>(c);
+			MC_CUDA(fork());
+			if (ctx->profile) MC_CUDA(cudaEventRecord(ctx->ev_coarse[0], cs));
+			k_match_coarse<1><<<grid, kCoarseThreads, kCoarseSmemBytes, cs>>>(c);
 			MC_LAUNCH_CHECK();
-			if (ctx->profile) { MC_CUDA(cudaEventRecord(ctx->ev_coarse[1], ctx->stream)); ctx->ev_valid = true; }
+			if (ctx->profile) { MC_CUDA(cudaEventRecord(ctx->ev_coarse[1], cs)); ctx->ev_valid = true; }
+			MC_CUDA(join());
 			r.kind = 1; r.q_scale = (const float *)ctx->q_scale.p; r.q_err = (const float *)ctx->q_err.p;
 			r.cand_score = (const uint32_t *)ctx->cand_score.p; r.cand_row = (const int32_t *)ctx->cand_row.p; r.n_cand = n_cand;
 			r.g_tau = (const uint32_t *)ctx->tau.p;
@@ -1144,13 +1186,15 @@ mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mo
 			                                                                      i8 ? (const int32_t *)ctx->flag_list2.p : nullptr, i8 ? d_counts : nullptr);
 			MC_LAUNCH_CHECK();
 			c.q_img = (const uint8_t *)ctx->q_img.p; c.db_img = (const uint8_t *)ctx->d_db_img;
-			c.tiles_per_split = tps2; c.n_splits = sp2; c.n_mtiles = m2; c.q_count = i8 ? d_counts : nullptr; c.a_signed = nullptr; c.stagger = ctx->match_stagger;
+			c.tiles_per_split = tps2; c.n_splits = sp2; c.n_mtiles = m2; c.q_count = i8 ? d_counts : nullptr; c.a_signed = nullptr; c.stagger = ctx->match_stagger; c.item_counter = (uint32_t *)d_counts + 3;
 			c.g_tau = (uint32_t *)tau2.p; c.cand_score = (uint32_t *)cs2.p; c.cand_row = (int32_t *)cr2.p;
 			const int grid = (int64_t)m2 * sp2 < ctas ? m2 * sp2 : ctas;
-			if (!i8 && ctx->profile) MC_CUDA(cudaEventRecord(ctx->ev_coarse[0], ctx->stream));
-			k_match_coarse<0><<<grid, kCoarseThreads, kCoarseSmemBytes, ctx->stream>>>(c);
+			MC_CUDA(fork());
+			if (!i8 && ctx->profile) MC_CUDA(cudaEventRecord(ctx->ev_coarse[0], cs));
+			k_match_coarse<0><<<grid, kCoarseThreads, kCoarseSmemBytes, cs>>>(c);
 			MC_LAUNCH_CHECK();
-			if (!i8 && ctx->profile) { MC_CUDA(cudaEventRecord(ctx->ev_coarse[1], ctx->stream)); ctx->ev_valid = true; }
+			if (!i8 && ctx->profile) { MC_CUDA(cudaEventRecord(ctx->ev_coarse[1], cs)); ctx->ev_valid = true; }
+			MC_CUDA(join());
 			r.kind = 0; r.q_scale = nullptr; r.q_err = nullptr;
 			r.list = i8 ? (const int32_t *)ctx->flag_list2.p : nullptr; r.list_count = i8 ? d_counts : nullptr; r.list_cap = cap2;
 			r.cand_score = (const uint32_t *)cs2.p; r.cand_row = (const int32_t *)cr2.p; r.n_cand = n_cand2; r.g_tau = (const uint32_t *)tau2.p;

@@ -417,8 +417,10 @@ static mc_status ensure_lanes(mc_ctx *ctx, int n) {
 		// latency-bound stage kernels of the lanes get the SM slots that free up first
 		int prio_least = 0, prio_greatest = 0;
 		cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-		if (cudaStreamCreateWithPriority(&lane->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-		    cudaEventCreateWithFlags(&lane->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+		bool ok;
+		if (ctx->green_stage) ok = sm_partition_stage_stream(ctx, &lane->stream, prio_greatest) == MC_OK;   // confined to the stage partition's SMs
+		else ok = cudaStreamCreateWithPriority(&lane->stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+		if (!ok || cudaEventCreateWithFlags(&lane->ev_done, cudaEventDisableTiming) != cudaSuccess) {
 			delete lane;
 			ctx->err = "process_frames: cannot create a lane stream";
 			return MC_ERR_CUDA;
