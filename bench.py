@@ -259,6 +259,7 @@ def resolve_auto(args, world):
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # the frame lanes are concurrent streams
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's banner ("NCCL version ...") must not land on stdout beside the JSON line
     import torch
     import torch.distributed as dist
     from moped_b200 import capi

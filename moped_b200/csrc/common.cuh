@@ -20,7 +20,10 @@ constexpr int kMTile = 256;             // queries per CTA (two 128-row halves)
 #define MC_TOPK 4
 #endif
 constexpr int kTopK = MC_TOPK;          // coarse candidates kept per (query, DB split) by the fp16 pass
-constexpr int kTopK8 = 8;               // ... by the 8-bit pass (its certificate charges a ~12x larger score error)
+#ifndef MC_TOPK8
+#define MC_TOPK8 8
+#endif
+constexpr int kTopK8 = MC_TOPK8;               // ... by the 8-bit pass (its certificate charges a ~12x larger score error)
 constexpr int kMaxSplits = 64;
 
 struct Camera {            // FrameData::images[i]: K=(fx,fy,cx,cy), TM = 3x4 of cameraPose (moped.hpp:226-241)

@@ -1060,19 +1060,22 @@ static mc_status exact_scan(mc_ctx *ctx, const float *d_q, int Q, const int32_t 
 	return MC_OK;
 }
 
-// DB splits for n_mtiles query tiles on `ctas` persistent CTAs. Work item = (query tile, DB split), all items equally long.
-// Few query tiles (one frame): one item per CTA, floor(ctas / tiles) splits. Many query tiles (frame batches): every CTA
-// walks several items; keep at least 8 splits so that every query has enough coarse candidates for the certificate, and
-// among 8..64 splits take the count that wastes the least of the last round.
+// DB splits for n_mtiles query tiles on `ctas` persistent CTAs. Work item = (query tile, DB split), all items equally long,
+// handed out dynamically. Few query tiles (one frame): one item per CTA, floor(ctas / tiles) splits. Many query tiles (frame
+// batches): keep at least 8 splits so that every query has enough candidate lists for the certificate, and take the SMALLEST
+// count in 8..16 whose last round is at least 97 % full (every split of a query starts one more list, i.e. costs insertions
+// and candidates; a search for the best-filled last round up to 64 splits once picked 31 splits for 124 CTAs and made the
+// pass 50 % slower).
 static void choose_splits(const mc_ctx *ctx, int n_mtiles, int ctas, int &n_splits, int &tiles_per_split) {
 	n_splits = ctas / n_mtiles;
 	if (n_splits < 8) {
 		double best = -1.0;
-		for (int sp = 8; sp <= kMaxSplits; sp++) {
+		for (int sp = 8; sp <= 16; sp++) {
 			const int64_t items = (int64_t)n_mtiles * sp;
 			const int64_t rounds = (items + ctas - 1) / ctas;
 			const double eff = (double)items / (double)(rounds * ctas);
-			if (eff > best + 0.01) { best = eff; n_splits = sp; }
+			if (eff > best) { best = eff; n_splits = sp; }
+			if (eff >= 0.97) { n_splits = sp; break; }
 		}
 	}
 	if (n_splits < 1) n_splits = 1;
@@ -1082,7 +1085,7 @@ static void choose_splits(const mc_ctx *ctx, int n_mtiles, int ctas, int &n_spli
 	n_splits = (int)((ctx->n_tiles + tiles_per_split - 1) / tiles_per_split);
 }
 
-constexpr int kSecondChanceCap = 4096;      // queries the fp16 second-chance pass of the cascade takes (16 query tiles); more go to the exact scan
+constexpr int kSecondChanceCap = 16384;     // queries the fp16 second-chance pass of the cascade takes (64 query tiles); more go to the exact scan
 
 mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mode, int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted) {
 	if (!ctx->d_db) { ctx->err = "mc_match: no database uploaded"; return MC_ERR_STATE; }

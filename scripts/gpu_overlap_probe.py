@@ -10,7 +10,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from moped_b200 import capi, synth  # noqa: E402
 
-B, Q, OBJ = int(os.environ.get("PROBE_FRAMES", 64)), 2000, 1000
+B, Q, OBJ = int(os.environ.get("PROBE_FRAMES", 64)), 2000, int(os.environ.get("PROBE_OBJECTS", 1000))
+SB = int(os.environ.get("PROBE_STAGE_FRAMES", B))      # frames whose stages run here (a rank of an N-GPU job matches all B frames, runs B/N)
 
 
 def nrm(x):
@@ -59,7 +60,7 @@ def match(r, d, a):
 
 
 def stages():
-    cs.process_frames_matched_dev(row.data_ptr(), acc.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, 0, B, params, MO,
+    cs.process_frames_matched_dev(row.data_ptr(), acc.data_ptr(), xy.data_ptr(), img.data_ptr(), fo, 0, SB, params, MO,
                                   o_info.data_ptr(), o_model.data_ptr(), o_pose.data_ptr(), o_score.data_ptr())
 
 
@@ -118,5 +119,5 @@ for part, graphs in [(int(x.split(":")[0]), int(x.split(":")[1])) for x in os.en
     m = timed(lambda: match(row2, dist2, acc2), None)
     s = timed(None, stages)
     both = timed(lambda: match(row2, dist2, acc2), stages)
-    print(json.dumps({"frames": B, "stage_sm_partition": part, "frame_graphs": graphs, "sms": sms, "same_objects": same, "match_alone_ms": m[0], "stages_alone_ms": s[1], "together_match_ms": both[0],
+    print(json.dumps({"frames": B, "stage_frames": SB, "db_objects": OBJ, "stage_sm_partition": part, "frame_graphs": graphs, "sms": sms, "same_objects": same, "match_alone_ms": m[0], "stages_alone_ms": s[1], "together_match_ms": both[0],
                       "together_stages_ms": both[1], "objects": int(o_info[:, 0].sum().item())}), flush=True)
