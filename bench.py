@@ -803,6 +803,134 @@ def run_ransac_ours(args, rank, world, local_rank):
 
 
 # ------------------------------------------------------------------------------------------------
+# --workload depthpose / linkage: moped3d's stages through their host-buffer C-ABI entries, one GPU
+# ------------------------------------------------------------------------------------------------
+DEPTH_PARAMS = (192, 100, 4, 5, 6, 8.0)     # moped3d POSE (config.hpp:46): MaxRANSACTests, MaxLMTests, MaxObjectsPerCluster, NPtsAlign, MinNPtsObject, ErrorThreshold
+DEPTH_ALPHA = 0.5
+
+
+def moped3d_config(args):
+    if args.workload == "depthpose":
+        return {"workload": f"moped3d POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH: {args.clusters} clusters x {args.hyp} explicit hypotheses, 80 points/cluster, "
+                            "50% outliers, sample fit (order-preserving LM, itmax 100) + consistency test + refit; bit-exact with the strict-IEEE reference",
+                "clusters": args.clusters, "hypotheses_per_cluster": args.hyp, "depth_team_lanes": args.depth_team, "parallelism": "single-gpu",
+                "l2": "working set (a few hundred KB) is cache resident by nature; not flushed"}
+    return {"workload": "moped3d CLUSTER_LINKAGE (average linkage, 3-D filter 2): 600 matches of one model (two instances + outliers), two 320x240 depth / "
+                        "fill-distance maps; a step = one mc_cluster_linkage call (host buffers in, clusters out)",
+            "matches": 600, "linkage_cached": 1, "parallelism": "single-gpu", "l2": "working set (1.4 MB similarity matrix + maps) is cache resident; not flushed"}
+
+
+def moped3d_inputs(args):
+    if args.workload == "depthpose":
+        cl = synth.make_depth_clusters(args.clusters, 80, 0.5)
+        hy = synth.make_hypotheses(dict(offsets=cl["offsets"]), args.hyp, 5)
+        return cl, hy
+    return synth.make_linkage_scene(1), None
+
+
+def moped3d_reference_rate(args, cl, hy, seconds):
+    """the reference's own class (oracle/_ref, its -ffast-math flags) on ONE host core for `seconds`: units per second"""
+    from oracle import ref3d
+    t0 = time.perf_counter()
+    n = 0
+    if args.workload == "depthpose":
+        per = [dict(xy=cl["xy"][a:b], xyz=cl["xyz"][a:b], world=cl["world"][a:b], fill=cl["fill"][a:b]) for a, b in zip(cl["offsets"][:-1], cl["offsets"][1:])]
+        while time.perf_counter() - t0 < seconds:
+            h = n % len(hy["hyp_cluster"])
+            ref3d.hypothesis(per[hy["hyp_cluster"][h]], synth.K_DEPTH, synth.CAM_IDENTITY, DEPTH_ALPHA, hy["sample_pos"][h], hy["init_quat"][h],
+                             DEPTH_PARAMS[1], DEPTH_PARAMS[5], DEPTH_PARAMS[4])
+            n += 1
+    else:
+        while time.perf_counter() - t0 < seconds:
+            ref3d.cluster_linkage(*cl)
+            n += 1
+    return n / (time.perf_counter() - t0)
+
+
+def run_moped3d_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import ref3d
+    unit = "hypotheses/s" if args.workload == "depthpose" else "clusterings/s"
+    if not ref3d.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmoped3d_ref.so missing and /root/reference not present to build it"}))
+        return
+    cl, hy = moped3d_inputs(args)
+    moped3d_reference_rate(args, cl, hy, 1.0)
+    v = moped3d_reference_rate(args, cl, hy, 3.0 * max(1, args.steps))
+    print(json.dumps({"impl": "reference", "metric": unit.replace("/", "_per_"), "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": moped3d_config(args),
+                      "cpu_baseline": {"value": v, "unit": unit, "cores": 1, "kind": "reference",
+                                       "sample": f"{3 * max(1, args.steps)} s of calls of the reference's own class on one host core (the class has no OpenMP)"},
+                      "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_moped3d_ours(args, rank, world, local_rank):
+    import torch
+    from moped_b200 import capi
+    if rank != 0:
+        return                                   # one GPU: the stages' host entries; N > 1 would be N replicas
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmoped_cuda has no CPU fallback")
+    ctx = capi.Context(local_rank)
+    cl, hy = moped3d_inputs(args)
+    depth = args.workload == "depthpose"
+    unit = "hypotheses/s" if depth else "clusterings/s"
+    if depth:
+        ctx.set_cameras(synth.K_DEPTH[None], synth.CAM_IDENTITY[None])
+        ctx.set_option("depth_team_lanes", args.depth_team)
+        units = len(hy["hyp_cluster"])
+        bytes_in = sum(cl[k].nbytes for k in ("offsets", "xy", "xyz", "world", "cauchy", "image")) + sum(hy[k].nbytes for k in hy)
+        bytes_out = units * (4 + 28 + 28 + 8)
+
+        def call():
+            return ctx.pose_depth_hypotheses(0, cl["offsets"], cl["xy"], cl["xyz"], cl["world"], cl["cauchy"], cl["image"], hy["hyp_cluster"],
+                                             hy["sample_pos"], hy["init_quat"], DEPTH_PARAMS, DEPTH_ALPHA, want_mask=False)
+    else:
+        ctx.set_option("linkage_cached", 1)
+        units = 1
+        bytes_in = sum(a.nbytes for a in cl)
+        bytes_out = 4 * (2 * len(cl[0]) + 3)
+
+        def call():
+            return ctx.cluster_linkage(*cl)
+    for _ in range(max(3, args.warmup)):
+        out = call()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = call()
+    sec = (time.perf_counter() - t0) / args.steps       # the entries take host buffers and return host results: the call IS the end-to-end path
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    v = units / sec
+    res = {"metric": unit.replace("/", "_per_"), "value": v, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": sec * 1e3,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": moped3d_config(args),
+           "gpu_launches": int(launches), "clocks": clocks,
+           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": int(bytes_out)},
+           "roofline": {"kernel": "k_depth_hypotheses<0>" if depth else "k_link_agglomerate_cached",
+                        "bound": "latency (dependent fp32 chains of the order-preserving LM / the serial merge sequence of the agglomeration: neither HBM nor tensor)",
+                        "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None}}
+    if depth:
+        res["accepted_fraction"] = float((out[0] > DEPTH_PARAMS[4]).mean())
+    else:
+        res["clusters"] = int(len(out[0]) - 1)
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import ref3d
+            if ref3d.available():
+                moped3d_reference_rate(args, cl, hy, 1.0)
+                res["cpu_baseline"] = {"value": moped3d_reference_rate(args, cl, hy, 10.0), "unit": unit, "cores": 1, "kind": "reference",
+                                       "sample": "10 s of calls of the reference's own class (oracle/_ref, -ffast-math) on one host core; the class has no OpenMP"}
+        except Exception as e:
+            res["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(res))
+
+
+# ------------------------------------------------------------------------------------------------
 # --workload sift: feature extraction (SURVEY.md §8f row 3), frames/s of FEAT on 640x480 frames
 # ------------------------------------------------------------------------------------------------
 def sift_config(args, world):
@@ -1136,9 +1264,10 @@ def main():
     ap.add_argument("--pipeline", type=int, default=-1,
                     help="frames workload: 1 = MATCH of step i+1 runs beside CLUSTER..FILTER2 of step i (one context, SM partition); 0 = one call per step; "
                          "-1 = by frames per GPU")
-    ap.add_argument("--workload", default="frames", choices=["frames", "ransac", "sift", "images"],
+    ap.add_argument("--workload", default="frames", choices=["frames", "ransac", "sift", "images", "depthpose", "linkage"],
                     help="frames = the BASELINE metric (default); ransac = BASELINE configs[3], hypotheses/s; "
-                         "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1; images = pixels in, objects out on real data")
+                         "sift = feature extraction (SURVEY 8f row 3), frames/s of step 1; images = pixels in, objects out on real data; "
+                         "depthpose / linkage = moped3d's depth-aware pose stage and linkage clustering (SURVEY 8f row 4)")
     ap.add_argument("--pose-mode", default="default", choices=["default", "exact"],
                     help="POSE / POSE2 arithmetic: default kernels (re-associating, fused multiply-add) or the order-preserving LM (bit-exact with "
                          "the oracle and the strict-IEEE build of the reference)")
@@ -1156,6 +1285,13 @@ def main():
         else:
             args.warmup = max(args.warmup, 3)
             run_ransac_ours(args, rank, world, local_rank)
+    elif args.workload in ("depthpose", "linkage"):
+        if args.workload == "depthpose" and args.hyp == 2048:
+            args.hyp = 256                       # 64 x 256 = 16 384 hypotheses per call
+        if args.impl == "reference":
+            run_moped3d_reference(args, rank, world)
+        else:
+            run_moped3d_ours(args, rank, world, local_rank)
     elif args.workload == "images":
         if args.impl == "reference":
             run_images_reference(args, rank, world)

@@ -162,3 +162,68 @@ def make_image(seed: int = 0, height: int = 480, width: int = 640, n_blobs: int 
         im[y0:y1, x0:x1] += a * np.exp(-(((yy[y0:y1, x0:x1] - cy) * e) ** 2 + ((xx[y0:y1, x0:x1] - cx) / e) ** 2) / (2 * s * s))
     im = np.clip(0.5 + im, 0.0, 1.0)
     return (im * 255.0 + 0.5).astype(np.uint8)
+
+
+# ---- moped3d (RGB-D) inputs: depth-aware pose stages and linkage clustering ----------------------------
+K_DEPTH = np.array([525.0, 525.0, 319.5, 239.5], dtype=np.float32)      # a Kinect-like camera
+
+
+def make_depth_clusters(n_clusters: int = 64, pts: int = 80, outlier_frac: float = 0.5, cauchy_scale: float = 0.100, seed: int = BASE_SEED):
+    """Clusters for moped3d's depth-aware pose stages: model points under a planted pose seen by the identity camera; coord2D =
+    projection + pixel noise, world3D = the camera-frame point with depth noise growing with depth^2, fill distances mostly 0
+    (measured depth) and sometimes up to 0.3 (hallucinated); cauchy = 1 / (1 + (fill / cauchy_scale)^2), the weight the stage
+    class computes per match (POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp:187-190; scale 25 for the reprojection variant).
+    Returns dict(offsets, xy, xyz, world, fill, cauchy, image, gt_pose)."""
+    rng = np.random.default_rng(seed + 32452843)
+    xy, xyz, world, cauchy, poses, fills = [], [], [], [], [], []
+    K = K_DEPTH
+    for _ in range(n_clusters):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        t = np.array([rng.uniform(-0.2, 0.2), rng.uniform(-0.15, 0.15), rng.uniform(0.6, 1.2)])
+        X = rng.uniform(-0.08, 0.08, size=(pts, 3))
+        cam3 = X @ quat_to_R(q).T + t
+        uv = np.stack([cam3[:, 0] / cam3[:, 2] * K[0] + K[2], cam3[:, 1] / cam3[:, 2] * K[1] + K[3]], 1) + rng.normal(0, 0.4, (pts, 2))
+        w = cam3 * (1 + rng.normal(0, 0.0035, (pts, 1)) * cam3[:, 2:3])
+        bad = rng.random(pts) < outlier_frac
+        uv[bad] = rng.uniform([0, 0], [640, 480], (int(bad.sum()), 2))
+        w[bad] = w[bad] + rng.normal(0, 0.2, (int(bad.sum()), 3))
+        fill = np.where(rng.random(pts) < 0.7, 0.0, rng.uniform(0, 0.3, pts)).astype(np.float32)
+        f = fill / np.float32(cauchy_scale)
+        xy.append(uv); xyz.append(X); world.append(w); cauchy.append((1.0 / (1 + f * f)).astype(np.float32)); fills.append(fill)
+        poses.append(np.concatenate([q, t]))
+    offsets = (np.arange(n_clusters + 1) * pts).astype(np.int32)
+    return dict(offsets=offsets, xy=np.concatenate(xy).astype(np.float32), xyz=np.concatenate(xyz).astype(np.float32),
+                world=np.concatenate(world).astype(np.float32), fill=np.concatenate(fills).astype(np.float32), cauchy=np.concatenate(cauchy).astype(np.float32),
+                image=np.zeros(n_clusters * pts, dtype=np.int32), gt_pose=np.stack(poses).astype(np.float32))
+
+
+def make_linkage_scene(seed: int = 1, n_per=(300, 200), n_out: int = 100, hallucinated: float = 0.2, W: int = 320, H: int = 240):
+    """Matches of ONE model seen twice (two instances at different places and depths) plus outliers, a 320x240 depth map with the
+    two instances as fronto-parallel patches over a slanted background, and its fill-distance map (0 = measured depth): the input
+    of moped3d's CLUSTER_LINKAGE_CPU::process for one model. Returns (xy, xyz, world, depth, distance)."""
+    rng = np.random.default_rng(BASE_SEED + 977 * seed)
+    K = K_DEPTH * np.float32(0.5)
+    depth = (1.6 + 0.002 * np.arange(W)[None, :] + 0.001 * np.arange(H)[:, None]).astype(np.float32)
+    dist = np.zeros((H, W), np.float32)
+    xy, xyz, world = [], [], []
+    for k, n in enumerate(n_per):
+        cx, cy = (90 + 140 * k + rng.uniform(-10, 10), 110 + rng.uniform(-20, 20))
+        z = 0.8 + 0.35 * k
+        half = 38
+        depth[int(cy) - half:int(cy) + half, int(cx) - half:int(cx) + half] = z
+        pts = rng.uniform(-0.07, 0.07, (n, 3)).astype(np.float32)
+        u = cx + pts[:, 0] * K[0] / z + rng.normal(0, 0.3, n)
+        v = cy + pts[:, 1] * K[1] / z + rng.normal(0, 0.3, n)
+        zz = z + pts[:, 2] * 0.1
+        xy.append(np.stack([u, v], 1)); xyz.append(pts)
+        world.append(np.stack([(u - K[2]) / K[0] * zz, (v - K[3]) / K[1] * zz, zz], 1))
+    ou = rng.uniform([5, 5], [W - 5, H - 5], (n_out, 2))
+    xy.append(ou); xyz.append(rng.uniform(-0.07, 0.07, (n_out, 3)))
+    oz = depth[ou[:, 1].astype(int), ou[:, 0].astype(int)]
+    world.append(np.stack([(ou[:, 0] - K[2]) / K[0] * oz, (ou[:, 1] - K[3]) / K[1] * oz, oz], 1))
+    xy, xyz, world = (np.concatenate(a).astype(np.float32) for a in (xy, xyz, world))
+    holes = rng.random((H, W)) < hallucinated
+    dist[holes] = rng.uniform(1, 40, int(holes.sum())).astype(np.float32)
+    perm = rng.permutation(len(xy))
+    return xy[perm], xyz[perm], world[perm], depth, dist
