@@ -620,9 +620,210 @@ def run_ours(args, rank, world, local_rank):
                     out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
             except Exception as e:  # the GPU numbers stand on their own
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        if world == 1 and args.other_configs and default_metric_config(args):
+            out["other_configs"] = other_config_lines()
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ours_cluster_partition(args, rank, world, local_rank):
+    """N > 1 with fewer frames than GPUs (BASELINE configs[2] as ONE sharded frame: `--frames 1 --gpus N`), or `--partition cluster`:
+    the database is sharded by object as always (every rank matches the frame's queries against its shard, one packed all-gather,
+    merge), and the stages after MATCH run on EVERY rank with the RANSAC tasks of POSE and POSE2 distributed by cluster
+    (mc_process_frame_sharded_dev: rank r runs the clusters c with c % N == r; two small in-place all-gathers of the task results).
+    north_star: "RANSAC work is distributed by cluster". Every rank ends with the frame's objects; rank 0 reads them back."""
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    import torch
+    import torch.distributed as dist
+    from moped_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmoped_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, Q = args.frames, args.features
+    QT = B * Q
+    db = synth.make_db(args.objects, args.pts)
+    n_pool = 2
+    pool = [[synth.make_frame(db, Q, n_visible=8, frame_id=p * B + i) for i in range(B)] for p in range(n_pool)]
+    dbn = host_norm_rows(db["desc"])
+    o0, o1, r0, r1 = shard_objects(db["n_pts"], world)[rank]
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.db_upload(dbn[r0:r1], db["xyz"][r0:r1], db["model_of_row"][r0:r1], args.objects, row_base=r0)
+    ctx.db_set_global_tables(db["xyz"], db["model_of_row"], args.objects)
+    ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    ctx.set_profiling(True)
+    ctx.set_tuning(args.lanes, 8, 1)                   # latency shape: 8 first-round hypotheses per task
+    ctx.set_option("match_coarse_kind", args.coarse_kind)
+    if args.pose_mode == "exact":
+        ctx.set_option("pose_exact_order", 1)
+    params = ctx.default_params()
+    MO = 64
+    h_q = [torch.from_numpy(np.concatenate([host_norm_rows(f["desc"]) for f in fr])).pin_memory() for fr in pool]
+    h_xy = [torch.from_numpy(np.concatenate([f["xy"] for f in fr])).pin_memory() for fr in pool]
+    h_img = [torch.from_numpy(np.concatenate([f["image_idx"] for f in fr])).pin_memory() for fr in pool]
+    d_q, d_xy, d_img = [t.to(dev) for t in h_q], [t.to(dev) for t in h_xy], [t.to(dev) for t in h_img]
+    e_q, e_xy, e_img = torch.empty_like(d_q[0]), torch.empty_like(d_xy[0]), torch.empty_like(d_img[0])
+    nn_blk = torch.empty((4 * QT,), dtype=torch.int32, device=dev)
+    nn_all = torch.empty((world, 4 * QT), dtype=torch.int32, device=dev)
+    nn_row = torch.empty((QT, 2), dtype=torch.int32, device=dev)
+    nn_dist = torch.empty((QT, 2), dtype=torch.float32, device=dev)
+    acc = torch.empty((QT,), dtype=torch.uint8, device=dev)
+    slot = ctx.frame_shard_slot_bytes(Q, params)
+    exch = torch.zeros((world, slot), dtype=torch.uint8, device=dev)
+    res = torch.zeros((B, 4 + MO * 9), dtype=torch.int32, device=dev)      # per frame: info[4] | model[MO] | pose[7 MO] | score[MO]
+    res_host = torch.zeros((B, 4 + MO * 9), dtype=torch.int32).pin_memory()
+    img_bytes = ((r1 - r0 + 127) // 128) * 32768
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if img_bytes < 2 * L2_BYTES else None
+    upload_q = (QT // world) * world == QT             # 1/N of the descriptors per rank + NVLink all-gather when it divides
+
+    def step(i, e2e):
+        k = i % n_pool
+        q, xy, img = d_q[k], d_xy[k], d_img[k]
+        if e2e:
+            if world > 1 and upload_q:
+                ql, qh = rank * (QT // world), (rank + 1) * (QT // world)
+                e_q[ql:qh].copy_(h_q[k][ql:qh], non_blocking=True)
+                dist.all_gather_into_tensor(e_q, e_q[ql:qh])
+            else:
+                e_q.copy_(h_q[k], non_blocking=True)
+            e_xy.copy_(h_xy[k], non_blocking=True)
+            e_img.copy_(h_img[k], non_blocking=True)
+            q, xy, img = e_q, e_xy, e_img
+        if world > 1:
+            ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, nn_blk.data_ptr(), nn_blk.data_ptr() + 8 * QT, acc.data_ptr())
+            dist.all_gather_into_tensor(nn_all, nn_blk)
+            ctx.match_merge_packed_dev(nn_all.data_ptr(), world, QT, params.match_ratio, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+        else:
+            ctx.match_dev(q.data_ptr(), QT, params.match_ratio, params.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+        for f in range(B):
+            o = res[f].data_ptr()
+            a = (nn_row.data_ptr() + 8 * f * Q, acc.data_ptr() + f * Q, xy.data_ptr() + 8 * f * Q, img.data_ptr() + 4 * f * Q, Q, params, rank, world,
+                 exch.data_ptr(), MO, o, o + 16, o + 16 + 4 * MO, o + 16 + 32 * MO)
+            for phase in range(3):
+                ctx.process_frame_sharded_dev(phase, *a)
+                if phase < 2 and world > 1:
+                    dist.all_gather_into_tensor(exch, exch[rank])
+        res_host.copy_(res, non_blocking=True)
+        stream.synchronize()
+        info = res_host[:, :4].numpy()
+        return int(info[:, 0].sum()), int(info[:, 2].sum())
+
+    def timed(e2e, steps, warmup, collect=False):
+        for i in range(warmup):
+            step(i, e2e)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        n_obj = n_match = 0
+        kms = []
+        l0 = ctx.launches
+        for i in range(steps):
+            if flush is not None:
+                flush.zero_()
+            ev[i][0].record(stream)
+            no, nm = step(warmup + i, e2e)
+            ev[i][1].record(stream)
+            n_obj += no
+            n_match += nm
+            if collect:
+                kms.append(ctx.coarse_kernel_ms())
+        launches = ctx.launches - l0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kms, launches, n_obj, n_match
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, kms, launches, n_obj, n_match = timed(False, args.steps, args.warmup, collect=True)
+    clocks = sampler.stop()
+    e2e_ms, _, _, _, _ = timed(True, args.steps, args.warmup)
+    if rank == 0:
+        peak_tf, _, peak_src = measured_peaks()
+        i8 = args.coarse_kind == 1
+        if i8:
+            peak_tf *= 2.0
+        ms_step = total_ms / args.steps
+        k_ms = float(np.mean(kms)) if kms else None
+        flops = 2.0 * QT * (r1 - r0) * 128
+        achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
+        cfg = workload_config(args, world)
+        cfg["parallelism"] = (f"db-sharded-by-object x{world}; CLUSTER / FILTER replicated, RANSAC tasks of POSE and POSE2 distributed by cluster x{world} "
+                              "(mc_process_frame_sharded_dev, two in-place all-gathers of the task results per frame)")
+        cfg["pipeline"] = "one frame after the other on the context's stream"
+        out = {"metric": METRIC, "value": B * 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "u8/s8 tensor-core coarse pass (exact int32 accumulation), f16 second-chance pass, f32 exact re-rank/LM" if i8 else
+                        "f16 tensor-core coarse pass + f32 exact re-rank/LM",
+               "data": "synthetic", "config": cfg, "frame_latency_ms": ms_step / B,
+               "objects_per_frame": n_obj / (args.steps * B), "matches_per_s": n_match / (total_ms * 1e-3),
+               "gpu_launches": int(launches), "clocks": clocks,
+               "e2e": {"value": B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(QT * 128 * 4 + world * QT * 12),
+                       "d2h_bytes_per_step": int(B * (16 + 36 * MO))},
+               "roofline": {"kernel": "k_match_coarse<1> (tcgen05 kind::i8)" if i8 else "k_match_coarse<0> (tcgen05 kind::f16)", "bound": "tensor",
+                            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                            "peak_source": f"{'2 x ' if i8 else ''}{peak_src} MEASURED_PEAKS.json bf16_tflops (burst)", "kernel_ms": k_ms,
+                            "algorithmic_flops_per_launch": flops,
+                            "note": "a single frame is a latency measurement: 2000 queries give the coarse kernel 16 query tiles, far from a full wave"}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def default_metric_config(args):
+    return (args.objects, args.pts, args.features, args.frames, args.pose_mode) == (1000, 1000, 2000, 64, "default")
+
+
+def other_config_lines():
+    """The other BASELINE.json configurations and the widened rows of SURVEY 8f as sub-results of the default line (single GPU): each is
+    this same script run as a child process with its own timed region (device timing, W >= 3 warm-up steps, clocks sampled), and the
+    child's JSON line is condensed to its headline numbers. A child that fails is reported as {"error": ...}; the main line stands."""
+    import subprocess
+    runs = {
+        "configs[1] 100 objects, one 2000-feature frame": ["--objects", "100", "--frames", "1", "--steps", "20"],
+        "configs[3] RANSAC-heavy 64 clusters x 2048 hypotheses": ["--workload", "ransac", "--steps", "5"],
+        "configs[4] 64 frames x 4000 features, 1000 objects": ["--features", "4000", "--steps", "5"],
+        "8f row 3 feature extraction, 64 frames 640x480": ["--workload", "sift", "--steps", "5"],
+        "8f row 4 moped3d depth pose stage (bit-exact LM)": ["--workload", "depthpose", "--steps", "3"],
+        "8f row 4 moped3d linkage clustering": ["--workload", "linkage", "--steps", "3"],
+    }
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "dtype")
+    res = {}
+    for name, extra in runs.items():
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--warmup", "3", "--no-cpu-baseline", "--other-configs", "0"] + extra
+        try:
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode != 0 or not lines:
+                res[name] = {"error": f"rc {r.returncode}: {(r.stderr or '').strip().splitlines()[-1:] or ''}"}
+                continue
+            d = json.loads(lines[-1])
+            e = {k: d.get(k) for k in keep}
+            e["e2e"] = (d.get("e2e") or {}).get("value")
+            e["clocks_sm_mhz"] = (d.get("clocks") or {}).get("sm_mhz")
+            e["throttle_reasons"] = (d.get("clocks") or {}).get("reasons")
+            if d.get("single_frame"):
+                e["single_frame_latency_ms"] = d["single_frame"].get("latency_ms")
+            if d.get("roofline") and d["roofline"].get("frac") is not None:
+                e["roofline"] = {k: d["roofline"].get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac")}
+            e["cmd"] = "bench.py " + " ".join(extra)
+            e["wall_s"] = round(time.perf_counter() - t0, 1)
+            res[name] = e
+        except Exception as ex:  # noqa: BLE001 - the main line stands on its own
+            res[name] = {"error": str(ex)[:200]}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -715,6 +916,7 @@ def run_ransac_ours(args, rank, world, local_rank):
     ctx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
     pp = capi.PoseParams.of(RANSAC_PARAMS)
     ctx.set_option("depth_team_lanes", args.depth_team)
+    ctx.set_option("pose_fit_stream", args.fit_stream)
     h_in = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
             (cl["offsets"], cl["xy"], cl["xyz"], cl["image"], hy["hyp_cluster"][mine], hy["sample_pos"][mine], hy["init_quat"][mine])]
     d_in = [t.to(dev) for t in h_in]
@@ -776,13 +978,13 @@ def run_ransac_ours(args, rank, world, local_rank):
         out = {"metric": "hypotheses_per_s", "value": Htot * 1e3 / ms_step, "unit": "hypotheses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": dict(ransac_config(args, world), l2="working set (a few hundred KB) is cache resident by nature; not flushed",
-                              pose_mode=args.pose_mode, depth_team_lanes=args.depth_team),
+                              pose_mode=args.pose_mode, depth_team_lanes=args.depth_team, fit_stream=args.fit_stream),
                "accepted_fraction_rank0": float((n_in > RANSAC_PARAMS[4]).mean()), "lm_failed_fraction_rank0": float((n_in < 0).mean()),
                "gpu_launches": int(launches), "clocks": clocks,
                "e2e": {"value": Htot * 1e3 / (e2e_ms / args.steps), "unit": "hypotheses/s",
                        "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_in)),
                        "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_out))},
-               "roofline": {"kernel": "k_pose_fit" if args.pose_mode == "default" else "k_depth_hypotheses<2>", "bound": "fp32-issue/divergence (latency-shaped; see profiles/ for the ncu issue-slot figures)",
+               "roofline": {"kernel": ("k_pose_fit_stream<5>" if args.fit_stream else "k_pose_fit_thread<5>") if args.pose_mode == "default" else "k_depth_hypotheses<2>", "bound": "fp32-issue/divergence (latency-shaped; see profiles/ for the ncu issue-slot figures)",
                             "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None}}
         if not args.no_cpu_baseline and world == 1:
             try:
@@ -1259,6 +1461,9 @@ def main():
     ap.add_argument("--coarse-kind", type=int, default=1, choices=[0, 1], help="1 = 8-bit integer coarse pass first (default), 0 = fp16 coarse pass only; same results")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent matching kernel leaves free for concurrent stage kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--other-configs", type=int, default=1,
+                    help="default line on one GPU: append the other BASELINE configurations (configs[1], [3], [4]) and the SURVEY 8f rows as "
+                         "sub-results, each from a child run of this script (0 = off)")
     ap.add_argument("--stage-sms", type=int, default=-1,
                     help="--pipeline: SMs of the stage partition (CUDA green contexts; multiple of 8, 0 = no partition, -1 = pick by frames per GPU)")
     ap.add_argument("--pipeline", type=int, default=-1,
@@ -1272,6 +1477,11 @@ def main():
                     help="POSE / POSE2 arithmetic: default kernels (re-associating, fused multiply-add) or the order-preserving LM (bit-exact with "
                          "the oracle and the strict-IEEE build of the reference)")
     ap.add_argument("--depth-team", type=int, default=32, choices=[8, 32], help="ransac workload, --pose-mode exact: lanes per hypothesis (same bits)")
+    ap.add_argument("--partition", default="auto", choices=["auto", "frame", "cluster"],
+                    help="frames workload, N > 1: stages after MATCH partitioned by frame (default) or, with fewer frames than GPUs / 'cluster', "
+                         "RANSAC tasks distributed by cluster on every rank (mc_process_frame_sharded_dev)")
+    ap.add_argument("--fit-stream", type=int, default=1, choices=[0, 1],
+                    help="ransac workload: 1 = persistent phase-synchronous thread-per-hypothesis kernel (default), 0 = the one-launch kernel; same results")
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--hyp", type=int, default=2048, help="hypotheses per cluster (ransac workload)")
     args = ap.parse_args()
@@ -1306,6 +1516,9 @@ def main():
             run_sift_ours(args, rank, world, local_rank)
     elif args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.partition == "cluster" or (args.partition == "auto" and world > 1 and args.frames < world):
+        args.warmup = max(args.warmup, 3)
+        run_ours_cluster_partition(args, rank, world, local_rank)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args, rank, world, local_rank)

@@ -257,6 +257,20 @@ mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, 
                                         const int32_t *q_image_dev, const int32_t *frame_offsets, int n_frames, int frame_begin, int frame_end,
                                         const mc_pipeline_params *params, int max_objects, int32_t *frame_info_dev, int32_t *obj_model_dev,
                                         float *obj_pose_dev, float *obj_score_dev);
+/* ONE frame with the RANSAC work distributed by cluster over shard_world ranks (north_star; the reference hands its (cluster, try)
+ * task list to worker threads, POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:275-282): every rank holds the merged nearest neighbours of
+ * the frame, runs compaction / CLUSTER / FILTER redundantly (identical on all ranks) and the POSE / POSE2 tasks of the clusters c
+ * with c % shard_world == shard_rank. A task's random stream depends on its index alone, so the result equals mc_process_matched_dev
+ * bit for bit for any shard_world. Three asynchronous calls per frame with the caller's exchange between them:
+ *   phase 0 -> all-gather `exchange_dev` in place (slot r = rank r's record) -> phase 1 -> all-gather again -> phase 2.
+ * exchange_dev: shard_world x mc_frame_shard_slot_bytes(n_features, params) bytes; this rank writes slot shard_rank only.
+ * The same arguments must be passed to all three phases. Outputs (phase 2, device): frame_info 4 ints {objects, status, accepted
+ * matches, clusters after CLUSTER}, obj_model max_objects, obj_pose 7*max_objects, obj_score max_objects — identical on every rank. */
+size_t mc_frame_shard_slot_bytes(int n_features, const mc_pipeline_params *params);
+mc_status mc_process_frame_sharded_dev(mc_ctx *ctx, int phase, const int32_t *nn_row_dev, const uint8_t *accepted_dev, const float *q_xy_dev,
+                                       const int32_t *q_image_dev, int n_features, const mc_pipeline_params *params, int shard_rank, int shard_world,
+                                       void *exchange_dev, int max_objects, int32_t *frame_info_dev, int32_t *obj_model_dev, float *obj_pose_dev,
+                                       float *obj_score_dev);
 /* With mc_set_option("defer_lane_join", 1) mc_process_frames_matched_dev returns WITHOUT ordering the context's stream after the frame
  * lanes, so that work enqueued next on that stream (MATCH and the exchange of the batch's next chunk) overlaps the stages just started;
  * mc_join_lanes orders the context's stream after everything the lanes were given since the last join. */
@@ -346,11 +360,15 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
 /* Named integer options (scheduling / kernel-shape choices; unknown keys are an error):
  *   "pose_fit_thread_min"  mc_pose_hypotheses* calls with at least this many hypotheses and no inlier masks run one
  *                          THREAD per hypothesis instead of one 8-lane group (default 16384; 1 = always)
+ *   "pose_fit_stream"      != 0 (default): those thread-per-hypothesis calls run the persistent phase-synchronous kernel (a finished
+ *                          lane fetches the next hypothesis at once; one residual evaluation per warp trip serves the start point,
+ *                          a Jacobian column or an LM trial point) followed by a scoring kernel; 0: the one-launch kernel (A/B aid).
+ *                          Same arithmetic per hypothesis.
  *   "depth_team_lanes"     32 (default) or 8: lanes that share one explicit hypothesis in mc_pose_depth_hypotheses* (8 = four hypotheses
  *                          per warp). Results do not depend on it (the LM keeps levmar's summation order for any team width).
  *   "linkage_cached"       != 0: mc_cluster_linkage / mc_linkage_agglomerate with average linkage keep a cached maximum per row
- *                          (same merge sequence and clusters; O(n) per merge instead of an O(n^2) scan). Default 0 until it has
- *                          run on a GPU.
+ *                          (same merge sequence and clusters; O(n) per merge instead of an O(n^2) scan). Default 1 (2.7x at 600 matches
+ *                          on B200); 0 = the O(n^2)-scan kernel.
  *   "pose_exact_order"     != 0: mc_pose_hypotheses / mc_pose_ransac (host entries) run the order-preserving LM of the depth stages
  *                          (pose_depth.cu, lm_exact.cuh) with the moped2 residual: every sum in levmar's order, unfused multiply-add —
  *                          poses, inlier masks and ||e||^2 equal the strict-IEEE build of POSE_RANSAC_LM_DIFF_REPROJECTION_CPU bit for

@@ -105,6 +105,9 @@ SIGNATURES = {
                                         _i32p, _i32p, _f32p, _f32p, C.c_void_p, C.c_void_p]),
     "mc_process_frames_matched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _i32p, C.c_int, C.c_int, C.c_int,
                                                 C.POINTER(PipelineParams), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mc_frame_shard_slot_bytes": (C.c_size_t, [C.c_int, C.POINTER(PipelineParams)]),
+    "mc_process_frame_sharded_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PipelineParams),
+                                               C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mc_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mc_kernel_launches": (C.c_int64, [C.c_void_p]),
     "mc_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -554,6 +557,19 @@ class Context:
         self._check(self.L.mc_process_frames_matched_dev(self.h, nn_row_ptr, acc_ptr, xy_ptr, img_ptr, fo, len(fo) - 1, int(frame_begin), int(frame_end),
                                                          C.byref(params), int(max_objects), info_ptr, model_ptr, pose_ptr, score_ptr),
                     "mc_process_frames_matched_dev")
+
+
+    def frame_shard_slot_bytes(self, n_features, params):
+        """bytes of one rank's exchange record of mc_process_frame_sharded_dev (the exchange buffer holds shard_world of them)"""
+        return int(self.L.mc_frame_shard_slot_bytes(int(n_features), C.byref(params)))
+
+    def process_frame_sharded_dev(self, phase, nn_row_ptr, acc_ptr, xy_ptr, img_ptr, n_features, params, shard_rank, shard_world, exchange_ptr,
+                                  max_objects, info_ptr, model_ptr, pose_ptr, score_ptr):
+        """One phase (0, 1, 2) of a frame whose RANSAC tasks are distributed by cluster over shard_world ranks; the caller all-gathers the
+        exchange buffer in place between the phases. Asynchronous on the context's stream."""
+        self._check(self.L.mc_process_frame_sharded_dev(self.h, int(phase), nn_row_ptr, acc_ptr, xy_ptr, img_ptr, int(n_features), C.byref(params),
+                                                        int(shard_rank), int(shard_world), exchange_ptr, int(max_objects), info_ptr, model_ptr,
+                                                        pose_ptr, score_ptr), "mc_process_frame_sharded_dev")
 
 
 class ModelDB:

@@ -185,6 +185,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	if (!ctx || !key) return MC_ERR_ARG;
 	const std::string k(key);
 	if (k == "pose_fit_thread_min") ctx->fit_thread_min = value < 1 ? 1 : value;
+	else if (k == "pose_fit_stream") ctx->fit_stream = value != 0;
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
 	else if (k == "defer_lane_join") ctx->defer_lane_join = value != 0;
@@ -205,7 +206,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "sift_two_pass") return sift_set_two_pass(ctx, (int)value);
 	else if (k == "sift_describe_gather") return sift_set_gather(ctx, (int)value);
 	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }
-	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs; }
+	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->fit_stream = ctx->fit_stream; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs; }
 	return MC_OK;
 }
 
@@ -763,6 +764,27 @@ mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, 
 	MC_CUDA(cudaSetDevice(ctx->device));
 	return process_frames_device(ctx, nullptr, q_xy_dev, q_image_dev, frame_offsets, frame_begin, frame_end, params, max_objects, nn_row_dev, accepted_dev,
 	                             frame_info_dev, obj_model_dev, obj_pose_dev, obj_score_dev, nullptr);
+}
+
+size_t mc_frame_shard_slot_bytes(int n_features, const mc_pipeline_params *params) {
+	if (!params || n_features <= 0) return 0;
+	return frame_shard_slot_bytes(n_features, params);
+}
+
+mc_status mc_process_frame_sharded_dev(mc_ctx *ctx, int phase, const int32_t *nn_row_dev, const uint8_t *accepted_dev, const float *q_xy_dev,
+                                       const int32_t *q_image_dev, int n_features, const mc_pipeline_params *params, int shard_rank, int shard_world,
+                                       void *exchange_dev, int max_objects, int32_t *frame_info_dev, int32_t *obj_model_dev, float *obj_pose_dev,
+                                       float *obj_score_dev) {
+	if (!ctx || !nn_row_dev || !accepted_dev || !q_xy_dev || !q_image_dev || !params || !exchange_dev || !frame_info_dev || !obj_model_dev ||
+	    !obj_pose_dev || !obj_score_dev || max_objects <= 0 || n_features <= 0) {
+		if (ctx) ctx->err = "mc_process_frame_sharded_dev: bad argument";
+		return MC_ERR_ARG;
+	}
+	if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) { ctx->err = "mc_process_frame_sharded_dev: bad shard rank / world"; return MC_ERR_ARG; }
+	if (phase < 0 || phase > 2) { ctx->err = "mc_process_frame_sharded_dev: phase must be 0, 1 or 2"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	return process_frame_sharded_device(ctx, phase, nn_row_dev, accepted_dev, q_xy_dev, q_image_dev, n_features, params, shard_rank, shard_world, exchange_dev,
+	                                    max_objects, frame_info_dev, obj_model_dev, obj_pose_dev, obj_score_dev);
 }
 
 mc_status mc_join_lanes(mc_ctx *ctx) {

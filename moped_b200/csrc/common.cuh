@@ -102,9 +102,11 @@ struct mc_ctx {
 	int n_lanes_wanted = 8;           // mc_set_tuning
 	int pose_warps = 8;               // warps per RANSAC task CTA (mc_set_tuning); results do not depend on it
 	int64_t fit_thread_min = 16384;   // mc_set_option: explicit-hypothesis calls with at least this many use one thread per hypothesis
+	bool fit_stream = true;           // mc_set_option "pose_fit_stream": the persistent phase-synchronous one-thread-per-hypothesis kernel (0: k_pose_fit_thread)
+	int ransac_shard_rank = 0, ransac_shard_world = 1;   // set around the RANSAC calls of mc_process_frame_sharded_dev (pose_staged.cuh)
 	bool ransac_fused = false;        // mc_set_option: the one-CTA-per-task RANSAC kernel instead of the staged kernels (A/B aid)
 	int depth_team_lanes = 32;        // mc_set_option: lanes per explicit hypothesis in k_depth_hypotheses (32 or 8)
-	bool linkage_cached = false;      // mc_set_option: cached-row-maximum agglomeration (linkage_cached.cuh) for average linkage
+	bool linkage_cached = true;       // mc_set_option: cached-row-maximum agglomeration (linkage_cached.cuh) for average linkage (0: the O(n^2)-scan kernel)
 	bool pose_exact_order = false;    // mc_set_option: mc_pose_hypotheses / mc_pose_ransac run the order-preserving LM (pose_depth.cu, variant 2)
 	bool lm_finite_check = false;     // mc_set_option: depth pose stages keep levmar's stop on a non-finite ||e||^2 (a strict-IEEE build of the reference)
 	int match_chunks = 1;             // MATCH launches per batch (mc_set_tuning): chunk c+1 matches while chunk c runs its lanes
@@ -186,6 +188,10 @@ mc_status sift_extract_device(mc_ctx *ctx, const uint8_t *d_gray, int B, int H, 
 mc_status process_frames_host(mc_ctx *ctx, const float *d_q, const float *d_qxy, const int32_t *d_qimg, const int32_t *frame_offsets, int n_frames,
                               const mc_pipeline_params *P, int max_objects, int32_t *n_objects, int32_t *obj_model, float *obj_pose, float *obj_score,
                               int32_t *frame_info, float *stage_ms);
+size_t frame_shard_slot_bytes(int Q, const mc_pipeline_params *P);
+mc_status process_frame_sharded_device(mc_ctx *ctx, int phase, const int32_t *d_nn_row, const uint8_t *d_accepted, const float *d_qxy,
+                                       const int32_t *d_qimg, int Q, const mc_pipeline_params *P, int shard_rank, int shard_world, void *d_exchange,
+                                       int max_objects, int32_t *d_out_info, int32_t *d_out_model, float *d_out_pose, float *d_out_score);
 mc_status match_device(mc_ctx *ctx, const float *d_q, int Q, float ratio, int mode,
                        int32_t *d_nn_row, float *d_nn_dist, uint8_t *d_accepted);
 mc_status match_merge_device(mc_ctx *ctx, const int32_t *rows_all, const float *dist_all, size_t stride, int n_shards, int Q, float ratio,

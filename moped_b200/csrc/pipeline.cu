@@ -388,6 +388,117 @@ mc_status process_frame_device(mc_ctx *ctx, const float *d_q, const float *d_qxy
 }
 
 // =============================================================================================
+// one frame, RANSAC partitioned by cluster across ranks (north_star: "RANSAC work is distributed by cluster";
+// the reference's task list: POSE_RANSAC_LM_DIFF_REPROJECTION_CPU.hpp:275-282 hands (cluster, try) tasks to its worker threads)
+// =============================================================================================
+// Every rank holds the frame's merged nearest neighbours and runs the cheap stages redundantly (compaction, CLUSTER, FILTER:
+// identical on all ranks by construction); the (cluster, try) tasks of POSE and POSE2 are dealt round-robin by cluster, rank r
+// running the clusters c with c % world == r. A task's random stream depends on its index alone, so the union of the ranks'
+// results is the single-GPU result bit for bit. The two exchange points are the caller's (an NCCL all-gather of one small
+// record per rank, in place in `exchange`), which is why the frame is three calls:
+//   phase 0  compaction, CLUSTER, POSE tasks of this rank        -> record in slot `rank` of `exchange`
+//   phase 1  (gathered records) objects, FILTER, POSE2 tasks     -> record in slot `rank`
+//   phase 2  (gathered records) objects, FILTER2, export
+// Record of a phase: found[task_cap] (bytes) | pose[task_cap][7] | n_tests[task_cap], each part 256-byte aligned.
+struct ShardSlot { uint8_t *found; float *pose; int32_t *n_tests; };
+
+static size_t shard_slot_bytes(int task_cap) {
+	auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+	return up((size_t)task_cap) + up(28ull * task_cap) + up(4ull * task_cap);
+}
+static ShardSlot shard_slot(void *exchange, int slot, int task_cap) {
+	auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+	char *b = (char *)exchange + (size_t)slot * shard_slot_bytes(task_cap);
+	ShardSlot s;
+	s.found = (uint8_t *)b; s.pose = (float *)(b + up((size_t)task_cap)); s.n_tests = (int32_t *)(b + up((size_t)task_cap) + up(28ull * task_cap));
+	return s;
+}
+
+// task t belongs to the rank that owns its cluster: take its result from that rank's record
+__global__ void k_shard_select(const uint8_t *__restrict__ exchange, size_t slot_bytes, size_t o_pose, size_t o_tests, int world, int n_tasks, int max_obj,
+                               uint8_t *__restrict__ found, float *__restrict__ pose, int32_t *__restrict__ n_tests) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tasks) return;
+	const uint8_t *b = exchange + (size_t)((t / max_obj) % world) * slot_bytes;
+	found[t] = b[t];
+	const float *sp = (const float *)(b + o_pose) + 7 * (size_t)t;
+#pragma unroll
+	for (int j = 0; j < 7; j++) pose[7 * (size_t)t + j] = sp[j];
+	n_tests[t] = ((const int32_t *)(b + o_tests))[t];
+}
+
+size_t frame_shard_slot_bytes(int Q, const mc_pipeline_params *P) { return shard_slot_bytes(frame_caps(Q, P).task_cap); }
+
+mc_status process_frame_sharded_device(mc_ctx *ctx, int phase, const int32_t *d_nn_row, const uint8_t *d_accepted, const float *d_qxy,
+                                       const int32_t *d_qimg, int Q, const mc_pipeline_params *P, int shard_rank, int shard_world, void *d_exchange,
+                                       int max_objects, int32_t *d_out_info, int32_t *d_out_model, float *d_out_pose, float *d_out_score) {
+	if (!ctx->d_cams) { ctx->err = "process_frame_sharded: cameras not set"; return MC_ERR_STATE; }
+	if (!ctx->d_xyz || !ctx->d_model_of_row) { ctx->err = "process_frame_sharded: no database tables (mc_db_upload / mc_db_set_global_tables)"; return MC_ERR_STATE; }
+	const FrameCaps caps = frame_caps(Q, P);
+	const int cl_cap = caps.cl_cap, obj_cap = caps.obj_cap, cl2_cap = obj_cap / 2;
+	FrameBufs B;
+	MC_TRY(carve(ctx, B, Q, ctx->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap));
+	const FrameDesc *fd = (const FrameDesc *)ctx->frame_desc.p;
+	const size_t slot_bytes = shard_slot_bytes(caps.task_cap);
+	const ShardSlot mine = shard_slot(d_exchange, shard_rank, caps.task_cap), base = shard_slot(d_exchange, 0, caps.task_cap);
+	const size_t o_pose = (size_t)((char *)base.pose - (char *)base.found), o_tests = (size_t)((char *)base.n_tests - (char *)base.found);
+	auto select = [&](int n_tasks, int max_obj) -> mc_status {
+		k_shard_select<<<(n_tasks + 255) / 256, 256, 0, ctx->stream>>>((const uint8_t *)d_exchange, slot_bytes, o_pose, o_tests, shard_world, n_tasks, max_obj,
+		                                                              B.found, B.task_pose, B.n_tests);
+		MC_LAUNCH_CHECK();
+		return MC_OK;
+	};
+	struct ShardScope {                    // the RANSAC launches inside read the partition from the context
+		mc_ctx *c;
+		ShardScope(mc_ctx *c_, int r, int w) : c(c_) { c->ransac_shard_rank = r; c->ransac_shard_world = w; }
+		~ShardScope() { c->ransac_shard_rank = 0; c->ransac_shard_world = 1; }
+	} scope(ctx, shard_rank, shard_world);
+	if (phase == 0) {
+		FrameDesc d;
+		d.nn_row = d_nn_row; d.accepted = d_accepted; d.q_xy = d_qxy; d.q_image = d_qimg; d.Q = Q; d.max_objects = max_objects;
+		d.out_info = d_out_info; d.out_model = d_out_model; d.out_pose = d_out_pose; d.out_score = d_out_score;
+		MC_TRY(set_frame_desc(ctx, d));
+		fd = (const FrameDesc *)ctx->frame_desc.p;
+		MC_CUDA(cudaMemsetAsync(B.status, 0, 64, ctx->stream));
+		MC_CUDA(cudaMemsetAsync(B.n_obj, 0, 64, ctx->stream));
+		k_match_compact<<<1, 1024, 0, ctx->stream>>>(fd, ctx->table_base, ctx->d_model_of_row, ctx->d_xyz, ctx->n_models,
+		                                            B.acc_list, B.match_offsets, B.match_query, B.match_row, B.match_image, B.match_xy, B.match_xyz, B.status);
+		MC_LAUNCH_CHECK();
+		MC_TRY(cluster_device(ctx, B.match_offsets, B.match_image, B.match_xy, ctx->n_models, ctx->n_images, Q, P->cluster_radius, P->cluster_merge,
+		                      P->cluster_min_pts, P->cluster_max_iterations, B.cl_n, B.cl_model, B.cl_offsets, B.cl_members));
+		k_gather_points<<<ctx->num_sms, 128, 0, ctx->stream>>>(B.cl_n, B.cl_model, B.cl_offsets, B.cl_members, B.match_offsets, B.match_image, B.match_xy,
+		                                                     B.match_xyz, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie);
+		MC_LAUNCH_CHECK();
+		return pose_ransac_device(ctx, B.cl_offsets, B.cl_n, cl_cap, Q, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie, &P->pose, mine.found, mine.pose, mine.n_tests);
+	}
+	if (phase == 1) {
+		MC_TRY(select(cl_cap * P->pose.max_objects_per_cluster, P->pose.max_objects_per_cluster));
+		MC_TRY(pose_append_device(ctx, B.cl_model, B.cl_n, cl_cap, P->pose.max_objects_per_cluster, B.found, B.task_pose, B.n_obj, obj_cap, B.obj_model, B.obj_pose));
+		MC_TRY(filter_device(ctx, B.match_offsets, B.match_image, B.match_xy, B.match_xyz, ctx->n_models, Q, B.obj_model, B.obj_pose, B.n_obj, obj_cap,
+		                     P->filter_min_points, P->filter_feature_distance, P->filter_min_score, B.keep, B.obj_score, B.f_n, B.f_model, B.f_offsets,
+		                     B.f_members, B.surv_model, B.surv_pose, B.surv_score));
+		k_copy_objects<<<1, 256, 0, ctx->stream>>>(B.f_n, B.surv_model, B.surv_pose, B.n_obj, B.obj_model, B.obj_pose);
+		MC_LAUNCH_CHECK();
+		k_gather_points<<<ctx->num_sms, 128, 0, ctx->stream>>>(B.f_n, B.f_model, B.f_offsets, B.f_members, B.match_offsets, B.match_image, B.match_xy,
+		                                                     B.match_xyz, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie);
+		MC_LAUNCH_CHECK();
+		return pose_ransac_device(ctx, B.f_offsets, B.f_n, cl2_cap, Q, B.pt_xy, B.pt_xyz, B.pt_image, B.pt_tie, &P->pose2, mine.found, mine.pose, mine.n_tests);
+	}
+	if (phase == 2) {
+		MC_TRY(select(cl2_cap * P->pose2.max_objects_per_cluster, P->pose2.max_objects_per_cluster));
+		MC_TRY(pose_append_device(ctx, B.f_model, B.f_n, cl2_cap, P->pose2.max_objects_per_cluster, B.found, B.task_pose, B.n_obj, obj_cap, B.obj_model, B.obj_pose));
+		MC_TRY(filter_device(ctx, B.match_offsets, B.match_image, B.match_xy, B.match_xyz, ctx->n_models, Q, B.obj_model, B.obj_pose, B.n_obj, obj_cap,
+		                     P->filter2_min_points, P->filter2_feature_distance, P->filter2_min_score, B.keep, B.obj_score, B.f_n, B.f_model, B.f_offsets,
+		                     B.f_members, B.surv_model, B.surv_pose, B.surv_score));
+		k_export_objects<<<1, 128, 0, ctx->stream>>>(fd, B.f_n, B.status, B.match_offsets, ctx->n_models, B.cl_n, B.surv_model, B.surv_pose, B.surv_score);
+		MC_LAUNCH_CHECK();
+		return MC_OK;
+	}
+	ctx->err = "process_frame_sharded: phase must be 0, 1 or 2";
+	return MC_ERR_ARG;
+}
+
+// =============================================================================================
 // frame batches (BASELINE.json configs[4])
 // =============================================================================================
 // A batch is a list of independent frames (each its own FrameData in the reference: moped.cpp:166-194 runs
@@ -404,7 +515,7 @@ static void lane_borrow(mc_ctx *ctx, mc_ctx *lane) {
 	lane->db_norm2_min = ctx->db_norm2_min; lane->db_norm2_max = ctx->db_norm2_max;
 	lane->d_cams = ctx->d_cams; lane->n_images = ctx->n_images;
 	lane->pose_warps = ctx->pose_warps;
-	lane->fit_thread_min = ctx->fit_thread_min; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs;
+	lane->fit_thread_min = ctx->fit_thread_min; lane->fit_stream = ctx->fit_stream; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs;
 	lane->pose_exact_order = ctx->pose_exact_order;
 }
 

@@ -497,6 +497,267 @@ k_pose_fit_thread(const int32_t *__restrict__ cluster_offsets, const float *__re
 	for (int j = 0; j < 7; j++) pose_lm[7 * h + j] = cnt >= 0 ? pose[j] : 0.f;
 }
 
+// ---- kernel A'': one thread per hypothesis, PERSISTENT and PHASE-SYNCHRONOUS (the default throughput shape) ----
+// k_pose_fit_thread keeps 9.9 of 32 lanes busy (ncu, profiles/ncu_stage_kernels_r1i.md): hypotheses leave the LM loop after different
+// iteration counts and the finite-difference Jacobian (7 residual evaluations, more instructions than the rest of an iteration) is
+// due at different iterations in different lanes, so a warp pays for it on almost every trip. Here a thread is a small state machine
+// and a warp trip has ONE residual evaluation that every lane uses for whatever it needs next:
+//   INIT   the residuals at the start pose of a freshly fetched hypothesis (a finished lane takes the next hypothesis from a global
+//          counter at once instead of idling until the slowest lane of its warp is done),
+//   JAC    column jc of the forward-difference Jacobian (a lane that needs a new Jacobian spends 7 trips here),
+//   SOLVE  the trial point p + Dp of an LM iteration (normal equations, the 7x7 solve before it; Broyden update, gain ratio after).
+// Per hypothesis the arithmetic and its order are those of lm_dif<1, S> (one lane, sequential sums). The Jacobian and the sample
+// points live in shared memory, element-major ([e][thread]: conflict-free), which brings the kernel from 254 to <= 168 registers.
+// Inlier scoring moved to k_pose_score (one 8-lane group per hypothesis): inside the state machine it would run with one or two
+// active lanes.
+constexpr int kStreamThreads = 128;
+enum { kModeIdle = 0, kModeInit = 1, kModeSolve = 2, kModeJac = 3 };
+
+template <int S, int MINB>
+__global__ void __launch_bounds__(kStreamThreads, MINB)
+k_pose_fit_stream(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
+                  const int32_t *__restrict__ image, const Camera *__restrict__ cams, const int32_t *__restrict__ hyp_cluster,
+                  const int32_t *__restrict__ sample_pos, const float *__restrict__ init_quat, int n_hyp, int n_align, int itmax,
+                  uint32_t *__restrict__ next_hyp, int32_t *__restrict__ n_inliers, float *__restrict__ pose_lm, float *__restrict__ lm_err) {
+	extern __shared__ float s_stream[];
+	const int nt = kStreamThreads;
+	float *Js = s_stream + threadIdx.x;                                  // J[s][r][j] at Js[((s * 2 + r) * 7 + j) * nt]
+	float *Ps = s_stream + (size_t)S * 14 * nt + threadIdx.x;            // point s, component c (u v X Y Z cam) at Ps[(s * 6 + c) * nt]
+	const float tau = 1E-03f, eps1 = 1E-17f, eps2 = 1E-17f, eps2_sq = 1E-17f * 1E-17f, eps3 = 1E-17f, delta = 1E-06f;
+	const int K = 10;
+	float p[7], hx[S][2], jtj[28], jte[7];
+	float mu = 0.f, jte_inf = 0.f, p_L2 = 0.f, p_eL2 = 0.f, dcur = 0.f;
+	int nu = 20, updjac = 0, updp = 1, newjac = 0, k = 0, jc = 0, h = -1, mode = kModeIdle;
+	bool more = true;
+#pragma unroll
+	for (int i = 0; i < 28; i++) jtj[i] = 0.f;
+#pragma unroll
+	for (int i = 0; i < 7; i++) { jte[i] = 0.f; p[i] = 0.f; }
+#pragma unroll
+	for (int i = 0; i < S; i++) { hx[i][0] = 0.f; hx[i][1] = 0.f; }
+
+	auto load_pts = [&](LmPoint (&pts)[S]) {
+#pragma unroll
+		for (int s = 0; s < S; s++) {
+			pts[s].u = Ps[(s * 6 + 0) * nt]; pts[s].v = Ps[(s * 6 + 1) * nt];
+			pts[s].X = Ps[(s * 6 + 2) * nt]; pts[s].Y = Ps[(s * 6 + 3) * nt]; pts[s].Z = Ps[(s * 6 + 4) * nt];
+			pts[s].cam = __float_as_int(Ps[(s * 6 + 5) * nt]);
+		}
+	};
+	// the hypothesis leaves the LM: optimizeCamera's epilogue (quaternion re-normalised; LM_ERROR leaves no pose)
+	auto finish = [&](int stop) {
+		if (stop == 4) {
+			n_inliers[h] = -1;
+			lm_err[2 * h] = -1.f; lm_err[2 * h + 1] = -2.f;
+#pragma unroll
+			for (int j = 0; j < 7; j++) pose_lm[7 * h + j] = 0.f;
+		} else {
+			float d = p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3];
+			d = 1.0f / sqrtf(d);
+			n_inliers[h] = 0;                                              // k_pose_score counts
+			lm_err[2 * h] = p_eL2; lm_err[2 * h + 1] = -2.f;
+#pragma unroll
+			for (int j = 0; j < 4; j++) pose_lm[7 * h + j] = p[j] * d;
+#pragma unroll
+			for (int j = 4; j < 7; j++) pose_lm[7 * h + j] = p[j];
+		}
+		mode = kModeIdle;
+	};
+
+	for (;;) {
+		if (mode == kModeIdle && more) {
+			h = (int)atomicAdd(next_hyp, 1u);
+			if (h >= n_hyp) more = false;
+			else {
+				const int c = hyp_cluster[h];
+				const int lo = cluster_offsets[c];
+#pragma unroll
+				for (int s = 0; s < S; s++) {
+					float u = 0.f, v = 0.f, X = 0.f, Y = 0.f, Z = 0.f; int cam = 0;
+					if (s < n_align) {
+						const int i = lo + sample_pos[(size_t)h * n_align + s];
+						u = xy[2 * i]; v = xy[2 * i + 1]; X = xyz[3 * i]; Y = xyz[3 * i + 1]; Z = xyz[3 * i + 2]; cam = image[i];
+					}
+					Ps[(s * 6 + 0) * nt] = u; Ps[(s * 6 + 1) * nt] = v; Ps[(s * 6 + 2) * nt] = X; Ps[(s * 6 + 3) * nt] = Y; Ps[(s * 6 + 4) * nt] = Z;
+					Ps[(s * 6 + 5) * nt] = __int_as_float(cam);
+				}
+				p[0] = init_quat[4 * h]; p[1] = init_quat[4 * h + 1]; p[2] = init_quat[4 * h + 2]; p[3] = init_quat[4 * h + 3];
+				p[4] = 0.f; p[5] = 0.f; p[6] = 0.5f;
+				mode = kModeInit;
+			}
+		}
+		if (!__any_sync(0xffffffffu, mode != kModeIdle)) break;
+
+		float x[7], Dp[7], Dp_L2 = 0.f;
+		bool ev = false;
+		// ---- top of an LM iteration (lm_core.c:484-520): stop tests, is a new Jacobian due? ----
+		if (mode == kModeSolve) {
+			if (k >= itmax) finish(3);
+			else if (p_eL2 <= eps3) finish(6);
+			else if ((updp && nu > 16) || updjac == K) { mode = kModeJac; jc = 0; }
+		}
+		// ---- normal equations and the damped solve ----
+		if (mode == kModeSolve) {
+			if (newjac) {
+				newjac = 0;
+#pragma unroll
+				for (int i = 0; i < 28; i++) jtj[i] = 0.f;
+#pragma unroll
+				for (int i = 0; i < 7; i++) jte[i] = 0.f;
+#pragma unroll
+				for (int s = 0; s < S; s++)
+#pragma unroll
+					for (int r = 0; r < 2; r++) {
+						float Jr[7];
+#pragma unroll
+						for (int j = 0; j < 7; j++) Jr[j] = Js[((s * 2 + r) * 7 + j) * nt];
+						const float e = -hx[s][r];
+#pragma unroll
+						for (int i = 0; i < 7; i++) {
+							const float alpha = Jr[i];
+#pragma unroll
+							for (int j = 0; j <= i; j++) jtj[tri(i, j)] += Jr[j] * alpha;
+							jte[i] += alpha * e;
+						}
+					}
+				p_L2 = 0.f; jte_inf = 0.f;
+#pragma unroll
+				for (int i = 0; i < 7; i++) {
+					jte_inf = fmaxf(jte_inf, fabsf(jte[i]));
+					p_L2 += p[i] * p[i];
+				}
+			}
+			if (jte_inf <= eps1) finish(1);
+			else {
+				if (k == 0) {
+					float t = -FLT_MAX;
+#pragma unroll
+					for (int i = 0; i < 7; i++) t = fmaxf(t, jtj[tri(i, i)]);
+					mu = tau * t;
+				}
+				if (lu_solve7(jtj, mu, jte, Dp)) {
+#pragma unroll
+					for (int i = 0; i < 7; i++) { x[i] = p[i] + Dp[i]; Dp_L2 += Dp[i] * Dp[i]; }
+					if (Dp_L2 <= eps2_sq * p_L2) finish(2);
+					else if (Dp_L2 >= (p_L2 + eps2) / (1E-12f * 1E-12f)) finish(4);
+					else ev = true;
+				} else {
+					mu *= nu;
+					const int nu2 = nu << 1;
+					if (nu2 <= nu) finish(5);
+					else { nu = nu2; ++k; }
+				}
+			}
+		} else if (mode == kModeJac) {
+#pragma unroll
+			for (int j = 0; j < 7; j++) {
+				x[j] = p[j];
+				if (j == jc) {
+					float d = fabsf(1E-04f * p[j]);
+					if (d < delta) d = delta;
+					dcur = d;
+					x[j] = p[j] + d;
+				}
+			}
+			ev = true;
+		} else if (mode == kModeInit) {
+#pragma unroll
+			for (int j = 0; j < 7; j++) x[j] = p[j];
+			ev = true;
+		}
+
+		// ---- the trip's residual evaluation ----
+		if (ev) {
+			float wrk[S][2];
+			{
+				LmPoint pts[S];
+				load_pts(pts);
+				eval_residuals<S>(x, pts, n_align, cams, wrk);
+			}
+			if (mode == kModeInit) {
+				float s2 = 0.f;
+#pragma unroll
+				for (int i = 0; i < S; i++) { hx[i][0] = wrk[i][0]; hx[i][1] = wrk[i][1]; s2 += wrk[i][0] * wrk[i][0] + wrk[i][1] * wrk[i][1]; }
+				p_eL2 = s2;
+				mu = 0.f; jte_inf = 0.f; p_L2 = 0.f;
+				nu = 20; updjac = 0; updp = 1; newjac = 0; k = 0;
+				mode = kModeSolve;
+			} else if (mode == kModeJac) {
+				const float dinv = 1.0f / dcur;
+#pragma unroll
+				for (int i = 0; i < S; i++) {
+					Js[((i * 2 + 0) * 7 + jc) * nt] = (wrk[i][0] - hx[i][0]) * dinv;
+					Js[((i * 2 + 1) * 7 + jc) * nt] = (wrk[i][1] - hx[i][1]) * dinv;
+				}
+				if (++jc == 7) { nu = 2; updjac = 0; updp = 0; newjac = 1; mode = kModeSolve; }
+			} else {
+				float s2 = 0.f;
+#pragma unroll
+				for (int i = 0; i < S; i++) s2 += wrk[i][0] * wrk[i][0] + wrk[i][1] * wrk[i][1];
+				const float pDp_eL2 = s2;
+				const float dF = p_eL2 - pDp_eL2;
+				if (updp || dF > 0.f) {
+					const float inv = 1.0f / Dp_L2;
+#pragma unroll
+					for (int s = 0; s < S; s++)
+#pragma unroll
+						for (int r = 0; r < 2; r++) {
+							float Jr[7];
+#pragma unroll
+							for (int j = 0; j < 7; j++) Jr[j] = Js[((s * 2 + r) * 7 + j) * nt];
+							float t = 0.f;
+#pragma unroll
+							for (int l = 0; l < 7; l++) t += Jr[l] * Dp[l];
+							t = (wrk[s][r] - hx[s][r] - t) * inv;
+#pragma unroll
+							for (int j = 0; j < 7; j++) Js[((s * 2 + r) * 7 + j) * nt] = Jr[j] + t * Dp[j];
+						}
+					++updjac; newjac = 1;
+				}
+				float dL = 0.f;
+#pragma unroll
+				for (int i = 0; i < 7; i++) dL += Dp[i] * (mu * Dp[i] + jte[i]);
+				if (dL > 0.f && dF > 0.f) {
+					float t = 2.0f * dF / dL - 1.0f;
+					t = 1.0f - t * t * t;
+					mu = mu * ((t >= 0.3333333334f) ? t : 0.3333333334f);
+					nu = 2;
+#pragma unroll
+					for (int i = 0; i < 7; i++) p[i] = x[i];
+#pragma unroll
+					for (int s = 0; s < S; s++) { hx[s][0] = wrk[s][0]; hx[s][1] = wrk[s][1]; }
+					p_eL2 = pDp_eL2;
+					updp = 1;
+					++k;
+				} else {
+					mu *= nu;
+					const int nu2 = nu << 1;
+					if (nu2 <= nu) finish(5);
+					else { nu = nu2; ++k; }
+				}
+			}
+		}
+	}
+}
+
+// inlier count of every sample-fit pose k_pose_fit_stream left (testAllPoints, POSE_..._CPU.hpp:166-180): one 8-lane group per hypothesis
+__global__ void __launch_bounds__(256)
+k_pose_score(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
+             const int32_t *__restrict__ image, const Camera *__restrict__ cams, const int32_t *__restrict__ hyp_cluster, int n_hyp, float thr,
+             int32_t *__restrict__ n_inliers, const float *__restrict__ pose_lm) {
+	const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
+	const unsigned mask = 0xFFu << (8 * grp);
+	const int h = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + grp;
+	if (h >= n_hyp || n_inliers[h] < 0) return;
+	const int c = hyp_cluster[h];
+	const int lo = cluster_offsets[c], n = cluster_offsets[c + 1] - lo;
+	float pose[7];
+#pragma unroll
+	for (int j = 0; j < 7; j++) pose[j] = pose_lm[7 * h + j];
+	const int cnt = count_inliers<8>(pose, n, xy + 2 * lo, xyz + 3 * lo, image + lo, cams, thr, mask, lig, nullptr);
+	if (lig == 0) n_inliers[h] = cnt;
+}
+
 // ---- kernel B: refit of every hypothesis with more than min_npts inliers; one warp per hypothesis ----
 __global__ void __launch_bounds__(kPoseThreads)
 k_pose_refit(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
@@ -519,6 +780,94 @@ k_pose_refit(const int32_t *__restrict__ cluster_offsets, const float *__restric
 	}
 	if (lane == 0)
 		for (int j = 0; j < 7; j++) pose_refit[7 * h + j] = pose[j];
+}
+
+// ---- kernel B': the same refit for MANY hypotheses of which few are accepted (the thread-per-hypothesis path) ----
+// k_pose_refit gives every hypothesis a warp and compiles for the largest refit (16 correspondences per lane: 255 registers, 8 warps
+// per SM). With 131072 hypotheses of which 2 % are accepted (BASELINE configs[3]) that is 128 k idle warps and a latency-bound LM at
+// two warps per scheduler. Here k_refit_buckets copies the sample-fit pose of every hypothesis and appends the accepted ones to one of
+// five lists by inlier count (<= 32, 64, 128, 256, more); k_pose_refit_list<S> / k_pose_refit_lists<1, 2> then run a persistent grid of warps over a list with S
+// correspondences per lane in registers, compiled for that S alone (S = 1, 2: 3 CTAs of 4 warps per SM). Same arithmetic as refit_warp.
+constexpr int kRefitBuckets = 5;
+
+__global__ void k_refit_buckets(int n_hyp, int min_npts, const int32_t *__restrict__ n_inliers, const float *__restrict__ pose_lm,
+                                float *__restrict__ pose_refit, int32_t *__restrict__ counts, int32_t *__restrict__ lists) {
+	const int h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h >= n_hyp) return;
+#pragma unroll
+	for (int j = 0; j < 7; j++) pose_refit[7 * (size_t)h + j] = pose_lm[7 * (size_t)h + j];
+	const int n = n_inliers[h];
+	if (n > min_npts) {
+		const int b = n <= 32 ? 0 : n <= 64 ? 1 : n <= 128 ? 2 : n <= 256 ? 3 : 4;
+		lists[(size_t)b * n_hyp + atomicAdd(&counts[b], 1)] = h;
+	}
+}
+
+// refit of hypothesis h by the calling warp with S correspondences per lane (list = 32 S ints of shared memory)
+template <int S>
+__device__ __forceinline__ void refit_item(int h, const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
+                                           const int32_t *__restrict__ image, const Camera *__restrict__ cams, const int32_t *__restrict__ hyp_cluster,
+                                           int max_lm, float thr, int lane, int *list, float *__restrict__ pose_refit, float *__restrict__ lm_err) {
+	const int c = hyp_cluster[h];
+	const int lo = cluster_offsets[c], n = cluster_offsets[c + 1] - lo;
+	const float *cxy = xy + 2 * lo, *cxyz = xyz + 3 * lo;
+	const int32_t *cim = image + lo;
+	float pose[7];
+#pragma unroll
+	for (int j = 0; j < 7; j++) pose[j] = pose_refit[7 * (size_t)h + j];
+	// inliers of `pose` in cluster order (refit_warp's list; the bucket guarantees that at most 32 S of them exist, 512 in the last one)
+	float T[12];
+	pose7_to_T(pose, T);
+	int n_inl = 0;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + lane;
+		bool in = false;
+		if (i < n) in = proj_err(T, cams[cim[i]], cxyz[3 * i], cxyz[3 * i + 1], cxyz[3 * i + 2], cxy[2 * i], cxy[2 * i + 1]) < thr;
+		const unsigned m = __ballot_sync(0xffffffffu, in);
+		if (in) {
+			const int k = n_inl + __popc(m & ((1u << lane) - 1));
+			if (k < 32 * S) list[k] = i;
+		}
+		n_inl += __popc(m);
+	}
+	__syncwarp();
+	if (n_inl > 32 * S) n_inl = 32 * S;
+	float err;
+	refit_S<S>(pose, n_inl, list, cxy, cxyz, cim, cams, max_lm, lane, err);
+	if (lane == 0) {
+		lm_err[2 * (size_t)h + 1] = err;
+#pragma unroll
+		for (int j = 0; j < 7; j++) pose_refit[7 * (size_t)h + j] = pose[j];
+	}
+	__syncwarp();
+}
+
+// a persistent grid of warps over TWO lists: the items of list B (SB correspondences per lane, the longer fits) first, then list A
+template <int SA, int SB, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_pose_refit_lists(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
+                   const int32_t *__restrict__ image, const Camera *__restrict__ cams, const int32_t *__restrict__ hyp_cluster, int max_lm, float thr,
+                   const int32_t *__restrict__ count_a, const int32_t *__restrict__ list_a, const int32_t *__restrict__ count_b,
+                   const int32_t *__restrict__ list_b, float *__restrict__ pose_refit, float *__restrict__ lm_err) {
+	__shared__ int s_list[4][32 * SB];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int na = *count_a, nb = *count_b;
+	for (int it = blockIdx.x * 4 + w; it < na + nb; it += gridDim.x * 4) {
+		if (it < nb) refit_item<SB>(list_b[it], cluster_offsets, xy, xyz, image, cams, hyp_cluster, max_lm, thr, lane, s_list[w], pose_refit, lm_err);
+		else refit_item<SA>(list_a[it - nb], cluster_offsets, xy, xyz, image, cams, hyp_cluster, max_lm, thr, lane, s_list[w], pose_refit, lm_err);
+	}
+}
+
+template <int S, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_pose_refit_list(const int32_t *__restrict__ cluster_offsets, const float *__restrict__ xy, const float *__restrict__ xyz,
+                  const int32_t *__restrict__ image, const Camera *__restrict__ cams, const int32_t *__restrict__ hyp_cluster, int max_lm, float thr,
+                  const int32_t *__restrict__ count, const int32_t *__restrict__ list, float *__restrict__ pose_refit, float *__restrict__ lm_err) {
+	__shared__ int s_list[4][32 * S];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int n_items = *count;
+	for (int it = blockIdx.x * 4 + w; it < n_items; it += gridDim.x * 4)
+		refit_item<S>(list[it], cluster_offsets, xy, xyz, image, cams, hyp_cluster, max_lm, thr, lane, s_list[w], pose_refit, lm_err);
 }
 
 // ---- kernel C: full RANSAC, one CTA per (cluster, try) task ----
@@ -635,7 +984,58 @@ mc_status pose_hypotheses_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, 
 	if (n_hyp <= 0) return MC_OK;
 	const int wpb = kPoseThreads / 32;
 	// many hypotheses and no inlier masks wanted: one thread per hypothesis; otherwise one 8-lane group per hypothesis
-	if (!d_mask && n_hyp >= ctx->fit_thread_min) {
+	if (!d_mask && n_hyp >= ctx->fit_thread_min && ctx->fit_stream) {
+		// persistent phase-synchronous kernel + scoring kernel (the default throughput shape)
+		MC_TRY(reserve(ctx, ctx->scratch[20], 256));
+		MC_CUDA(cudaMemsetAsync(ctx->scratch[20].p, 0, 256, ctx->stream));
+#define MC_FIT_STREAM(S, MINB)                                                                                                               \
+		do {                                                                                                                                 \
+			const size_t smem = (size_t)(S) * 20 * kStreamThreads * sizeof(float);                                                           \
+			MC_CUDA(cudaFuncSetAttribute(k_pose_fit_stream<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+			int per_sm = 0;                                                                                                                  \
+			MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pose_fit_stream<S, MINB>, kStreamThreads, smem));               \
+			if (per_sm < 1) per_sm = 1;                                                                                                      \
+			const int64_t want = ((int64_t)n_hyp + kStreamThreads - 1) / kStreamThreads, cap = (int64_t)per_sm * ctx->num_sms;                \
+			k_pose_fit_stream<S, MINB><<<(unsigned)(want < cap ? want : cap), kStreamThreads, smem, ctx->stream>>>(                          \
+			    d_cluster_offsets, d_xy, d_xyz, d_image, ctx->d_cams, d_hyp_cluster, d_sample_pos, d_init_quat, n_hyp, pp->n_pts_align,      \
+			    pp->max_lm_tests, (uint32_t *)ctx->scratch[20].p, d_n_inliers, d_pose_lm, d_lm_err);                                         \
+		} while (0)
+		if (pp->n_pts_align <= 5) MC_FIT_STREAM(5, 3);       // (4 CTAs per SM at 128 registers: measured, no gain — 5.00 vs 4.95 ms per 131072 hypotheses)
+		else if (pp->n_pts_align == 6) MC_FIT_STREAM(6, 3);
+		else MC_FIT_STREAM(8, 2);
+#undef MC_FIT_STREAM
+		MC_LAUNCH_CHECK();
+		k_pose_score<<<(n_hyp + 31) / 32, 256, 0, ctx->stream>>>(d_cluster_offsets, d_xy, d_xyz, d_image, ctx->d_cams, d_hyp_cluster, n_hyp,
+		                                                        pp->error_threshold, d_n_inliers, d_pose_lm);
+		MC_LAUNCH_CHECK();
+		// refit of the accepted ones from per-size lists
+		MC_TRY(reserve(ctx, ctx->scratch[21], 256 + sizeof(int32_t) * (size_t)kRefitBuckets * n_hyp));
+		int32_t *counts = (int32_t *)ctx->scratch[21].p, *lists = counts + 64;
+		MC_CUDA(cudaMemsetAsync(counts, 0, 256, ctx->stream));
+		k_refit_buckets<<<(n_hyp + 255) / 256, 256, 0, ctx->stream>>>(n_hyp, pp->min_npts_object, d_n_inliers, d_pose_lm, d_pose_refit, counts, lists);
+		MC_LAUNCH_CHECK();
+		const int64_t warps_cap = ((int64_t)n_hyp + 3) / 4;
+#define MC_REFIT_LIST(S, MINB, B)                                                                                                            \
+		do {                                                                                                                                 \
+			const int64_t g = (int64_t)ctx->num_sms * (MINB);                                                                                \
+			k_pose_refit_list<S, MINB><<<(unsigned)(g < warps_cap ? g : warps_cap), 128, 0, ctx->stream>>>(                                  \
+			    d_cluster_offsets, d_xy, d_xyz, d_image, ctx->d_cams, d_hyp_cluster, pp->max_lm_tests, pp->error_threshold, counts + (B),    \
+			    lists + (size_t)(B) * n_hyp, d_pose_refit, d_lm_err);                                                                        \
+			MC_LAUNCH_CHECK();                                                                                                               \
+		} while (0)
+		{                                     // the two small buckets share one launch (each alone leaves the GPU half empty for one LM chain length)
+			const int64_t g = (int64_t)ctx->num_sms * 3;
+			k_pose_refit_lists<1, 2, 3><<<(unsigned)(g < warps_cap ? g : warps_cap), 128, 0, ctx->stream>>>(
+			    d_cluster_offsets, d_xy, d_xyz, d_image, ctx->d_cams, d_hyp_cluster, pp->max_lm_tests, pp->error_threshold, counts + 0, lists,
+			    counts + 1, lists + (size_t)n_hyp, d_pose_refit, d_lm_err);
+			MC_LAUNCH_CHECK();
+		}
+		MC_REFIT_LIST(4, 2, 2);
+		MC_REFIT_LIST(8, 2, 3);
+		MC_REFIT_LIST(16, 2, 4);
+#undef MC_REFIT_LIST
+		return MC_OK;
+	} else if (!d_mask && n_hyp >= ctx->fit_thread_min) {
 		const int grid = (n_hyp + 127) / 128;
 #define MC_FIT_THREAD(S)                                                                                                                     \
 		k_pose_fit_thread<S><<<grid, 128, 0, ctx->stream>>>(d_cluster_offsets, d_xy, d_xyz, d_image, ctx->d_cams, d_hyp_cluster, d_sample_pos, \
@@ -672,6 +1072,7 @@ mc_status pose_ransac_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, cons
 	const int warps = ctx->pose_warps < 1 ? 1 : (ctx->pose_warps > kPoseThreads / 32 ? kPoseThreads / 32 : ctx->pose_warps);
 	if (ctx->pose_exact_order)               // mc_set_option "pose_exact_order": the order-preserving LM (pose_exact.cu), bit-exact with the oracle
 		return pose_ransac_exact_device(ctx, d_cluster_offsets, d_n_clusters, n_clusters_cap, n_points_cap, d_xy, d_xyz, d_image, d_tie, pp, d_found, d_pose, d_n_tests);
+	if (ctx->ransac_fused && ctx->ransac_shard_world > 1) { ctx->err = "pose: the one-CTA-per-task A/B kernel has no cluster partition"; return MC_ERR_STATE; }
 	if (ctx->ransac_fused) {                 // A/B aid (mc_set_option "ransac_fused"): the one-CTA-per-task kernel
 		k_pose_ransac<<<n_tasks, 32 * warps, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, d_tie, ctx->d_cams,
 		                                                       pp->max_objects_per_cluster, pp->max_ransac_tests, pp->max_lm_tests, pp->n_pts_align,

@@ -55,7 +55,11 @@ struct RansacState {
 	float *fit_pose;      // [tasks][HA][7] sample-fit pose of successful first-round hypotheses
 	float *chunk_pose;    // [queue pos][slots][7] sample-fit pose of each work item's lowest success
 	float *refit_scratch; // policy-defined global scratch of the refit kernel (nullptr = none), carved per task
+	int shard_rank, shard_world;   // RANSAC tasks partitioned by cluster (north_star: "RANSAC work is distributed by cluster"): this call runs the
+	                               // tasks of clusters c with c % shard_world == shard_rank and reports found = 0 for the others
 };
+
+__device__ __forceinline__ bool ransac_owns(const RansacState &S, int c) { return S.shard_world <= 1 || c % S.shard_world == S.shard_rank; }
 
 // offset of task t's slice inside RansacState::refit_scratch: tasks of cluster c (points [lo, lo + n)) lie back to back
 template <class P>
@@ -84,7 +88,7 @@ k_ransac_first(const int32_t *__restrict__ cluster_offsets, const int32_t *__res
 	const int task = g / HA, h = g - task * HA;
 	const int n_clusters = n_clusters_p ? min(*n_clusters_p, n_clusters_cap) : n_clusters_cap;
 	const int c = task / max_obj;
-	if (c >= n_clusters || h >= max_ransac) return;
+	if (c >= n_clusters || h >= max_ransac || !ransac_owns(S, c)) return;
 	const int lo = cluster_offsets[c], n = cluster_offsets[c + 1] - lo;
 	const float *cxy = xy + 2 * lo, *cxyz = xyz + 3 * lo;
 	const int32_t *cim = image + lo, *ctie = tie ? tie + lo : nullptr;
@@ -187,7 +191,7 @@ k_ransac_refit(const int32_t *__restrict__ cluster_offsets, const int32_t *__res
 	if (task >= n_tasks) return;
 	const int n_clusters = n_clusters_p ? min(*n_clusters_p, n_clusters_cap) : n_clusters_cap;
 	const int c = task / max_obj;
-	if (c >= n_clusters) { if (lane == 0) { found[task] = 0; n_tests[task] = 0; } return; }
+	if (c >= n_clusters || !ransac_owns(S, c)) { if (lane == 0) { found[task] = 0; n_tests[task] = 0; } return; }
 	const int f = S.first[task];
 	if (f == kNone) {
 		if (lane == 0) { found[task] = 0; n_tests[task] = S.fail[task] ? 0 : max_ransac; }
@@ -250,6 +254,7 @@ mc_status ransac_staged_launch(mc_ctx *ctx, const int32_t *d_cluster_offsets, co
 	S.first = (int32_t *)(b + o_first); S.done = (int32_t *)(b + o_done); S.qpos = (int32_t *)(b + o_qpos); S.queue = (int32_t *)(b + o_queue);
 	S.counters = (int32_t *)(b + o_cnt); S.fail = (uint8_t *)(b + o_fail); S.fit_pose = (float *)(b + o_fit); S.chunk_pose = (float *)(b + o_chunk);
 	S.refit_scratch = refit_floats ? (float *)(b + o_refit) : nullptr;
+	S.shard_rank = ctx->ransac_shard_rank; S.shard_world = ctx->ransac_shard_world;
 	k_ransac_init<<<(n_tasks + 255) / 256, 256, 0, ctx->stream>>>(S, n_tasks);
 	MC_LAUNCH_CHECK();
 	const int64_t groups = (int64_t)n_tasks * HA;

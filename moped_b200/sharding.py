@@ -81,3 +81,17 @@ def ransac_shard_seed(seed: int, first_cluster: int, max_objects_per_cluster: in
     """The `seed` a shard passes so that its LOCAL task t (cluster first_cluster + t // MaxObjectsPerCluster) draws from the
     stream of GLOBAL task first_cluster * MaxObjectsPerCluster + t: seed + stride * first_task, modulo 2^64."""
     return (seed + RANSAC_STREAM_STRIDE * first_cluster * max_objects_per_cluster) & 0xFFFFFFFFFFFFFFFF
+
+
+def ransac_task_owner(task: int, max_objects_per_cluster: int, world: int) -> int:
+    """Frame pipeline with the RANSAC work distributed by cluster (mc_process_frame_sharded_dev): task t = (cluster, try) belongs to the
+    rank that owns its cluster, cluster c -> rank c % world (the cluster count is only known on the device, so the deal is round-robin)."""
+    return (task // max_objects_per_cluster) % world
+
+
+def select_task_records(records: np.ndarray, max_objects_per_cluster: int) -> np.ndarray:
+    """What k_shard_select does after the all-gather: records[r][t] is rank r's record of task t (zeros unless r owns t); the result
+    takes every task from its owner."""
+    world, n_tasks = records.shape[:2]
+    owner = (np.arange(n_tasks) // max_objects_per_cluster) % world
+    return records[owner, np.arange(n_tasks)]

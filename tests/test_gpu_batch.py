@@ -175,6 +175,71 @@ def test_sharded_batch_equals_single_context(ctx30, batch_case):
         cx.close()
 
 
+@pytest.mark.parametrize("world,exact", [(2, 0), (3, 0), (2, 1)])
+def test_cluster_partitioned_frame_equals_single_context(ctx30, batch_case, world, exact):
+    """north_star: "RANSAC work is distributed by cluster". mc_process_frame_sharded_dev on `world` contexts of one GPU, each standing for
+    a rank: all run compaction / CLUSTER / FILTER on the same nearest neighbours and the POSE / POSE2 tasks of their own clusters
+    (cluster % world == rank); the records are copied between the ranks' exchange buffers like the in-place all-gather does. Objects
+    (model, pose, score) and the frame info equal the single-context frame bit for bit on every rank — a task's random stream depends
+    on its index alone — also in exact-order mode."""
+    import torch
+    from moped_b200 import capi, synth
+    c = batch_case
+    dev = torch.device("cuda", 0)
+    MO = 32
+    ctxs = []
+    for r in range(world):
+        cx = capi.Context(0)
+        cx.db_upload(c["dbn"], c["db"]["xyz"], c["db"]["model_of_row"], 30)
+        cx.set_cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+        cx.set_tuning(4, 2 + r, 1)                                   # the first-round width must not matter either
+        cx.set_option("pose_exact_order", exact)
+        ctxs.append(cx)
+    ctx30.set_option("pose_exact_order", exact)
+    try:
+        n_checked = 0
+        for fi in (0, 3, 5, 8):
+            qn, xy, img = c["qn"][fi], c["xy"][fi], c["img"][fi]
+            Q = len(qn)
+            ref = ctx30.process_frame(qn, xy, img, max_objects=MO)
+            dq, dxy, dimg = torch.from_numpy(qn).to(dev), torch.from_numpy(xy).to(dev), torch.from_numpy(img).to(dev)
+            nn_row = torch.empty((Q, 2), dtype=torch.int32, device=dev); nn_dist = torch.empty((Q, 2), dtype=torch.float32, device=dev)
+            acc = torch.empty(Q, dtype=torch.uint8, device=dev)
+            p = ctxs[0].default_params()
+            ctxs[0].match_dev(dq.data_ptr(), Q, p.match_ratio, p.match_mode, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
+            ctxs[0].synchronize()
+            slot = ctxs[0].frame_shard_slot_bytes(Q, p)
+            assert slot > 0 and slot % 256 == 0
+            exch = [torch.zeros((world, slot), dtype=torch.uint8, device=dev) for _ in ctxs]      # every rank's own buffer, as over NCCL
+            outs = [dict(info=torch.zeros(4, dtype=torch.int32, device=dev), model=torch.zeros(MO, dtype=torch.int32, device=dev),
+                         pose=torch.zeros((MO, 7), dtype=torch.float32, device=dev), score=torch.zeros(MO, dtype=torch.float32, device=dev)) for _ in ctxs]
+            for phase in range(3):
+                for r, cx in enumerate(ctxs):
+                    o = outs[r]
+                    cx.process_frame_sharded_dev(phase, nn_row.data_ptr(), acc.data_ptr(), dxy.data_ptr(), dimg.data_ptr(), Q, p, r, world,
+                                                 exch[r].data_ptr(), MO, o["info"].data_ptr(), o["model"].data_ptr(), o["pose"].data_ptr(), o["score"].data_ptr())
+                for cx in ctxs:
+                    cx.synchronize()
+                for r in range(world):                                # the in-place all-gather: slot s of every buffer <- rank s's record
+                    for s_ in range(world):
+                        if s_ != r:
+                            exch[r][s_].copy_(exch[s_][s_])
+                torch.cuda.synchronize()
+            for r, o in enumerate(outs):
+                info = o["info"].cpu().numpy()
+                n = int(info[0])
+                assert info[1] == 0 and n == len(ref["model"]), (fi, r, info, len(ref["model"]))
+                assert np.array_equal(o["model"].cpu().numpy()[:n], ref["model"]), (fi, r)
+                assert np.array_equal(o["pose"].cpu().numpy()[:n], ref["pose"]), (fi, r)
+                assert np.array_equal(o["score"].cpu().numpy()[:n], ref["score"]), (fi, r)
+            n_checked += len(ref["model"])
+        assert n_checked >= 6
+    finally:
+        ctx30.set_option("pose_exact_order", 0)
+        for cx in ctxs:
+            cx.close()
+
+
 def test_frame_graphs_equal_eager_launches(ctx30, batch_case):
     """mc_process_frames replays one CUDA graph per frame for the stages after MATCH (captured per lane and per
     feature-count bucket). Replays, re-captures after a bucket change and the eager path give identical results,

@@ -239,7 +239,7 @@ def test_moped3d_chain_after_cluster_inside_its_own_pipeline(tmp_path):
 
 
 def test_cached_agglomeration_equals_default_kernel(gpu_ctx):
-    """mc_set_option("linkage_cached", 1): the cached-row-maximum agglomeration (linkage_cached.cuh) gives the oracle's clusters —
+    """mc_set_option("linkage_cached", 1) (the default): the cached-row-maximum agglomeration (linkage_cached.cuh) gives the oracle's clusters —
     and therefore the default kernel's — on the oracle's own similarity matrices, on tie-heavy quantised ones and on a 600-match
     block-structured one (the host-emulated source already does: tests/test_linkage_cached_host.py)."""
     from test_oracle3d_linkage import make_scene
@@ -256,12 +256,14 @@ def test_cached_agglomeration_equals_default_kernel(gpu_ctx):
     K = np.where((g[:, None] == g[None, :]) & (g[:, None] < groups), 0.6 + 0.4 * rng.random((n, n)), 0.05 * rng.random((n, n))).astype(np.float32)
     K = np.maximum(K, K.T); np.fill_diagonal(K, 1.0)
     mats.append((K, 0.1, 7))
-    gpu_ctx.set_option("linkage_cached", 1)
     try:
-        for K, cutoff, min_pts in mats:
-            oo, om = oracle.linkage_agglomerate(K, cutoff, min_pts, 1)
-            go, gm = gpu_ctx.linkage_agglomerate(K, cutoff, min_pts, 1)
-            assert np.array_equal(oo, go) and np.array_equal(om, gm), (len(K), cutoff, min_pts)
+        for cached in (1, 0):                       # 1 is the default since it was timed on B200 (profiles/linkage_bench_r2.jsonl); 0 = the O(n^2)-scan kernel
+            gpu_ctx.set_option("linkage_cached", cached)
+            for K, cutoff, min_pts in mats:
+                oo, om = oracle.linkage_agglomerate(K, cutoff, min_pts, 1)
+                go, gm = gpu_ctx.linkage_agglomerate(K, cutoff, min_pts, 1)
+                assert np.array_equal(oo, go) and np.array_equal(om, gm), (cached, len(K), cutoff, min_pts)
+        gpu_ctx.set_option("linkage_cached", 1)
         # other linkage types keep the default kernel
         K = mats[3][0]
         for linkage in (0, 2):
@@ -269,7 +271,7 @@ def test_cached_agglomeration_equals_default_kernel(gpu_ctx):
             go, gm = gpu_ctx.linkage_agglomerate(K, 0.5, 1, linkage)
             assert np.array_equal(oo, go) and np.array_equal(om, gm), linkage
     finally:
-        gpu_ctx.set_option("linkage_cached", 0)
+        gpu_ctx.set_option("linkage_cached", 1)
 
 
 def test_match_adaptive_stage_class_inside_moped3ds_own_pipeline():

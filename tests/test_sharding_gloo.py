@@ -297,3 +297,78 @@ def test_two_rank_depth_ransac_by_cluster_is_independent_of_the_number_of_ranks(
             assert np.array_equal(np.array(merged[t][2:], np.float32), p), t
         found += f
     assert found >= 5
+
+
+def _cluster_partition_frame_rank(rank, world, port, q):
+    """mc_process_frame_sharded_dev's protocol with the oracle in the kernels' place: CLUSTER / FILTER replicated, the (cluster, try)
+    tasks of POSE and POSE2 dealt by cluster, the task records all-gathered (gloo) and every task taken from its owner."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle_chain as oc
+    from conftest import cluster_points
+    from oracle import oracle
+    from moped_b200 import synth
+    from moped_b200.sharding import ransac_task_owner, select_task_records
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    db = synth.make_db(6, 300, seed=4)
+    fr = synth.make_frame(db, 500, n_visible=3, frame_id=2)
+    dbn, qn = oracle.norm_rows(db["desc"]), oracle.norm_rows(fr["desc"])
+    cams = oracle.cameras(synth.K_DEFAULT, synth.CAM_IDENTITY)
+    m, _, _ = oracle.match(dbn, db["xyz"], db["model_of_row"], 6, qn, fr["xy"], fr["image_idx"], 0.8)
+
+    def pose_step_sharded(clusters, params, seed, objects):
+        xy, xyz, img, tie, co = cluster_points(m, clusters)
+        n_tasks = len(clusters["model"]) * params[2]
+        rec = np.zeros((n_tasks, 8), np.float32)                       # found | pose[7]
+        mine = 0
+        for task in range(n_tasks):
+            if ransac_task_owner(task, params[2], world) != rank:
+                continue
+            mine += 1
+            k = task // params[2]
+            sl = slice(co[k], co[k + 1])
+            f, p, _ = oracle.ransac(xy[sl], xyz[sl], img[sl], tie[sl], cams, params, (seed + oc.GOLDEN * (task + 1)) & oc.M64)
+            rec[task, 0] = float(f)
+            rec[task, 1:] = p
+        out = [torch.empty((n_tasks, 8), dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(out, torch.from_numpy(rec))
+        sel = select_task_records(torch.stack(out).numpy(), params[2])
+        for task in range(n_tasks):
+            if sel[task, 0]:
+                objects.append((int(clusters["model"][task // params[2]]), sel[task, 1:].copy()))
+        return mine, n_tasks
+
+    cl = oracle.cluster(m, 1)
+    objects = []
+    mine1, n1 = pose_step_sharded(cl, oc.POSE1, 1, objects)
+    objects, cl2, _ = oc.filter_step(m, cams, objects, oc.FILTER1)
+    mine2, n2 = pose_step_sharded(cl2, oc.POSE2, 2, objects)
+    objects, _, score = oc.filter_step(m, cams, objects, oc.FILTER2)
+    want = oc.frame(dbn, db["xyz"], db["model_of_row"], 6, qn, fr["xy"], fr["image_idx"], synth.K_DEFAULT, synth.CAM_IDENTITY)
+    ok = len(objects) == len(want["model"]) and len(objects) >= 2
+    ok = ok and [o[0] for o in objects] == want["model"].tolist()
+    ok = ok and all(np.array_equal(o[1].astype(np.float32), w) for o, w in zip(objects, want["pose"])) and np.array_equal(score, want["score"])
+    q.put((rank, bool(ok), (mine1, n1, mine2, n2), len(objects)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_frame_with_ransac_distributed_by_cluster_equals_the_single_process_chain():
+    """north_star: "RANSAC work is distributed by cluster" inside the frame pipeline. Bit-identical objects on both ranks, every task run
+    by exactly one rank."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cluster_partition_frame_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    (a1, n1, a2, n2), (b1, _, b2, _) = res[0][2], res[1][2]
+    assert a1 + b1 == n1 and a2 + b2 == n2 and n1 > 0, res
+    assert res[0][3] == res[1][3]
