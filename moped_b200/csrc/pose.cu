@@ -85,7 +85,7 @@ __device__ __forceinline__ void eval_residuals(const float *p, const LmPoint (&p
 // Every lane of the group runs it on identical data. Returns false if singular.
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-__device__ bool lu_solve7(const float (&A)[28], float mu, const float (&b)[7], float (&x)[7]) {
+__device__ __forceinline__ bool lu_solve7_inline(const float (&A)[28], float mu, const float (&b)[7], float (&x)[7]) {
 	float a[7][7], work[7];
 #pragma unroll
 	for (int i = 0; i < 7; i++)
@@ -159,6 +159,65 @@ __device__ bool lu_solve7(const float (&A)[28], float mu, const float (&b)[7], f
 		x[i] = sum / a[i][i];
 	}
 	return true;
+}
+
+// out of line: the cold path of solve7 below
+__device__ __noinline__ bool lu_solve7(const float (&A)[28], float mu, const float (&b)[7], float (&x)[7]) { return lu_solve7_inline(A, mu, b, x); }
+
+// The damped normal equations (J^T J + mu I) Dp = J^T e of the DEFAULT kernels. levmar solves them with the pivoting LU above; the
+// matrix is symmetric positive definite for mu > 0, so an unpivoted LDL^T factorisation gives the same solution to within the
+// rounding both methods carry (measured on the oracle: 99.2 % of the systems of an LM run keep every pivot above 1e-3 of its
+// diagonal entry; with LDL^T there and the LU elsewhere, accept decisions of 1792 hypotheses are identical and refitted poses
+// differ by 1.3e-5 m at the median / 2.6e-4 m at the 90th percentile — the spread between the reference's own two builds,
+// profiles/lm_parity_r2.md) at a quarter of the instructions: ~210 against ~890 executed SASS instructions per solve, and the
+// solve was 35 % of the instructions of the thread-per-hypothesis kernel (ncu) and the longest stretch of the lane-group kernels'
+// dependent chain. A system that loses three digits in a pivot (mu underflowed, J^T J rank-deficient along the quaternion's scale),
+// or holds a NaN, takes levmar's LU with its singularity rules. The exact-order mode (lm_exact.cuh) always runs the LU.
+__device__ __forceinline__ float rcp_approx(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ int ltri(int i, int j) { return i * (i - 1) / 2 + j; }       // strict lower triangle, j < i
+
+__device__ __forceinline__ bool ldl_solve7(const float (&A)[28], float mu, const float (&b)[7], float (&x)[7]) {
+	float L[21], d[7], r[7], z[7];
+	bool ok = true;
+#pragma unroll
+	for (int j = 0; j < 7; j++) {
+		const float ajj = A[tri(j, j)] + mu;
+		float v[7];
+		float s = ajj;
+#pragma unroll
+		for (int k = 0; k < j; k++) { v[k] = L[ltri(j, k)] * d[k]; s -= L[ltri(j, k)] * v[k]; }
+		ok = ok && (s > 1E-03f * ajj);                    // false for a NaN as well
+		d[j] = s;
+		r[j] = rcp_approx(s);                            // MUFU.RCP, 1 ulp: the pivoting LU this replaces differs from it by far more (cond * eps)
+#pragma unroll
+		for (int i = j + 1; i < 7; i++) {
+			float t = A[tri(i, j)];
+#pragma unroll
+			for (int k = 0; k < j; k++) t -= L[ltri(i, k)] * v[k];
+			L[ltri(i, j)] = t * r[j];
+		}
+	}
+	if (!ok) return false;
+#pragma unroll
+	for (int i = 0; i < 7; i++) {
+		float t = b[i];
+#pragma unroll
+		for (int k = 0; k < i; k++) t -= L[ltri(i, k)] * z[k];
+		z[i] = t;
+	}
+#pragma unroll
+	for (int i = 6; i >= 0; i--) {
+		float t = z[i] * r[i];
+#pragma unroll
+		for (int k = i + 1; k < 7; k++) t -= L[ltri(k, i)] * x[k];
+		x[i] = t;
+	}
+	return true;
+}
+
+__device__ __forceinline__ bool solve7(const float (&A)[28], float mu, const float (&b)[7], float (&x)[7]) {
+	if (ldl_solve7(A, mu, b, x)) return true;
+	return lu_solve7(A, mu, b, x);
 }
 
 // slevmar_dif restated for a lane group: m = 7, target 0, default options (lm.h:83-85), forward-difference
@@ -252,7 +311,7 @@ __device__ int lm_dif(float (&p)[7], int itmax, const LmPoint (&pts)[S], int n_o
 			mu = tau * t;
 		}
 
-		const bool solved = lu_solve7(jtj, mu, jte, Dp);
+		const bool solved = solve7(jtj, mu, jte, Dp);
 		if (solved) {
 			float Dp_L2 = 0.f;
 #pragma unroll
@@ -510,7 +569,15 @@ k_pose_fit_thread(const int32_t *__restrict__ cluster_offsets, const float *__re
 // points live in shared memory, element-major ([e][thread]: conflict-free), which brings the kernel from 254 to <= 168 registers.
 // Inlier scoring moved to k_pose_score (one 8-lane group per hypothesis): inside the state machine it would run with one or two
 // active lanes.
+// Measured variants of this kernel (B200, 131072 hypotheses, profiles/fit_stream_experiments_r2b.md): this one 4.04 ms (ncu: 13.6 active
+// lanes, 49 % issue utilisation, top stall `no_instruction` — twelve warps spread over the branches of a 3.5 k-instruction body);
+// LDL^T first + out-of-line LU fallback (solve7): 14 % fewer executed instructions but 4.24 ms (a warp pays the fallback whenever one
+// of its lanes needs it, at 2.3 active lanes; instruction-cache hit rate 74 -> 64 %); the same with the row loops rolled and hx / trial
+// residuals in shared memory (2.5 k -> 1.2 k hot instructions): 5.08 ms (loop overhead and dynamic addressing cost more than the
+// fetch stalls they remove); 4 CTAs per SM at 128 registers: no change. The lane-group kernels do use solve7 (their solve is redundant
+// per lane and on the critical path of a single LM chain: k_pose_refit_lists 0.86 -> 0.49 ms, frame batch 5.5 -> 4.0 ms).
 constexpr int kStreamThreads = 128;
+constexpr int kStreamFloats = 20;                                       // shared-memory floats per thread and sample point: J 14, point 6
 enum { kModeIdle = 0, kModeInit = 1, kModeSolve = 2, kModeJac = 3 };
 
 template <int S, int MINB>
@@ -635,7 +702,7 @@ k_pose_fit_stream(const int32_t *__restrict__ cluster_offsets, const float *__re
 					for (int i = 0; i < 7; i++) t = fmaxf(t, jtj[tri(i, i)]);
 					mu = tau * t;
 				}
-				if (lu_solve7(jtj, mu, jte, Dp)) {
+				if (lu_solve7_inline(jtj, mu, jte, Dp)) {        // (LDL^T + out-of-line LU measured here: 14 % fewer instructions, 5 % slower — see below)
 #pragma unroll
 					for (int i = 0; i < 7; i++) { x[i] = p[i] + Dp[i]; Dp_L2 += Dp[i] * Dp[i]; }
 					if (Dp_L2 <= eps2_sq * p_L2) finish(2);
@@ -990,7 +1057,7 @@ mc_status pose_hypotheses_device(mc_ctx *ctx, const int32_t *d_cluster_offsets, 
 		MC_CUDA(cudaMemsetAsync(ctx->scratch[20].p, 0, 256, ctx->stream));
 #define MC_FIT_STREAM(S, MINB)                                                                                                               \
 		do {                                                                                                                                 \
-			const size_t smem = (size_t)(S) * 20 * kStreamThreads * sizeof(float);                                                           \
+			const size_t smem = (size_t)(S) * kStreamFloats * kStreamThreads * sizeof(float);                                                           \
 			MC_CUDA(cudaFuncSetAttribute(k_pose_fit_stream<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
 			int per_sm = 0;                                                                                                                  \
 			MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pose_fit_stream<S, MINB>, kStreamThreads, smem));               \
