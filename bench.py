@@ -224,6 +224,25 @@ def run_reference(args, rank, world):
     print(json.dumps(out))
 
 
+def init_nccl_quietly(dist, dev):
+    """NCCL prints its banner ("NCCL version ...") on STDOUT when the communicator is created (at init with device_id, or lazily at the
+    first collective), whatever NCCL_DEBUG_FILE says; rank 0's stdout must carry ONE JSON line. File descriptor 1 points at stderr while
+    the process group and its communicator come up (a tiny all-reduce forces the creation), then it is restored."""
+    import torch
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)
+        torch.cuda.synchronize(dev)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def workload_config(args, world):
     """The SAME dict on both arms (the driver compares them): the workload, and how our arm schedules it."""
     img_bytes = ((args.objects * args.pts // world + 127) // 128) * 32768
@@ -269,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
 
     log(f"[bench] rank {rank}/{world} on cuda:{local_rank}: pipeline={args.pipeline} stage_sms={args.stage_sms} lanes={args.lanes}")
     B, Q = args.frames, args.features
@@ -643,7 +662,7 @@ def run_ours_cluster_partition(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
     B, Q = args.frames, args.features
     QT = B * Q
     db = synth.make_db(args.objects, args.pts)
@@ -904,7 +923,7 @@ def run_ransac_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
     cl = synth.make_ransac_clusters(args.clusters, 80, 0.5)
     hy = synth.make_hypotheses(cl, args.hyp, 5)
     mine = cluster_partition(hy["hyp_cluster"], world, rank)           # clusters round-robin over the ranks
@@ -1186,7 +1205,7 @@ def run_sift_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
     lo, hi = frame_range(args.frames, world, rank)                               # frames are independent: partition, no collective
     B = hi - lo
     pool = [sift_images(B, first=1000 * p + lo) for p in range(2)]               # two different batches, alternated
@@ -1372,7 +1391,7 @@ def run_images_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
     g, frames_all = images_setup(args)
     lo, hi = frame_range(args.frames, world, rank)
     frames = np.ascontiguousarray(frames_all[lo:hi])

@@ -383,6 +383,9 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
  *                          rate) first and the fp16 pass only for the queries whose certificate it fails; 0: fp16 pass for all
  *                          queries. Same results bit for bit (both end in the exact re-rank and, failing the certificate, in the
  *                          exhaustive scan).
+ *   "match_splits"         database splits per query tile in the tensor-core coarse pass (every split of a query keeps its own candidate
+ *                          lists); 0 (default) = chosen from the grid and the shard size. A tuning knob: the cascade certifies or
+ *                          re-does every query, so results never depend on it.
  *   "match_stagger"        != 0 (default): the CTAs that scan the same database split at the same time start at different tiles
  *                          (kept as a switch for A/B measurements; results do not depend on it)
  *   "stage_sm_partition"   0 (default) or a multiple of 8 up to 96: partition the GPU with CUDA green contexts — this many SMs for the

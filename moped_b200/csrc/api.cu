@@ -191,6 +191,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "defer_lane_join") ctx->defer_lane_join = value != 0;
 	else if (k == "match_coarse_kind") { if (value != 0 && value != 1) { ctx->err = "mc_set_option: match_coarse_kind must be 0 (fp16) or 1 (8-bit first)"; return MC_ERR_ARG; } ctx->coarse_kind = (int)value; }
 	else if (k == "match_stagger") ctx->match_stagger = value != 0;
+	else if (k == "match_splits") { if (value < 0 || value > 64) { ctx->err = "mc_set_option: match_splits must be in 0..64"; return MC_ERR_ARG; } ctx->match_splits = (int)value; }
 	else if (k == "stage_sm_partition") {
 		if (value < 0 || value > 96 || value % 8) { ctx->err = "mc_set_option: stage_sm_partition must be 0 or a multiple of 8 up to 96"; return MC_ERR_ARG; }
 		MC_CUDA(cudaSetDevice(ctx->device));

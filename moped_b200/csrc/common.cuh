@@ -83,6 +83,7 @@ struct mc_ctx {
 	cudaStream_t match_green_stream = nullptr;
 	cudaEvent_t ev_green[2] = {nullptr, nullptr};
 	int match_sms = 0, stage_sms = 0; // SMs of the two partitions (0 = no partition)
+	int match_splits = 0;             // mc_set_option "match_splits": database splits per query tile in the coarse pass (0 = chosen from the grid)
 	int match_stagger = 1;            // mc_set_option "match_stagger": CTAs of one DB split start at different tiles
 	int match_reserve_sms = 0;        // mc_set_option "match_reserve_sms": SMs the persistent matching kernel leaves to concurrent work
 	mc::DevBuf nn_row, nn_dist, accepted, q_xy, q_image;

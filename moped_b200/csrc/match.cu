@@ -1068,7 +1068,14 @@ static mc_status exact_scan(mc_ctx *ctx, const float *d_q, int Q, const int32_t 
 // pass 50 % slower).
 static void choose_splits(const mc_ctx *ctx, int n_mtiles, int ctas, int &n_splits, int &tiles_per_split) {
 	n_splits = ctas / n_mtiles;
-	if (n_splits < 8) {
+	if (ctx->match_splits > 0) n_splits = ctx->match_splits;      // mc_set_option "match_splits": tuning override (the cascade stays exact)
+	else if (n_splits < 8 && ctx->n_tiles <= 4800) {
+		// shards up to ~600 k rows (the ranks of a 2..8-GPU job): 4 splits. Work items are handed out dynamically, so a ragged last round
+		// costs little, while every split of a query starts two more cold candidate lists (insertions) and adds 16 candidates to the
+		// re-rank; fewer than 4 sends too many queries to the fp16 second-chance pass. Whole MATCH pass, 128 000 queries, B200
+		// (profiles/coarse_splits_r2b.md): 125 k rows 4.01 -> 3.42 ms, 500 k rows 9.42 -> 9.08 ms; at 1 M rows 4 / 6 / 9 splits are equal.
+		n_splits = 4;
+	} else if (n_splits < 8) {
 		double best = -1.0;
 		for (int sp = 8; sp <= 16; sp++) {
 			const int64_t items = (int64_t)n_mtiles * sp;

@@ -37,8 +37,10 @@ ref = None
 import subprocess  # noqa: E402
 old_lib = bool(os.environ.get("DBG_OLD"))
 configs = ((0, 0, 0),) if old_lib else tuple(tuple(int(v) for v in c.split(":")) for c in os.environ.get("DBG_CONFIGS", "1:0:1,1:0:0,0:0:1,0:0:0,1:8:1").split(","))
-for kind, reserve, stagger in configs:
+splits_list = [int(v) for v in os.environ.get("DBG_SPLITS", "0").split(",")]
+for kind, reserve, stagger, splits in [(c[0], c[1], c[2], sp) for c in configs for sp in splits_list]:
     if not old_lib:
+        ctx.set_option("match_splits", splits)
         ctx.set_option("match_coarse_kind", kind)
         ctx.set_option("match_reserve_sms", reserve)
         ctx.set_option("match_stagger", stagger)
@@ -46,15 +48,14 @@ for kind, reserve, stagger in configs:
     smi = subprocess.Popen(["nvidia-smi", "--id=0", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "20"],
                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     for i in range(int(os.environ.get("DBG_ITERS", 12))):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import time
         torch.cuda.synchronize()
-        e0.record()
+        t0 = time.perf_counter()                 # (the context runs its own stream: wall clock around the synchronised pass, launch overhead included)
         ctx.match_dev(q.data_ptr(), QT, 0.8, capi.MATCH_TENSOR, nn_row.data_ptr(), nn_dist.data_ptr(), acc.data_ptr())
-        e1.record()
         ctx.synchronize()
+        tot.append((time.perf_counter() - t0) * 1e3)
         torch.cuda.synchronize()
         ms.append(ctx.coarse_kernel_ms())
-        tot.append(e0.elapsed_time(e1))
     smi.terminate()
     clk = [ln.split(",") for ln in smi.stdout.read().strip().splitlines() if "," in ln]
     sm_mhz = float(np.median([float(c[0]) for c in clk])) if clk else None
@@ -63,7 +64,7 @@ for kind, reserve, stagger in configs:
     same = True if ref is None else all(np.array_equal(a, b) for a, b in zip(ref, res))
     ref = ref or res
     km = float(np.median(ms[2:]))
-    print(json.dumps({"label": label, "coarse_kind": kind, "reserve_sms": reserve, "stagger": stagger, "rows": len(dbn), "queries": QT, "coarse_ms": km,
+    print(json.dumps({"label": label, "coarse_kind": kind, "reserve_sms": reserve, "stagger": stagger, "splits": splits, "rows": len(dbn), "queries": QT, "coarse_ms": km, "match_ms": float(np.median(tot[2:])),
                       "tera_ops": 2.0 * len(dbn) * QT * 128 / (km * 1e-3) / 1e12,
                       "sm_mhz": sm_mhz, "watts": watts, "clock_samples": len(clk),
                       "tiers": None if old_lib else ctx.match_tier_stats().tolist(), "stats": ctx.match_last_stats().tolist(), "same_bits_as_first": same}), flush=True)
