@@ -206,6 +206,20 @@ mc_status mc_filter_projection(mc_ctx *ctx, const int32_t *match_offsets, const 
                                int min_points, float feature_distance, float min_score,
                                uint8_t *keep, float *score, int32_t *n_survivors, int32_t *cluster_offsets, int32_t *members);
 
+/* moped3d's FILTER_PROJECTION_DEPTH_CPU::process (moped3d/libmoped/src/filter/FILTER_PROJECTION_DEPTH_CPU.hpp:145-329): the projection
+ * filter with a penalty from the depth map. test_offsets / test_xyz: the test points of every model (all its keypoints, or the
+ * TestSampleSize the class draws once, :94-118 — the caller's choice, e.g. the stage class FILTER_PROJECTION_DEPTH_CUDA). depth /
+ * fill_distance: height x width planes (Image::getDepth of the depth map, getProb of its ".distance" map), depth_K / depth_pose: the
+ * depth camera's intrinsics (fx, fy, cx, cy) and pose (quaternion x y z w, translation). An object's score is its projection score
+ * minus the penalty (:276); features are owned by the best PROJECTION score (:283), pruning uses the penalised one (:314).
+ * Outputs as mc_filter_projection. */
+mc_status mc_filter_projection_depth(mc_ctx *ctx, const int32_t *match_offsets, const int32_t *match_image, const float *match_xy,
+                                     const float *match_xyz, int n_models, const int32_t *obj_model, const float *obj_pose, int n_objects,
+                                     int min_points, float feature_distance, float plausible_sq_distance, float min_score, float depth_fraction,
+                                     float min_keypoint_fraction, const int32_t *test_offsets, const float *test_xyz, const float *depth_K,
+                                     const float *depth_pose, int width, int height, const float *depth, const float *fill_distance,
+                                     uint8_t *keep, float *score, int32_t *n_survivors, int32_t *cluster_offsets, int32_t *members);
+
 /* ---- whole frame on the device: MATCH..FILTER2 chained without leaving HBM ---- */
 typedef struct {
 	float match_ratio; int32_t match_mode;

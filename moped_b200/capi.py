@@ -67,6 +67,9 @@ SIGNATURES = {
                                        C.c_float, _u8p, _f32p, _i32p]),
     "mc_filter_projection": (C.c_int, [C.c_void_p, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float,
                                        _u8p, _f32p, C.POINTER(C.c_int32), _i32p, _i32p]),
+    "mc_filter_projection_depth": (C.c_int, [C.c_void_p, _i32p, _i32p, _f32p, _f32p, C.c_int, _i32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                             C.c_float, C.c_float, C.c_float, _i32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p,
+                                             _u8p, _f32p, C.POINTER(C.c_int32), _i32p, _i32p]),
     "mc_model_db_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "mc_model_db_destroy": (None, [C.c_void_p]),
     "mc_model_db_last_error": (C.c_char_p, [C.c_void_p]),
@@ -358,6 +361,33 @@ class Context:
                                                 _i32(pt_image), tie.ctypes.data if tie is not None else None, C.byref(pp), float(alpha), found, pose,
                                                 n_tests), "mc_pose_depth_ransac")
         return found.astype(bool), pose, n_tests
+
+    def filter_depth(self, matches, obj_model, obj_pose, params, test_offsets, test_xyz, depth_K, depth_pose, depth, fill_distance):
+        """moped3d's FILTER_PROJECTION_DEPTH. params = (MinPoints, FeatureDistance, PlausibleSqDistance, MinScore, DepthFraction,
+        MinKeypointFraction); depth / fill_distance: H x W float planes."""
+        off = _i32(matches["offsets"])
+        M = int(off[-1])
+        om, op = _i32(obj_model), _f32(obj_pose).reshape(-1, 7)
+        n = len(om)
+        keep = np.zeros(n + 1, np.uint8)
+        score = np.zeros(n + 1, np.float32)
+        ns = C.c_int32(0)
+        co = np.zeros(n + 2, np.int32)
+        mem = np.zeros(M + 2, np.int32)
+        img = _i32(matches["image"]) if M else np.zeros(1, np.int32)
+        xy = _f32(matches["xy"]) if M else np.zeros((1, 2), np.float32)
+        xyz = _f32(matches["xyz"]) if M else np.zeros((1, 3), np.float32)
+        if n == 0:
+            om, op = np.zeros(1, np.int32), np.zeros((1, 7), np.float32)
+        to = _i32(test_offsets)
+        tx = _f32(test_xyz).reshape(-1, 3) if int(to[-1]) else np.zeros((1, 3), np.float32)
+        d, f = _f32(depth), _f32(fill_distance)
+        self._check(self.L.mc_filter_projection_depth(self.h, off, img, xy, xyz, len(off) - 1, om, op, n, int(params[0]), float(params[1]),
+                                                      float(params[2]), float(params[3]), float(params[4]), float(params[5]), to, tx, _f32(depth_K),
+                                                      _f32(depth_pose), d.shape[1], d.shape[0], d, f, keep, score, C.byref(ns), co, mem),
+                    "mc_filter_projection_depth")
+        s = ns.value
+        return dict(keep=keep[:n].astype(bool), score=score[:n].copy(), offsets=co[:s + 1].copy(), members=mem[:co[s]].copy())
 
     # ---- FILTER
     def filter(self, matches, obj_model, obj_pose, params=(5, 4096.0, 2.0)):

@@ -8,6 +8,15 @@
 #include <algorithm>
 
 namespace mc {
+mc_status filter_depth_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
+                              const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
+                              const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score,
+                              const int32_t *d_test_offsets, const float *d_test_xyz, const float *depth_K4, const float *depth_TM12, int width,
+                              int height, const float *d_depth, const float *d_fill, float plausible_dist, float depth_fraction,
+                              float min_keypoint_fraction, uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model,
+                              int32_t *d_cluster_offsets, int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score);
+}
+namespace mc {
 mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
                          int n_models, int n_images, int max_matches, float radius, float merge, int min_pts, int max_iter,
                          int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets, int32_t *d_members);
@@ -650,6 +659,68 @@ mc_status mc_filter_projection(mc_ctx *ctx, const int32_t *match_offsets, const 
 	                     (int32_t *)(b + o_om), (float *)(b + o_op), nullptr, n_objects, min_points, feature_distance, min_score,
 	                     (uint8_t *)(b + o_keep), (float *)(b + o_sc), (int32_t *)(b + o_n), (int32_t *)(b + o_cm), (int32_t *)(b + o_co),
 	                     (int32_t *)(b + o_mem), (int32_t *)(b + o_sm), (float *)(b + o_sp), (float *)(b + o_ss)));
+	int32_t hn[2] = { 0, 0 };
+	MC_TRY(d2h(ctx, hn, (const int32_t *)(b + o_n), 2));
+	MC_TRY(d2h(ctx, keep, (const uint8_t *)(b + o_keep), (size_t)n_objects));
+	MC_TRY(d2h(ctx, score, (const float *)(b + o_sc), (size_t)n_objects));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	*n_survivors = hn[0];
+	MC_TRY(d2h(ctx, cluster_offsets, (const int32_t *)(b + o_co), (size_t)hn[0] + 1));
+	MC_TRY(d2h(ctx, members, (const int32_t *)(b + o_mem), (size_t)hn[1]));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+mc_status mc_filter_projection_depth(mc_ctx *ctx, const int32_t *match_offsets, const int32_t *match_image, const float *match_xy,
+                                     const float *match_xyz, int n_models, const int32_t *obj_model, const float *obj_pose, int n_objects,
+                                     int min_points, float feature_distance, float plausible_sq_distance, float min_score, float depth_fraction,
+                                     float min_keypoint_fraction, const int32_t *test_offsets, const float *test_xyz, const float *depth_K,
+                                     const float *depth_pose, int width, int height, const float *depth, const float *fill_distance,
+                                     uint8_t *keep, float *score, int32_t *n_survivors, int32_t *cluster_offsets, int32_t *members) {
+	if (!ctx || !match_offsets || !n_survivors || !cluster_offsets || !members || !test_offsets || !depth_K || !depth_pose || !depth || !fill_distance ||
+	    n_models <= 0 || n_objects < 0 || width <= 0 || height <= 0) {
+		if (ctx) ctx->err = "mc_filter_projection_depth: bad argument";
+		return MC_ERR_ARG;
+	}
+	for (int m = 0; m < n_models; m++)
+		if (test_offsets[m + 1] < test_offsets[m] || test_offsets[0] != 0) { ctx->err = "mc_filter_projection_depth: test_offsets must start at 0 and ascend"; return MC_ERR_ARG; }
+	if (test_offsets[n_models] > 0 && !test_xyz) { ctx->err = "mc_filter_projection_depth: bad argument"; return MC_ERR_ARG; }
+	MC_CUDA(cudaSetDevice(ctx->device));
+	const int M = match_offsets[n_models];
+	const int NT = test_offsets[n_models];
+	const size_t px = (size_t)width * height;
+	const int no = n_objects > 0 ? n_objects : 1;
+	Arena A; A.ctx = ctx;
+	const size_t o_off = A.plan(4ull * (n_models + 1)), o_img = A.plan(4ull * (M + 1)), o_xy = A.plan(8ull * (M + 1)), o_xyz = A.plan(12ull * (M + 1));
+	const size_t o_om = A.plan(4ull * no), o_op = A.plan(28ull * no), o_keep = A.plan(no), o_sc = A.plan(4ull * no), o_n = A.plan(64);
+	const size_t o_cm = A.plan(4ull * (no + 2)), o_co = A.plan(4ull * (no + 2)), o_mem = A.plan(4ull * (M + 2));
+	const size_t o_sm = A.plan(4ull * no), o_sp = A.plan(28ull * no), o_ss = A.plan(4ull * no);
+	const size_t o_to = A.plan(4ull * (n_models + 1)), o_tx = A.plan(12ull * (NT + 1)), o_d = A.plan(4ull * px), o_f = A.plan(4ull * px);
+	MC_TRY(reserve(ctx, ctx->scratch[14], A.off));
+	char *b = (char *)ctx->scratch[14].p;
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_off), match_offsets, (size_t)n_models + 1));
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_img), match_image, (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_xy), match_xy, 2 * (size_t)M));
+	MC_TRY(h2d(ctx, (float *)(b + o_xyz), match_xyz, 3 * (size_t)M));
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_om), obj_model, (size_t)n_objects));
+	MC_TRY(h2d(ctx, (float *)(b + o_op), obj_pose, 7 * (size_t)n_objects));
+	MC_TRY(h2d(ctx, (int32_t *)(b + o_to), test_offsets, (size_t)n_models + 1));
+	MC_TRY(h2d(ctx, (float *)(b + o_tx), test_xyz, 3 * (size_t)NT));
+	MC_TRY(h2d(ctx, (float *)(b + o_d), depth, px));
+	MC_TRY(h2d(ctx, (float *)(b + o_f), fill_distance, px));
+	float TM[12];
+	{
+		const float *q = depth_pose, *t = q + 4;             // depthmap->TM.init(cameraPose), like mc_set_cameras
+		TM[0] = 1 - 2 * q[1] * q[1] - 2 * q[2] * q[2]; TM[1] = 2 * q[0] * q[1] - 2 * q[3] * q[2]; TM[2] = 2 * q[0] * q[2] + 2 * q[3] * q[1]; TM[3] = t[0];
+		TM[4] = 2 * q[0] * q[1] + 2 * q[3] * q[2]; TM[5] = 1 - 2 * q[0] * q[0] - 2 * q[2] * q[2]; TM[6] = 2 * q[1] * q[2] - 2 * q[3] * q[0]; TM[7] = t[1];
+		TM[8] = 2 * q[0] * q[2] - 2 * q[3] * q[1]; TM[9] = 2 * q[1] * q[2] + 2 * q[3] * q[0]; TM[10] = 1 - 2 * q[0] * q[0] - 2 * q[1] * q[1]; TM[11] = t[2];
+	}
+	MC_TRY(filter_depth_device(ctx, (int32_t *)(b + o_off), (int32_t *)(b + o_img), (float *)(b + o_xy), (float *)(b + o_xyz), n_models, M,
+	                           (int32_t *)(b + o_om), (float *)(b + o_op), nullptr, n_objects, min_points, feature_distance, min_score,
+	                           (int32_t *)(b + o_to), (float *)(b + o_tx), depth_K, TM, width, height, (float *)(b + o_d), (float *)(b + o_f),
+	                           plausible_sq_distance, depth_fraction, min_keypoint_fraction,
+	                           (uint8_t *)(b + o_keep), (float *)(b + o_sc), (int32_t *)(b + o_n), (int32_t *)(b + o_cm), (int32_t *)(b + o_co),
+	                           (int32_t *)(b + o_mem), (int32_t *)(b + o_sm), (float *)(b + o_sp), (float *)(b + o_ss)));
 	int32_t hn[2] = { 0, 0 };
 	MC_TRY(d2h(ctx, hn, (const int32_t *)(b + o_n), 2));
 	MC_TRY(d2h(ctx, keep, (const uint8_t *)(b + o_keep), (size_t)n_objects));

@@ -7,6 +7,8 @@
 //                    match with the same (coord2D, image) key — `bestPoints` (:117-129)
 //   k_filter_rebuild one thread per object: owned matches of its own model -> new cluster; keep/prune (:135-160)
 //   k_filter_compact survivors' clusters in reference order (model-major, list order)
+// moped3d's FILTER_PROJECTION_DEPTH_CPU (moped3d/libmoped/src/filter/FILTER_PROJECTION_DEPTH_CPU.hpp:145-329) is the same filter with a
+// penalty from the depth map subtracted from the score before pruning (k_filter_depth_adjust); ownership keeps the unpenalised score.
 #include "common.cuh"
 
 #include <math_constants.h>
@@ -187,11 +189,95 @@ __global__ void k_filter_compact(const int32_t *__restrict__ match_offsets, int 
 	(void)s_rank;
 }
 
+// ---- moped3d: the depth-map penalty of FILTER_PROJECTION_DEPTH_CPU (:197-270) ----
+// One warp per object. (1) clusterSize = matches of its model within PlausibleSqDistance (:201-203). (2) the "incorrect score": every test
+// point of the model is moved by the object's pose into the depth camera and projected (:222-231); points off the image or on a pixel
+// whose depth was filled in (fill distance > 0) are skipped, the others count as usable; a usable point the depth map does not
+// occlude adds 1 - 1/(1 + ((z - d) / (DepthFraction d))^2), accumulated in test-point order as float <- double like the reference
+// (:259-263). (3) IS = 0 unless more than MinKeypointFraction of the points were usable, else IS *= clusterSize / usable; final score
+// = score - IS (:268-280). The float -> int conversions of a NaN / out-of-range coordinate follow x86 (0x80000000: off the image).
+struct DepthFilterArgs {
+	const int32_t *test_offsets;      // [n_models + 1]
+	const float *test_xyz;            // test points of all models, model-major
+	Camera depth_cam;
+	int width, height;
+	const float *depth, *fill;        // height x width planes: Image::getDepth / the ".distance" map's getProb
+	float plausible_dist, depth_fraction, min_keypoint_fraction;
+};
+
+__global__ void k_filter_depth_adjust(const int32_t *__restrict__ match_offsets, const int32_t *__restrict__ match_image,
+                                      const float *__restrict__ match_xy, const float *__restrict__ match_xyz, const Camera *__restrict__ cams,
+                                      const int32_t *__restrict__ obj_model, const float *__restrict__ obj_pose, const int32_t *__restrict__ n_obj_p,
+                                      int n_obj_cap, DepthFilterArgs D, const float *__restrict__ raw_score, float *__restrict__ final_score) {
+	const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
+	if (o >= n_obj) return;
+	const int m = obj_model[o];
+	float T[12];
+	pose_matrix(obj_pose + 7 * o, obj_pose + 7 * o + 4, T);
+	int cluster_size = 0;
+	for (int j = match_offsets[m] + lane; j < match_offsets[m + 1]; j += 32)
+		cluster_size += reproj_err(T, cams[match_image[j]], match_xyz + 3 * j, match_xy[2 * j], match_xy[2 * j + 1]) < D.plausible_dist;
+	for (int off = 16; off; off >>= 1) cluster_size += __shfl_xor_sync(0xffffffffu, cluster_size, off);
+	const int t0 = D.test_offsets[m], n_test = D.test_offsets[m + 1] - t0;
+	const Camera &dc = D.depth_cam;
+	float IS = 0.f;
+	int used = 0;
+	for (int k0 = 0; k0 < n_test; k0 += 32) {
+		const int k = k0 + lane;
+		bool usable = false, adds = false;
+		float term = 0.f;
+		if (k < n_test) {
+			const float *X = D.test_xyz + 3 * (size_t)(t0 + k);
+			const float x = __fadd_rn(dot3_rn(X[0], T[0], X[1], T[1], X[2], T[2]), T[3]);
+			const float y = __fadd_rn(dot3_rn(X[0], T[4], X[1], T[5], X[2], T[6]), T[7]);
+			const float z = __fadd_rn(dot3_rn(X[0], T[8], X[1], T[9], X[2], T[10]), T[11]);
+			const float a = __fsub_rn(x, dc.TM[3]), b = __fsub_rn(y, dc.TM[7]), c = __fsub_rn(z, dc.TM[11]);
+			const float cx = dot3_rn(a, dc.TM[0], b, dc.TM[4], c, dc.TM[8]);
+			const float cy = dot3_rn(a, dc.TM[1], b, dc.TM[5], c, dc.TM[9]);
+			const float cz = dot3_rn(a, dc.TM[2], b, dc.TM[6], c, dc.TM[10]);
+			const float u = __fadd_rn(__fmul_rn(__fdiv_rn(cx, cz), dc.K[0]), dc.K[2]);
+			const float v = __fadd_rn(__fmul_rn(__fdiv_rn(cy, cz), dc.K[1]), dc.K[3]);
+			if (u > -2147483648.f && u < 2147483648.f && v > -2147483648.f && v < 2147483648.f) {
+				const int ix = (int)u, iy = (int)v;                       // truncation, like the reference's casts
+				if (ix >= 0 && ix < D.width && iy >= 0 && iy < D.height && !(D.fill[(size_t)iy * D.width + ix] > 0.f)) {
+					usable = true;
+					const float kinect = D.depth[(size_t)iy * D.width + ix];
+					if (!(kinect < cz)) {
+						adds = true;
+						term = __fdiv_rn(__fsub_rn(cz, kinect), __fmul_rn(D.depth_fraction, kinect));
+						term = __fmul_rn(term, term);
+					}
+				}
+			}
+		}
+		used += __popc(__ballot_sync(0xffffffffu, usable));
+		unsigned msk = __ballot_sync(0xffffffffu, adds);
+		while (msk) {                                       // terms in test-point order
+			const int l = __ffs(msk) - 1;
+			msk &= msk - 1;
+			const float t = __shfl_sync(0xffffffffu, term, l);
+			IS = __double2float_rn(__dadd_rn((double)IS, __dsub_rn(1.0, __ddiv_rn(1.0, __dadd_rn(1.0, (double)t)))));
+		}
+	}
+	if (lane == 0) {
+		if (used <= __float2int_rz(__fmul_rn(D.min_keypoint_fraction, (float)n_test))) IS = 0.f;
+		else IS = __fmul_rn(IS, __fdiv_rn((float)cluster_size, (float)used));
+		final_score[o] = __fsub_rn(raw_score[o], IS);
+	}
+}
+
 __global__ void k_match_model_of(const int32_t *__restrict__ match_offsets, int n_models, int32_t *__restrict__ match_model) {
 	const int m = blockIdx.x * blockDim.x + threadIdx.x;
 	if (m >= n_models) return;
 	for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) match_model[j] = m;
 }
+
+static mc_status filter_device_impl(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
+                        const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
+                        const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score, const DepthFilterArgs *D,
+                        uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets,
+                        int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score);
 
 // device entry. n_obj_dev (nullable) = device-side object count (<= n_obj_cap).
 // Outputs: keep/score per input object; out_n = {#survivors, #members}; survivors' clusters (model-major) and
@@ -199,6 +285,35 @@ __global__ void k_match_model_of(const int32_t *__restrict__ match_offsets, int 
 mc_status filter_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
                         const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
                         const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score,
+                        uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets,
+                        int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score) {
+	return filter_device_impl(ctx, d_match_offsets, d_match_image, d_match_xy, d_match_xyz, n_models, max_matches, d_obj_model, d_obj_pose, d_n_obj,
+	                          n_obj_cap, min_points, feat_dist, min_score, nullptr, d_keep, d_score, d_out_n, d_cluster_model, d_cluster_offsets,
+	                          d_members, d_surv_model, d_surv_pose, d_surv_score);
+}
+
+// moped3d's FILTER_PROJECTION_DEPTH: D.* are device pointers / host values
+mc_status filter_depth_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
+                              const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
+                              const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score,
+                              const int32_t *d_test_offsets, const float *d_test_xyz, const float *depth_K4, const float *depth_TM12, int width,
+                              int height, const float *d_depth, const float *d_fill, float plausible_dist, float depth_fraction,
+                              float min_keypoint_fraction, uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model,
+                              int32_t *d_cluster_offsets, int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score) {
+	DepthFilterArgs D;
+	D.test_offsets = d_test_offsets; D.test_xyz = d_test_xyz;
+	for (int i = 0; i < 4; i++) D.depth_cam.K[i] = depth_K4[i];
+	for (int i = 0; i < 12; i++) D.depth_cam.TM[i] = depth_TM12[i];
+	D.width = width; D.height = height; D.depth = d_depth; D.fill = d_fill;
+	D.plausible_dist = plausible_dist; D.depth_fraction = depth_fraction; D.min_keypoint_fraction = min_keypoint_fraction;
+	return filter_device_impl(ctx, d_match_offsets, d_match_image, d_match_xy, d_match_xyz, n_models, max_matches, d_obj_model, d_obj_pose, d_n_obj,
+	                          n_obj_cap, min_points, feat_dist, min_score, &D, d_keep, d_score, d_out_n, d_cluster_model, d_cluster_offsets,
+	                          d_members, d_surv_model, d_surv_pose, d_surv_score);
+}
+
+static mc_status filter_device_impl(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
+                        const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
+                        const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score, const DepthFilterArgs *D,
                         uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets,
                         int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score) {
 	if (!ctx->d_cams) { ctx->err = "filter: cameras not set (mc_set_cameras)"; return MC_ERR_STATE; }
@@ -209,16 +324,24 @@ mc_status filter_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int32
 	MC_TRY(reserve(ctx, b_owner, sizeof(int32_t) * (size_t)(max_matches + 1)));
 	MC_TRY(reserve(ctx, b_owned, sizeof(int32_t) * (size_t)(cap + 1)));
 	MC_TRY(reserve(ctx, b_mm, sizeof(int32_t) * (size_t)(max_matches + 1)));
+	// depth variant: ownership is decided by the projection score (d_raw), pruning and output use the penalised one (d_score)
+	float *d_raw = d_score;
+	if (D) { MC_TRY(reserve(ctx, ctx->scratch[22], sizeof(float) * (size_t)(cap + 1))); d_raw = (float *)ctx->scratch[22].p; }
 	if (n_obj_cap > 0) {
 		k_filter_score<<<(n_obj_cap * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, d_match_xyz, ctx->d_cams, d_obj_model,
-		                                                          d_obj_pose, d_n_obj, n_obj_cap, feat_dist, stride, (uint8_t *)b_in.p, d_score);
+		                                                          d_obj_pose, d_n_obj, n_obj_cap, feat_dist, stride, (uint8_t *)b_in.p, d_raw);
 		MC_LAUNCH_CHECK();
+		if (D) {
+			k_filter_depth_adjust<<<(n_obj_cap * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, d_match_xyz, ctx->d_cams,
+			                                                                          d_obj_model, d_obj_pose, d_n_obj, n_obj_cap, *D, d_raw, d_score);
+			MC_LAUNCH_CHECK();
+		}
 	}
 	k_match_model_of<<<(n_models + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, n_models, (int32_t *)b_mm.p);
 	MC_LAUNCH_CHECK();
 	if (max_matches > 0) {
 		k_filter_own<<<max_matches, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy, (const int32_t *)b_mm.p,
-		                                                            d_obj_model, d_n_obj, n_obj_cap, stride, (const uint8_t *)b_in.p, d_score,
+		                                                            d_obj_model, d_n_obj, n_obj_cap, stride, (const uint8_t *)b_in.p, d_raw,
 		                                                            (int32_t *)b_owner.p);
 		MC_LAUNCH_CHECK();
 	}

@@ -227,3 +227,57 @@ def make_linkage_scene(seed: int = 1, n_per=(300, 200), n_out: int = 100, halluc
     dist[holes] = rng.uniform(1, 40, int(holes.sum())).astype(np.float32)
     perm = rng.permutation(len(xy))
     return xy[perm], xyz[perm], world[perm], depth, dist
+
+
+def make_filter_depth_scene(seed: int = 1, n_models: int = 3, pts_per_model: int = 120, W: int = 320, H: int = 240, n_wrong: int = 2):
+    """A frame state for moped3d's FILTER_PROJECTION_DEPTH step (inputs only): `n_models` box-like models (keypoints on a 12 cm cube), each
+    seen once at a true pose in front of a Kinect-like camera, with a depth map that shows the objects as patches at their true depth over a
+    far background, a fill-distance map with holes (> 0 = hallucinated depth), matches of every model (true correspondences + outliers)
+    and an object list holding, per model, the true pose (slightly perturbed), a copy of it that competes for the same features and
+    `n_wrong` poses floating in free space in front of the background (what the depth penalty is there to reject).
+    Returns a dict of flat arrays in the C-ABI layout."""
+    rng = np.random.default_rng(BASE_SEED + 977 * seed)
+    K = np.array([262.0, 262.0, W / 2.0, H / 2.0], np.float32)
+    depth = np.full((H, W), 2.5, np.float32) + (0.0005 * np.arange(W)[None, :]).astype(np.float32)
+    fill = np.zeros((H, W), np.float32)
+    model_xyz, model_off = [], [0]
+    m_off, m_xy, m_xyz = [0], [], []
+    obj_model, obj_pose = [], []
+    for m in range(n_models):
+        pts = rng.uniform(-0.06, 0.06, (pts_per_model + 17 * m, 3)).astype(np.float32)
+        model_xyz.append(pts)
+        model_off.append(model_off[-1] + len(pts))
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        t = np.array([-0.35 + 0.35 * m + rng.uniform(-0.03, 0.03), rng.uniform(-0.1, 0.1), 0.9 + 0.25 * m], np.float64)
+        R = quat_to_R(q.astype(np.float32)).astype(np.float64)
+        cam = pts.astype(np.float64) @ R.T + t
+        u = cam[:, 0] / cam[:, 2] * K[0] + K[2]
+        v = cam[:, 1] / cam[:, 2] * K[1] + K[3]
+        cu, cv = int(np.clip(u.mean(), 45, W - 45)), int(np.clip(v.mean(), 45, H - 45))
+        depth[cv - 40:cv + 40, cu - 40:cu + 40] = np.float32(t[2] - 0.02)
+        seen = rng.random(len(pts)) < 0.5                                  # half of the keypoints are matched
+        n_seen = int(seen.sum())
+        xy = np.stack([u[seen] + rng.normal(0, 0.4, n_seen), v[seen] + rng.normal(0, 0.4, n_seen)], 1)
+        n_out = 12
+        xy = np.concatenate([xy, rng.uniform([5, 5], [W - 5, H - 5], (n_out, 2))])
+        xyz = np.concatenate([pts[seen], rng.uniform(-0.06, 0.06, (n_out, 3)).astype(np.float32)])
+        perm = rng.permutation(len(xy))
+        m_xy.append(xy[perm]); m_xyz.append(xyz[perm])
+        m_off.append(m_off[-1] + len(xy))
+        true_pose = np.concatenate([q, t]).astype(np.float32)
+        near = true_pose.copy(); near[4:] += rng.normal(0, 0.002, 3).astype(np.float32)
+        obj_model += [m, m]
+        obj_pose += [true_pose, near]
+        for _ in range(n_wrong):                                            # same view direction, 60 cm in front of where the depth map says anything is
+            w = true_pose.copy()
+            w[4:] = (t * (0.35 / t[2])).astype(np.float32) + rng.normal(0, 0.01, 3).astype(np.float32)
+            obj_model.append(m); obj_pose.append(w)
+    holes = rng.random((H, W)) < 0.15
+    fill[holes] = rng.uniform(1, 30, int(holes.sum())).astype(np.float32)
+    order = rng.permutation(len(obj_model))                                 # the object list is not model-major
+    return dict(K=K, cam_pose=CAM_IDENTITY.copy(), depth_K=K.copy(), depth_pose=CAM_IDENTITY.copy(), depth=depth, fill=fill, width=W, height=H,
+                model_offsets=np.array(model_off, np.int32), model_xyz=np.concatenate(model_xyz).astype(np.float32),
+                match_offsets=np.array(m_off, np.int32), match_xy=np.concatenate(m_xy).astype(np.float32),
+                match_xyz=np.concatenate(m_xyz).astype(np.float32), match_image=np.zeros(m_off[-1], np.int32),
+                obj_model=np.array(obj_model, np.int32)[order], obj_pose=np.stack(obj_pose).astype(np.float32)[order])

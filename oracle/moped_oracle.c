@@ -719,6 +719,132 @@ int mo_filter(int n_models, const int *match_offsets, const int *match_image, co
 	return ns;
 }
 
+/* ==== moped3d: FILTER_PROJECTION_DEPTH_CPU (moped3d/libmoped/src/filter/FILTER_PROJECTION_DEPTH_CPU.hpp:50-331) =================
+ * The projection filter above plus a penalty from the depth map ("incorrect score", :209-269): the model's TEST POINTS (all its
+ * keypoints, or TestSampleSize of them drawn once by randSample, :77-118) are transformed by the object's pose into the depth camera;
+ * a point that lands on a pixel with measured depth (fill distance <= 0) and is not occluded (measured depth >= its own) adds
+ * 1 - 1/(1 + ((z - measured) / (DepthFraction * measured))^2). If more than MinKeypointFraction of the test points were usable, the sum
+ * is rescaled by (#matches within PlausibleSqDistance) / (#usable points) and subtracted from the projection score. Ownership of the
+ * image features is decided by the projection score WITHOUT the penalty (:276-289, `point.first < score`), pruning by the score
+ * with it (:314). Pinned against the class itself compiled into oracle/_ref/libmoped3d_ref_strict.so (ref3d_harness.cpp,
+ * tests/test_oracle3d_filter.py). Compiled without -fsingle-precision-constant: the literals are double. */
+
+/* randSample (:77-92): keys (Float)rand() in keypoint order, pairs sorted by (key, index), the first n_samples indices in that order */
+typedef struct { float key; int idx; } mo_skey;
+static int skey_cmp(const void *a, const void *b) {
+	const mo_skey *p = (const mo_skey *)a, *q = (const mo_skey *)b;
+	if (p->key != q->key) return p->key < q->key ? -1 : 1;
+	return p->idx < q->idx ? -1 : (p->idx > q->idx ? 1 : 0);
+}
+int mo_filter_depth_select(uint64_t *state, int n_keypoints, int sample_size, int *out_idx) {
+	if (n_keypoints <= sample_size) { for (int i = 0; i < n_keypoints; i++) out_idx[i] = i; return n_keypoints; }
+	mo_skey *k = (mo_skey *)malloc(sizeof(mo_skey) * (size_t)n_keypoints);
+	for (int i = 0; i < n_keypoints; i++) { k[i].key = (float)mo_rand(state); k[i].idx = i; }
+	qsort(k, n_keypoints, sizeof(mo_skey), skey_cmp);
+	for (int i = 0; i < sample_size; i++) out_idx[i] = k[i].idx;
+	free(k);
+	return sample_size;
+}
+
+/* the penalty of one object: test points [0, n_test) of its model; depth / fill_distance are width x height row-major planes
+ * (Image::getDepth / getProb). *used = usable test points. */
+float mo_filter_depth_penalty(const float *pose7, int n_test, const float *test_xyz, const mo_camera *depth_cam, int width, int height,
+                              const float *depth, const float *fill_distance, float depth_fraction, int *used) {
+	float T[12], IS = 0.0;
+	int n_used = 0;
+	tm_init(T, pose7, pose7 + 4);
+	for (int k = 0; k < n_test; k++) {
+		float p3[3], p2[2];
+		tm_transform(T, p3, test_xyz + 3 * k);
+		tm_inverse(depth_cam->TM, p3, p3);
+		p2[0] = p3[0] / p3[2] * depth_cam->K[0] + depth_cam->K[2];
+		p2[1] = p3[1] / p3[2] * depth_cam->K[1] + depth_cam->K[3];
+		/* (int) of a NaN, an infinity or a value beyond int range is the x86 "integer indefinite" 0x80000000: negative, off the image */
+		if (!(p2[0] > -2147483648.f && p2[0] < 2147483648.f) || !(p2[1] > -2147483648.f && p2[1] < 2147483648.f)) continue;
+		int ix = (int)p2[0], iy = (int)p2[1];
+		if (ix < 0 || ix >= width || iy < 0 || iy >= height) continue;
+		float distance = fill_distance[(size_t)iy * width + ix];
+		if (distance > 0) continue;
+		n_used++;
+		float kinect = depth[(size_t)iy * width + ix], putative = p3[2];
+		if (kinect < putative) continue;
+		float scale = depth_fraction * kinect;
+		float term = (putative - kinect) / scale;
+		term *= term;
+		IS += 1.0 - (1.0 / (1.0 + term));
+	}
+	*used = n_used;
+	return IS;
+}
+
+int mo_filter_depth(int n_models, const int *match_offsets, const int *match_image, const float *match_xy, const float *match_xyz,
+                    const mo_camera *cams, int n_obj, const int *obj_model, const float *obj_pose, int min_points, float feat_dist,
+                    float plausible_dist, float min_score, float depth_fraction, float min_keypoint_fraction,
+                    const int *test_offsets, const float *test_xyz, const mo_camera *depth_cam, int width, int height,
+                    const float *depth, const float *fill_distance,
+                    unsigned char *keep, float *score, int *cluster_offsets, int *members) {
+	int M = match_offsets[n_models];
+	mo_key *keys = (mo_key *)malloc(sizeof(mo_key) * (M + 1));
+	int *key_of = (int *)malloc(sizeof(int) * (M + 1));
+	for (int j = 0; j < M; j++) { keys[j].image = match_image[j]; keys[j].x = match_xy[2 * j]; keys[j].y = match_xy[2 * j + 1]; keys[j].match = j; }
+	qsort(keys, M, sizeof(mo_key), key_cmp);
+	int nk = 0;
+	for (int j = 0; j < M; j++) {
+		if (j == 0 || key_cmp(&keys[j - 1], &keys[j]) != 0) nk++;
+		key_of[keys[j].match] = nk - 1;
+	}
+	float *best_score = (float *)calloc(nk + 1, sizeof(float));
+	int *best_obj = (int *)malloc(sizeof(int) * (nk + 1));
+	for (int i = 0; i < nk; i++) best_obj[i] = -1;
+	unsigned char *in_cl = (unsigned char *)malloc(M + 1);
+
+	for (int m = 0; m < n_models; m++)
+		for (int o = 0; o < n_obj; o++) {
+			if (obj_model[o] != m) continue;
+			float s = 0.f;
+			int cluster_size = 0;
+			for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) {
+				float uv[2];
+				mo_project(obj_pose + 7 * o, match_xyz + 3 * j, &cams[match_image[j]], uv);
+				float a = uv[0] - match_xy[2 * j], b = uv[1] - match_xy[2 * j + 1];
+				float err = a * a + b * b;
+				in_cl[j] = err < feat_dist;
+				if (in_cl[j]) s += 1. / (err + 1.);
+				if (err < plausible_dist) cluster_size++;
+			}
+			const int n_test = test_offsets[m + 1] - test_offsets[m];
+			int used = 0;
+			float IS = mo_filter_depth_penalty(obj_pose + 7 * o, n_test, test_xyz + 3 * (size_t)test_offsets[m], depth_cam, width, height, depth,
+			                                   fill_distance, depth_fraction, &used);
+			if (used <= (int)(min_keypoint_fraction * n_test)) IS = 0;
+			else IS *= ((float)cluster_size) / used;
+			score[o] = s - IS;
+			for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++)
+				if (in_cl[j] && best_score[key_of[j]] < s) { best_score[key_of[j]] = s; best_obj[key_of[j]] = o; }
+		}
+
+	int *owned = (int *)calloc(n_obj + 1, sizeof(int));
+	for (int m = 0; m < n_models; m++)
+		for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) {
+			int o = best_obj[key_of[j]];
+			if (o >= 0 && obj_model[o] == m) owned[o]++;
+		}
+	int ns = 0, t = 0;
+	cluster_offsets[0] = 0;
+	for (int o = 0; o < n_obj; o++) keep[o] = 0;
+	for (int m = 0; m < n_models; m++)
+		for (int o = 0; o < n_obj; o++) {
+			if (obj_model[o] != m) continue;
+			if (owned[o] < min_points || score[o] < min_score) continue;
+			keep[o] = 1;
+			for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++)
+				if (best_obj[key_of[j]] == o) members[t++] = j - match_offsets[m];
+			cluster_offsets[++ns] = t;
+		}
+	free(keys); free(key_of); free(best_score); free(best_obj); free(in_cl); free(owned);
+	return ns;
+}
+
 /* ==== moped3d: depth-aware pose stage ====================================================
  * Restates POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU (moped3d/libmoped/src/pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp);
  * pinned against the class itself compiled into oracle/_ref/libmoped3d_ref.so (ref3d_harness.cpp, tests/test_oracle3d_pose.py).

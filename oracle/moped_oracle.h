@@ -52,6 +52,17 @@ int mo_filter(int n_models, const int *match_offsets, const int *match_image, co
               const mo_camera *cams, int n_obj, const int *obj_model, const float *obj_pose, int min_points, float feat_dist,
               float min_score, unsigned char *keep, float *score, int *cluster_offsets, int *members);
 
+/* FILTER, moped3d's depth-map variant (FILTER_PROJECTION_DEPTH_CPU) */
+int mo_filter_depth_select(uint64_t *state, int n_keypoints, int sample_size, int *out_idx);
+float mo_filter_depth_penalty(const float *pose7, int n_test, const float *test_xyz, const mo_camera *depth_cam, int width, int height,
+                              const float *depth, const float *fill_distance, float depth_fraction, int *used);
+int mo_filter_depth(int n_models, const int *match_offsets, const int *match_image, const float *match_xy, const float *match_xyz,
+                    const mo_camera *cams, int n_obj, const int *obj_model, const float *obj_pose, int min_points, float feat_dist,
+                    float plausible_dist, float min_score, float depth_fraction, float min_keypoint_fraction,
+                    const int *test_offsets, const float *test_xyz, const mo_camera *depth_cam, int width, int height,
+                    const float *depth, const float *fill_distance,
+                    unsigned char *keep, float *score, int *cluster_offsets, int *members);
+
 void mo_set_lm_finite_check(int on);   /* 0 (default): -ffinite-math-only semantics of the reference build; 1: levmar's stop=7 as in a strict build */
 
 /* POSE, moped3d depth-aware variant (oracle only so far) ---------------------------------- */

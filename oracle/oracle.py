@@ -76,6 +76,9 @@ def _load():
         "mo_sift_set_conv_fma": (None, [C.c_int]),
         "mo_filter": (C.c_int, [C.c_int, _i32p, _i32p, _f32p, _f32p, camp, C.c_int, _i32p, _f32p, C.c_int, C.c_float, C.c_float,
                                 _u8p, _f32p, _i32p, _i32p]),
+        "mo_filter_depth_select": (C.c_int, [_u64p, C.c_int, C.c_int, _i32p]),
+        "mo_filter_depth": (C.c_int, [C.c_int, _i32p, _i32p, _f32p, _f32p, camp, C.c_int, _i32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, _i32p, _f32p, camp, C.c_int, C.c_int, _f32p, _f32p, _u8p, _f32p, _i32p, _i32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -223,6 +226,39 @@ def filter_objects(matches, cams, obj_model, obj_pose, params=(5, 4096.0, 2.0)):
     mem = np.zeros(M + 1, np.int32)
     ns = lib().mo_filter(len(off) - 1, off, _i32(matches["image"]), _f32(matches["xy"]), _f32(matches["xyz"]), cams, n,
                          obj_model, obj_pose, params[0], params[1], params[2], keep, score, co, mem)
+    return dict(keep=keep[:n].astype(bool), score=score[:n].copy(), offsets=co[:ns + 1].copy(), members=mem[:co[ns]].copy())
+
+
+def filter_depth_test_points(model_offsets, model_xyz, sample_size, seed):
+    """selectTestPoints (FILTER_PROJECTION_DEPTH_CPU.hpp:94-118): per model all keypoints, or `sample_size` of them drawn by randSample from
+    the seedable stream (the models are visited in order, the stream runs on). Returns (test_offsets[n_models+1], test_xyz)."""
+    mo = _i32(model_offsets)
+    xyz = _f32(model_xyz).reshape(-1, 3)
+    state = C.c_uint64(int(seed))
+    offs, out = [0], []
+    for m in range(len(mo) - 1):
+        n = int(mo[m + 1] - mo[m])
+        idx = np.zeros(max(n, 1), np.int32)
+        k = lib().mo_filter_depth_select(C.byref(state), n, int(sample_size), idx)
+        out.append(xyz[mo[m] + idx[:k]])
+        offs.append(offs[-1] + k)
+    return np.array(offs, np.int32), (np.concatenate(out) if out else np.zeros((0, 3), np.float32)).astype(np.float32)
+
+
+def filter_depth(matches, cams, obj_model, obj_pose, params, test_offsets, test_xyz, depth_cam, depth, fill_distance):
+    """params = (MinPoints, FeatureDistance, PlausibleSqDistance, MinScore, DepthFraction, MinKeypointFraction); depth / fill_distance: H x W."""
+    off = _i32(matches["offsets"])
+    M = int(off[-1])
+    obj_model, obj_pose = _i32(obj_model), _f32(obj_pose).reshape(-1, 7)
+    n = len(obj_model)
+    keep = np.zeros(n + 1, np.uint8)
+    score = np.zeros(n + 1, np.float32)
+    co = np.zeros(n + 2, np.int32)
+    mem = np.zeros(M + 1, np.int32)
+    d, f = _f32(depth), _f32(fill_distance)
+    ns = lib().mo_filter_depth(len(off) - 1, off, _i32(matches["image"]), _f32(matches["xy"]), _f32(matches["xyz"]), cams, n, obj_model, obj_pose,
+                               int(params[0]), params[1], params[2], params[3], params[4], params[5], _i32(test_offsets), _f32(test_xyz), depth_cam,
+                               d.shape[1], d.shape[0], d, f, keep, score, co, mem)
     return dict(keep=keep[:n].astype(bool), score=score[:n].copy(), offsets=co[:ns + 1].copy(), members=mem[:co[ns]].copy())
 
 

@@ -56,6 +56,10 @@ def lib():
                                             C.c_float, C.c_int, C.c_float, C.c_float, _i32p, _i32p]
         L.ref3d_linkage_agglomerate.restype = C.c_int
         L.ref3d_linkage_agglomerate.argtypes = [_f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p]
+        L.ref3d_filter_depth.restype = C.c_int
+        L.ref3d_filter_depth.argtypes = [C.c_int, _i32p, _f32p, _i32p, _f32p, _f32p, C.c_int, _i32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float,
+                                         C.c_float, C.c_int, C.c_float, C.c_uint64, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p,
+                                         _u8p, _f32p, _i32p, _i32p]
         L.ref3d_bench_log.restype = C.c_int
         L.ref3d_bench_log.argtypes = [C.c_char_p, C.c_int, _i32p, _f32p, _i32p, _f32p, C.c_int, _i32p, _i32p, _i32p, C.c_int, _i32p, _f32p, _f32p,
                                       _f32p, _f32p]
@@ -131,3 +135,23 @@ def bench_log(out_dir, fr):
         raise RuntimeError("ref3d_bench_log failed")
     with open(os.path.join(out_dir, "outputMopedBench.txt")) as f:
         return f.read()
+
+
+def filter_depth(n_model_pts, model_xyz, match_offsets, match_xy, match_xyz, obj_model, obj_pose, params, test_sample_size, seed, K4, cam_pose7,
+                 depth_K4, depth_pose7, depth, fill_distance):
+    """FILTER_PROJECTION_DEPTH_CPU::process compiled from the reference. params = (MinPoints, FeatureDistance, PlausibleSqDistance, MinScore,
+    DepthFraction, MinKeypointFraction)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)      # noqa: E731
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)        # noqa: E731
+    mo = i32(match_offsets)
+    om, op = i32(obj_model), f32(obj_pose).reshape(-1, 7)
+    n = len(om)
+    keep = np.zeros(n + 1, np.uint8)
+    score = np.zeros(n + 1, np.float32)
+    co = np.zeros(n + 2, np.int32)
+    mem = np.zeros(int(mo[-1]) + 1, np.int32)
+    d, f = f32(depth), f32(fill_distance)
+    ns = lib().ref3d_filter_depth(len(mo) - 1, i32(n_model_pts), f32(model_xyz), mo, f32(match_xy), f32(match_xyz), n, om, op, int(params[0]),
+                                  params[1], params[2], params[3], params[4], int(test_sample_size), params[5], int(seed), f32(K4), f32(cam_pose7),
+                                  f32(depth_K4), f32(depth_pose7), d.shape[1], d.shape[0], d, f, keep, score, co, mem)
+    return dict(keep=keep[:n].astype(bool), score=score[:n].copy(), offsets=co[:ns + 1].copy(), members=mem[:co[ns]].copy())

@@ -36,6 +36,8 @@ extern "C" void ref3d_srand(uint64_t seed) { g_rng_state = seed; }
 #include <pose/POSE_RANSAC_LM_DIFF_BACKPROJECTION_DEPTH_CPU.hpp>
 #include <pose/POSE_RANSAC_LM_DIFF_REPROJECTION_DEPTH_CPU.hpp>
 #include <cluster/CLUSTER_LINKAGE_CPU.hpp>
+#include <filter/FILTER_PROJECTION_DEPTH_CPU.hpp>
+#include <iostream>
 #undef class
 #undef rand
 
@@ -276,6 +278,92 @@ int ref3d_linkage_agglomerate(const float *K, int n, float cutoff, int minPts, i
 		cluster_offsets[++nc] = k;
 	}
 	return nc;
+}
+
+/* FILTER_PROJECTION_DEPTH_CPU::process (filter/FILTER_PROJECTION_DEPTH_CPU.hpp:145-329) on one frame state: models (keypoints = the
+ * population the class draws its test points from, TestSampleSize of them with the harness's seedable rand() when a model has more),
+ * matches per model (coord2D, coord3D, all seen by the grey camera image 0), objects in list order, a depth map (4 floats per pixel,
+ * depth in the third: Image::getDepth) with its own intrinsics / pose and the fill-distance map "<name>.distance".
+ * Outputs: keep / score per input object, clusters of the survivors (model-major, list order). Returns #survivors. */
+int ref3d_filter_depth(int n_models, const int *n_model_pts, const float *model_xyz, const int *match_offsets, const float *match_xy,
+                       const float *match_xyz, int n_obj, const int *obj_model, const float *obj_pose7,
+                       int minPoints, float featureDistance, float plausibleSqDistance, float minScore, float depthFraction, int testSampleSize,
+                       float minKeypointFraction, uint64_t seed, const float *K4, const float *cam_pose7, const float *depthK4,
+                       const float *depth_pose7, int width, int height, const float *depth, const float *fill_distance,
+                       unsigned char *keep, float *score, int *cluster_offsets, int *members) {
+	FtzGuard g;
+	ref3d_srand(seed);
+	vector<SP_Model> models;
+	size_t row = 0;
+	for (int m = 0; m < n_models; m++) {
+		SP_Model mod(new Model); mod->name = "obj" + toString(m);
+		vector<Model::IP> &ips = mod->IPs["SIFT"];
+		ips.resize(n_model_pts[m]);
+		for (int i = 0; i < n_model_pts[m]; i++, row++) ips[i].coord3D.init(model_xyz[3 * row], model_xyz[3 * row + 1], model_xyz[3 * row + 2]);
+		models.push_back(mod);
+	}
+	FrameData fd;
+	list<SP_Object> objects;
+	fd.objects = &objects;
+	SP_Image im(new Image(IMAGE_TYPE_GRAY_IMAGE));
+	im->name = "cam"; im->width = width; im->height = height;
+	im->intrinsicLinearCalibration.init(K4[0], K4[1], K4[2], K4[3]);
+	im->cameraPose.rotation.init(cam_pose7[0], cam_pose7[1], cam_pose7[2], cam_pose7[3]);
+	im->cameraPose.translation.init(cam_pose7[4], cam_pose7[5], cam_pose7[6]);
+	im->TM.init(im->cameraPose);
+	fd.images.push_back(im);
+	SP_Image dm(new Image(IMAGE_TYPE_DEPTH_MAP));
+	dm->name = "depth"; dm->width = width; dm->height = height;
+	dm->intrinsicLinearCalibration.init(depthK4[0], depthK4[1], depthK4[2], depthK4[3]);
+	dm->cameraPose.rotation.init(depth_pose7[0], depth_pose7[1], depth_pose7[2], depth_pose7[3]);
+	dm->cameraPose.translation.init(depth_pose7[4], depth_pose7[5], depth_pose7[6]);
+	dm->TM.init(dm->cameraPose);
+	dm->data.resize((size_t)width * height * 4 * sizeof(Float));
+	for (int y = 0; y < height; y++) for (int x = 0; x < width; x++) dm->setDepth(x, y, depth[(size_t)y * width + x]);
+	fd.images.push_back(dm);
+	SP_Image fm(new Image(IMAGE_TYPE_PROB_MAP));
+	fm->name = "depth.distance"; fm->width = width; fm->height = height;
+	fm->data.resize((size_t)width * height * sizeof(Float));
+	for (int y = 0; y < height; y++) for (int x = 0; x < width; x++) fm->setProb(x, y, fill_distance[(size_t)y * width + x]);
+	fd.images.push_back(fm);
+	fd.matches.resize(n_models);
+	for (int m = 0; m < n_models; m++) {
+		fd.matches[m].resize(match_offsets[m + 1] - match_offsets[m]);
+		for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) {
+			FrameData::Match &ma = fd.matches[m][j - match_offsets[m]];
+			ma.coord2D.init(match_xy[2 * j], match_xy[2 * j + 1]);
+			ma.coord3D.init(match_xyz[3 * j], match_xyz[3 * j + 1], match_xyz[3 * j + 2]);
+			ma.imageIdx = 0;
+		}
+	}
+	vector<Object *> raw;
+	for (int o = 0; o < n_obj; o++) {
+		SP_Object ob(new Object);
+		ob->model = models[obj_model[o]];
+		ob->pose.rotation.init(obj_pose7[7 * o], obj_pose7[7 * o + 1], obj_pose7[7 * o + 2], obj_pose7[7 * o + 3]);
+		ob->pose.translation.init(obj_pose7[7 * o + 4], obj_pose7[7 * o + 5], obj_pose7[7 * o + 6]);
+		ob->score = 0;
+		objects.push_back(ob);
+		raw.push_back(ob.get());
+	}
+	vector<SP_Object> hold(objects.begin(), objects.end());      /* erased objects stay alive: their scores are read below */
+	FILTER_PROJECTION_DEPTH_CPU alg(minPoints, featureDistance, plausibleSqDistance, minScore, depthFraction, testSampleSize, minKeypointFraction);
+	alg.modelsUpdated(models);
+	std::streambuf *saved = std::cerr.rdbuf(NULL);                /* the class narrates every object on stderr */
+	alg.process(fd);
+	std::cerr.rdbuf(saved);
+	std::cerr.clear();
+	for (int o = 0; o < n_obj; o++) { keep[o] = 0; score[o] = raw[o]->score; }
+	for (list<SP_Object>::iterator it = objects.begin(); it != objects.end(); ++it)
+		for (int o = 0; o < n_obj; o++) if (raw[o] == it->get()) keep[o] = 1;
+	int ns = 0, t = 0;
+	cluster_offsets[0] = 0;
+	for (int m = 0; m < n_models; m++)
+		for (size_t c = 0; c < fd.clusters[m].size(); c++) {
+			for (list<int>::iterator it = fd.clusters[m][c].begin(); it != fd.clusters[m][c].end(); ++it) members[t++] = *it;
+			cluster_offsets[++ns] = t;
+		}
+	return ns;
 }
 
 /* Runs MopedBench (MopedBench.cpp:185-227) over one frame state the way Moped::processImages drives it — init(), then
