@@ -411,6 +411,10 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
  *                          concurrent work (the frame lanes' stage kernels of an earlier chunk or step) finds free SMs
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
  *                          MATCH instead of ~40 kernel launches (same kernels, same results)
+ *   "batch_graph"          != 0 (default): the stage chains of ALL frames of an mc_process_frames* call are captured into ONE CUDA graph
+ *                          (a branch per lane) and replayed with one launch per batch: graph branches are not bound by the 32
+ *                          hardware stream connections, so 64 frames on 64 lanes run together instead of in two rounds. Not used
+ *                          with "defer_lane_join" / an SM partition or several MATCH chunks. Same kernels, same results.
  *   "sift_two_pass"        != 0: mc_sift_extract* blur with the separate row / column kernels instead of the fused
  *                          shared-memory kernel (same bits; kept for A/B measurements)
  *   "sift_describe_gather" != 0: descriptors by the cell-gather kernel (one CTA per keypoint) instead of the default

@@ -158,6 +158,8 @@ static void free_scratch(mc_ctx *ctx) {
 	cudaFree(ctx->frame_desc.p);
 	for (auto &g : ctx->fgraphs) cudaGraphExecDestroy(g.exec);
 	ctx->fgraphs.clear();
+	for (auto &g : ctx->bgraphs) cudaGraphExecDestroy(g.exec);
+	ctx->bgraphs.clear();
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
 }
 
@@ -197,6 +199,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "pose_fit_stream") ctx->fit_stream = value != 0;
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
+	else if (k == "batch_graph") ctx->batch_graph = value != 0;
 	else if (k == "defer_lane_join") ctx->defer_lane_join = value != 0;
 	else if (k == "match_coarse_kind") { if (value != 0 && value != 1) { ctx->err = "mc_set_option: match_coarse_kind must be 0 (fp16) or 1 (8-bit first)"; return MC_ERR_ARG; } ctx->coarse_kind = (int)value; }
 	else if (k == "match_stagger") ctx->match_stagger = value != 0;

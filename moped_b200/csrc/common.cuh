@@ -118,6 +118,9 @@ struct mc_ctx {
 	mc::DevBuf frame_desc;            // device copy of the current frame's FrameDesc
 	struct FrameGraph { uint64_t cfg, ptr_key; cudaGraphExec_t exec; int nodes; };
 	std::vector<FrameGraph> fgraphs;  // one per configuration seen on this lane (sizes, parameters), most recent last
+	struct BatchGraph { uint64_t key; cudaGraphExec_t exec; int nodes; };
+	std::vector<BatchGraph> bgraphs;  // one graph per batch configuration: the stage chains of all frames of a call as parallel branches (pipeline.cu)
+	bool batch_graph = true;          // mc_set_option "batch_graph"
 	bool capturing = false;           // reserve() must not allocate while the lane's stream is being captured
 	bool frame_graphs = true;         // mc_set_option "frame_graphs"
 	bool defer_lane_join = false;     // mc_set_option "defer_lane_join": mc_process_frames_matched_dev returns without ordering the context's

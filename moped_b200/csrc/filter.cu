@@ -60,9 +60,9 @@ __global__ void k_filter_score(const int32_t *__restrict__ match_offsets, const 
                                const float *__restrict__ match_xy, const float *__restrict__ match_xyz, const Camera *__restrict__ cams,
                                const int32_t *__restrict__ obj_model, const float *__restrict__ obj_pose, const int32_t *__restrict__ n_obj_p,
                                int n_obj_cap, float feat_dist, int stride, uint8_t *__restrict__ in_cluster, float *__restrict__ score) {
-	const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31;
 	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
-	if (o >= n_obj) return;
+	for (int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; o < n_obj; o += (gridDim.x * blockDim.x) >> 5) {      // bounded grid, see k_filter_own
 	const int m = obj_model[o];
 	const int lo = match_offsets[m], hi = match_offsets[m + 1];
 	float T[12];
@@ -83,6 +83,7 @@ __global__ void k_filter_score(const int32_t *__restrict__ match_offsets, const 
 		}
 	}
 	if (lane == 0) score[o] = s;
+	}
 }
 
 __device__ __forceinline__ bool better(float s, int m, int o, float bs, int bm, int bo) {
@@ -100,9 +101,10 @@ __global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_mo
                              const uint8_t *__restrict__ in_cluster, const float *__restrict__ score, int32_t *__restrict__ owner) {
 	__shared__ float s_bs[4]; __shared__ int s_bm[4], s_bo[4];
 	const int M = match_offsets[n_models];
-	const int j = blockIdx.x;
-	if (j >= M) return;
 	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
+	// a bounded grid walks the matches: a frame has a few hundred of them while the launch bound is the feature count, and a batch of
+	// 64 frames would otherwise start 260 000 CTAs that exit at once (CTA launch rate, not work, bounded the stages of a batch)
+	for (int j = blockIdx.x; j < M; j += gridDim.x) {
 	const float x = match_xy[2 * j], y = match_xy[2 * j + 1];
 	const int im = match_image[j];
 	float bs = 0.f; int bm = 0x7fffffff, bo = -1;
@@ -129,6 +131,8 @@ __global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_mo
 		for (int k = 1; k < (int)(blockDim.x >> 5); k++)
 			if (s_bo[k] >= 0 && (bo < 0 || better(s_bs[k], s_bm[k], s_bo[k], bs, bm, bo))) { bs = s_bs[k]; bm = s_bm[k]; bo = s_bo[k]; }
 		owner[j] = bo;
+	}
+	__syncthreads();
 	}
 }
 
@@ -328,7 +332,8 @@ static mc_status filter_device_impl(mc_ctx *ctx, const int32_t *d_match_offsets,
 	float *d_raw = d_score;
 	if (D) { MC_TRY(reserve(ctx, ctx->scratch[22], sizeof(float) * (size_t)(cap + 1))); d_raw = (float *)ctx->scratch[22].p; }
 	if (n_obj_cap > 0) {
-		k_filter_score<<<(n_obj_cap * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, d_match_xyz, ctx->d_cams, d_obj_model,
+		const int score_grid = (n_obj_cap * 32 + 127) / 128 < ctx->num_sms ? (n_obj_cap * 32 + 127) / 128 : ctx->num_sms;
+		k_filter_score<<<score_grid, 128, 0, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, d_match_xyz, ctx->d_cams, d_obj_model,
 		                                                          d_obj_pose, d_n_obj, n_obj_cap, feat_dist, stride, (uint8_t *)b_in.p, d_raw);
 		MC_LAUNCH_CHECK();
 		if (D) {
@@ -340,7 +345,7 @@ static mc_status filter_device_impl(mc_ctx *ctx, const int32_t *d_match_offsets,
 	k_match_model_of<<<(n_models + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, n_models, (int32_t *)b_mm.p);
 	MC_LAUNCH_CHECK();
 	if (max_matches > 0) {
-		k_filter_own<<<max_matches, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy, (const int32_t *)b_mm.p,
+		k_filter_own<<<max_matches < 2 * ctx->num_sms ? max_matches : 2 * ctx->num_sms, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy, (const int32_t *)b_mm.p,
 		                                                            d_obj_model, d_n_obj, n_obj_cap, stride, (const uint8_t *)b_in.p, d_raw,
 		                                                            (int32_t *)b_owner.p);
 		MC_LAUNCH_CHECK();

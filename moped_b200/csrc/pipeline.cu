@@ -604,6 +604,134 @@ mc_status process_frames_device(mc_ctx *ctx, const float *d_q, const float *d_qx
 		cudaEventCreate(&t0);
 		cudaEventRecord(t0, ctx->stream);
 	}
+	// ---- one CUDA graph for the stage chains of ALL frames of the call ("batch graph") ----
+	// Lane streams are host-visible queues and the hardware has 32 of them: 64 frames on 64 lane streams run as two rounds of 32
+	// (traced), which is why a 64-frame batch spent two chain latencies after MATCH. The branches of ONE graph are not bound by
+	// that: a graph of 128 independent 10-kernel chains runs in 1.3 chain latencies on a B200 (scripts/probe/graph_branches.cu,
+	// profiles/graph_branches_r2b.jsonl). So the fork to the lanes, every frame's descriptor + chain and the join are captured once
+	// into a single graph (keyed by everything the chains read: descriptors, sizes, parameters, scratch addresses) and replayed
+	// with one launch per batch. Not used with a deferred lane join / an SM partition (there the lanes must stay separate streams
+	// that run beside the next MATCH), with several MATCH chunks, or while a lane still has to grow its scratch (that call runs
+	// the per-lane path below, which allocates; the next one captures).
+	const bool own_stream = ctx->stream != nullptr && ctx->stream != cudaStreamLegacy && ctx->stream != cudaStreamPerThread;
+	if (ctx->batch_graph && ctx->frame_graphs && !ctx->defer_lane_join && !ctx->green_stage && n_chunks == 1 && !trace && own_stream && nf > 1) {
+		const int cq_lo = frame_offsets[f_begin], cq = frame_offsets[f_end] - cq_lo;
+		if (do_match && cq > 0)
+			MC_TRY(match_device(ctx, d_q + (size_t)cq_lo * ctx->D, cq, P->match_ratio, P->match_mode, (int32_t *)nn_row + 2 * (size_t)cq_lo,
+			                    (float *)ctx->nn_dist.p + 2 * (size_t)(cq_lo - q_lo), (uint8_t *)accepted + cq_lo));
+		if (ev3) MC_CUDA(cudaEventRecord(ev3[1], ctx->stream));
+		std::vector<FrameDesc> descs((size_t)nf);
+		std::vector<int> Qs((size_t)nf);
+		for (int s = 0; s < nf; s++) {
+			const int f = f_begin + s;
+			const int q0 = frame_offsets[f], Q = frame_offsets[f + 1] - q0;
+			FrameDesc &d = descs[(size_t)s];
+			memset(&d, 0, sizeof d);
+			d.nn_row = nn_row + 2 * (size_t)q0; d.accepted = accepted + q0; d.q_xy = d_qxy + 2 * (size_t)q0; d.q_image = d_qimg + q0;
+			d.Q = Q; d.max_objects = max_objects;
+			d.out_info = d_out_info + 4 * (size_t)s; d.out_model = d_out_model + (size_t)s * max_objects;
+			d.out_pose = d_out_pose + 7 * (size_t)s * max_objects; d.out_score = d_out_score + (size_t)s * max_objects;
+			Qs[(size_t)s] = Q;
+		}
+		auto batch_key = [&]() {
+			uint64_t k = fnv(1469598103934665603ULL, descs.data(), sizeof(FrameDesc) * descs.size());
+			k = fnv(k, P, sizeof *P);
+			const int64_t ints[] = { nf, n_lanes, ctx->n_models, ctx->n_images, ctx->table_base, ctx->pose_warps, ctx->ransac_fused, (int64_t)ctx->num_sms,
+			                         ctx->pose_exact_order, max_objects };
+			k = fnv(k, ints, sizeof ints);
+			const void *ptrs[] = { ctx->d_cams, ctx->d_xyz, ctx->d_model_of_row };
+			k = fnv(k, ptrs, sizeof ptrs);
+			for (int l = 0; l < n_lanes; l++) {
+				for (const DevBuf &b : ctx->lanes[(size_t)l]->scratch) k = fnv(k, &b.p, sizeof b.p);
+				k = fnv(k, &ctx->lanes[(size_t)l]->frame_desc.p, sizeof(void *));
+			}
+			return k;
+		};
+		uint64_t key = batch_key();
+		bool launched = false;
+		for (size_t i = 0; i < ctx->bgraphs.size() && !launched; i++)
+			if (ctx->bgraphs[i].key == key) {
+				MC_CUDA(cudaGraphLaunch(ctx->bgraphs[i].exec, ctx->stream));
+				ctx->launches += ctx->bgraphs[i].nodes;
+				launched = true;
+			}
+		if (!launched) {
+			mc_status st = MC_OK;
+			for (int l = 0; l < n_lanes; l++) ctx->lanes[(size_t)l]->launches = 0;
+			MC_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+			cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);
+			for (int l = 0; l < n_lanes && e == cudaSuccess; l++) { ctx->lanes[(size_t)l]->capturing = true; e = cudaStreamWaitEvent(ctx->lanes[(size_t)l]->stream, ctx->ev_fork, 0); }
+			for (int s = 0; s < nf && st == MC_OK && e == cudaSuccess; s++) {
+				mc_ctx *lane = ctx->lanes[(size_t)(s % n_lanes)];
+				if (Qs[(size_t)s] <= 0) {
+					k_export_empty<<<1, 32, 0, lane->stream>>>(descs[(size_t)s].out_info);
+					lane->launches++;
+					continue;
+				}
+				st = set_frame_desc(lane, descs[(size_t)s]);
+				if (st != MC_OK) break;
+				const int q_cap = (Qs[(size_t)s] + 511) & ~511;
+				const FrameCaps caps = frame_caps(q_cap, P);
+				FrameBufs B;
+				st = carve(lane, B, q_cap, lane->n_models, caps.cl_cap, caps.task_cap, caps.obj_cap);
+				if (st == MC_OK) st = frame_enqueue(lane, nullptr, q_cap, P, B, caps, nullptr, true);
+			}
+			int nodes = 0;
+			for (int l = 0; l < n_lanes; l++) {
+				mc_ctx *lane = ctx->lanes[(size_t)l];
+				lane->capturing = false;
+				if (e == cudaSuccess) e = cudaEventRecord(lane->ev_done, lane->stream);
+				if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, lane->ev_done, 0);
+				nodes += (int)lane->launches; lane->launches = 0;
+			}
+			cudaGraph_t graph = nullptr;
+			const cudaError_t e_end = cudaStreamEndCapture(ctx->stream, &graph);
+			if (st == MC_OK && e == cudaSuccess && e_end == cudaSuccess && graph) {
+				mc_ctx::BatchGraph g;
+				g.key = batch_key();                 // (set_frame_desc may have made a lane's first descriptor buffer: addresses are final now)
+				g.nodes = nodes; g.exec = nullptr;
+				const cudaError_t e_inst = cudaGraphInstantiate(&g.exec, graph, 0);
+				cudaGraphDestroy(graph);
+				if (e_inst != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate (batch graph): ") + cudaGetErrorString(e_inst); return MC_ERR_CUDA; }
+				if (ctx->bgraphs.size() >= 6) { cudaGraphExecDestroy(ctx->bgraphs.front().exec); ctx->bgraphs.erase(ctx->bgraphs.begin()); }
+				ctx->bgraphs.push_back(g);
+				MC_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+				ctx->launches += nodes;
+				launched = true;
+			} else {
+				if (graph) cudaGraphDestroy(graph);
+				cudaGetLastError();
+				if (st != MC_OK && st != MC_ERR_STATE) { ctx->err = ctx->lanes[0]->err; for (mc_ctx *lane : ctx->lanes) if (!lane->err.empty()) ctx->err = lane->err; return st; }
+				if (st == MC_OK) { ctx->err = std::string("batch graph capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e_end); return MC_ERR_CUDA; }
+				// a lane has to grow a scratch buffer: this call takes the per-lane path (which allocates)
+			}
+		}
+		if (launched) {
+			if (ev3) MC_CUDA(cudaEventRecord(ev3[2], ctx->stream));
+			ctx->batch_stats[0] = nf; ctx->batch_stats[3] = n_lanes;
+			return MC_OK;
+		}
+		// fall through to the per-lane path WITHOUT matching again
+		for (int s = 0; s < nf; s++) {
+			mc_ctx *lane = ctx->lanes[(size_t)(s % n_lanes)];
+			if (s < n_lanes) {
+				MC_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+				MC_CUDA(cudaStreamWaitEvent(lane->stream, ctx->ev_fork, 0));
+			}
+			mc_status st = MC_OK;
+			if (Qs[(size_t)s] <= 0) { k_export_empty<<<1, 32, 0, lane->stream>>>(descs[(size_t)s].out_info); lane->launches++; }
+			else {
+				st = set_frame_desc(lane, descs[(size_t)s]);
+				if (st == MC_OK) st = frame_chain(lane, Qs[(size_t)s], P, nullptr);
+			}
+			if (st != MC_OK) { ctx->err = lane->err; return st; }
+		}
+		if (n_lanes > ctx->lanes_pending) ctx->lanes_pending = n_lanes;
+		MC_TRY(join_lanes(ctx));
+		if (ev3) MC_CUDA(cudaEventRecord(ev3[2], ctx->stream));
+		ctx->batch_stats[0] = nf; ctx->batch_stats[3] = n_lanes;
+		return MC_OK;
+	}
 	for (int c = 0; c < n_chunks; c++) {
 		const int fb = f_begin + (int)((int64_t)nf * c / n_chunks), fe = f_begin + (int)((int64_t)nf * (c + 1) / n_chunks);
 		const int cq_lo = frame_offsets[fb], cq = frame_offsets[fe] - cq_lo;

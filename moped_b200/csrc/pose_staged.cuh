@@ -265,7 +265,10 @@ mc_status ransac_staged_launch(mc_ctx *ctx, const int32_t *d_cluster_offsets, co
 	for (int l = 0; l < kLevels; l++) {
 		if (L.h_begin[l + 1] <= L.h_begin[l]) continue;
 		// persistent grids: queue length and success state are only known on the device; CTAs without items exit at once
-		const int grid = level_warps[l] == 1 ? ctx->num_sms * 8 : ctx->num_sms;
+		// a lane of a frame batch (ctx->parent) shares the GPU with up to 63 other frames: small grids there (a frame queues a handful of
+		// tasks; the CTAs loop over the items whatever their number) — the thousands of CTAs that found an empty queue were a third of
+		// all CTA launches of a batch
+		const int grid = ctx->parent ? (level_warps[l] == 1 ? 64 : 37) : (level_warps[l] == 1 ? ctx->num_sms * 8 : ctx->num_sms);
 		k_ransac_level<P><<<grid, 32 * level_warps[l], 0, ctx->stream>>>(d_cluster_offsets, d_xy, d_xyz, d_image, d_tie, ctx->d_cams, pp->max_objects_per_cluster,
 		                                                                R, pp->max_lm_tests, pp->n_pts_align, pp->min_npts_object, pp->error_threshold, pp->seed,
 		                                                                L.h_begin[l], L.h_begin[l + 1], L.slot_base[l], L.slots, S);

@@ -240,6 +240,42 @@ def test_cluster_partitioned_frame_equals_single_context(ctx30, batch_case, worl
             cx.close()
 
 
+def test_batch_graph_equals_per_lane_graphs(ctx30, batch_case):
+    """mc_set_option("batch_graph"): the stage chains of all frames of a call captured into ONE CUDA graph (a branch per lane) give what
+    the per-lane path gives — on the capture call, on replays, after a change of the batch (another key), with fewer lanes than frames
+    (several frames per branch), with empty frames, and through the device-resident entry."""
+    import torch
+    c = batch_case
+    fo = np.concatenate([[0], np.cumsum(c["sizes"])]).astype(np.int32)
+    q, xy, img = np.concatenate(c["qn"]), np.concatenate(c["xy"]), np.concatenate(c["img"])
+    order2 = [8, 0, 3, 1]
+    q2 = np.concatenate([c["qn"][i] for i in order2]); xy2 = np.concatenate([c["xy"][i] for i in order2]); img2 = np.concatenate([c["img"][i] for i in order2])
+    fo2 = np.concatenate([[0], np.cumsum([c["sizes"][i] for i in order2])]).astype(np.int32)
+    try:
+        ctx30.set_option("batch_graph", 0)
+        ctx30.set_tuning(16, 4, 1)
+        want = ctx30.process_frames(q, xy, img, fo, max_objects=64)
+        want2 = ctx30.process_frames(q2, xy2, img2, fo2, max_objects=64)
+        assert sum(len(w["model"]) for w in want) >= 12
+        ctx30.set_option("batch_graph", 1)
+        for lanes in (16, 3):
+            ctx30.set_tuning(lanes, 4, 1)
+            l0 = ctx30.launches
+            for rep in range(4):                                   # allocation call, capture call, replays
+                _same(ctx30.process_frames(q, xy, img, fo, max_objects=64), want)
+            assert ctx30.launches > l0
+            _same(ctx30.process_frames(q2, xy2, img2, fo2, max_objects=64), want2)
+            _same(ctx30.process_frames(q2, xy2, img2, fo2, max_objects=64), want2)
+            _same(ctx30.process_frames(q, xy, img, fo, max_objects=64), want)
+        dev = torch.device("cuda", 0)
+        dq, dxy, dimg = torch.from_numpy(q).to(dev), torch.from_numpy(xy).to(dev), torch.from_numpy(img).to(dev)
+        for rep in range(3):
+            _same(ctx30.process_frames_dev(dq.data_ptr(), dxy.data_ptr(), dimg.data_ptr(), fo, ctx30.default_params(), 64), want)
+    finally:
+        ctx30.set_option("batch_graph", 1)
+        ctx30.set_tuning(8, 8, 1)
+
+
 def test_frame_graphs_equal_eager_launches(ctx30, batch_case):
     """mc_process_frames replays one CUDA graph per frame for the stages after MATCH (captured per lane and per
     feature-count bucket). Replays, re-captures after a bucket change and the eager path give identical results,
