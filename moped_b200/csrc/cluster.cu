@@ -166,11 +166,30 @@ __device__ void meanshift_group(const MsArrays &A, int n, float sq_radius, float
 	__syncthreads();
 }
 
-// grid = models. Output per model m (region = the model's match range [lo, hi)):
+// The models that can have a cluster at all (>= min_pts matches), and model_count = 0 for everybody. One CTA. A frame matches a
+// handful of the database's models: k_meanshift then starts a CTA per listed model instead of one per model — 1000 CTAs of 70 KB of
+// shared memory each, all but ~8 of which only found out that they had nothing to do (and, 64 frames at a time, kept each other's
+// working CTAs waiting for shared memory).
+__global__ void k_cluster_nonempty(const int32_t *__restrict__ match_offsets, int n_models, int min_pts, int32_t *__restrict__ model_count,
+                                   int32_t *__restrict__ list, int32_t *__restrict__ n_list) {
+	__shared__ int s_n;
+	if (threadIdx.x == 0) s_n = 0;
+	__syncthreads();
+	for (int m = threadIdx.x; m < n_models; m += blockDim.x) {
+		model_count[m] = 0;
+		const int cnt = match_offsets[m + 1] - match_offsets[m];
+		if (cnt >= min_pts && cnt > 0) list[atomicAdd(&s_n, 1)] = m;        // any order: the models are independent
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) *n_list = s_n;
+}
+
+// One CTA per LISTED model (grid-stride if there are more than CTAs). Output per model m (region = the model's match range [lo, hi)):
 //   model_count[m] = #clusters, sizes[lo + k] = size of its k-th cluster, members[lo ...] = concatenated members
 __global__ void __launch_bounds__(kClusterThreads)
 k_meanshift(const int32_t *__restrict__ match_offsets, const int32_t *__restrict__ match_image, const float *__restrict__ match_xy,
-            int n_images, float radius, float merge, int min_pts, int max_iter,
+            int n_models, int n_images, float radius, float merge, int min_pts, int max_iter,
+            const int32_t *__restrict__ list, const int32_t *__restrict__ n_list,
             int32_t *__restrict__ model_count, int32_t *__restrict__ sizes, int32_t *__restrict__ members,
             float *__restrict__ gscratch_f, int32_t *__restrict__ gscratch_i) {
 	extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -178,10 +197,12 @@ k_meanshift(const int32_t *__restrict__ match_offsets, const int32_t *__restrict
 	int *s_i = reinterpret_cast<int *>(s_f + 4 * kCap);
 	unsigned *s_bits = reinterpret_cast<unsigned *>(s_i + 7 * kCap);
 	__shared__ int sh_n, sh_n_alive, sh_done;
-	const int m = blockIdx.x, tid = threadIdx.x;
+	const int tid = threadIdx.x;
+	const int n_listed = *n_list;
+	for (int li = blockIdx.x; li < n_listed; li += gridDim.x) {
+	__syncthreads();
+	const int m = list[li];
 	const int lo = match_offsets[m], hi = match_offsets[m + 1], cnt = hi - lo;
-	if (tid == 0) model_count[m] = 0;
-	if (cnt < min_pts || cnt <= 0) return;
 	MsArrays A;
 	int *pid;
 	if (cnt <= kCap) {
@@ -189,7 +210,7 @@ k_meanshift(const int32_t *__restrict__ match_offsets, const int32_t *__restrict
 		A.size = s_i; A.target = s_i + kCap; A.alive = s_i + 2 * kCap; A.head = s_i + 3 * kCap; A.tail = s_i + 4 * kCap; A.next = s_i + 5 * kCap;
 		pid = s_i + 6 * kCap;
 	} else {
-		const int tot = match_offsets[gridDim.x];
+		const int tot = match_offsets[n_models];
 		A.cx = gscratch_f + lo; A.cy = gscratch_f + tot + lo; A.ax = gscratch_f + 2 * tot + lo; A.ay = gscratch_f + 3 * tot + lo;
 		A.size = gscratch_i + lo; A.target = gscratch_i + tot + lo; A.alive = gscratch_i + 2 * tot + lo; A.head = gscratch_i + 3 * tot + lo;
 		A.tail = gscratch_i + 4 * tot + lo; A.next = gscratch_i + 5 * tot + lo;
@@ -219,6 +240,7 @@ k_meanshift(const int32_t *__restrict__ match_offsets, const int32_t *__restrict
 		if (n == 0) continue;
 		meanshift_group(A, n, sq_radius, sq_merge, min_pts, max_iter, pid, &model_count[m], sizes + lo, members + lo, n_clusters, n_members,
 		                &sh_n_alive, &sh_done, s_bits);
+	}
 	}
 }
 
@@ -284,7 +306,12 @@ mc_status cluster_device(mc_ctx *ctx, const int32_t *d_match_offsets, const int3
 	MC_TRY(reserve(ctx, b_members, sizeof(int32_t) * (max_matches + 1)));
 	MC_TRY(reserve(ctx, b_f, sizeof(float) * 4 * (size_t)(max_matches + 1)));
 	MC_TRY(reserve(ctx, b_i, sizeof(int32_t) * 7 * (size_t)(max_matches + 1)));
-	k_meanshift<<<n_models, kClusterThreads, kClusterSmem, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, n_images, radius, merge, min_pts, max_iter,
+	MC_TRY(reserve(ctx, ctx->scratch[8], sizeof(int32_t) * (size_t)(n_models + 16)));
+	int32_t *d_list = (int32_t *)ctx->scratch[8].p + 16, *d_n_list = (int32_t *)ctx->scratch[8].p;
+	k_cluster_nonempty<<<1, 1024, 0, ctx->stream>>>(d_match_offsets, n_models, min_pts, (int32_t *)b_count.p, d_list, d_n_list);
+	MC_LAUNCH_CHECK();
+	k_meanshift<<<n_models < 64 ? n_models : 64, kClusterThreads, kClusterSmem, ctx->stream>>>(d_match_offsets, d_match_image, d_match_xy, n_models, n_images,
+	                                                         radius, merge, min_pts, max_iter, d_list, d_n_list,
 	                                                         (int32_t *)b_count.p, (int32_t *)b_sizes.p, (int32_t *)b_members.p,
 	                                                         (float *)b_f.p, (int32_t *)b_i.p);
 	MC_LAUNCH_CHECK();

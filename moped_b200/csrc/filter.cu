@@ -5,8 +5,8 @@
 //                    in-cluster flag per (object, match), score = sum 1/(err+1) in match order (:95-115)
 //   k_filter_own     one thread per match: best (score, visit order) over the objects whose cluster holds a
 //                    match with the same (coord2D, image) key — `bestPoints` (:117-129)
-//   k_filter_rebuild one thread per object: owned matches of its own model -> new cluster; keep/prune (:135-160)
-//   k_filter_compact survivors' clusters in reference order (model-major, list order)
+//   k_filter_compact one CTA: owned matches of every object's own model, keep/prune (:135-160), then the survivors' clusters in
+//                    reference order (model-major, list order)
 // moped3d's FILTER_PROJECTION_DEPTH_CPU (moped3d/libmoped/src/filter/FILTER_PROJECTION_DEPTH_CPU.hpp:145-329) is the same filter with a
 // penalty from the depth map subtracted from the score before pruning (k_filter_depth_adjust); ownership keeps the unpenalised score.
 #include "common.cuh"
@@ -86,6 +86,16 @@ __global__ void k_filter_score(const int32_t *__restrict__ match_offsets, const 
 	}
 }
 
+// model whose match range holds match j (match_offsets ascending, empty models allowed): the last m with match_offsets[m] <= j
+__device__ __forceinline__ int model_of_match(const int32_t *__restrict__ match_offsets, int n_models, int j) {
+	int lo = 0, hi = n_models - 1;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (match_offsets[mid] <= j) lo = mid; else hi = mid - 1;
+	}
+	return lo;
+}
+
 __device__ __forceinline__ bool better(float s, int m, int o, float bs, int bm, int bo) {
 	// strictly higher score wins; on equal score the object visited first (model-major, then list order)
 	if (s != bs) return s > bs;
@@ -96,7 +106,7 @@ __device__ __forceinline__ bool better(float s, int m, int o, float bs, int bm, 
 // owner[j] = object owning match j's (coord2D, image) key, or -1. One CTA per match: the threads scan all
 // matches for the same key (usually only j itself), candidates are reduced by (score desc, visit order asc).
 __global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_models, const int32_t *__restrict__ match_image,
-                             const float *__restrict__ match_xy, const int32_t *__restrict__ match_model,
+                             const float *__restrict__ match_xy,
                              const int32_t *__restrict__ obj_model, const int32_t *__restrict__ n_obj_p, int n_obj_cap, int stride,
                              const uint8_t *__restrict__ in_cluster, const float *__restrict__ score, int32_t *__restrict__ owner) {
 	__shared__ float s_bs[4]; __shared__ int s_bm[4], s_bo[4];
@@ -110,7 +120,7 @@ __global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_mo
 	float bs = 0.f; int bm = 0x7fffffff, bo = -1;
 	for (int j2 = threadIdx.x; j2 < M; j2 += blockDim.x) {
 		if (match_image[j2] != im || match_xy[2 * j2] != x || match_xy[2 * j2 + 1] != y) continue;
-		const int m2 = match_model[j2];
+		const int m2 = model_of_match(match_offsets, n_models, j2);
 		const int lo2 = match_offsets[m2];
 		for (int o = 0; o < n_obj; o++) {
 			if (obj_model[o] != m2 || !in_cluster[(size_t)o * stride + (j2 - lo2)]) continue;
@@ -136,27 +146,12 @@ __global__ void k_filter_own(const int32_t *__restrict__ match_offsets, int n_mo
 	}
 }
 
-// per object: number of owned matches of its own model, keep flag
-__global__ void k_filter_rebuild(const int32_t *__restrict__ match_offsets, const int32_t *__restrict__ obj_model,
-                                 const int32_t *__restrict__ n_obj_p, int n_obj_cap, const int32_t *__restrict__ owner,
-                                 const float *__restrict__ score, int min_points, float min_score,
-                                 int32_t *__restrict__ owned, uint8_t *__restrict__ keep) {
-	const int o = blockIdx.x * blockDim.x + threadIdx.x;
-	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
-	if (o >= n_obj) return;
-	const int m = obj_model[o];
-	int c = 0;
-	for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) c += owner[j] == o;
-	owned[o] = c;
-	keep[o] = (c < min_points || score[o] < min_score) ? 0 : 1;
-}
-
 // one CTA: survivors in (model, list order) -> cluster CSR; also the surviving object list in list order.
 // out_n = {#survivors, #members}
 __global__ void k_filter_compact(const int32_t *__restrict__ match_offsets, int n_models, const int32_t *__restrict__ obj_model,
                                  const float *__restrict__ obj_pose, const int32_t *__restrict__ n_obj_p, int n_obj_cap,
-                                 const int32_t *__restrict__ owner, const int32_t *__restrict__ owned, const uint8_t *__restrict__ keep,
-                                 const float *__restrict__ score,
+                                 const int32_t *__restrict__ owner, int32_t *__restrict__ owned, uint8_t *__restrict__ keep,
+                                 const float *__restrict__ score, int min_points, float min_score,
                                  int32_t *__restrict__ out_n, int32_t *__restrict__ cluster_model, int32_t *__restrict__ cluster_offsets,
                                  int32_t *__restrict__ members, int32_t *__restrict__ surv_model, float *__restrict__ surv_pose,
                                  float *__restrict__ surv_score) {
@@ -165,6 +160,14 @@ __global__ void k_filter_compact(const int32_t *__restrict__ match_offsets, int 
 	const int n_obj = n_obj_p ? min(*n_obj_p, n_obj_cap) : n_obj_cap;
 	const int tid = threadIdx.x;
 	if (tid == 0) { s_tot[0] = 0; s_tot[1] = 0; }
+	// per object: number of owned matches of its own model, keep flag (:135-160)
+	for (int o = tid; o < n_obj; o += blockDim.x) {
+		const int m = obj_model[o];
+		int c = 0;
+		for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) c += owner[j] == o;
+		owned[o] = c;
+		keep[o] = (c < min_points || score[o] < min_score) ? 0 : 1;
+	}
 	__syncthreads();
 	// rank of every survivor in (model, list index) order and start of its members: O(n_obj^2), n_obj is small
 	for (int o = tid; o < n_obj; o += blockDim.x) {
@@ -271,12 +274,6 @@ __global__ void k_filter_depth_adjust(const int32_t *__restrict__ match_offsets,
 	}
 }
 
-__global__ void k_match_model_of(const int32_t *__restrict__ match_offsets, int n_models, int32_t *__restrict__ match_model) {
-	const int m = blockIdx.x * blockDim.x + threadIdx.x;
-	if (m >= n_models) return;
-	for (int j = match_offsets[m]; j < match_offsets[m + 1]; j++) match_model[j] = m;
-}
-
 static mc_status filter_device_impl(mc_ctx *ctx, const int32_t *d_match_offsets, const int32_t *d_match_image, const float *d_match_xy,
                         const float *d_match_xyz, int n_models, int max_matches, const int32_t *d_obj_model, const float *d_obj_pose,
                         const int32_t *d_n_obj, int n_obj_cap, int min_points, float feat_dist, float min_score, const DepthFilterArgs *D,
@@ -321,13 +318,12 @@ static mc_status filter_device_impl(mc_ctx *ctx, const int32_t *d_match_offsets,
                         uint8_t *d_keep, float *d_score, int32_t *d_out_n, int32_t *d_cluster_model, int32_t *d_cluster_offsets,
                         int32_t *d_members, int32_t *d_surv_model, float *d_surv_pose, float *d_surv_score) {
 	if (!ctx->d_cams) { ctx->err = "filter: cameras not set (mc_set_cameras)"; return MC_ERR_STATE; }
-	DevBuf &b_in = ctx->scratch[5], &b_owner = ctx->scratch[6], &b_owned = ctx->scratch[7], &b_mm = ctx->scratch[8];
+	DevBuf &b_in = ctx->scratch[5], &b_owner = ctx->scratch[6], &b_owned = ctx->scratch[7];
 	const int stride = max_matches > 0 ? max_matches : 1;
 	const int cap = n_obj_cap > 0 ? n_obj_cap : 1;
 	MC_TRY(reserve(ctx, b_in, (size_t)cap * stride));
 	MC_TRY(reserve(ctx, b_owner, sizeof(int32_t) * (size_t)(max_matches + 1)));
 	MC_TRY(reserve(ctx, b_owned, sizeof(int32_t) * (size_t)(cap + 1)));
-	MC_TRY(reserve(ctx, b_mm, sizeof(int32_t) * (size_t)(max_matches + 1)));
 	// depth variant: ownership is decided by the projection score (d_raw), pruning and output use the penalised one (d_score)
 	float *d_raw = d_score;
 	if (D) { MC_TRY(reserve(ctx, ctx->scratch[22], sizeof(float) * (size_t)(cap + 1))); d_raw = (float *)ctx->scratch[22].p; }
@@ -342,21 +338,14 @@ static mc_status filter_device_impl(mc_ctx *ctx, const int32_t *d_match_offsets,
 			MC_LAUNCH_CHECK();
 		}
 	}
-	k_match_model_of<<<(n_models + 127) / 128, 128, 0, ctx->stream>>>(d_match_offsets, n_models, (int32_t *)b_mm.p);
-	MC_LAUNCH_CHECK();
 	if (max_matches > 0) {
-		k_filter_own<<<max_matches < 2 * ctx->num_sms ? max_matches : 2 * ctx->num_sms, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy, (const int32_t *)b_mm.p,
+		k_filter_own<<<max_matches < 2 * ctx->num_sms ? max_matches : 2 * ctx->num_sms, 128, 0, ctx->stream>>>(d_match_offsets, n_models, d_match_image, d_match_xy,
 		                                                            d_obj_model, d_n_obj, n_obj_cap, stride, (const uint8_t *)b_in.p, d_raw,
 		                                                            (int32_t *)b_owner.p);
 		MC_LAUNCH_CHECK();
 	}
-	if (n_obj_cap > 0) {
-		k_filter_rebuild<<<(n_obj_cap + 63) / 64, 64, 0, ctx->stream>>>(d_match_offsets, d_obj_model, d_n_obj, n_obj_cap, (const int32_t *)b_owner.p, d_score,
-		                                                            min_points, min_score, (int32_t *)b_owned.p, d_keep);
-		MC_LAUNCH_CHECK();
-	}
 	k_filter_compact<<<1, 256, 0, ctx->stream>>>(d_match_offsets, n_models, d_obj_model, d_obj_pose, d_n_obj, n_obj_cap, (const int32_t *)b_owner.p,
-	                                            (const int32_t *)b_owned.p, d_keep, d_score, d_out_n, d_cluster_model, d_cluster_offsets, d_members,
+	                                            (int32_t *)b_owned.p, d_keep, d_score, min_points, min_score, d_out_n, d_cluster_model, d_cluster_offsets, d_members,
 	                                            d_surv_model, d_surv_pose, d_surv_score);
 	MC_LAUNCH_CHECK();
 	return MC_OK;

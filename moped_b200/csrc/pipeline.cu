@@ -37,7 +37,7 @@ k_match_compact(const FrameDesc *__restrict__ fd, int64_t row_base,
                 const int32_t *__restrict__ model_of_row, const float *__restrict__ db_xyz, int n_models, int32_t *__restrict__ acc_list,
                 int32_t *__restrict__ match_offsets, int32_t *__restrict__ match_query, int32_t *__restrict__ match_row,
                 int32_t *__restrict__ match_image, float *__restrict__ match_xy, float *__restrict__ match_xyz,
-                int32_t *__restrict__ status) {
+                int32_t *__restrict__ status, int32_t *__restrict__ n_obj) {
 	const int32_t *__restrict__ nn_row = fd->nn_row;
 	const uint8_t *__restrict__ accepted = fd->accepted;
 	const float *__restrict__ q_xy = fd->q_xy;
@@ -47,7 +47,7 @@ k_match_compact(const FrameDesc *__restrict__ fd, int64_t row_base,
 	__shared__ int s_warp[32];
 	__shared__ int s_base;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-	if (tid == 0) s_base = 0;
+	if (tid == 0) { s_base = 0; status[0] = 0; n_obj[0] = 0; }      // (two memset nodes of the frame chain less)
 	__syncthreads();
 	for (int q0 = 0; q0 < Q; q0 += 1024) {
 		const int q = q0 + tid;
@@ -209,12 +209,10 @@ static mc_status frame_enqueue(mc_ctx *ctx, const float *d_q, int Q, const mc_pi
 	const FrameDesc *fd = (const FrameDesc *)ctx->frame_desc.p;
 	const int cl_cap = caps.cl_cap, obj_cap = caps.obj_cap;
 	auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], ctx->stream); };
-	MC_CUDA(cudaMemsetAsync(B.status, 0, 64, ctx->stream));
-	MC_CUDA(cudaMemsetAsync(B.n_obj, 0, 64, ctx->stream));
-	mark(0);
+	mark(0);                                             // (B.status / B.n_obj are zeroed by k_match_compact)
 	if (d_q) MC_TRY(match_device(ctx, d_q, Q, P->match_ratio, P->match_mode, B.nn_row, B.nn_dist, B.accepted));
 	k_match_compact<<<1, 1024, 0, ctx->stream>>>(fd, ctx->table_base, ctx->d_model_of_row, ctx->d_xyz, ctx->n_models,
-	                                            B.acc_list, B.match_offsets, B.match_query, B.match_row, B.match_image, B.match_xy, B.match_xyz, B.status);
+	                                            B.acc_list, B.match_offsets, B.match_query, B.match_row, B.match_image, B.match_xy, B.match_xyz, B.status, B.n_obj);
 	MC_LAUNCH_CHECK();
 	mark(1);
 	// CLUSTER
@@ -459,10 +457,8 @@ mc_status process_frame_sharded_device(mc_ctx *ctx, int phase, const int32_t *d_
 		d.out_info = d_out_info; d.out_model = d_out_model; d.out_pose = d_out_pose; d.out_score = d_out_score;
 		MC_TRY(set_frame_desc(ctx, d));
 		fd = (const FrameDesc *)ctx->frame_desc.p;
-		MC_CUDA(cudaMemsetAsync(B.status, 0, 64, ctx->stream));
-		MC_CUDA(cudaMemsetAsync(B.n_obj, 0, 64, ctx->stream));
 		k_match_compact<<<1, 1024, 0, ctx->stream>>>(fd, ctx->table_base, ctx->d_model_of_row, ctx->d_xyz, ctx->n_models,
-		                                            B.acc_list, B.match_offsets, B.match_query, B.match_row, B.match_image, B.match_xy, B.match_xyz, B.status);
+		                                            B.acc_list, B.match_offsets, B.match_query, B.match_row, B.match_image, B.match_xy, B.match_xyz, B.status, B.n_obj);
 		MC_LAUNCH_CHECK();
 		MC_TRY(cluster_device(ctx, B.match_offsets, B.match_image, B.match_xy, ctx->n_models, ctx->n_images, Q, P->cluster_radius, P->cluster_merge,
 		                      P->cluster_min_pts, P->cluster_max_iterations, B.cl_n, B.cl_model, B.cl_offsets, B.cl_members));

@@ -84,11 +84,15 @@ k_ransac_first(const int32_t *__restrict__ cluster_offsets, const int32_t *__res
 	__shared__ float s_fit[P::kFitSmemFloats > 0 ? 16 * P::kFitSmemFloats : 1];
 	const int lane = threadIdx.x & 31, lig = lane & 7, grp = lane >> 3;
 	const unsigned mask = 0xFFu << (8 * grp);
-	const int g = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + grp;
-	const int task = g / HA, h = g - task * HA;
 	const int n_clusters = n_clusters_p ? min(*n_clusters_p, n_clusters_cap) : n_clusters_cap;
+	// the grid may be smaller than the task bound (a lane of a frame batch: the clusters that exist are the first few tasks): groups
+	// are walked with the grid's stride, the ones beyond the clusters that exist cost one comparison
+	const int64_t n_groups = (int64_t)n_clusters * max_obj * HA;
+	for (int64_t g64 = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + grp; g64 < n_groups; g64 += (int64_t)gridDim.x * (blockDim.x >> 5) * 4) {
+	const int g = (int)g64;
+	const int task = g / HA, h = g - task * HA;
 	const int c = task / max_obj;
-	if (c >= n_clusters || h >= max_ransac || !ransac_owns(S, c)) return;
+	if (c >= n_clusters || h >= max_ransac || !ransac_owns(S, c)) continue;
 	const int lo = cluster_offsets[c], n = cluster_offsets[c + 1] - lo;
 	const float *cxy = xy + 2 * lo, *cxyz = xyz + 3 * lo;
 	const int32_t *cim = image + lo, *ctie = tie ? tie + lo : nullptr;
@@ -121,6 +125,7 @@ k_ransac_first(const int32_t *__restrict__ cluster_offsets, const int32_t *__res
 				S.queue[q] = task; S.qpos[task] = q;
 			}
 		}
+	}
 	}
 }
 
@@ -187,15 +192,14 @@ k_ransac_refit(const int32_t *__restrict__ cluster_offsets, const int32_t *__res
                int n_tasks, uint8_t *__restrict__ found, float *__restrict__ pose_out, int32_t *__restrict__ n_tests) {
 	__shared__ int s_list[4][P::kRefitListInts];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int task = blockIdx.x * 4 + w;
-	if (task >= n_tasks) return;
 	const int n_clusters = n_clusters_p ? min(*n_clusters_p, n_clusters_cap) : n_clusters_cap;
+	for (int task = blockIdx.x * 4 + w; task < n_tasks; task += gridDim.x * 4) {       // (bounded grid on the lanes of a frame batch)
 	const int c = task / max_obj;
-	if (c >= n_clusters || !ransac_owns(S, c)) { if (lane == 0) { found[task] = 0; n_tests[task] = 0; } return; }
+	if (c >= n_clusters || !ransac_owns(S, c)) { if (lane == 0) { found[task] = 0; n_tests[task] = 0; } continue; }
 	const int f = S.first[task];
 	if (f == kNone) {
 		if (lane == 0) { found[task] = 0; n_tests[task] = S.fail[task] ? 0 : max_ransac; }
-		return;
+		continue;
 	}
 	const float *src = S.fit_pose + ((size_t)task * HA + f) * 7;
 	if (f >= HA) {
@@ -214,6 +218,8 @@ k_ransac_refit(const int32_t *__restrict__ cluster_offsets, const int32_t *__res
 #pragma unroll
 		for (int j = 0; j < 7; j++) pose_out[7 * task + j] = pose[j];
 		found[task] = 1; n_tests[task] = f + 1;
+	}
+	__syncwarp();
 	}
 }
 
@@ -258,7 +264,10 @@ mc_status ransac_staged_launch(mc_ctx *ctx, const int32_t *d_cluster_offsets, co
 	k_ransac_init<<<(n_tasks + 255) / 256, 256, 0, ctx->stream>>>(S, n_tasks);
 	MC_LAUNCH_CHECK();
 	const int64_t groups = (int64_t)n_tasks * HA;
-	k_ransac_first<P><<<(unsigned)((groups + 15) / 16), 128, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, d_tie,
+	// lanes of a frame batch: at most half an SM count of CTAs per launch (1184 groups / 296 refits at a time; the rest by the grid stride) —
+	// the bounds cl_cap x max_obj are hundreds of times the clusters a frame has, and 64 frames' worth of such grids queue behind each other
+	const int64_t first_ctas = (groups + 15) / 16, refit_ctas = ((int64_t)n_tasks + 3) / 4, lane_cap = ctx->num_sms / 2;
+	k_ransac_first<P><<<(unsigned)(ctx->parent && first_ctas > lane_cap ? lane_cap : first_ctas), 128, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, d_tie,
 	                                                                          ctx->d_cams, pp->max_objects_per_cluster, R, pp->max_lm_tests,
 	                                                                          pp->n_pts_align, pp->min_npts_object, pp->error_threshold, pp->seed, HA, S);
 	MC_LAUNCH_CHECK();
@@ -274,7 +283,7 @@ mc_status ransac_staged_launch(mc_ctx *ctx, const int32_t *d_cluster_offsets, co
 		                                                                L.h_begin[l], L.h_begin[l + 1], L.slot_base[l], L.slots, S);
 		MC_LAUNCH_CHECK();
 	}
-	k_ransac_refit<P><<<(n_tasks + 3) / 4, 128, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, ctx->d_cams,
+	k_ransac_refit<P><<<(unsigned)(ctx->parent && refit_ctas > lane_cap ? lane_cap : refit_ctas), 128, 0, ctx->stream>>>(d_cluster_offsets, d_n_clusters, n_clusters_cap, d_xy, d_xyz, d_image, ctx->d_cams,
 	                                                             pp->max_objects_per_cluster, R, pp->max_lm_tests, pp->error_threshold, HA,
 	                                                             L, S, n_tasks, d_found, d_pose, d_n_tests);
 	MC_LAUNCH_CHECK();
