@@ -253,7 +253,7 @@ def workload_config(args, world):
             "frames_per_step": args.frames,
             "parallelism": f"db-sharded-by-object x{world}, frames after MATCH partitioned x{world}" if world > 1 else "single-gpu",
             "l2": "db tile image > 2x L2, not flushed" if img_bytes >= 2 * L2_BYTES else "L2 flushed between steps (256 MiB write)",
-            "pose_mode": args.pose_mode, "match_coarse_kind": args.coarse_kind, "match_reserve_sms": args.reserve_sms, "batches_pool": 2, "frame_lanes": args.lanes, "batch_graph": args.batch_graph, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
+            "pose_mode": args.pose_mode, "match_coarse_kind": args.coarse_kind, "match_reserve_sms": args.reserve_sms, "batches_pool": 2, "frame_lanes": args.lanes, "batch_graph": args.batch_graph, "ransac_merge_levels": args.merge_levels, "pose_warps_per_task": args.pose_warps, "match_chunks": args.chunks,
             "pipeline": (f"software-pipelined on one context: MATCH of step i+1 (mc_match_dev, coarse kernel on the MATCH partition) runs beside "
                          f"CLUSTER..FILTER2 of step i (mc_process_frames_matched_dev with deferred lane join, lanes on a {args.stage_sms}-SM stage "
                          "partition, CUDA green contexts); every step completes inside the timed region" if args.pipeline else "one mc_process_frames* call per step")}
@@ -270,8 +270,8 @@ def resolve_auto(args, world):
         args.stage_sms = 16 if args.pipeline else 0
     if args.pipeline and args.stage_sms and args.lanes > 16:
         args.lanes = 16            # lane streams + the MATCH streams must stay below the 32 hardware connections (no false dependencies)
-    if args.pose_warps <= 0:       # first-round hypotheses per RANSAC task: with a whole batch on the GPU speculation costs throughput (3.14 vs 3.35 ms
-        args.pose_warps = 1 if per_gpu >= 32 else 4      # per 64 frames); with few frames per GPU it buys latency
+    if args.pose_warps <= 0:       # first-round hypotheses per RANSAC task (with levels 1 and 2 merged: 4 -> 2.74 ms, 1 -> 3.95 ms per 64 frames)
+        args.pose_warps = 4
     if args.lanes <= 0:            # not pipelined: one lane per frame, all chains of a batch in one CUDA graph ("batch_graph")
         args.lanes = 16 if args.pipeline else min(64, max(1, per_gpu))
     return args
@@ -320,6 +320,7 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_option("match_coarse_kind", args.coarse_kind)
     ctx.set_option("match_reserve_sms", args.reserve_sms)
     ctx.set_option("batch_graph", args.batch_graph)
+    ctx.set_option("ransac_merge_levels", args.merge_levels)
     if args.pose_mode == "exact":          # POSE / POSE2 with the order-preserving LM: every frame equals the oracle chain bit for bit
         ctx.set_option("pose_exact_order", 1)
     params = ctx.default_params()
@@ -1480,8 +1481,9 @@ def main():
     ap.add_argument("--features", type=int, default=2000)
     ap.add_argument("--frames", type=int, default=64, help="independent frames per step (batch)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent frames after MATCH (mc_set_tuning); 0 = one per frame of a GPU's share, at most 64")
+    ap.add_argument("--merge-levels", type=int, default=1, choices=[0, 1], help="frames workload: RANSAC levels 1 and 2 in one launch (mc_set_option ransac_merge_levels)")
     ap.add_argument("--batch-graph", type=int, default=1, choices=[0, 1], help="frames workload: the stage chains of a batch as ONE CUDA graph (default) or one graph per frame on the lane streams")
-    ap.add_argument("--pose-warps", type=int, default=0, help="first-round hypotheses per RANSAC task (mc_set_tuning); 0 = 1 with >= 32 frames per GPU, else 4")
+    ap.add_argument("--pose-warps", type=int, default=0, help="first-round hypotheses per RANSAC task (mc_set_tuning); 0 = 4")
     ap.add_argument("--chunks", type=int, default=1, help="MATCH launches per batch (mc_set_tuning)")
     ap.add_argument("--coarse-kind", type=int, default=1, choices=[0, 1], help="1 = 8-bit integer coarse pass first (default), 0 = fp16 coarse pass only; same results")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent matching kernel leaves free for concurrent stage kernels")

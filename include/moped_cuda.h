@@ -411,6 +411,10 @@ mc_status mc_linkage_agglomerate(mc_ctx *ctx, const float *similarity, int n, fl
  *                          concurrent work (the frame lanes' stage kernels of an earlier chunk or step) finds free SMs
  *   "frame_graphs"         != 0 (default): mc_process_frames* replay one CUDA graph per frame for the stages after
  *                          MATCH instead of ~40 kernel launches (same kernels, same results)
+ *   "ransac_merge_levels"  != 0 (default): the staged RANSAC tests the 36 hypotheses after the first round in one launch (8-warp CTAs)
+ *                          instead of 4 and then 32 in two: a task whose first hypotheses fail costs one more LM chain latency instead
+ *                          of two, at the price of more speculative fits (CLUSTER..FILTER2 of a 64-frame batch 3.2 -> 2.7 ms with 4
+ *                          first-round hypotheses per task). Same winner (the lowest successful hypothesis index).
  *   "batch_graph"          != 0 (default): the stage chains of ALL frames of an mc_process_frames* call are captured into ONE CUDA graph
  *                          (a branch per lane) and replayed with one launch per batch: graph branches are not bound by the 32
  *                          hardware stream connections, so 64 frames on 64 lanes run together instead of in two rounds. Not used

@@ -198,6 +198,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	if (k == "pose_fit_thread_min") ctx->fit_thread_min = value < 1 ? 1 : value;
 	else if (k == "pose_fit_stream") ctx->fit_stream = value != 0;
 	else if (k == "ransac_fused") ctx->ransac_fused = value != 0;
+	else if (k == "ransac_merge_levels") ctx->ransac_merge_levels = value != 0;
 	else if (k == "frame_graphs") ctx->frame_graphs = value != 0;
 	else if (k == "batch_graph") ctx->batch_graph = value != 0;
 	else if (k == "defer_lane_join") ctx->defer_lane_join = value != 0;
@@ -219,7 +220,7 @@ mc_status mc_set_option(mc_ctx *ctx, const char *key, int64_t value) {
 	else if (k == "sift_two_pass") return sift_set_two_pass(ctx, (int)value);
 	else if (k == "sift_describe_gather") return sift_set_gather(ctx, (int)value);
 	else { ctx->err = "mc_set_option: unknown key '" + k + "'"; return MC_ERR_ARG; }
-	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->fit_stream = ctx->fit_stream; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs; }
+	for (mc_ctx *lane : ctx->lanes) { lane->fit_thread_min = ctx->fit_thread_min; lane->fit_stream = ctx->fit_stream; lane->ransac_merge_levels = ctx->ransac_merge_levels; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs; }
 	return MC_OK;
 }
 

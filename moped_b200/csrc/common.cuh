@@ -105,6 +105,7 @@ struct mc_ctx {
 	int64_t fit_thread_min = 16384;   // mc_set_option: explicit-hypothesis calls with at least this many use one thread per hypothesis
 	bool fit_stream = true;           // mc_set_option "pose_fit_stream": the persistent phase-synchronous one-thread-per-hypothesis kernel (0: k_pose_fit_thread)
 	int ransac_shard_rank = 0, ransac_shard_world = 1;   // set around the RANSAC calls of mc_process_frame_sharded_dev (pose_staged.cuh)
+	bool ransac_merge_levels = true;  // mc_set_option "ransac_merge_levels" (pose_staged.cuh)
 	bool ransac_fused = false;        // mc_set_option: the one-CTA-per-task RANSAC kernel instead of the staged kernels (A/B aid)
 	int depth_team_lanes = 32;        // mc_set_option: lanes per explicit hypothesis in k_depth_hypotheses (32 or 8)
 	bool linkage_cached = true;       // mc_set_option: cached-row-maximum agglomeration (linkage_cached.cuh) for average linkage (0: the O(n^2)-scan kernel)

@@ -284,7 +284,7 @@ static mc_status frame_chain(mc_ctx *lane, int Q, const mc_pipeline_params *P, c
 	}
 	uint64_t cfg = fnv(1469598103934665603ULL, &q_cap, sizeof q_cap);
 	cfg = fnv(cfg, P, sizeof *P);
-	const int64_t ints[] = { lane->n_models, lane->n_images, lane->table_base, lane->pose_warps, lane->ransac_fused, (int64_t)lane->num_sms, lane->pose_exact_order };
+	const int64_t ints[] = { lane->n_models, lane->n_images, lane->table_base, lane->pose_warps, lane->ransac_fused, (int64_t)lane->num_sms, lane->pose_exact_order, lane->ransac_merge_levels };
 	cfg = fnv(cfg, ints, sizeof ints);
 	const void *ptrs[] = { lane->d_cams, lane->d_xyz, lane->d_model_of_row };
 	cfg = fnv(cfg, ptrs, sizeof ptrs);
@@ -511,7 +511,7 @@ static void lane_borrow(mc_ctx *ctx, mc_ctx *lane) {
 	lane->db_norm2_min = ctx->db_norm2_min; lane->db_norm2_max = ctx->db_norm2_max;
 	lane->d_cams = ctx->d_cams; lane->n_images = ctx->n_images;
 	lane->pose_warps = ctx->pose_warps;
-	lane->fit_thread_min = ctx->fit_thread_min; lane->fit_stream = ctx->fit_stream; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs;
+	lane->fit_thread_min = ctx->fit_thread_min; lane->fit_stream = ctx->fit_stream; lane->ransac_merge_levels = ctx->ransac_merge_levels; lane->ransac_fused = ctx->ransac_fused; lane->frame_graphs = ctx->frame_graphs;
 	lane->pose_exact_order = ctx->pose_exact_order;
 }
 
@@ -633,7 +633,7 @@ mc_status process_frames_device(mc_ctx *ctx, const float *d_q, const float *d_qx
 			uint64_t k = fnv(1469598103934665603ULL, descs.data(), sizeof(FrameDesc) * descs.size());
 			k = fnv(k, P, sizeof *P);
 			const int64_t ints[] = { nf, n_lanes, ctx->n_models, ctx->n_images, ctx->table_base, ctx->pose_warps, ctx->ransac_fused, (int64_t)ctx->num_sms,
-			                         ctx->pose_exact_order, max_objects };
+			                         ctx->pose_exact_order, max_objects, ctx->ransac_merge_levels };
 			k = fnv(k, ints, sizeof ints);
 			const void *ptrs[] = { ctx->d_cams, ctx->d_xyz, ctx->d_model_of_row };
 			k = fnv(k, ptrs, sizeof ptrs);

@@ -29,6 +29,8 @@ constexpr int kPoseThreads = 256;
 //                     level 1: the next 4 hypotheses, one warp per task (a fit succeeds with probability ~1/2 on a real
 //                              cluster, so almost every task ends here);
 //                     level 2: the next 32, one CTA of 8 warps per task;
+//                     (default since round 2, "ransac_merge_levels": levels 1 and 2 as ONE launch over the next 36 — the batch of a
+//                      step always holds some task that escalates, and every escalation step is one LM chain latency for the batch)
 //                     level 3: ALL remaining ones at once, 32 per item, chunk-major. A cluster that fails all
 //                              MaxRANSACTests tests occupies the machine for about one LM latency instead of one SM for
 //                              MaxRANSACTests/32 of them. (Running level 3 straight after the first kernel was measured:
@@ -236,8 +238,10 @@ mc_status ransac_staged_launch(mc_ctx *ctx, const int32_t *d_cluster_offsets, co
 	const int R = pp->max_ransac_tests;
 	const int HA = warps < R ? warps : (R > 0 ? R : 1);
 	RansacLevels L;
-	const int level_warps[kLevels] = { 1, 8, 8 };
-	const int level_span[kLevels] = { 4, 32, 1 << 30 };
+	// mc_set_option "ransac_merge_levels": levels 1 and 2 as ONE launch of 8-warp CTAs over the next 36 hypotheses (a task whose first
+	// hypotheses fail then costs one more LM chain latency instead of two; more speculative work)
+	const int level_warps[kLevels] = { ctx->ransac_merge_levels ? 8 : 1, 8, 8 };
+	const int level_span[kLevels] = { ctx->ransac_merge_levels ? 36 : 4, ctx->ransac_merge_levels ? 0 : 32, 1 << 30 };
 	L.h_begin[0] = HA < R ? HA : R;
 	L.slots = 0;
 	for (int l = 0; l < kLevels; l++) {

@@ -334,6 +334,12 @@ def test_staged_ransac_equals_one_cta_per_task_kernel(gpu_ctx, first_round):
             assert np.array_equal(f0, f1), max_ransac
             assert np.array_equal(n0, n1), (max_ransac, n0, n1)
             assert np.array_equal(p0[f0], p1[f1]), max_ransac
+            gpu_ctx.set_option("ransac_merge_levels", 1)                 # levels 1 and 2 in one launch: the same winner
+            try:
+                f2, p2, n2 = gpu_ctx.pose_ransac(off, xy, xyz, img, P, seed=11)
+            finally:
+                gpu_ctx.set_option("ransac_merge_levels", 0)
+            assert np.array_equal(f0, f2) and np.array_equal(n0, n2) and np.array_equal(p0[f0], p2[f2]), max_ransac
             assert not f1[-4:].any() and (n1[-4:] == 0).all()            # too few distinct points
             assert (n1[-8:-4] == max_ransac).all() or f1[-8:-4].any()     # the junk cluster normally exhausts its tests
         assert f1[:24].all()
