@@ -278,7 +278,8 @@ mc_status mc_process_frames_matched_dev(mc_ctx *ctx, const int32_t *nn_row_dev, 
  * bit for bit for any shard_world. Three asynchronous calls per frame with the caller's exchange between them:
  *   phase 0 -> all-gather `exchange_dev` in place (slot r = rank r's record) -> phase 1 -> all-gather again -> phase 2.
  * exchange_dev: shard_world x mc_frame_shard_slot_bytes(n_features, params) bytes; this rank writes slot shard_rank only.
- * The same arguments must be passed to all three phases. Outputs (phase 2, device): frame_info 4 ints {objects, status, accepted
+ * The same arguments must be passed to all three phases, and no other frame / stage call may run on this context between phase 0 and
+ * phase 2 (the frame's intermediate state lives in the context's scratch buffers). Outputs (phase 2, device): frame_info 4 ints {objects, status, accepted
  * matches, clusters after CLUSTER}, obj_model max_objects, obj_pose 7*max_objects, obj_score max_objects — identical on every rank. */
 size_t mc_frame_shard_slot_bytes(int n_features, const mc_pipeline_params *params);
 mc_status mc_process_frame_sharded_dev(mc_ctx *ctx, int phase, const int32_t *nn_row_dev, const uint8_t *accepted_dev, const float *q_xy_dev,
