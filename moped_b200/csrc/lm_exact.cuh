@@ -7,6 +7,10 @@
 // and every reduction runs in the order of libs.tgz!levmar-2.4 (lm_core.c:427-836, misc_core.c:135-168,712-790,
 // Axb_core.c:888-1035), i.e. the result is the strict-IEEE build's, bit for bit, however many lanes work on it.
 //
+// Provenance: this file is DERIVED FROM levmar 2.4 (Manolis Lourakis; GPL; vendored by the reference as libs.tgz!levmar-2.4): the LM driver,
+// the Jacobian approximation and the LU solve restate lm_core.c / misc_core.c / Axb_core.c operation by operation — bit-exactness
+// with the reference leaves no freedom there. The lane-team decomposition below is this repository's.
+//
 // How the work is split without touching the order:
 //   * residuals, the finite-difference Jacobian and the Broyden rank-1 update are independent per correspondence /
 //     per residual row  -> lanes stride over them;

@@ -12,6 +12,12 @@
 // redundantly by every lane (no communication). Inlier scoring is a ballot over the cluster's points.
 // Compiled with -ftz=true: the reference process runs with FTZ/DAZ and its dominant LM exit is an
 // underflow of ||Dp||^2.
+//
+// Provenance: lm_dif and lu_solve7 are DERIVED FROM levmar 2.4 (Manolis Lourakis; GPL; vendored by the reference as
+// libs.tgz!levmar-2.4): the control flow of slevmar_dif (lm_core.c:427-836: damping, Broyden updates, the stop tests and their order),
+// the forward-difference Jacobian (misc_core.c:135-168) and the Crout LU with implicit scaling (Axb_core.c:888-1035) follow that
+// code step for step, with its variable names, because the result has to follow its arithmetic. The parallel decomposition (lane
+// groups, butterfly sums, the persistent state machine, LDL^T in front of the LU) is this repository's.
 #include "common.cuh"
 #include "ransac_sample.cuh"
 #include "pose_staged.cuh"
